@@ -97,6 +97,8 @@ class RefSim:
     def set_params(self, offset, gravity, method, blend=1.0, density=1.0, skin=0.1, stiffness=5.0,
                    extrap_iters=1, cfl_number=3.0):
         self.offset, self.gravity, self.method = _v3(offset), _v3(gravity), int(method)
+        self.blend, self.density, self.skin, self.stiffness = blend, density, skin, stiffness
+        self.extrap_iters, self.cfl_number = extrap_iters, cfl_number
         self.L.ref_set_params(self.ptr, _p(self.offset), _p(self.gravity), self.method, blend, density, skin,
                               stiffness, extrap_iters, cfl_number)
 
