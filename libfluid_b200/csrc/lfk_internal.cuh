@@ -1,0 +1,267 @@
+// Internal declarations shared by the lfk translation units (not part of the ABI).
+#pragma once
+
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <cstdio>
+#include <string>
+#include <vector>
+
+#include "lfk.h"
+
+// ---------------------------------------------------------------------------------------------------------
+// Device-side description of the (slab of the) MAC grid.
+//
+// Every per-cell device array covers the cells this rank owns PLUS one ghost layer in z on either side:
+//   local raw index  lr = x + nx * (y + ny * lz),   lz = z - z0 + 1  in [0, nzl + 2)
+// x and y are not padded.  At the outer domain boundary the ghost layers are "outside the grid": type solid,
+// velocity 0, no particles -- which is exactly how the reference treats out-of-range neighbours
+// (mac_grid::get_cell_and_type, reference src/mac_grid.cpp:26-38).  Between ranks they mirror the neighbour's
+// boundary layer.
+// ---------------------------------------------------------------------------------------------------------
+struct GridDesc {
+	int nx, ny, nz;     // global size
+	int z0, nzl;        // first owned global z, number of owned layers
+	int nlz;            // nzl + 2
+	long long sxy;      // nx * ny
+	long long ncl;      // nx * ny * nlz  (local cells incl. ghosts)
+	long long nown;     // nx * ny * nzl
+	double h;           // cell_size
+	double off[3];      // grid_offset
+};
+
+enum { PF_PX = 0, PF_PY, PF_PZ, PF_VX, PF_VY, PF_VZ, PF_C0, PF_OX = 15, PF_OY, PF_OZ, PF_COUNT = 18 };
+
+struct ParticleSoA {
+	double *f[PF_COUNT];
+};
+
+// scalars of the PCG loop, kept on the device so that the iteration needs no host round trip
+struct PcgScalars {
+	double sigma;      // z.r of the previous iteration
+	double zs;         // z.s
+	double sigma_new;  // z.r
+	double resmax;     // max |r|
+	double bb;         // sum b^2
+	double alpha, beta;
+	unsigned long long iters;
+	int done;          // 1 once converged / early-out
+	int pad;
+};
+
+struct MgLevel {
+	int nx, ny, nlz;         // local size incl. z ghosts
+	int nzl;
+	long long sxy, ncl;
+	float *diag, *cx, *cy, *cz; // Galerkin 7-point operator (level >= 1); level 0 uses the flags
+	float *x, *b, *r;        // solution / rhs / residual scratch (fp32)
+};
+
+struct lfk_ctx {
+	int device = 0;
+	cudaStream_t stream = nullptr;
+	bool own_stream = false;
+	int nranks = 1, rank = 0;
+	void *comm = nullptr; // ncclComm_t
+	GridDesc g{};
+	lfk_params prm{};
+	std::string err;
+
+	// particles
+	uint64_t np = 0, cap = 0;
+	ParticleSoA P{}, Palt{};
+	uint32_t *key = nullptr, *key_alt = nullptr, *slot = nullptr, *perm = nullptr;
+	bool old_valid = false;   // false: old_position == position (not materialised)
+	bool table_valid = false;
+	bool keys_valid = false;
+
+	// grid (local cells incl. ghosts)
+	double *vel[3] = { nullptr, nullptr, nullptr };
+	double *vel_old[3] = { nullptr, nullptr, nullptr };
+	uint8_t *typ = nullptr;
+	uint32_t *cnt = nullptr, *begin = nullptr; // begin has ncl + 1 entries
+	double *ctr[3] = { nullptr, nullptr, nullptr }; // cell-centre coordinates per axis (reference: repeated addition)
+	uint8_t *valid[2] = { nullptr, nullptr };
+
+	// solver
+	uint8_t *flags = nullptr;
+	double *b = nullptr, *p = nullptr, *r = nullptr, *z = nullptr, *s = nullptr;
+	bool system_valid = false; double system_dt = 0.0;
+	bool pressure_valid = false;
+	PcgScalars *d_scal = nullptr, *h_scal = nullptr;
+	double *partials = nullptr;     // [4][MAX_PARTIAL_BLOCKS]
+	unsigned *ticket = nullptr;     // last-block counters
+	uint32_t *ordinal = nullptr;    // exclusive scan of (cnt > 0) over local cells, ncl + 1 entries
+	bool ordinal_valid = false;
+	std::vector<MgLevel> mg;
+	bool mg_valid = false;
+
+	// scratch
+	void *staging = nullptr; size_t staging_bytes = 0;
+	uint32_t *scan_tmp = nullptr; size_t scan_tmp_n = 0;
+	uint32_t *bigcells = nullptr; unsigned *bigcount = nullptr; unsigned bigcap = 0;
+	double *d_reduce = nullptr;     // small device scratch for reductions (cfl etc.)
+	double *h_reduce = nullptr;     // pinned
+
+	// stats
+	lfk_stats stats{};
+	bool timing = false;
+	int timer_depth = 0;
+	cudaEvent_t ev[2] = { nullptr, nullptr };
+};
+
+#define LFK_MAX_PARTIAL_BLOCKS 2048
+
+int lfk_fail(lfk_ctx *ctx, int code, const char *what, const char *file, int line);
+const char *lfk_cuda_err_name(cudaError_t e);
+
+#define LFK_CUDA(ctx, expr) do { cudaError_t e__ = (expr); if (e__ != cudaSuccess) { \
+	return lfk_fail((ctx), -(int)e__, cudaGetErrorString(e__), __FILE__, __LINE__); } } while (0)
+#define LFK_TRY(expr) do { int rc__ = (expr); if (rc__ != 0) { return rc__; } } while (0)
+#define LFK_REQUIRE(ctx, cond, code, msg) do { if (!(cond)) { \
+	return lfk_fail((ctx), (code), (msg), __FILE__, __LINE__); } } while (0)
+// kernel launch + launch counter + launch-error check
+#define LFK_LAUNCH(ctx, kernel, grid, block, smem, ...) do { \
+	kernel<<<(grid), (block), (smem), (ctx)->stream>>>(__VA_ARGS__); \
+	++(ctx)->stats.kernel_launches; \
+	LFK_CUDA((ctx), cudaPeekAtLastError()); } while (0)
+
+static inline unsigned lfk_blocks(long long n, int block) {
+	long long b = (n + block - 1) / block;
+	return (unsigned)(b < 1 ? 1 : b);
+}
+
+struct PhaseTimer { // accumulates device time of a phase into stats.phase_ms when timing is enabled
+	lfk_ctx *c; int phase; bool outer;
+	PhaseTimer(lfk_ctx *ctx, int ph) : c(ctx), phase(ph), outer(false) { // nested timers: only the outermost counts
+		if (c->timing && c->timer_depth++ == 0) {
+			outer = true;
+			cudaEventRecord(c->ev[0], c->stream);
+		}
+	}
+	~PhaseTimer() {
+		if (c->timing) { --c->timer_depth; }
+		if (outer) {
+			cudaEventRecord(c->ev[1], c->stream);
+			cudaEventSynchronize(c->ev[1]);
+			float ms = 0.f;
+			cudaEventElapsedTime(&ms, c->ev[0], c->ev[1]);
+			c->stats.phase_ms[phase] += ms;
+		}
+	}
+};
+
+// ---- implemented in particles.cu ----
+int lfkp_aos_to_soa(lfk_ctx *c, const void *d_aos, uint64_t n);
+int lfkp_soa_to_aos(lfk_ctx *c, void *d_aos, uint64_t n);
+int lfkp_positions_to_aos(lfk_ctx *c, double *d_xyz, uint64_t n);
+int lfkp_hash(lfk_ctx *c);
+int lfkp_advect(lfk_ctx *c, double dt);
+int lfkp_collide(lfk_ctx *c);
+int lfkp_advect_collide(lfk_ctx *c, double dt);       // fused, no old_position traffic
+int lfkp_correct(lfk_ctx *c, double dt);
+int lfkp_correct_collide(lfk_ctx *c, double dt);      // fused
+int lfkp_g2p(lfk_ctx *c);
+int lfkp_cfl(lfk_ctx *c, double *value);
+int lfkp_seed_box(lfk_ctx *c, const double *start, const double *size, const double *vel, uint32_t dens,
+	uint64_t seed, int append);
+int lfkp_exclusive_scan_u32(lfk_ctx *c, const uint32_t *in, uint32_t *out, long long n, int from_flags);
+int lfkp_reserve_particles(lfk_ctx *c, uint64_t n);
+
+// ---- implemented in p2g.cu ----
+int lfkg_p2g(lfk_ctx *c, double gravity_dt, bool add_gravity);
+int lfkg_gravity(lfk_ctx *c, double dt);
+
+// ---- implemented in pressure.cu ----
+int lfks_build_system(lfk_ctx *c, double dt);
+int lfks_solve(lfk_ctx *c, double dt, double *residual, uint64_t *iters);
+int lfks_apply_pressure(lfk_ctx *c, double dt);
+int lfks_extrapolate(lfk_ctx *c);
+int lfks_apply_a(lfk_ctx *c, double dt, const double *d_v_dense, double *d_out_dense);
+int lfks_synthetic_projection(lfk_ctx *c, uint64_t seed);
+int lfks_compact(lfk_ctx *c, const double *dense, double *d_out, const uint8_t *dense_u8, uint8_t *d_out_u8);
+int lfks_expand(lfk_ctx *c, const double *d_compact, double *dense);
+int lfks_ensure_ordinal(lfk_ctx *c);
+int lfks_fluid_cells(lfk_ctx *c, uint64_t *d_out);
+int lfks_export_flags(lfk_ctx *c, uint8_t *d_out_compact);
+
+// ---- implemented in exchange.cu (multi-GPU; no-ops when nranks == 1) ----
+int lfkx_init(lfk_ctx *c, const void *nccl_id128);
+int lfkx_destroy(lfk_ctx *c);
+int lfkx_halo_f64(lfk_ctx *c, double *field);          // fill both z ghost layers of a cell array from the neighbours
+int lfkx_halo_f32(lfk_ctx *c, float *field, int nx, int ny, int nzl);
+int lfkx_halo_u8(lfk_ctx *c, uint8_t *field);
+int lfkx_allreduce_sum(lfk_ctx *c, double *d_vals, int n);
+int lfkx_allreduce_max(lfk_ctx *c, double *d_vals, int n);
+
+// device helpers ------------------------------------------------------------------------------------------
+#ifdef __CUDACC__
+__device__ __forceinline__ double dmax_std(double a, double b) { // std::max(a, b)
+	return (a < b) ? b : a;
+}
+__device__ __forceinline__ double dclamp_std(double v, double lo, double hi) { // std::clamp
+	return (v < lo) ? lo : (hi < v) ? hi : v;
+}
+__device__ __forceinline__ unsigned long long mix64(unsigned long long x) {
+	x ^= x >> 30;
+	x *= 0xbf58476d1ce4e5b9ull;
+	x ^= x >> 27;
+	x *= 0x94d049bb133111ebull;
+	x ^= x >> 31;
+	return x;
+}
+// deterministic last-block reduction of per-block partials: every block stores its partial, the last block to
+// arrive (ticket) reduces all of them in a fixed order.  Returns true in thread 0 of the last block.
+__device__ __forceinline__ bool lfk_last_block(unsigned *ticket) {
+	__shared__ bool is_last;
+	__threadfence();
+	if (threadIdx.x == 0) {
+		unsigned t = atomicInc(ticket, gridDim.x - 1); // wraps back to 0 for the next use
+		is_last = (t == gridDim.x - 1);
+	}
+	__syncthreads();
+	return is_last;
+}
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+	for (int o = 16; o > 0; o >>= 1) {
+		v += __shfl_xor_sync(0xffffffffu, v, o);
+	}
+	return v;
+}
+__device__ __forceinline__ double warp_max(double v) {
+#pragma unroll
+	for (int o = 16; o > 0; o >>= 1) {
+		v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+	}
+	return v;
+}
+// block-wide sum / max (blockDim.x multiple of 32, <= 1024); result valid in thread 0
+__device__ __forceinline__ double block_sum(double v) {
+	__shared__ double sm[32];
+	int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+	v = warp_sum(v);
+	__syncthreads();
+	if (lane == 0) { sm[w] = v; }
+	__syncthreads();
+	if (w == 0) {
+		v = lane < (int)((blockDim.x + 31) >> 5) ? sm[lane] : 0.0;
+		v = warp_sum(v);
+	}
+	return v;
+}
+__device__ __forceinline__ double block_max(double v) {
+	__shared__ double sm[32];
+	int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+	v = warp_max(v);
+	__syncthreads();
+	if (lane == 0) { sm[w] = v; }
+	__syncthreads();
+	if (w == 0) {
+		v = lane < (int)((blockDim.x + 31) >> 5) ? sm[lane] : -1.0e300;
+		v = warp_max(v);
+	}
+	return v;
+}
+#endif

@@ -1,0 +1,984 @@
+// Per-particle kernels: AoS<->SoA, cell keys + stable cell sort, advection, collisions, position correction,
+// CFL reduction, grid-to-particle transfer.
+//
+// This file is compiled with --fmad=false: the reference's x86-64 build performs no FMA contraction, and the
+// particle-motion code is branchy (DDA marching, clamps, truncations), so keeping plain IEEE mul/add makes cell
+// indices bit-exact and positions reproducible against the CPU path.  All of these kernels are bandwidth bound;
+// the split mul/add costs nothing measurable.
+#include "lfk_internal.cuh"
+
+#include <cstring>
+
+// =========================================================================================================
+// AoS (152-byte reference records) <-> SoA, staged through shared memory so that both sides are coalesced
+// =========================================================================================================
+#define AOS_WORDS 19 // 18 doubles + size_t
+#define AOS_TILE 128
+
+__global__ void __launch_bounds__(AOS_TILE) k_aos_to_soa(const unsigned long long *__restrict__ aos, ParticleSoA P,
+	uint32_t *__restrict__ key, unsigned long long n, long long key_shift) {
+	__shared__ unsigned long long sm[AOS_TILE * AOS_WORDS];
+	unsigned long long base = (unsigned long long)blockIdx.x * AOS_TILE;
+	unsigned long long cnt = n - base < AOS_TILE ? n - base : AOS_TILE;
+	for (unsigned k = threadIdx.x; k < cnt * AOS_WORDS; k += AOS_TILE) {
+		sm[k] = aos[base * AOS_WORDS + k];
+	}
+	__syncthreads();
+	if (threadIdx.x < cnt) {
+		const unsigned long long *rec = sm + threadIdx.x * AOS_WORDS; // stride 19 words: conflict-free (odd)
+#pragma unroll
+		for (int f = 0; f < PF_COUNT; ++f) {
+			P.f[f][base + threadIdx.x] = __longlong_as_double((long long)rec[f]);
+		}
+		key[base + threadIdx.x] = (uint32_t)((long long)rec[18] + key_shift);
+	}
+}
+
+__global__ void __launch_bounds__(AOS_TILE) k_soa_to_aos(unsigned long long *__restrict__ aos, ParticleSoA P,
+	const uint32_t *__restrict__ key, unsigned long long n, int old_valid, long long key_shift) {
+	__shared__ unsigned long long sm[AOS_TILE * AOS_WORDS];
+	unsigned long long base = (unsigned long long)blockIdx.x * AOS_TILE;
+	unsigned long long cnt = n - base < AOS_TILE ? n - base : AOS_TILE;
+	if (threadIdx.x < cnt) {
+		unsigned long long *rec = sm + threadIdx.x * AOS_WORDS;
+		unsigned long long i = base + threadIdx.x;
+#pragma unroll
+		for (int f = 0; f < 15; ++f) {
+			rec[f] = (unsigned long long)__double_as_longlong(P.f[f][i]);
+		}
+#pragma unroll
+		for (int f = 0; f < 3; ++f) { // old_position == position unless materialised
+			rec[15 + f] = (unsigned long long)__double_as_longlong(old_valid ? P.f[PF_OX + f][i] : P.f[PF_PX + f][i]);
+		}
+		rec[18] = (unsigned long long)((long long)key[i] - key_shift);
+	}
+	__syncthreads();
+	for (unsigned k = threadIdx.x; k < cnt * AOS_WORDS; k += AOS_TILE) {
+		aos[base * AOS_WORDS + k] = sm[k];
+	}
+}
+
+__global__ void k_positions_interleave(double *__restrict__ xyz, const double *__restrict__ px,
+	const double *__restrict__ py, const double *__restrict__ pz, unsigned long long n) {
+	unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+	if (i < n) {
+		xyz[3 * i] = px[i];
+		xyz[3 * i + 1] = py[i];
+		xyz[3 * i + 2] = pz[i];
+	}
+}
+
+int lfkp_aos_to_soa(lfk_ctx *c, const void *d_aos, uint64_t n) {
+	if (n == 0) { return 0; }
+	// raw_cell_index is a whole-grid raw index; device keys are local (one ghost layer below the slab)
+	long long shift = ((long long)1 - c->g.z0) * c->g.sxy;
+	LFK_LAUNCH(c, k_aos_to_soa, lfk_blocks((long long)n, AOS_TILE), AOS_TILE, 0,
+		(const unsigned long long*)d_aos, c->P, c->key, (unsigned long long)n, shift);
+	return 0;
+}
+int lfkp_soa_to_aos(lfk_ctx *c, void *d_aos, uint64_t n) {
+	if (n == 0) { return 0; }
+	long long shift = ((long long)1 - c->g.z0) * c->g.sxy;
+	LFK_LAUNCH(c, k_soa_to_aos, lfk_blocks((long long)n, AOS_TILE), AOS_TILE, 0,
+		(unsigned long long*)d_aos, c->P, c->key, (unsigned long long)n, c->old_valid ? 1 : 0, shift);
+	return 0;
+}
+int lfkp_positions_to_aos(lfk_ctx *c, double *d_xyz, uint64_t n) {
+	if (n == 0) { return 0; }
+	LFK_LAUNCH(c, k_positions_interleave, lfk_blocks((long long)n, 256), 256, 0,
+		d_xyz, c->P.f[PF_PX], c->P.f[PF_PY], c->P.f[PF_PZ], (unsigned long long)n);
+	return 0;
+}
+
+// =========================================================================================================
+// K1: cell keys (reference src/simulation.cpp:251-261) -- must be bit-exact: IEEE sub, IEEE div, truncation
+// =========================================================================================================
+__device__ __forceinline__ int cell_coord_clamped(double pos, double off, double h, int n) {
+	double g = __ddiv_rn(__dsub_rn(pos, off), h);
+	g = dmax_std(g, 0.0);
+	// static_cast<size_t>: truncation toward zero; cvt.rzi.u64.f64 saturates, and anything >= n clamps to n - 1
+	unsigned long long v = (unsigned long long)g;
+	return (int)(v < (unsigned long long)(n - 1) ? v : (unsigned long long)(n - 1));
+}
+
+__global__ void k_keys_hist(GridDesc G, const double *__restrict__ px, const double *__restrict__ py,
+	const double *__restrict__ pz, uint32_t *__restrict__ key, uint32_t *__restrict__ slot,
+	uint32_t *__restrict__ cnt, unsigned long long n) {
+	unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+	bool active = i < n;
+	unsigned amask = __ballot_sync(0xffffffffu, active);
+	if (!active) { return; }
+	int x = cell_coord_clamped(px[i], G.off[0], G.h, G.nx);
+	int y = cell_coord_clamped(py[i], G.off[1], G.h, G.ny);
+	int z = cell_coord_clamped(pz[i], G.off[2], G.h, G.nz);
+	int lz = z - G.z0 + 1;
+	lz = lz < 0 ? 0 : (lz > G.nlz - 1 ? G.nlz - 1 : lz); // migrants are handled by the exchange layer
+	uint32_t k = (uint32_t)(x + (long long)G.nx * (y + (long long)G.ny * lz));
+	key[i] = k;
+	// warp-aggregated histogram: particles arrive nearly sorted, so a warp touches only a handful of cells
+	unsigned peers = __match_any_sync(amask, k);
+	int lane = threadIdx.x & 31;
+	int leader = __ffs(peers) - 1;
+	uint32_t basev = 0;
+	if (lane == leader) {
+		basev = atomicAdd(cnt + k, (uint32_t)__popc(peers));
+	}
+	basev = __shfl_sync(peers, basev, leader);
+	slot[i] = basev + (uint32_t)__popc(peers & ((1u << lane) - 1u));
+}
+
+// ---- exclusive scan over u32 (cell counts -> begin offsets) ------------------------------------------------
+#define SCAN_THREADS 256
+#define SCAN_ITEMS 8
+#define SCAN_TILE (SCAN_THREADS * SCAN_ITEMS)
+
+__device__ __forceinline__ uint32_t scan_load(const uint32_t *in, long long i, long long n, int from_flags) {
+	if (i >= n) { return 0u; }
+	uint32_t v = in[i];
+	return from_flags ? (v > 0u ? 1u : 0u) : v;
+}
+
+__global__ void __launch_bounds__(SCAN_THREADS) k_scan_tile_sums(const uint32_t *__restrict__ in,
+	uint32_t *__restrict__ tile_sum, long long n, int from_flags) {
+	__shared__ uint32_t sm[SCAN_THREADS / 32];
+	long long base = (long long)blockIdx.x * SCAN_TILE + (long long)threadIdx.x * SCAN_ITEMS;
+	uint32_t s = 0;
+#pragma unroll
+	for (int k = 0; k < SCAN_ITEMS; ++k) {
+		s += scan_load(in, base + k, n, from_flags);
+	}
+#pragma unroll
+	for (int o = 16; o > 0; o >>= 1) {
+		s += __shfl_xor_sync(0xffffffffu, s, o);
+	}
+	if ((threadIdx.x & 31) == 0) { sm[threadIdx.x >> 5] = s; }
+	__syncthreads();
+	if (threadIdx.x == 0) {
+		uint32_t t = 0;
+		for (int k = 0; k < SCAN_THREADS / 32; ++k) { t += sm[k]; }
+		tile_sum[blockIdx.x] = t;
+	}
+}
+
+// single block: exclusive scan of the tile sums in place, total appended at [ntiles]
+__global__ void __launch_bounds__(1024) k_scan_tile_offsets(uint32_t *__restrict__ tile_sum, long long ntiles) {
+	__shared__ uint32_t warp_tot[32];
+	__shared__ uint32_t carry;
+	if (threadIdx.x == 0) { carry = 0; }
+	__syncthreads();
+	int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+	for (long long base = 0; base < ntiles; base += 1024) {
+		long long i = base + threadIdx.x;
+		uint32_t v = i < ntiles ? tile_sum[i] : 0u, incl = v;
+#pragma unroll
+		for (int o = 1; o < 32; o <<= 1) {
+			uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+			if (lane >= o) { incl += t; }
+		}
+		if (lane == 31) { warp_tot[w] = incl; }
+		__syncthreads();
+		if (w == 0) {
+			uint32_t t = warp_tot[lane], ti = t;
+#pragma unroll
+			for (int o = 1; o < 32; o <<= 1) {
+				uint32_t u = __shfl_up_sync(0xffffffffu, ti, o);
+				if (lane >= o) { ti += u; }
+			}
+			warp_tot[lane] = ti - t; // exclusive
+		}
+		__syncthreads();
+		uint32_t excl = carry + warp_tot[w] + incl - v;
+		if (i < ntiles) { tile_sum[i] = excl; }
+		__syncthreads();
+		if (threadIdx.x == 1023) { carry = excl + v; }
+		__syncthreads();
+	}
+	if (threadIdx.x == 0) { tile_sum[ntiles] = carry; }
+}
+
+__global__ void __launch_bounds__(SCAN_THREADS) k_scan_apply(const uint32_t *__restrict__ in,
+	const uint32_t *__restrict__ tile_off, uint32_t *__restrict__ out, long long n, long long ntiles, int from_flags) {
+	__shared__ uint32_t warp_tot[SCAN_THREADS / 32];
+	long long base = (long long)blockIdx.x * SCAN_TILE + (long long)threadIdx.x * SCAN_ITEMS;
+	uint32_t v[SCAN_ITEMS], s = 0;
+#pragma unroll
+	for (int k = 0; k < SCAN_ITEMS; ++k) {
+		v[k] = scan_load(in, base + k, n, from_flags);
+		s += v[k];
+	}
+	int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+	uint32_t incl = s;
+#pragma unroll
+	for (int o = 1; o < 32; o <<= 1) {
+		uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+		if (lane >= o) { incl += t; }
+	}
+	if (lane == 31) { warp_tot[w] = incl; }
+	__syncthreads();
+	uint32_t wbase = 0;
+	for (int k = 0; k < w; ++k) { wbase += warp_tot[k]; }
+	uint32_t run = tile_off[blockIdx.x] + wbase + incl - s;
+#pragma unroll
+	for (int k = 0; k < SCAN_ITEMS; ++k) {
+		if (base + k < n) { out[base + k] = run; }
+		run += v[k];
+	}
+	if (blockIdx.x == 0 && threadIdx.x == 0) { out[n] = tile_off[ntiles]; }
+}
+
+int lfkp_exclusive_scan_u32(lfk_ctx *c, const uint32_t *in, uint32_t *out, long long n, int from_flags) {
+	long long ntiles = (n + SCAN_TILE - 1) / SCAN_TILE;
+	if (ntiles < 1) { ntiles = 1; }
+	if ((size_t)(ntiles + 1) > c->scan_tmp_n) {
+		if (c->scan_tmp) { cudaFree(c->scan_tmp); c->scan_tmp = nullptr; }
+		LFK_CUDA(c, cudaMalloc(&c->scan_tmp, (size_t)(ntiles + 1) * sizeof(uint32_t)));
+		c->scan_tmp_n = (size_t)(ntiles + 1);
+	}
+	LFK_LAUNCH(c, k_scan_tile_sums, (unsigned)ntiles, SCAN_THREADS, 0, in, c->scan_tmp, n, from_flags);
+	LFK_LAUNCH(c, k_scan_tile_offsets, 1, 1024, 0, c->scan_tmp, ntiles);
+	LFK_LAUNCH(c, k_scan_apply, (unsigned)ntiles, SCAN_THREADS, 0, in, c->scan_tmp, out, n, ntiles, from_flags);
+	return 0;
+}
+
+// ---- K2: counting sort by cell, made stable by canonicalising the order inside each cell -------------------
+__global__ void k_scatter_perm(const uint32_t *__restrict__ key, const uint32_t *__restrict__ slot,
+	const uint32_t *__restrict__ begin, uint32_t *__restrict__ perm, unsigned long long n) {
+	unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+	if (i < n) {
+		perm[begin[key[i]] + slot[i]] = (uint32_t)i;
+	}
+}
+
+#define SMALL_CELL 32
+#define BIG_CELL_LIMIT 16384
+// The atomics above hand out in-cell slots in arrival order.  Sorting each cell's slice of `perm` by source
+// index turns the counting sort into a STABLE sort by key => run-to-run deterministic particle order.
+__global__ void k_sort_within_cells(const uint32_t *__restrict__ begin, uint32_t *__restrict__ perm,
+	long long ncl, uint32_t *__restrict__ bigcells, unsigned *__restrict__ bigcount, unsigned bigcap) {
+	long long cidx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+	if (cidx >= ncl) { return; }
+	uint32_t b = begin[cidx], e = begin[cidx + 1], n = e - b;
+	if (n < 2) { return; }
+	if (n > SMALL_CELL) {
+		if (n <= BIG_CELL_LIMIT) {
+			unsigned k = atomicAdd(bigcount, 1u);
+			if (k < bigcap) { bigcells[k] = (uint32_t)cidx; }
+		}
+		return; // beyond BIG_CELL_LIMIT (pathological pile-up) the order stays arrival order
+	}
+	uint32_t a[SMALL_CELL];
+	for (uint32_t k = 0; k < n; ++k) { a[k] = perm[b + k]; }
+	for (uint32_t k = 1; k < n; ++k) { // insertion sort; slices are short and almost sorted
+		uint32_t v = a[k];
+		int j = (int)k - 1;
+		while (j >= 0 && a[j] > v) {
+			a[j + 1] = a[j];
+			--j;
+		}
+		a[j + 1] = v;
+	}
+	for (uint32_t k = 0; k < n; ++k) { perm[b + k] = a[k]; }
+}
+
+// one block per crowded cell: odd-even transposition sort in place
+__global__ void __launch_bounds__(256) k_sort_big_cells(const uint32_t *__restrict__ begin,
+	uint32_t *__restrict__ perm, const uint32_t *__restrict__ bigcells, const unsigned *__restrict__ bigcount,
+	unsigned bigcap) {
+	unsigned nbig = *bigcount < bigcap ? *bigcount : bigcap;
+	for (unsigned bc = blockIdx.x; bc < nbig; bc += gridDim.x) {
+		uint32_t cidx = bigcells[bc];
+		uint32_t b = begin[cidx], n = begin[cidx + 1] - b;
+		uint32_t *a = perm + b;
+		for (uint32_t phase = 0; phase < n; ++phase) {
+			for (uint32_t k = 2 * threadIdx.x + (phase & 1u); k + 1 < n; k += 2 * blockDim.x) {
+				uint32_t lo = a[k], hi = a[k + 1];
+				if (lo > hi) {
+					a[k] = hi;
+					a[k + 1] = lo;
+				}
+			}
+			__syncthreads();
+		}
+	}
+}
+
+__global__ void k_gather_particles(ParticleSoA dst, ParticleSoA src, uint32_t *__restrict__ key_dst,
+	const uint32_t *__restrict__ key_src, const uint32_t *__restrict__ perm, unsigned long long n, int nfields) {
+	unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n) { return; }
+	uint32_t s = perm[i];
+	key_dst[i] = key_src[s];
+#pragma unroll 5
+	for (int f = 0; f < 15; ++f) {
+		dst.f[f][i] = src.f[f][s];
+	}
+	if (nfields > 15) {
+		for (int f = 15; f < 18; ++f) {
+			dst.f[f][i] = src.f[f][s];
+		}
+	}
+}
+
+int lfkp_hash(lfk_ctx *c) {
+	PhaseTimer T(c, LFK_PHASE_SORT);
+	const GridDesc &G = c->g;
+	LFK_CUDA(c, cudaMemsetAsync(c->cnt, 0, (size_t)G.ncl * sizeof(uint32_t), c->stream));
+	uint64_t n = c->np;
+	if (n > 0) {
+		LFK_LAUNCH(c, k_keys_hist, lfk_blocks((long long)n, 256), 256, 0, G, c->P.f[PF_PX], c->P.f[PF_PY],
+			c->P.f[PF_PZ], c->key, c->slot, c->cnt, (unsigned long long)n);
+	}
+	LFK_TRY(lfkp_exclusive_scan_u32(c, c->cnt, c->begin, G.ncl, 0));
+	if (n > 0) {
+		LFK_LAUNCH(c, k_scatter_perm, lfk_blocks((long long)n, 256), 256, 0, c->key, c->slot, c->begin, c->perm,
+			(unsigned long long)n);
+		LFK_CUDA(c, cudaMemsetAsync(c->bigcount, 0, sizeof(unsigned), c->stream));
+		LFK_LAUNCH(c, k_sort_within_cells, lfk_blocks(G.ncl, 128), 128, 0, c->begin, c->perm, G.ncl, c->bigcells,
+			c->bigcount, c->bigcap);
+		// crowded cells (> 32 particles) are rare; a small grid strides over however many there are
+		if (n > SMALL_CELL) {
+			LFK_LAUNCH(c, k_sort_big_cells, 296, 256, 0, c->begin, c->perm, c->bigcells, c->bigcount, c->bigcap);
+		}
+		LFK_LAUNCH(c, k_gather_particles, lfk_blocks((long long)n, 256), 256, 0, c->Palt, c->P, c->key_alt, c->key,
+			c->perm, (unsigned long long)n, c->old_valid ? 18 : 15);
+		ParticleSoA t = c->P; c->P = c->Palt; c->Palt = t;
+		uint32_t *kt = c->key; c->key = c->key_alt; c->key_alt = kt;
+	}
+	c->table_valid = true;
+	c->keys_valid = true;
+	c->ordinal_valid = false;
+	c->system_valid = false;
+	return 0;
+}
+
+// =========================================================================================================
+// A1: advection (reference src/simulation.cpp:240-248)
+// =========================================================================================================
+struct MotionParams {
+	double lo[3], hi[3]; // advect clamp corners
+	double gmin[3], gmax[3]; // correct clamp corners
+	double skin, skin_max;
+	double dt, corr_factor, re2;
+};
+
+static MotionParams motion_params(const lfk_ctx *c, double dt) {
+	MotionParams m;
+	const GridDesc &G = c->g;
+	const double size[3] = { (double)G.nx, (double)G.ny, (double)G.nz };
+	double skin = c->prm.boundary_skin_width;
+	for (int d = 0; d < 3; ++d) {
+		m.lo[d] = G.off[d] + skin;                      // grid_offset + skin_width
+		m.hi[d] = G.h * size[d] + G.off[d] - skin;       // cell_size * size + grid_offset - skin_width
+		m.gmin[d] = G.off[d];
+		m.gmax[d] = G.off[d] + size[d] * G.h;            // grid_offset + size * cell_size
+	}
+	m.skin = skin;
+	m.skin_max = G.h - skin;
+	m.dt = dt;
+	double re = G.h / sqrt(2.0);
+	m.corr_factor = dt * c->prm.correction_stiffness * re;
+	m.re2 = re * re;
+	return m;
+}
+
+__device__ __forceinline__ void advect_one(const MotionParams &M, double *p, const double *v) {
+#pragma unroll
+	for (int d = 0; d < 3; ++d) {
+		p[d] = dclamp_std(p[d] + v[d] * M.dt, M.lo[d], M.hi[d]);
+	}
+}
+
+// =========================================================================================================
+// A2: collisions = DDA march old -> new through the cell types + skin push-out
+// (reference src/simulation.cpp:612-683, include/fluid/data_structures/grid.h:140-209)
+// =========================================================================================================
+__device__ __forceinline__ bool cell_is_free(const GridDesc &G, const uint8_t *__restrict__ typ, int x, int y, int z) {
+	if (x < 0 || y < 0 || z < 0 || x >= G.nx || y >= G.ny || z >= G.nz) {
+		return false;
+	}
+	int lz = z - G.z0 + 1;
+	if (lz < 0 || lz >= G.nlz) { // beyond this rank's halo: cannot be decided here, treat as free (see exchange.cu)
+		return true;
+	}
+	return typ[x + (long long)G.nx * (y + (long long)G.ny * lz)] != LFK_CELL_SOLID;
+}
+
+__device__ void collide_one(const GridDesc &G, const MotionParams &M, const uint8_t *__restrict__ typ,
+	double *from, double *to) {
+	const double h = G.h;
+	for (int j = 0; j < 3; ++j) {
+		bool into_wall = false;
+		double gf[3], inv[3], normal[3], t[3];
+		int cur[3], tc[3], adv[3];
+#pragma unroll
+		for (int d = 0; d < 3; ++d) {
+			gf[d] = (from[d] - G.off[d]) / h;
+			double gt = (to[d] - G.off[d]) / h;
+			cur[d] = (int)floor(gf[d]);
+			tc[d] = (int)floor(gt);
+			double diff = gt - gf[d];
+			int face;
+			if (diff > 0.0) {
+				adv[d] = 1;
+				face = 1;
+			} else {
+				adv[d] = -1;
+				face = 0;
+			}
+			inv[d] = 1.0 / fabs(diff);
+			normal[d] = -(double)adv[d];
+			t[d] = fabs((double)(cur[d] + face) - gf[d]) * inv[d];
+		}
+		while (cur[0] != tc[0] || cur[1] != tc[1] || cur[2] != tc[2]) {
+			int mc = 0;
+			double mint = 2.0;
+#pragma unroll
+			for (int d = 0; d < 3; ++d) {
+				if (t[d] < mint) {
+					mint = t[d];
+					mc = d;
+				}
+			}
+			if (!(mint <= 1.0)) {
+				break;
+			}
+			// (dynamic indexing avoided: select by mc)
+			if (mc == 0) { cur[0] += adv[0]; } else if (mc == 1) { cur[1] += adv[1]; } else { cur[2] += adv[2]; }
+			if (!cell_is_free(G, typ, cur[0], cur[1], cur[2])) {
+				double offv[3] = { to[0] - from[0], to[1] - from[1], to[2] - from[2] };
+				double nrm[3] = { 0.0, 0.0, 0.0 };
+				double tm = mc == 0 ? t[0] : (mc == 1 ? t[1] : t[2]);
+				double nm = mc == 0 ? normal[0] : (mc == 1 ? normal[1] : normal[2]);
+				if (mc == 0) { nrm[0] = nm; } else if (mc == 1) { nrm[1] = nm; } else { nrm[2] = nm; }
+				double dotv = 0.0;
+				dotv += offv[0] * nrm[0];
+				dotv += offv[1] * nrm[1];
+				dotv += offv[2] * nrm[2];
+				double tt = tm + M.skin / dotv;
+				tt = dmax_std(tt, 0.0);
+#pragma unroll
+				for (int d = 0; d < 3; ++d) {
+					from[d] = tt * to[d] + (1.0 - tt) * from[d];
+				}
+				if (mc == 0) { to[0] = from[0]; } else if (mc == 1) { to[1] = from[1]; } else { to[2] = from[2]; }
+				into_wall = true;
+				break;
+			}
+			if (mc == 0) { t[0] += inv[0]; } else if (mc == 1) { t[1] += inv[1]; } else { t[2] += inv[2]; }
+		}
+		if (!into_wall) {
+			break;
+		}
+	}
+	// skin push-out: cell index and in-cell position are computed once, before the per-axis pushes
+	double cp[3];
+	int ci[3];
+#pragma unroll
+	for (int d = 0; d < 3; ++d) {
+		double gp = to[d] - G.off[d];
+		unsigned long long idx = (unsigned long long)(gp / h);
+		ci[d] = (int)(idx < 0x7fffffffull ? idx : 0x7fffffffull);
+		cp[d] = gp - (double)idx * h;
+	}
+	const int size[3] = { G.nx, G.ny, G.nz };
+#pragma unroll
+	for (int d = 0; d < 3; ++d) {
+		int q[3] = { ci[0], ci[1], ci[2] };
+		if (cp[d] < M.skin) {
+			q[d] = ci[d] - 1;
+			if (ci[d] == 0 || !cell_is_free(G, typ, q[0], q[1], q[2])) {
+				to[d] += M.skin - cp[d];
+			}
+		}
+		if (cp[d] > M.skin_max) {
+			q[d] = ci[d] + 1;
+			if (ci[d] + 1 >= size[d] || !cell_is_free(G, typ, q[0], q[1], q[2])) {
+				to[d] += M.skin_max - cp[d];
+			}
+		}
+	}
+}
+
+__global__ void k_advect(MotionParams M, ParticleSoA P, unsigned long long n) {
+	unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n) { return; }
+	double p[3] = { P.f[PF_PX][i], P.f[PF_PY][i], P.f[PF_PZ][i] };
+	double v[3] = { P.f[PF_VX][i], P.f[PF_VY][i], P.f[PF_VZ][i] };
+	advect_one(M, p, v);
+	P.f[PF_PX][i] = p[0];
+	P.f[PF_PY][i] = p[1];
+	P.f[PF_PZ][i] = p[2];
+}
+
+__global__ void k_collide(GridDesc G, MotionParams M, ParticleSoA P, const uint8_t *__restrict__ typ,
+	unsigned long long n, int old_valid) {
+	unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n) { return; }
+	double to[3] = { P.f[PF_PX][i], P.f[PF_PY][i], P.f[PF_PZ][i] };
+	double from[3] = { to[0], to[1], to[2] };
+	if (old_valid) {
+		from[0] = P.f[PF_OX][i];
+		from[1] = P.f[PF_OY][i];
+		from[2] = P.f[PF_OZ][i];
+	}
+	collide_one(G, M, typ, from, to);
+	P.f[PF_PX][i] = to[0];
+	P.f[PF_PY][i] = to[1];
+	P.f[PF_PZ][i] = to[2];
+}
+
+// advect + collide in one pass: old_position is the pre-advection position held in registers
+__global__ void k_advect_collide(GridDesc G, MotionParams M, ParticleSoA P, const uint8_t *__restrict__ typ,
+	unsigned long long n) {
+	unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n) { return; }
+	double from[3] = { P.f[PF_PX][i], P.f[PF_PY][i], P.f[PF_PZ][i] };
+	double v[3] = { P.f[PF_VX][i], P.f[PF_VY][i], P.f[PF_VZ][i] };
+	double to[3] = { from[0], from[1], from[2] };
+	advect_one(M, to, v);
+	collide_one(G, M, typ, from, to);
+	P.f[PF_PX][i] = to[0];
+	P.f[PF_PY][i] = to[1];
+	P.f[PF_PZ][i] = to[2];
+}
+
+static int materialise_old(lfk_ctx *c) {
+	if (!c->old_valid && c->np > 0) {
+		for (int d = 0; d < 3; ++d) {
+			LFK_CUDA(c, cudaMemcpyAsync(c->P.f[PF_OX + d], c->P.f[PF_PX + d], c->np * sizeof(double),
+				cudaMemcpyDeviceToDevice, c->stream));
+		}
+	}
+	c->old_valid = true;
+	return 0;
+}
+
+int lfkp_advect(lfk_ctx *c, double dt) {
+	PhaseTimer T(c, LFK_PHASE_ADVECT_COLLIDE);
+	LFK_TRY(materialise_old(c));
+	if (c->np == 0) { return 0; }
+	LFK_LAUNCH(c, k_advect, lfk_blocks((long long)c->np, 256), 256, 0, motion_params(c, dt), c->P,
+		(unsigned long long)c->np);
+	c->table_valid = false;
+	return 0;
+}
+
+int lfkp_collide(lfk_ctx *c) {
+	PhaseTimer T(c, LFK_PHASE_ADVECT_COLLIDE);
+	if (c->np > 0) {
+		LFK_LAUNCH(c, k_collide, lfk_blocks((long long)c->np, 128), 128, 0, c->g, motion_params(c, 0.0), c->P, c->typ,
+			(unsigned long long)c->np, c->old_valid ? 1 : 0);
+	}
+	c->old_valid = false; // old_position = position (reference src/simulation.cpp:57-59,115-117)
+	return 0;
+}
+
+int lfkp_advect_collide(lfk_ctx *c, double dt) {
+	PhaseTimer T(c, LFK_PHASE_ADVECT_COLLIDE);
+	if (c->old_valid) { // a host upload left old != position: honour it with the unfused pair
+		LFK_TRY(lfkp_advect(c, dt));
+		return lfkp_collide(c);
+	}
+	if (c->np > 0) {
+		LFK_LAUNCH(c, k_advect_collide, lfk_blocks((long long)c->np, 128), 128, 0, c->g, motion_params(c, dt), c->P,
+			c->typ, (unsigned long long)c->np);
+	}
+	c->table_valid = false;
+	return 0;
+}
+
+// =========================================================================================================
+// A3: position correction (reference src/simulation.cpp:562-610)
+// =========================================================================================================
+__device__ __forceinline__ void degenerate_kick(const double *p, const double *o, double *out3) {
+	unsigned long long s = 0x9e3779b97f4a7c15ull;
+#pragma unroll
+	for (int k = 0; k < 3; ++k) { s = mix64(s ^ (unsigned long long)__double_as_longlong(p[k])); }
+#pragma unroll
+	for (int k = 0; k < 3; ++k) { s = mix64(s ^ (unsigned long long)__double_as_longlong(o[k])); }
+#pragma unroll
+	for (int d = 0; d < 3; ++d) {
+		s = mix64(s + 0x9e3779b97f4a7c15ull);
+		out3[d] = (double)(s >> 11) * (2.0 / 9007199254740992.0) - 1.0;
+	}
+}
+
+template <bool COLLIDE> __global__ void __launch_bounds__(128) k_correct(GridDesc G, MotionParams M, ParticleSoA P,
+	double *__restrict__ nx_, double *__restrict__ ny_, double *__restrict__ nz_,
+	const uint32_t *__restrict__ begin, const uint8_t *__restrict__ typ, unsigned long long n) {
+	unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n) { return; }
+	const double *__restrict__ px = P.f[PF_PX], *__restrict__ py = P.f[PF_PY], *__restrict__ pz = P.f[PF_PZ];
+	double p[3] = { px[i], py[i], pz[i] };
+	int lo[3], hi[3];
+	const int size[3] = { G.nx, G.ny, G.nz };
+#pragma unroll
+	for (int d = 0; d < 3; ++d) { // compute_cell_index (no clamp), then for_each_in_range_checked
+		unsigned long long ci = (unsigned long long)((p[d] - G.off[d]) / G.h);
+		long long cl = ci > 0x7fffffffull ? 0x7fffffffll : (long long)ci;
+		lo[d] = (int)(cl < 1 ? 0 : cl - 1);
+		long long h2 = cl + 2;
+		hi[d] = (int)(h2 < size[d] ? h2 : size[d]);
+	}
+	double sx = 0.0, sy = 0.0, sz = 0.0;
+	for (int cz = lo[2]; cz < hi[2]; ++cz) {
+		int lz = cz - G.z0 + 1;
+		for (int cy = lo[1]; cy < hi[1]; ++cy) {
+			if (lo[0] >= hi[0]) { continue; }
+			// cells lo[0]..hi[0]-1 of one row are contiguous in the sorted particle array
+			long long row = (long long)G.nx * (cy + (long long)G.ny * lz);
+			uint32_t qb = begin[row + lo[0]], qe = begin[row + hi[0]];
+			for (uint32_t q = qb; q < qe; ++q) {
+				if (q == i) { continue; }
+				double o[3] = { px[q], py[q], pz[q] };
+				double ox = p[0] - o[0], oy = p[1] - o[1], oz = p[2] - o[2];
+				double sq = 0.0;
+				sq += ox * ox;
+				sq += oy * oy;
+				sq += oz * oz;
+				if (sq < 1e-12) {
+					double kick[3];
+					degenerate_kick(p, o, kick);
+					sx += kick[0];
+					sy += kick[1];
+					sz += kick[2];
+				} else {
+					double kl = 1.0 - sq / M.re2;
+					if (kl > 0.0) { // kernel == 0 otherwise: adds +-0 in the reference, a no-op
+						double kern = kl * kl * kl;
+						double sc = kern / sqrt(sq);
+						sx += sc * ox;
+						sy += sc * oy;
+						sz += sc * oz;
+					}
+				}
+			}
+		}
+	}
+	double np3[3] = { p[0] + sx * M.corr_factor, p[1] + sy * M.corr_factor, p[2] + sz * M.corr_factor };
+#pragma unroll
+	for (int d = 0; d < 3; ++d) {
+		np3[d] = dclamp_std(np3[d], M.gmin[d], M.gmax[d]);
+	}
+	if (COLLIDE) { // second _detect_collisions of the step: old_position == pre-correction position
+		collide_one(G, M, typ, p, np3);
+	}
+	nx_[i] = np3[0];
+	ny_[i] = np3[1];
+	nz_[i] = np3[2];
+}
+
+static int correct_impl(lfk_ctx *c, double dt, bool fuse_collide) {
+	PhaseTimer T(c, LFK_PHASE_CORRECT_COLLIDE);
+	LFK_REQUIRE(c, c->table_valid, LFK_E_STATE, "lfk_correct needs the cell table of lfk_hash");
+	if (c->np == 0) { return 0; }
+	MotionParams M = motion_params(c, dt);
+	unsigned nb = lfk_blocks((long long)c->np, 128);
+	if (fuse_collide) {
+		LFK_LAUNCH(c, k_correct<true>, nb, 128, 0, c->g, M, c->P, c->Palt.f[PF_PX], c->Palt.f[PF_PY],
+			c->Palt.f[PF_PZ], c->begin, c->typ, (unsigned long long)c->np);
+	} else {
+		LFK_TRY(materialise_old(c));
+		LFK_LAUNCH(c, k_correct<false>, nb, 128, 0, c->g, M, c->P, c->Palt.f[PF_PX], c->Palt.f[PF_PY],
+			c->Palt.f[PF_PZ], c->begin, c->typ, (unsigned long long)c->np);
+	}
+	for (int d = 0; d < 3; ++d) {
+		double *t = c->P.f[PF_PX + d];
+		c->P.f[PF_PX + d] = c->Palt.f[PF_PX + d];
+		c->Palt.f[PF_PX + d] = t;
+	}
+	return 0;
+}
+int lfkp_correct(lfk_ctx *c, double dt) { return correct_impl(c, dt, false); }
+int lfkp_correct_collide(lfk_ctx *c, double dt) {
+	if (c->old_valid) {
+		LFK_TRY(correct_impl(c, dt, false));
+		return lfkp_collide(c);
+	}
+	return correct_impl(c, dt, true);
+}
+
+// =========================================================================================================
+// A4: CFL (reference src/simulation.cpp:199-205)
+// =========================================================================================================
+__global__ void k_max_speed2(const double *__restrict__ vx, const double *__restrict__ vy,
+	const double *__restrict__ vz, unsigned long long n, unsigned long long *__restrict__ out_bits) {
+	double m = 0.0;
+	for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+		i += (unsigned long long)gridDim.x * blockDim.x) {
+		double s = 0.0;
+		s += vx[i] * vx[i];
+		s += vy[i] * vy[i];
+		s += vz[i] * vz[i];
+		m = dmax_std(m, s);
+	}
+	m = block_max(m);
+	if (threadIdx.x == 0) {
+		atomicMax(out_bits, (unsigned long long)__double_as_longlong(m)); // non-negative doubles order like u64
+	}
+}
+
+int lfkp_cfl(lfk_ctx *c, double *value) {
+	PhaseTimer T(c, LFK_PHASE_CFL);
+	LFK_CUDA(c, cudaMemsetAsync(c->d_reduce, 0, sizeof(double), c->stream));
+	if (c->np > 0) {
+		unsigned nb = lfk_blocks((long long)c->np, 256);
+		if (nb > 148 * 8) { nb = 148 * 8; }
+		LFK_LAUNCH(c, k_max_speed2, nb, 256, 0, c->P.f[PF_VX], c->P.f[PF_VY], c->P.f[PF_VZ],
+			(unsigned long long)c->np, (unsigned long long*)c->d_reduce);
+	}
+	if (c->nranks > 1) {
+		LFK_TRY(lfkx_allreduce_max(c, c->d_reduce, 1));
+	}
+	LFK_CUDA(c, cudaMemcpyAsync(c->h_reduce, c->d_reduce, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+	LFK_CUDA(c, cudaStreamSynchronize(c->stream));
+	*value = c->g.h / sqrt(c->h_reduce[0]);
+	return 0;
+}
+
+// =========================================================================================================
+// G1-G4: grid -> particle (reference src/mac_grid.cpp:40-112, src/simulation.cpp:447-560)
+// =========================================================================================================
+__device__ __forceinline__ double lerp1(double a, double b, double t) {
+	return a * (1.0 - t) + b * t;
+}
+__device__ __forceinline__ double trilerp8(const double *v, double t1, double t2, double t3) {
+	double b0 = lerp1(lerp1(v[0], v[1], t3), lerp1(v[2], v[3], t3), t2);
+	double b1 = lerp1(lerp1(v[4], v[5], t3), lerp1(v[6], v[7], t3), t2);
+	return lerp1(b0, b1, t1);
+}
+// c = sum over the 8 corners of grad_kernel(corner) * sample, in the reference's corner order
+__device__ __forceinline__ void c_vector(double h, const double *v, double tx, double ty, double tz, double *out) {
+	double ax = 0.0, ay = 0.0, az = 0.0;
+#pragma unroll
+	for (int k = 0; k < 8; ++k) {
+		double px = (k & 1) ? tx - 1.0 : tx, py = (k & 2) ? ty - 1.0 : ty, pz = (k & 4) ? tz - 1.0 : tz;
+		double sx = px > 0.0 ? -1.0 : 1.0, sy = py > 0.0 ? -1.0 : 1.0, sz = pz > 0.0 ? -1.0 : 1.0;
+		double nx = 1.0 - fabs(px), ny = 1.0 - fabs(py), nz = 1.0 - fabs(pz);
+		double gx = sx * ny * nz / h, gy = nx * sy * nz / h, gz = nx * ny * sz / h;
+		if (k == 0) {
+			ax = gx * v[k];
+			ay = gy * v[k];
+			az = gz * v[k];
+		} else {
+			ax += gx * v[k];
+			ay += gy * v[k];
+			az += gz * v[k];
+		}
+	}
+	out[0] = ax;
+	out[1] = ay;
+	out[2] = az;
+}
+
+struct FaceFetch { // the 3 clamped cell coordinates per axis of get_face_samples, and their "clamped" bits
+	int ci[3][3];
+	bool cl[3][3];
+};
+
+__device__ __forceinline__ void face_fetch_setup(const GridDesc &G, const long long *gi, FaceFetch &F) {
+	const int size[3] = { G.nx, G.ny, G.nz };
+#pragma unroll
+	for (int a = 0; a < 3; ++a) {
+#pragma unroll
+		for (int d = 0; d < 3; ++d) {
+			long long val = gi[a] + d; // _clamp(val, 1, max) then -1
+			if (val < 1) {
+				F.ci[a][d] = 0;
+				F.cl[a][d] = true;
+			} else if (val >= size[a]) {
+				F.ci[a][d] = size[a] - 1;
+				F.cl[a][d] = true;
+			} else {
+				F.ci[a][d] = (int)val - 1;
+				F.cl[a][d] = false;
+			}
+		}
+	}
+}
+
+template <int K> __device__ __forceinline__ void face_samples_comp(const GridDesc &G, const FaceFetch &F,
+	const double *__restrict__ comp, const int *dsel, double *s) {
+#pragma unroll
+	for (int k = 0; k < 8; ++k) {
+		int bx = k & 1, by = (k >> 1) & 1, bz = (k >> 2) & 1;
+		int dx = K == 0 ? bx : dsel[0] + bx;
+		int dy = K == 1 ? by : dsel[1] + by;
+		int dz = K == 2 ? bz : dsel[2] + bz;
+		bool clamped = K == 0 ? F.cl[0][dx] : (K == 1 ? F.cl[1][dy] : F.cl[2][dz]);
+		int lz = F.ci[2][dz] - G.z0 + 1;
+		long long idx = F.ci[0][dx] + (long long)G.nx * (F.ci[1][dy] + (long long)G.ny * lz);
+		s[k] = clamped ? 0.0 : __ldg(comp + idx);
+	}
+}
+
+template <int METHOD> __global__ void __launch_bounds__(128) k_g2p(GridDesc G, ParticleSoA P,
+	const double *__restrict__ u, const double *__restrict__ v, const double *__restrict__ w,
+	const double *__restrict__ uo, const double *__restrict__ vo, const double *__restrict__ wo,
+	double blend, unsigned long long n) {
+	unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n) { return; }
+	double p[3] = { P.f[PF_PX][i], P.f[PF_PY][i], P.f[PF_PZ][i] };
+	long long gi[3];
+	double t[3], tmid[3];
+	int dsel[3];
+#pragma unroll
+	for (int d = 0; d < 3; ++d) { // compute_cell_index_and_position: no clamping
+		double f = (p[d] - G.off[d]) / G.h;
+		unsigned long long ci = (unsigned long long)f;
+		gi[d] = ci > 0x7fffffffull ? 0x7fffffffll : (long long)ci;
+		t[d] = f - (double)ci;
+		tmid[d] = t[d] - 0.5;
+		dsel[d] = 1;
+		if (tmid[d] < 0.0) {
+			dsel[d] = 0;
+			tmid[d] += 1.0;
+		}
+	}
+	FaceFetch F;
+	face_fetch_setup(G, gi, F);
+	double sx[8], sy[8], sz[8];
+	face_samples_comp<0>(G, F, u, dsel, sx);
+	face_samples_comp<1>(G, F, v, dsel, sy);
+	face_samples_comp<2>(G, F, w, dsel, sz);
+	double vn[3];
+	vn[0] = trilerp8(sx, tmid[2], tmid[1], t[0]);
+	vn[1] = trilerp8(sy, tmid[2], t[1], tmid[0]);
+	vn[2] = trilerp8(sz, t[2], tmid[1], tmid[0]);
+	if (METHOD == LFK_METHOD_FLIP) {
+		double ox[8], oy[8], oz[8];
+		face_samples_comp<0>(G, F, uo, dsel, ox);
+		face_samples_comp<1>(G, F, vo, dsel, oy);
+		face_samples_comp<2>(G, F, wo, dsel, oz);
+		double vold[3];
+		vold[0] = trilerp8(ox, tmid[2], tmid[1], t[0]);
+		vold[1] = trilerp8(oy, tmid[2], t[1], tmid[0]);
+		vold[2] = trilerp8(oz, t[2], tmid[1], tmid[0]);
+		P.f[PF_VX][i] = vn[0] + (P.f[PF_VX][i] - vold[0]) * blend;
+		P.f[PF_VY][i] = vn[1] + (P.f[PF_VY][i] - vold[1]) * blend;
+		P.f[PF_VZ][i] = vn[2] + (P.f[PF_VZ][i] - vold[2]) * blend;
+	} else {
+		P.f[PF_VX][i] = vn[0];
+		P.f[PF_VY][i] = vn[1];
+		P.f[PF_VZ][i] = vn[2];
+		if (METHOD == LFK_METHOD_APIC) {
+			double cv[3];
+			c_vector(G.h, sx, t[0], tmid[1], tmid[2], cv);
+			P.f[PF_C0 + 0][i] = cv[0];
+			P.f[PF_C0 + 1][i] = cv[1];
+			P.f[PF_C0 + 2][i] = cv[2];
+			c_vector(G.h, sy, tmid[0], t[1], tmid[2], cv);
+			P.f[PF_C0 + 3][i] = cv[0];
+			P.f[PF_C0 + 4][i] = cv[1];
+			P.f[PF_C0 + 5][i] = cv[2];
+			c_vector(G.h, sz, tmid[0], tmid[1], t[2], cv);
+			P.f[PF_C0 + 6][i] = cv[0];
+			P.f[PF_C0 + 7][i] = cv[1];
+			P.f[PF_C0 + 8][i] = cv[2];
+		}
+	}
+}
+
+int lfkp_g2p(lfk_ctx *c) {
+	PhaseTimer T(c, LFK_PHASE_G2P);
+	if (c->np == 0) { return 0; }
+	unsigned nb = lfk_blocks((long long)c->np, 128);
+	unsigned long long n = c->np;
+	switch (c->prm.method) {
+	case LFK_METHOD_PIC:
+		LFK_LAUNCH(c, k_g2p<LFK_METHOD_PIC>, nb, 128, 0, c->g, c->P, c->vel[0], c->vel[1], c->vel[2],
+			c->vel_old[0], c->vel_old[1], c->vel_old[2], c->prm.blending_factor, n);
+		break;
+	case LFK_METHOD_FLIP:
+		LFK_LAUNCH(c, k_g2p<LFK_METHOD_FLIP>, nb, 128, 0, c->g, c->P, c->vel[0], c->vel[1], c->vel[2],
+			c->vel_old[0], c->vel_old[1], c->vel_old[2], c->prm.blending_factor, n);
+		break;
+	default:
+		LFK_LAUNCH(c, k_g2p<LFK_METHOD_APIC>, nb, 128, 0, c->g, c->P, c->vel[0], c->vel[1], c->vel[2],
+			c->vel_old[0], c->vel_old[1], c->vel_old[2], c->prm.blending_factor, n);
+		break;
+	}
+	return 0;
+}
+
+// =========================================================================================================
+// Synthetic seeding (bench scenes): jittered sub-cell sampling like simulation::seed_func
+// (reference include/fluid/simulation.h:80-115), with a counter-based hash RNG instead of pcg32.
+// =========================================================================================================
+__global__ void k_seed_box(GridDesc G, ParticleSoA P, uint32_t *__restrict__ key, int cx0, int cy0, int cz0,
+	int ex, int ey, int ez, double s0, double s1, double s2, double e0, double e1, double e2, double vx, double vy,
+	double vz, uint32_t dens, unsigned long long seed, unsigned long long base, unsigned long long *__restrict__ counter,
+	unsigned long long capacity) {
+	unsigned long long per_cell = (unsigned long long)dens * dens * dens;
+	unsigned long long total = (unsigned long long)ex * ey * ez * per_cell;
+	unsigned long long tid = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+	if (tid >= total) { return; }
+	unsigned long long sub = tid % per_cell, cell = tid / per_cell;
+	int x = cx0 + (int)(cell % ex), y = cy0 + (int)((cell / ex) % ey), z = cz0 + (int)(cell / ((unsigned long long)ex * ey));
+	// reference loop nest: sx outermost, sz innermost
+	int sz_ = (int)(sub % dens), sy_ = (int)((sub / dens) % dens), sx_ = (int)(sub / ((unsigned long long)dens * dens));
+	double small = G.h / (double)dens;
+	unsigned long long gid = ((unsigned long long)(x + (long long)G.nx * (y + (long long)G.ny * z))) * per_cell + sub;
+	unsigned long long r = mix64(seed ^ mix64(gid + 0x9e3779b97f4a7c15ull));
+	double j[3];
+#pragma unroll
+	for (int d = 0; d < 3; ++d) {
+		r = mix64(r + 0x9e3779b97f4a7c15ull);
+		j[d] = (double)(r >> 11) * (1.0 / 9007199254740992.0) * small;
+	}
+	double px = G.off[0] + (double)x * G.h + (double)sx_ * small + j[0];
+	double py = G.off[1] + (double)y * G.h + (double)sy_ * small + j[1];
+	double pz = G.off[2] + (double)z * G.h + (double)sz_ * small + j[2];
+	if (!(px > s0 && py > s1 && pz > s2 && px < e0 && py < e1 && pz < e2)) { return; }
+	unsigned long long slot = atomicAdd(counter, 1ull);
+	if (base + slot >= capacity) { return; }
+	unsigned long long i = base + slot;
+	P.f[PF_PX][i] = px;
+	P.f[PF_PY][i] = py;
+	P.f[PF_PZ][i] = pz;
+	P.f[PF_VX][i] = vx;
+	P.f[PF_VY][i] = vy;
+	P.f[PF_VZ][i] = vz;
+#pragma unroll
+	for (int f = PF_C0; f < PF_C0 + 9; ++f) { P.f[f][i] = 0.0; }
+	key[i] = (uint32_t)(x + (long long)G.nx * (y + (long long)G.ny * (z - G.z0 + 1)));
+}
+
+int lfkp_seed_box(lfk_ctx *c, const double *start, const double *size, const double *vel, uint32_t dens,
+	uint64_t seed, int append) {
+	const GridDesc &G = c->g;
+	if (!append) { c->np = 0; }
+	double end[3] = { start[0] + size[0], start[1] + size[1], start[2] + size[2] };
+	int c0[3], c1[3];
+	const int gsz[3] = { G.nx, G.ny, G.nz };
+	for (int d = 0; d < 3; ++d) { // world_position_to_cell_index_unclamped + seed_func's clamp of the end
+		double a = (start[d] - G.off[d]) / G.h, b = (end[d] - G.off[d]) / G.h;
+		long long ca = (long long)(a > 0.0 ? a : 0.0), cb = (long long)(b > 0.0 ? b : 0.0) + 1;
+		if (cb > gsz[d]) { cb = gsz[d]; }
+		if (ca > cb) { ca = cb; }
+		c0[d] = (int)ca;
+		c1[d] = (int)cb;
+	}
+	// this rank seeds only the cells of its slab
+	if (c0[2] < G.z0) { c0[2] = G.z0; }
+	if (c1[2] > G.z0 + G.nzl) { c1[2] = G.z0 + G.nzl; }
+	long long ex = c1[0] - c0[0], ey = c1[1] - c0[1], ez = c1[2] - c0[2];
+	if (ex <= 0 || ey <= 0 || ez <= 0) { return 0; }
+	unsigned long long per_cell = (unsigned long long)dens * dens * dens;
+	unsigned long long total = (unsigned long long)ex * ey * ez * per_cell;
+	LFK_TRY(lfkp_reserve_particles(c, c->np + total));
+	unsigned long long *counter = (unsigned long long*)c->d_reduce;
+	LFK_CUDA(c, cudaMemsetAsync(counter, 0, sizeof(unsigned long long), c->stream));
+	LFK_LAUNCH(c, k_seed_box, lfk_blocks((long long)total, 256), 256, 0, G, c->P, c->key, c0[0], c0[1], c0[2],
+		(int)ex, (int)ey, (int)ez, start[0], start[1], start[2], end[0], end[1], end[2], vel[0], vel[1], vel[2],
+		dens, (unsigned long long)seed, (unsigned long long)c->np, counter, (unsigned long long)c->cap);
+	LFK_CUDA(c, cudaMemcpyAsync(c->h_reduce, counter, sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
+	LFK_CUDA(c, cudaStreamSynchronize(c->stream));
+	unsigned long long added;
+	memcpy(&added, c->h_reduce, sizeof(added));
+	c->np += added;
+	c->old_valid = false;
+	c->table_valid = false;
+	c->keys_valid = false;
+	return 0;
+}

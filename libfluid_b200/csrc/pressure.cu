@@ -1,0 +1,609 @@
+// MAC-grid pressure projection on the dense (slab-local) grid: matrix flags + right-hand side, matrix-free
+// 7-point PCG with device-resident scalars, pressure-gradient update, velocity extrapolation.
+// Reference: fluid::pressure_solver (src/pressure_solver.cpp:14-371), simulation::_extrapolate_velocities
+// (src/simulation.cpp:685-754).
+//
+// Unknowns live on the dense cell grid (vectors are indexed by local raw cell index and are ZERO on every cell
+// that is not in the reference's fluid-cell list), so the stencil needs no index map: the 8-byte-per-cell
+// ordinal grid of the reference (pressure_solver.h:47-48) disappears and neighbour access is coalesced.
+#include "lfk_internal.cuh"
+
+#include <cmath>
+#include <cstring>
+
+// flag byte per cell: bits 0-2 nonsolid neighbour count (diagonal), bit 3 "is an unknown" (cell holds particles,
+// reference src/simulation.cpp:83-87), bit 4 type == fluid, bits 5-7 type(+x/+y/+z neighbour) == fluid.
+#define FL_N(f) ((f) & 7u)
+#define FL_L 8u
+#define FL_SELF 16u
+#define FL_XP 32u
+#define FL_YP 64u
+#define FL_ZP 128u
+
+#define RED_BLOCKS 1184 // 148 SMs x 8 resident blocks of 256 threads
+#define RED_THREADS 256
+
+__device__ __forceinline__ void cell_xyz(const GridDesc &G, long long own, int &x, int &y, int &lz) {
+	x = (int)(own % G.nx);
+	long long rest = own / G.nx;
+	y = (int)(rest % G.ny);
+	lz = (int)(rest / G.ny) + 1;
+}
+
+// ---- S1-S3: flags + b (src/pressure_solver.cpp:150-242) ---------------------------------------------------
+__global__ void k_build_system(GridDesc G, const uint32_t *__restrict__ cnt, const uint8_t *__restrict__ typ,
+	const double *__restrict__ u, const double *__restrict__ v, const double *__restrict__ w,
+	uint8_t *__restrict__ flags, double *__restrict__ b, double *__restrict__ p, double inv_h) {
+	long long own = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+	if (own >= G.nown) { return; }
+	int x, y, lz;
+	cell_xyz(G, own, x, y, lz);
+	long long c = own + G.sxy;
+	p[c] = 0.0;
+	if (cnt[c] == 0) {
+		flags[c] = 0;
+		b[c] = 0.0;
+		return;
+	}
+	const uint8_t S = LFK_CELL_SOLID, F = LFK_CELL_FLUID;
+	// out-of-grid neighbours read as solid (mac_grid::get_cell_and_type); the z ghost layers carry that already
+	uint8_t txp = x + 1 < G.nx ? typ[c + 1] : S, txn = x > 0 ? typ[c - 1] : S;
+	uint8_t typ_ = y + 1 < G.ny ? typ[c + G.nx] : S, tyn = y > 0 ? typ[c - G.nx] : S;
+	uint8_t tzp = typ[c + G.sxy], tzn = typ[c - G.sxy];
+	unsigned n = (txp != S) + (typ_ != S) + (tzp != S) + (txn != S) + (tyn != S) + (tzn != S);
+	unsigned f = n | FL_L;
+	if (typ[c] == F) { f |= FL_SELF; }
+	if (txp == F) { f |= FL_XP; }
+	if (typ_ == F) { f |= FL_YP; }
+	if (tzp == F) { f |= FL_ZP; }
+	flags[c] = (uint8_t)f;
+
+	double vx = u[c], vy = v[c], vz = w[c];
+	double value = -(vx + vy + vz);
+	int z = lz - 1 + G.z0;
+	if (x > 0) {
+		double q = u[c - 1];
+		value += q;
+		if (txn == S) { value -= q; }
+	}
+	if (y > 0) {
+		double q = v[c - G.nx];
+		value += q;
+		if (tyn == S) { value -= q; }
+	}
+	if (z > 0) {
+		double q = w[c - G.sxy];
+		value += q;
+		if (tzn == S) { value -= q; }
+	}
+	if (txp == S) { value += vx; }
+	if (typ_ == S) { value += vy; }
+	if (tzp == S) { value += vz; }
+	b[c] = inv_h * value;
+}
+
+// ---- S6: out = a_scale * A v (src/pressure_solver.cpp:334-362), same subtraction order as the reference ------
+__device__ __forceinline__ double stencil_apply(const GridDesc &G, unsigned f, const double *__restrict__ s,
+	long long c, int x, int y, double a_scale) {
+	double value = (double)FL_N(f) * s[c];
+	if (f & FL_SELF) { // coupling to -neighbours is the neighbour's "fluid_pos" flag == type(self) == fluid
+		if (x > 0) { value -= s[c - 1]; }
+		if (y > 0) { value -= s[c - G.nx]; }
+		value -= s[c - G.sxy];
+	}
+	if (f & FL_XP) { value -= s[c + 1]; }
+	if (f & FL_YP) { value -= s[c + G.nx]; }
+	if (f & FL_ZP) { value -= s[c + G.sxy]; }
+	return a_scale * value;
+}
+
+// deterministic finish of a block-partial reduction: `op` 0 sum, 1 max
+__device__ __forceinline__ double finish_partials(double *partials, unsigned nblocks, int op) {
+	double acc = op ? -1.0e300 : 0.0;
+	for (unsigned k = threadIdx.x; k < nblocks; k += blockDim.x) {
+		double t = partials[k];
+		acc = op ? fmax(acc, t) : acc + t;
+	}
+	return op ? block_max(acc) : block_sum(acc);
+}
+
+// ---- finalisers of the PCG scalars: run by the last block on one GPU, or by k_finalize after the NCCL
+// all-reduce of the local partial results on several GPUs ------------------------------------------------------
+enum { FIN_BB = 0, FIN_ALPHA = 1, FIN_RESID = 2, FIN_BETA_FIRST = 3, FIN_BETA = 4 };
+__device__ __forceinline__ void pcg_finalize(PcgScalars *scal, int which, double tolerance) {
+	switch (which) {
+	case FIN_BB: // early-out of the reference (src/pressure_solver.cpp:29-35)
+		scal->iters = 0;
+		scal->resmax = 0.0;
+		scal->done = scal->bb < 1e-6 ? 1 : 0;
+		break;
+	case FIN_ALPHA:
+		scal->alpha = scal->sigma / scal->zs;
+		break;
+	case FIN_RESID: // :54-58 (two-sided: max |r|, which implies the reference's one-sided max r < tolerance)
+		scal->iters += 1;
+		if (scal->resmax < tolerance) { scal->done = 1; }
+		break;
+	case FIN_BETA_FIRST: // :38-42
+		scal->sigma = scal->sigma_new;
+		scal->beta = 0.0;
+		break;
+	default: // :62-68
+		scal->beta = scal->sigma_new / scal->sigma;
+		scal->sigma = scal->sigma_new;
+		break;
+	}
+}
+__global__ void k_finalize(PcgScalars *scal, int which, double tolerance) {
+	if (which != FIN_BB && scal->done) { return; }
+	pcg_finalize(scal, which, tolerance);
+}
+
+__global__ void __launch_bounds__(RED_THREADS) k_spmv_dot(GridDesc G, const uint8_t *__restrict__ flags,
+	const double *__restrict__ s, double *__restrict__ z, double a_scale, PcgScalars *scal,
+	double *partials, unsigned *ticket, int finalize) {
+	if (scal->done) { return; }
+	double acc = 0.0;
+	for (long long own = (long long)blockIdx.x * blockDim.x + threadIdx.x; own < G.nown;
+		own += (long long)gridDim.x * blockDim.x) {
+		long long c = own + G.sxy;
+		unsigned f = flags[c];
+		double out = 0.0;
+		if (f & FL_L) {
+			int x, y, lz;
+			cell_xyz(G, own, x, y, lz);
+			out = stencil_apply(G, f, s, c, x, y, a_scale);
+			acc += out * s[c];
+		}
+		z[c] = out;
+	}
+	acc = block_sum(acc);
+	if (threadIdx.x == 0) { partials[blockIdx.x] = acc; }
+	if (lfk_last_block(ticket)) {
+		double tot = finish_partials(partials, gridDim.x, 0);
+		if (threadIdx.x == 0) {
+			scal->zs = tot;
+			if (finalize) { pcg_finalize(scal, FIN_ALPHA, 0.0); }
+		}
+	}
+}
+
+__global__ void k_spmv_plain(GridDesc G, const uint8_t *__restrict__ flags, const double *__restrict__ s,
+	double *__restrict__ z, double a_scale) {
+	long long own = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+	if (own >= G.nown) { return; }
+	long long c = own + G.sxy;
+	unsigned f = flags[c];
+	double out = 0.0;
+	if (f & FL_L) {
+		int x, y, lz;
+		cell_xyz(G, own, x, y, lz);
+		out = stencil_apply(G, f, s, c, x, y, a_scale);
+	}
+	z[c] = out;
+}
+
+// r = b, sum b^2
+__global__ void __launch_bounds__(RED_THREADS) k_pcg_init(GridDesc G, const double *__restrict__ b,
+	double *__restrict__ r, PcgScalars *scal, double *partials, unsigned *ticket, int finalize) {
+	double acc = 0.0;
+	for (long long own = (long long)blockIdx.x * blockDim.x + threadIdx.x; own < G.nown;
+		own += (long long)gridDim.x * blockDim.x) {
+		long long c = own + G.sxy;
+		double v = b[c];
+		r[c] = v;
+		acc += v * v;
+	}
+	acc = block_sum(acc);
+	if (threadIdx.x == 0) { partials[blockIdx.x] = acc; }
+	if (lfk_last_block(ticket)) {
+		double tot = finish_partials(partials, gridDim.x, 0);
+		if (threadIdx.x == 0) {
+			scal->bb = tot;
+			scal->sigma = 0.0;
+			if (finalize) { pcg_finalize(scal, FIN_BB, 0.0); }
+		}
+	}
+}
+
+// Jacobi: z = r / (a_scale * n)
+__global__ void k_precond_jacobi(GridDesc G, const uint8_t *__restrict__ flags, const double *__restrict__ r,
+	double *__restrict__ z, double a_scale, const PcgScalars *scal) {
+	if (scal->done) { return; }
+	long long own = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+	if (own >= G.nown) { return; }
+	long long c = own + G.sxy;
+	unsigned f = flags[c];
+	double out = 0.0;
+	if ((f & FL_L) && FL_N(f) > 0) {
+		out = r[c] / (a_scale * (double)FL_N(f));
+	}
+	z[c] = out;
+}
+
+// sigma_new = z.r
+__global__ void __launch_bounds__(RED_THREADS) k_dot_zr(GridDesc G, const double *__restrict__ z,
+	const double *__restrict__ r, PcgScalars *scal, double *partials, unsigned *ticket, int finalize, int first) {
+	if (scal->done) { return; }
+	double acc = 0.0;
+	for (long long own = (long long)blockIdx.x * blockDim.x + threadIdx.x; own < G.nown;
+		own += (long long)gridDim.x * blockDim.x) {
+		long long c = own + G.sxy;
+		acc += z[c] * r[c];
+	}
+	acc = block_sum(acc);
+	if (threadIdx.x == 0) { partials[blockIdx.x] = acc; }
+	if (lfk_last_block(ticket)) {
+		double tot = finish_partials(partials, gridDim.x, 0);
+		if (threadIdx.x == 0) {
+			scal->sigma_new = tot;
+			if (finalize) { pcg_finalize(scal, first ? FIN_BETA_FIRST : FIN_BETA, 0.0); }
+		}
+	}
+}
+
+// p += alpha s ; r -= alpha z ; residual = max |r|
+__global__ void __launch_bounds__(RED_THREADS) k_update_pr(GridDesc G, double *__restrict__ p,
+	double *__restrict__ r, const double *__restrict__ s, const double *__restrict__ z, PcgScalars *scal,
+	double *partials, unsigned *ticket, double tolerance, int finalize) {
+	if (scal->done) { return; }
+	const double alpha = scal->alpha;
+	double m = 0.0;
+	for (long long own = (long long)blockIdx.x * blockDim.x + threadIdx.x; own < G.nown;
+		own += (long long)gridDim.x * blockDim.x) {
+		long long c = own + G.sxy;
+		p[c] = p[c] + alpha * s[c];
+		double rv = r[c] + (-alpha) * z[c];
+		r[c] = rv;
+		m = fmax(m, fabs(rv));
+	}
+	m = block_max(m);
+	if (threadIdx.x == 0) { partials[blockIdx.x] = m; }
+	if (lfk_last_block(ticket)) {
+		double tot = finish_partials(partials, gridDim.x, 1);
+		if (threadIdx.x == 0) {
+			scal->resmax = tot;
+			if (finalize) { pcg_finalize(scal, FIN_RESID, tolerance); }
+		}
+	}
+}
+
+// s = z + beta s  (first iteration: beta == 0 => s = z)
+__global__ void k_xpby(GridDesc G, double *__restrict__ s, const double *__restrict__ z, const PcgScalars *scal) {
+	if (scal->done) { return; }
+	const double beta = scal->beta;
+	long long own = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+	if (own >= G.nown) { return; }
+	long long c = own + G.sxy;
+	s[c] = beta == 0.0 ? z[c] : z[c] + beta * s[c];
+}
+
+int lfks_build_system(lfk_ctx *c, double dt) {
+	PhaseTimer T(c, LFK_PHASE_SOLVE_SETUP);
+	const GridDesc &G = c->g;
+	if (c->nranks > 1) {
+		LFK_TRY(lfkx_halo_u8(c, c->typ));
+		for (int d = 0; d < 3; ++d) { LFK_TRY(lfkx_halo_f64(c, c->vel[d])); }
+	}
+	LFK_LAUNCH(c, k_build_system, lfk_blocks(G.nown, 256), 256, 0, G, c->cnt, c->typ, c->vel[0], c->vel[1],
+		c->vel[2], c->flags, c->b, c->p, 1.0 / G.h);
+	if (c->nranks > 1) {
+		LFK_TRY(lfkx_halo_u8(c, c->flags));
+	}
+	c->system_valid = true;
+	c->system_dt = dt;
+	c->mg_valid = false;
+	return 0;
+}
+
+static inline unsigned red_blocks(long long n) {
+	unsigned nb = lfk_blocks(n, RED_THREADS);
+	return nb > RED_BLOCKS ? RED_BLOCKS : nb;
+}
+
+static int allreduce_scalar(lfk_ctx *c, double *field, bool is_max, int which, double tol) {
+	if (c->nranks > 1) {
+		LFK_TRY(is_max ? lfkx_allreduce_max(c, field, 1) : lfkx_allreduce_sum(c, field, 1));
+		LFK_LAUNCH(c, k_finalize, 1, 1, 0, c->d_scal, which, tol);
+	}
+	return 0;
+}
+
+int lfkm_setup(lfk_ctx *c, double a_scale);                       // mg.cu
+int lfkm_apply(lfk_ctx *c, const double *r, double *z, double a_scale); // mg.cu
+
+static int apply_preconditioner(lfk_ctx *c, double a_scale) {
+	const GridDesc &G = c->g;
+	if (c->prm.preconditioner == LFK_PRECOND_MULTIGRID) {
+		return lfkm_apply(c, c->r, c->z, a_scale);
+	}
+	LFK_LAUNCH(c, k_precond_jacobi, lfk_blocks(G.nown, 256), 256, 0, G, c->flags, c->r, c->z, a_scale, c->d_scal);
+	return 0;
+}
+
+// pressure_solver::solve (src/pressure_solver.cpp:19-71)
+int lfks_solve(lfk_ctx *c, double dt, double *residual, uint64_t *iters) {
+	const GridDesc &G = c->g;
+	if (!c->system_valid || c->system_dt != dt) {
+		LFK_TRY(lfks_build_system(c, dt));
+	}
+	PhaseTimer T(c, LFK_PHASE_PCG);
+	const double a_scale = dt / (c->prm.density * G.h * G.h);
+	const double tol = c->prm.tolerance;
+	const int fin = c->nranks == 1 ? 1 : 0;
+	const unsigned nb = red_blocks(G.nown), eb = lfk_blocks(G.nown, 256);
+	if (c->prm.preconditioner == LFK_PRECOND_MULTIGRID && !c->mg_valid) {
+		LFK_TRY(lfkm_setup(c, a_scale));
+	}
+	LFK_LAUNCH(c, k_pcg_init, nb, RED_THREADS, 0, G, c->b, c->r, c->d_scal, c->partials, c->ticket, fin);
+	LFK_TRY(allreduce_scalar(c, &c->d_scal->bb, false, FIN_BB, tol));
+	LFK_TRY(apply_preconditioner(c, a_scale));
+	LFK_LAUNCH(c, k_dot_zr, nb, RED_THREADS, 0, G, c->z, c->r, c->d_scal, c->partials, c->ticket, fin, 1);
+	LFK_TRY(allreduce_scalar(c, &c->d_scal->sigma_new, false, FIN_BETA_FIRST, tol));
+	LFK_LAUNCH(c, k_xpby, eb, 256, 0, G, c->s, c->z, c->d_scal);
+
+	// The loop runs entirely from device-resident scalars; the host only polls the `done` flag now and then.
+	// Kernels issued after convergence return immediately, so the iteration count stays exact.
+	const int max_it = c->prm.max_iterations;
+	int poll = G.nown >= (1ll << 22) ? 2 : (G.nown >= (1ll << 18) ? 8 : 16);
+	int issued = 0;
+	bool done = false;
+	while (!done) {
+		int burst = max_it - issued < poll ? max_it - issued : poll;
+		for (int k = 0; k < burst; ++k) {
+			if (c->nranks > 1) { LFK_TRY(lfkx_halo_f64(c, c->s)); }
+			LFK_LAUNCH(c, k_spmv_dot, nb, RED_THREADS, 0, G, c->flags, c->s, c->z, a_scale, c->d_scal, c->partials,
+				c->ticket, fin);
+			LFK_TRY(allreduce_scalar(c, &c->d_scal->zs, false, FIN_ALPHA, tol));
+			LFK_LAUNCH(c, k_update_pr, nb, RED_THREADS, 0, G, c->p, c->r, c->s, c->z, c->d_scal, c->partials,
+				c->ticket, tol, fin);
+			LFK_TRY(allreduce_scalar(c, &c->d_scal->resmax, true, FIN_RESID, tol));
+			if (issued + k + 1 < max_it) { // the reference leaves the loop after max_iterations updates of p, r
+				LFK_TRY(apply_preconditioner(c, a_scale));
+				LFK_LAUNCH(c, k_dot_zr, nb, RED_THREADS, 0, G, c->z, c->r, c->d_scal, c->partials, c->ticket, fin, 0);
+				LFK_TRY(allreduce_scalar(c, &c->d_scal->sigma_new, false, FIN_BETA, tol));
+				LFK_LAUNCH(c, k_xpby, eb, 256, 0, G, c->s, c->z, c->d_scal);
+			}
+		}
+		issued += burst;
+		LFK_CUDA(c, cudaMemcpyAsync(c->h_scal, c->d_scal, sizeof(PcgScalars), cudaMemcpyDeviceToHost, c->stream));
+		LFK_CUDA(c, cudaStreamSynchronize(c->stream));
+		done = c->h_scal->done != 0 || issued >= max_it;
+		if (poll < 8) { poll *= 2; }
+	}
+	c->stats.pcg_iterations = c->h_scal->iters;
+	c->stats.pcg_residual = c->h_scal->resmax;
+	if (residual) { *residual = c->h_scal->resmax; }
+	if (iters) { *iters = c->h_scal->iters; }
+	c->pressure_valid = true;
+	return 0;
+}
+
+// out = A v on dense vectors (parity hook for _apply_a)
+int lfks_apply_a(lfk_ctx *c, double dt, const double *d_v_dense, double *d_out_dense) {
+	const GridDesc &G = c->g;
+	if (!c->system_valid || c->system_dt != dt) {
+		LFK_TRY(lfks_build_system(c, dt));
+	}
+	const double a_scale = dt / (c->prm.density * G.h * G.h);
+	LFK_LAUNCH(c, k_spmv_plain, lfk_blocks(G.nown, 256), 256, 0, G, c->flags, d_v_dense, d_out_dense, a_scale);
+	return 0;
+}
+
+// ---- S9: pressure-gradient update, face-centric (src/pressure_solver.cpp:73-148) ---------------------------
+// Every +face is owned by exactly one cell c; the reference touches it from c (if c is an unknown: "+face" rule)
+// and then from the neighbour d = c + e (if d is an unknown: "-face" rule), in that order (c < d in raw order).
+__device__ __forceinline__ double face_update(double val, bool Lc, bool Ld, uint8_t tc, uint8_t td, double pc,
+	double pd, double coeff) {
+	if (Lc) {
+		if (td != LFK_CELL_SOLID) {
+			double otherp = td == LFK_CELL_FLUID ? pd : 0.0;
+			val -= coeff * (otherp - pc);
+		} else {
+			val = 0.0;
+		}
+	}
+	if (Ld) {
+		if (tc == LFK_CELL_AIR) {
+			val -= coeff * pd;
+		} else if (tc == LFK_CELL_SOLID) {
+			val = 0.0;
+		}
+	}
+	return val;
+}
+
+__global__ void k_apply_pressure(GridDesc G, const uint8_t *__restrict__ flags, const uint8_t *__restrict__ typ,
+	const double *__restrict__ p, double *__restrict__ u, double *__restrict__ v, double *__restrict__ w,
+	double coeff) {
+	long long own = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+	if (own >= G.nown) { return; }
+	int x, y, lz;
+	cell_xyz(G, own, x, y, lz);
+	long long c = own + G.sxy;
+	const bool Lc = flags[c] & FL_L;
+	const uint8_t tc = typ[c];
+	const double pc = p[c];
+	{
+		bool in = x + 1 < G.nx;
+		bool Ld = in && (flags[c + 1] & FL_L);
+		if (Lc || Ld) {
+			u[c] = face_update(u[c], Lc, Ld, tc, in ? typ[c + 1] : (uint8_t)LFK_CELL_SOLID, pc, in ? p[c + 1] : 0.0, coeff);
+		}
+	}
+	{
+		bool in = y + 1 < G.ny;
+		bool Ld = in && (flags[c + G.nx] & FL_L);
+		if (Lc || Ld) {
+			v[c] = face_update(v[c], Lc, Ld, tc, in ? typ[c + G.nx] : (uint8_t)LFK_CELL_SOLID, pc,
+				in ? p[c + G.nx] : 0.0, coeff);
+		}
+	}
+	{ // z: the ghost layer is solid / not an unknown at the domain boundary, the neighbour's cells otherwise
+		bool Ld = flags[c + G.sxy] & FL_L;
+		if (Lc || Ld) {
+			w[c] = face_update(w[c], Lc, Ld, tc, typ[c + G.sxy], pc, p[c + G.sxy], coeff);
+		}
+	}
+}
+
+int lfks_apply_pressure(lfk_ctx *c, double dt) {
+	PhaseTimer T(c, LFK_PHASE_APPLY_PRESSURE);
+	LFK_REQUIRE(c, c->system_valid && c->pressure_valid, LFK_E_STATE,
+		"lfk_apply_pressure needs lfk_pressure_solve (or lfk_upload_pressure) first");
+	const GridDesc &G = c->g;
+	if (c->nranks > 1) { LFK_TRY(lfkx_halo_f64(c, c->p)); }
+	double coeff = dt / (c->prm.density * G.h);
+	LFK_LAUNCH(c, k_apply_pressure, lfk_blocks(G.nown, 256), 256, 0, G, c->flags, c->typ, c->p, c->vel[0],
+		c->vel[1], c->vel[2], coeff);
+	return 0;
+}
+
+// ---- E1: velocity extrapolation (src/simulation.cpp:685-754) ----------------------------------------------
+__global__ void k_valid_from_counts(long long ncl, const uint32_t *__restrict__ cnt, uint8_t *__restrict__ valid) {
+	long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+	if (i < ncl) { valid[i] = cnt[i] > 0 ? 1 : 0; }
+}
+
+__global__ void k_extrapolate(GridDesc G, const uint8_t *__restrict__ valid, uint8_t *__restrict__ valid_next,
+	const uint8_t *__restrict__ typ, double *__restrict__ u, double *__restrict__ v, double *__restrict__ w) {
+	long long own = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+	if (own >= G.nown) { return; }
+	long long c = own + G.sxy;
+	if (valid[c]) { return; }
+	int x, y, lz;
+	cell_xyz(G, own, x, y, lz);
+	int z = lz - 1 + G.z0;
+	int nvalid = 0;
+	double s0 = 0.0, s1 = 0.0, s2 = 0.0;
+	uint8_t tp0 = LFK_CELL_SOLID, tp1 = LFK_CELL_SOLID, tp2 = LFK_CELL_SOLID;
+#define TAKE(nb) do { s0 += u[nb]; s1 += v[nb]; s2 += w[nb]; ++nvalid; } while (0)
+	if (x > 0 && valid[c - 1]) { TAKE(c - 1); }
+	if (x + 1 < G.nx && valid[c + 1]) { TAKE(c + 1); tp0 = typ[c + 1]; }
+	if (y > 0 && valid[c - G.nx]) { TAKE(c - G.nx); }
+	if (y + 1 < G.ny && valid[c + G.nx]) { TAKE(c + G.nx); tp1 = typ[c + G.nx]; }
+	if (z > 0 && valid[c - G.sxy]) { TAKE(c - G.sxy); }
+	if (z + 1 < G.nz && valid[c + G.sxy]) { TAKE(c + G.sxy); tp2 = typ[c + G.sxy]; }
+#undef TAKE
+	if (nvalid > 0) {
+		// only cells WITHOUT particles are written and only cells WITH particles are read: no race in place
+		uint8_t t = typ[c];
+		double dn = (double)nvalid;
+		if (t == tp0) { u[c] = s0 / dn; }
+		if (t == tp1) { v[c] = s1 / dn; }
+		if (t == tp2) { w[c] = s2 / dn; }
+		valid_next[c] = 1;
+	}
+}
+
+int lfks_extrapolate(lfk_ctx *c) {
+	PhaseTimer T(c, LFK_PHASE_EXTRAPOLATE);
+	const GridDesc &G = c->g;
+	int iters = c->prm.extrapolation_iterations;
+	if (iters <= 0) { return 0; }
+	LFK_LAUNCH(c, k_valid_from_counts, lfk_blocks(G.ncl, 256), 256, 0, G.ncl, c->cnt, c->valid[0]);
+	int cur = 0;
+	for (int it = 0; it < iters; ++it) {
+		if (c->nranks > 1) {
+			LFK_TRY(lfkx_halo_u8(c, c->valid[cur]));
+			for (int d = 0; d < 3; ++d) { LFK_TRY(lfkx_halo_f64(c, c->vel[d])); }
+		}
+		if (it + 1 < iters) {
+			LFK_CUDA(c, cudaMemcpyAsync(c->valid[cur ^ 1], c->valid[cur], (size_t)G.ncl, cudaMemcpyDeviceToDevice,
+				c->stream));
+		}
+		LFK_LAUNCH(c, k_extrapolate, lfk_blocks(G.nown, 256), 256, 0, G, c->valid[cur], c->valid[cur ^ 1], c->typ,
+			c->vel[0], c->vel[1], c->vel[2]);
+		cur ^= 1;
+	}
+	return 0;
+}
+
+// ---- fluid-cell ordinals: compaction between the dense grid and the reference's fluid-cell list --------------
+int lfks_ensure_ordinal(lfk_ctx *c) {
+	if (c->ordinal_valid) { return 0; }
+	LFK_TRY(lfkp_exclusive_scan_u32(c, c->cnt, c->ordinal, c->g.ncl, 1));
+	c->ordinal_valid = true;
+	return 0;
+}
+
+__global__ void k_compact_f64(long long ncl, const uint32_t *__restrict__ cnt, const uint32_t *__restrict__ ord,
+	const double *__restrict__ dense, double *__restrict__ out) {
+	long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+	if (i < ncl && cnt[i] > 0) { out[ord[i]] = dense[i]; }
+}
+__global__ void k_compact_flags(long long ncl, const uint32_t *__restrict__ cnt, const uint32_t *__restrict__ ord,
+	const uint8_t *__restrict__ flags, uint8_t *__restrict__ out) {
+	long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+	if (i < ncl && cnt[i] > 0) {
+		unsigned f = flags[i];
+		out[ord[i]] = (uint8_t)(FL_N(f) | (((f >> 5) & 7u) << 3)); // reference cell_data bit order
+	}
+}
+__global__ void k_expand_f64(long long ncl, const uint32_t *__restrict__ cnt, const uint32_t *__restrict__ ord,
+	const double *__restrict__ in, double *__restrict__ dense) {
+	long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+	if (i < ncl) { dense[i] = cnt[i] > 0 ? in[ord[i]] : 0.0; }
+}
+__global__ void k_fluid_cells(long long ncl, long long shift, const uint32_t *__restrict__ cnt,
+	const uint32_t *__restrict__ ord, unsigned long long *__restrict__ out) {
+	long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+	if (i < ncl && cnt[i] > 0) { out[ord[i]] = (unsigned long long)(i + shift); }
+}
+
+int lfks_compact(lfk_ctx *c, const double *dense, double *d_out, const uint8_t *dense_u8, uint8_t *d_out_u8) {
+	LFK_TRY(lfks_ensure_ordinal(c));
+	unsigned nb = lfk_blocks(c->g.ncl, 256);
+	if (dense) { LFK_LAUNCH(c, k_compact_f64, nb, 256, 0, c->g.ncl, c->cnt, c->ordinal, dense, d_out); }
+	if (dense_u8) { LFK_LAUNCH(c, k_compact_flags, nb, 256, 0, c->g.ncl, c->cnt, c->ordinal, dense_u8, d_out_u8); }
+	return 0;
+}
+int lfks_expand(lfk_ctx *c, const double *d_compact, double *dense) {
+	LFK_TRY(lfks_ensure_ordinal(c));
+	LFK_LAUNCH(c, k_expand_f64, lfk_blocks(c->g.ncl, 256), 256, 0, c->g.ncl, c->cnt, c->ordinal, d_compact, dense);
+	return 0;
+}
+int lfks_fluid_cells(lfk_ctx *c, uint64_t *d_out) {
+	LFK_TRY(lfks_ensure_ordinal(c));
+	long long shift = ((long long)c->g.z0 - 1) * c->g.sxy; // local raw -> whole-grid raw
+	LFK_LAUNCH(c, k_fluid_cells, lfk_blocks(c->g.ncl, 256), 256, 0, c->g.ncl, shift, c->cnt, c->ordinal,
+		(unsigned long long*)d_out);
+	return 0;
+}
+
+// ---- config 5: projection-only synthetic system --------------------------------------------------------------
+__global__ void k_synthetic_projection(GridDesc G, uint8_t *__restrict__ typ, uint32_t *__restrict__ cnt,
+	double *__restrict__ u, double *__restrict__ v, double *__restrict__ w, unsigned long long seed) {
+	long long own = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+	if (own >= G.nown) { return; }
+	int x, y, lz;
+	cell_xyz(G, own, x, y, lz);
+	long long c = own + G.sxy;
+	long long graw = c + ((long long)G.z0 - 1) * G.sxy;
+	bool air = y == G.ny - 1; // free surface: top layer is air => the system is non-singular
+	typ[c] = air ? LFK_CELL_AIR : LFK_CELL_FLUID;
+	cnt[c] = air ? 0u : 1u;
+	unsigned long long r = mix64(seed ^ mix64((unsigned long long)graw + 0x9e3779b97f4a7c15ull));
+	double f[3];
+#pragma unroll
+	for (int d = 0; d < 3; ++d) {
+		r = mix64(r + 0x9e3779b97f4a7c15ull);
+		f[d] = (double)(r >> 11) * (2.0 / 9007199254740992.0) - 1.0;
+	}
+	u[c] = f[0];
+	v[c] = f[1];
+	w[c] = f[2];
+}
+
+int lfks_synthetic_projection(lfk_ctx *c, uint64_t seed) {
+	const GridDesc &G = c->g;
+	LFK_CUDA(c, cudaMemsetAsync(c->cnt, 0, (size_t)G.ncl * sizeof(uint32_t), c->stream));
+	LFK_LAUNCH(c, k_synthetic_projection, lfk_blocks(G.nown, 256), 256, 0, G, c->typ, c->cnt, c->vel[0], c->vel[1],
+		c->vel[2], (unsigned long long)seed);
+	c->np = 0;
+	c->table_valid = false;
+	c->ordinal_valid = false;
+	c->system_valid = false;
+	c->pressure_valid = false;
+	return 0;
+}
