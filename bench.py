@@ -1,0 +1,288 @@
+#!/usr/bin/env python
+"""bench.py -- particle-substeps/s of a full libfluid time step (BASELINE.json metric).
+
+  python bench.py --gpus N --steps K --warmup W            the CUDA path (this repo)
+  python bench.py --impl reference --steps K --warmup W     the reference's own CPU code on the host cores
+
+A "step" is one simulation::time_step() (CFL-limited dt, src/simulation.cpp:127-129) over the resident scene:
+advect + collide, cell sort, P2G (+gravity), pressure solve, pressure update, position correction + collide,
+extrapolation, G2P.  N = 1: 256^3 grid, APIC, 8 particles per cell, ~130 M particles (BASELINE configs[2], the
+configuration the metric is quoted on).  N > 1: the same slab per GPU (weak scaling), z-slab decomposition.
+One JSON line on stdout (rank 0).
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "particle-substeps/s at 256^3 APIC (8 ppc)"
+UNIT = "particle-substeps/s"
+GRAVITY = (0.0, -981.0, 0.0)
+
+
+def scene_boxes(n, nz):
+    """tidal step: water fills the box up to y = n - 2 on the left half and n - 14 (scaled) on the right half"""
+    hi, lo = n - max(2, n // 128), n - max(3, (14 * n) // 256)
+    return [((0.0, 0.0, 0.0), (n / 2.0, float(hi), float(nz))), ((n / 2.0, 0.0, 0.0), (n / 2.0, float(lo), float(nz)))]
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        super().__init__(daemon=True)
+        self.gpu_index, self.rows, self.proc = gpu_index, [], None
+
+    def run(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu_index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            for line in self.proc.stdout:
+                self.rows.append([c.strip() for c in line.split(",")])
+        except Exception:
+            pass
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": len(self.rows)}
+        sm = [float(r[1]) for r in self.rows if len(r) >= 8 and r[1].replace(".", "").isdigit()]
+        if sm:
+            loaded = sorted(sm)[len(sm) // 4:]  # drop the idle quarter at either end of the window
+            out["sm_mhz"] = statistics.median(loaded)
+            out["sm_max_mhz"] = float(self.rows[0][2])
+            names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+            for k, nm in enumerate(names):
+                if any(len(r) >= 8 and r[4 + k].lower().startswith("active") for r in self.rows):
+                    out["reasons"].append(nm)
+        return out
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# ------------------------------------------------------------------------------------------------ reference arm
+def run_reference(args, n=None, steps=None, warmup=None, quiet=False):
+    """The reference's own CPU implementation (oracle/_ref = unmodified libfluid sources) on the host cores, on a
+    bounded sample of the workload: the same tidal-step scene on a smaller grid."""
+    from oracle import refbind as RB
+    kind = "reference"
+    n = n or args.ref_grid
+    steps = steps if steps is not None else args.steps
+    warmup = warmup if warmup is not None else args.warmup
+    cores = os.cpu_count() or 1
+    os.environ.setdefault("OMP_NUM_THREADS", str(cores))
+    if not RB.available():
+        raise SystemExit("oracle/_ref/libfluid_ref.so is missing (built by __graft_entry__.build() where "
+                         "/root/reference exists)")
+    sim = RB.RefSim((n, n, n), gravity=GRAVITY, method=RB.APIC)
+    for start, size in scene_boxes(n, n):
+        sim.seed_box(start, size)
+    sim.reset_space_hash()
+    npart = sim.num_particles()
+    for _ in range(warmup):
+        sim.time_step()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        sim.time_step()
+    dt = time.perf_counter() - t0
+    value = npart * steps / dt
+    sample = "tidal-step scene at %d^3 (%d particles, 8 ppc), %d steps of simulation::time_step()" % (n, npart, steps)
+    base = {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample}
+    if quiet:
+        return base
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": steps, "warmup": warmup,
+            "ms_per_step": 1e3 * dt / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic", "impl": "reference",
+            "config": {"workload": "256^3 APIC tidal-step full time_step; reference CPU arm runs " + sample},
+            "cpu_baseline": base,
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+    return base
+
+
+# ------------------------------------------------------------------------------------------------------ our arm
+def run_ours(args):
+    import torch
+    from libfluid_b200 import capi
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dist = None
+    nccl_id = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        box = [capi.nccl_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(box, src=0)
+        nccl_id = box[0]
+
+    n = args.grid
+    nz = n * world  # weak scaling: one n^3 slab per GPU
+    stream = torch.cuda.current_stream().cuda_stream
+    ctx = capi.Context((n, n, nz), device=local_rank, stream=stream, nranks=world, rank=rank, nccl_id=nccl_id,
+                       cell_size=1.0, gravity=GRAVITY, method=capi.APIC, max_iterations=args.max_iterations,
+                       preconditioner=capi.PRECOND_MULTIGRID)
+    for k, (start, size) in enumerate(scene_boxes(n, nz)):
+        ctx.seed_box_device(start, size, density=2, seed=20261017, append=k > 0)
+    np_local = ctx.num_particles()
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def allsum(v):
+        if dist is None:
+            return v
+        t = torch.tensor([float(v)], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t)
+        return float(t.item())
+
+    def allmax(v):
+        if dist is None:
+            return v
+        t = torch.tensor([float(v)], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    np_total = int(allsum(np_local))
+    for _ in range(args.warmup):
+        ctx.time_step()
+    # ---- timed region: device resident, CUDA events on the launching stream, max over ranks ----
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    ctx.reset_stats()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    iters = 0
+    for _ in range(args.steps):
+        ctx.time_step()
+        iters += ctx.stats()["pcg_iterations"]
+    e1.record()
+    barrier()
+    ms = allmax(e0.elapsed_time(e1))
+    clocks = sampler.stop()
+    launches = ctx.stats()["kernel_launches"]
+    value = np_total * args.steps / (ms * 1e-3)
+
+    # ---- per-phase device times (separate instrumented steps; the event pairs serialise the phases) ----
+    ctx.set_timing(True)
+    ctx.reset_stats()
+    prof_steps = max(1, min(args.steps, 3))
+    prof_iters = 0
+    for _ in range(prof_steps):
+        ctx.time_step()
+        prof_iters += ctx.stats()["pcg_iterations"]
+    st = ctx.stats()
+    ctx.set_timing(False)
+    phase = {k: v / prof_steps for k, v in st["phase_ms"].items() if v > 0}
+    nf = ctx.num_fluid_cells()
+    ncl = n * n * n
+    peak, peak_src = measured_peak()
+    # algorithmic bytes per launch (DESIGN.md "Kernels"): single-kernel phases only
+    alg = {"p2g": 120 * np_local + 26 * ncl, "g2p": 120 * np_local + 24 * ncl,
+           "correct_collide": 48 * np_local + ncl, "advect_collide": 72 * np_local + ncl}
+    single = {k: phase[k] for k in alg if k in phase}
+    dom = max(single, key=single.get)
+    ach = alg[dom] / (single[dom] * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                "traffic": None, "peak_source": peak_src, "ms": single[dom],
+                "all": {k: {"ms": single[k], "GB/s": alg[k] / (single[k] * 1e-3) / 1e9} for k in single}}
+    if "pcg" in phase and prof_iters:
+        it_ms = phase["pcg"] * prof_steps / prof_iters
+        roofline["all"]["pcg_iteration"] = {"ms": it_ms, "GB/s": 105 * nf / (it_ms * 1e-3) / 1e9,
+                                           "iters_per_step": prof_iters / prof_steps, "iters_per_s": 1e3 / it_ms}
+
+    # ---- end to end through the C ABI with HOST buffers: AoS particles + cells up, step, AoS particles + cells down
+    e2e = None
+    if not args.no_e2e:
+        import numpy as np
+        nbytes = np_local * 152
+        host_p = torch.empty(max(nbytes, 8), dtype=torch.uint8, pin_memory=True)
+        host_c = torch.empty(n * n * nz * 32, dtype=torch.uint8, pin_memory=True)
+        cells_np = host_c.numpy().view(capi.CELL_DTYPE)
+        ctx.download_particles((host_p.data_ptr(), np_local))
+        ctx.download_cells(cells_np)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.e2e_steps):
+            ctx.upload_cells(cells_np)
+            ctx.upload_particles((host_p.data_ptr(), np_local))
+            ctx.time_step()
+            ctx.download_particles((host_p.data_ptr(), np_local))
+            ctx.download_cells(cells_np)
+        barrier()
+        dt_e2e = allmax(time.perf_counter() - t0)
+        own_cells = n * n * n
+        e2e = {"value": np_total * args.e2e_steps / dt_e2e, "unit": UNIT,
+               "h2d_bytes_per_step": int(nbytes + min(n * n * nz, own_cells + 2 * n * n) * 32),
+               "d2h_bytes_per_step": int(nbytes + own_cells * 32), "steps": args.e2e_steps,
+               "what": "lfk_upload_cells + lfk_upload_particles (pinned AoS, reference layouts) + lfk_time_step_cfl"
+                       " + lfk_download_particles + lfk_download_cells, per step, wall clock"}
+        del host_p, host_c
+
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "%dx%dx%d MAC grid (one %d^3 z-slab per GPU), APIC, tidal-step scene, 8 ppc, "
+                                   "%d particles, full simulation::time_step() with CFL dt" % (n, n, nz, n, np_total),
+                       "particles": np_total, "fluid_cells_rank0": nf, "pcg_iters_per_step": iters / args.steps,
+                       "l2_policy": "inputs (>= 16 GB of particle state per step) are far larger than the 126 MB L2",
+                       "preconditioner": "aggregation multigrid V(2,2), fp32", "tolerance": 1e-6},
+            "phase_ms": phase, "roofline": roofline, "clocks": clocks, "gpu_launches": int(launches), "e2e": e2e}
+    ctx.close()
+    if rank == 0:
+        if world == 1 and not args.no_cpu_baseline:
+            try:
+                line["cpu_baseline"] = run_reference(args, n=args.ref_grid, steps=2, warmup=1, quiet=True)
+            except SystemExit as ex:
+                line["cpu_baseline"] = {"unavailable": str(ex)}
+        print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--grid", type=int, default=256)
+    ap.add_argument("--ref-grid", type=int, default=64, help="grid of the bounded CPU sample")
+    ap.add_argument("--max-iterations", type=int, default=1000)
+    ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        if int(os.environ.get("RANK", "0")) == 0:
+            run_reference(args)
+        return
+    run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -95,6 +95,7 @@ struct lfk_ctx {
 	uint32_t *ordinal = nullptr;    // exclusive scan of (cnt > 0) over local cells, ncl + 1 entries
 	bool ordinal_valid = false;
 	std::vector<MgLevel> mg;
+	std::vector<int> mg_z0;        // global z of the first owned layer, per level (red-black parity)
 	bool mg_valid = false;
 
 	// scratch

@@ -456,6 +456,7 @@ int lfks_apply_pressure(lfk_ctx *c, double dt) {
 	double coeff = dt / (c->prm.density * G.h);
 	LFK_LAUNCH(c, k_apply_pressure, lfk_blocks(G.nown, 256), 256, 0, G, c->flags, c->typ, c->p, c->vel[0],
 		c->vel[1], c->vel[2], coeff);
+	c->system_valid = false; // b was built from the pre-projection velocities
 	return 0;
 }
 
@@ -516,6 +517,7 @@ int lfks_extrapolate(lfk_ctx *c) {
 			c->vel[0], c->vel[1], c->vel[2]);
 		cur ^= 1;
 	}
+	c->system_valid = false;
 	return 0;
 }
 

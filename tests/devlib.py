@@ -12,7 +12,7 @@ from libfluid_b200 import capi
 # tolerances (fp64 device arithmetic, same inputs): see DESIGN.md "Parity"
 TOL_P2G = 1e-12        # rel-L2 of post-P2G face velocities
 TOL_RHS = 1e-12        # rel-L2 of b
-TOL_PRESSURE = 1e-6    # rel-L2 of p (both solvers stop at |r| < 1e-6)
+TOL_PRESSURE = 1e-5    # rel-L2 of p where |b| >> tolerance (both solvers stop at an ABSOLUTE |r| < 1e-6)
 TOL_FACES = 1e-12      # rel-L2 of faces after apply_pressure / extrapolation given the same pressure
 TOL_PARTICLE = 1e-12   # rel-L2 of positions / velocities / c given the same inputs
 
@@ -112,10 +112,25 @@ def check_device_against_record(ctx, rec, orc, exact=False):
     if int(rec["solve/iters"]) == 0:
         need("solve_early_out", iters == 0 and res == 0.0 and not p.any(), "iters %d res %g" % (iters, res))
     else:
-        true_res = np.abs(ob - orc.apply_a(a_scale, fluid, imap, oflags, p)).max() if p.size else 0.0
+        A = lambda x: orc.apply_a(a_scale, fluid, imap, oflags, x)  # noqa: E731
+        true_res = np.abs(ob - A(p)).max()
         need("solve_residual", res < ctx.params.tolerance and true_res < 2e-6,
              "reported %.3e true %.3e iters %d" % (res, true_res, iters))
-        close("pressure", p, rec["solve/p"], 1e-5 if exact else TOL_PRESSURE)
+        # Both solvers stop on an ABSOLUTE residual of 1e-6, so the two pressures agree to within their stopping
+        # criteria: |A (p_dev - p_ref)|_inf <= |r_dev|_inf + |r_ref|_inf.  Where the system is well scaled
+        # (|b| >> tolerance) that also pins p itself to rel-L2 1e-6.
+        pref = rec["solve/p"]
+        ref_res = np.abs(ob - A(pref)).max()
+        gap = np.abs(A(p - pref)).max()
+        need("pressure_residual_gap", gap <= true_res + ref_res + 1e-9, "%.3e > %.3e + %.3e" % (gap, true_res, ref_res))
+        if np.abs(ob).max() > 1.0:
+            close("pressure", p, pref, TOL_PRESSURE)
+        # post-projection faces with the device's own pressure against the reference's (1e-7)
+        ctx.apply_pressure(dt)
+        e = PL.rel_l2(ctx.download_cells()["vel"], rec["apply_pressure/cells"]["vel"])
+        need("faces_after_own_solve", e <= 1e-7, "rel_l2 %.3e (|b|max %.2e)" % (e, np.abs(ob).max()))
+        ctx.upload_cells(rec["gravity/cells"])
+        bvec, flags = ctx.download_rhs(dt)
     # ---- S9 apply_pressure with the reference's pressure ----
     ctx.upload_pressure(rec["solve/p"])
     ctx.apply_pressure(dt)
