@@ -41,19 +41,25 @@ class ClockSampler(threading.Thread):
 
     def __init__(self, gpu_index):
         super().__init__(daemon=True)
-        self.gpu_index, self.rows, self.proc = gpu_index, [], None
+        self.gpu_index, self.rows, self.proc, self.stopped = gpu_index, [], None, False
 
     def run(self):
-        try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu_index), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "200"],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            for line in self.proc.stdout:
-                self.rows.append([c.strip() for c in line.split(",")])
-        except Exception:
-            pass
+        for q in (self.Q, self.Q.replace("clocks_event_reasons", "clocks_throttle_reasons")):
+            try:
+                self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu_index), "--query-gpu=" + q,
+                                              "--format=csv,noheader,nounits", "-lms", "200"],
+                                             stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                for line in self.proc.stdout:
+                    cols = [c.strip() for c in line.split(",")]
+                    if len(cols) >= 8:
+                        self.rows.append(cols)
+            except Exception:
+                pass
+            if self.rows or self.stopped:
+                break
 
     def stop(self):
+        self.stopped = True
         if self.proc:
             self.proc.terminate()
         out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": len(self.rows)}
@@ -139,7 +145,11 @@ def run_ours(args):
 
     n = args.grid
     nz = n * world  # weak scaling: one n^3 slab per GPU
-    stream = torch.cuda.current_stream().cuda_stream
+    # a real (non-default) torch stream: lfk launches on it and torch.cuda.Event times on it
+    tstream = torch.cuda.Stream(device=local_rank)
+    torch.cuda.set_stream(tstream)
+    stream = tstream.cuda_stream
+    assert stream != 0
     ctx = capi.Context((n, n, nz), device=local_rank, stream=stream, nranks=world, rank=rank, nccl_id=nccl_id,
                        cell_size=1.0, gravity=GRAVITY, method=capi.APIC, max_iterations=args.max_iterations,
                        preconditioner=capi.PRECOND_MULTIGRID)

@@ -334,8 +334,9 @@ class Context:
         return n.value
 
     def seed_box_device(self, start, size, velocity=(0, 0, 0), density=2, seed=1, append=False):
-        self._ck(self.L.lfk_seed_box_device(self.ptr, _ptr(_v3(start)), _ptr(_v3(size)), _ptr(_v3(velocity)),
-                                            int(density), int(seed), int(append)))
+        a, b, v = _v3(start), _v3(size), _v3(velocity)  # keep the temporaries alive across the call
+        self._ck(self.L.lfk_seed_box_device(self.ptr, _ptr(a), _ptr(b), _ptr(v), int(density), int(seed),
+                                            int(append)))
 
     def synthetic_projection_device(self, seed=1):
         self._ck(self.L.lfk_synthetic_projection_device(self.ptr, int(seed)))
