@@ -12,14 +12,16 @@ ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
 OUT_DIR = os.path.join(HERE, "_lib")
 LIB = os.path.join(OUT_DIR, "liblfk.so")
-SOURCES = ["lfk_api.cu", "particles.cu", "p2g.cu", "pressure.cu", "mg.cu", "exchange.cu"]
+SOURCES = ["lfk_api.cu", "particles.cu", "p2g.cu", "p2g_brick.cu", "pressure.cu", "mg.cu", "exchange.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 # --fmad=false: the reference's CPU build does no FMA contraction; particle motion / classification must be
-# bit-exact and every kernel here is bandwidth bound.  p2g_fast.cu opts back in per file.
-COMMON = ["-O3", "-lineinfo", "-std=c++17", "--fmad=false", "-Xcompiler", "-fPIC", "-I" + os.path.join(ROOT, "include"),
+# bit-exact and every kernel there is bandwidth bound; FMAD_ON lists the exceptions.
+COMMON = ["-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC", "-I" + os.path.join(ROOT, "include"),
           "-I" + CSRC]
-PER_FILE = {}
+# fused multiply-add only where the summation order already differs from the reference (tolerance-checked)
+FMAD_ON = {"p2g_brick.cu", "mg.cu"}
+PER_FILE = {src: (["--fmad=true"] if src in FMAD_ON else ["--fmad=false"]) for src in SOURCES}
 
 
 def _stamp():

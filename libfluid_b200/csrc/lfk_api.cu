@@ -225,6 +225,8 @@ extern "C" int lfk_create(lfk_ctx **out, uint64_t nx, uint64_t ny, uint64_t nz, 
 	G.ncl = G.sxy * G.nlz;
 	G.nown = G.sxy * G.nzl;
 	G.h = NAN;
+	G.inv_h = NAN;
+	G.hpow2 = 0;
 	G.off[0] = G.off[1] = G.off[2] = 0.0;
 	size_t ncl = (size_t)G.ncl;
 	for (int d = 0; d < 3; ++d) {
@@ -301,6 +303,11 @@ extern "C" int lfk_set_params(lfk_ctx *c, const lfk_params *p) {
 		c->g.off[2] != p->grid_offset[2] || std::isnan(c->g.h);
 	c->prm = *p;
 	c->g.h = p->cell_size;
+	c->g.inv_h = 1.0 / p->cell_size;
+	{
+		int ex = 0;
+		c->g.hpow2 = std::frexp(p->cell_size, &ex) == 0.5 ? 1 : 0;
+	}
 	for (int d = 0; d < 3; ++d) {
 		c->g.off[d] = p->grid_offset[d];
 	}

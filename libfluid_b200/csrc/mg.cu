@@ -128,29 +128,85 @@ __global__ void __launch_bounds__(256) k_mg_rbgs(LevelDev L, int colour, const P
 	L.x[c] = (L.b[c] + lv_offdiag_sum(L, L.x, c)) / d;
 }
 
-// coarsest level: one block, symmetric sweeps until the error is gone (the level has at most a few thousand cells)
-__global__ void __launch_bounds__(1024) k_mg_coarsest(LevelDev L, int sweeps, const PcgScalars *scal) {
-	if (scal->done) { return; }
+// ---- the coarse tail: every level with at most MG_COARSE_MAX_CELLS cells is handled by ONE block in ONE launch
+// (pre-smooth / restrict down, symmetric sweeps on the coarsest grid, prolong / post-smooth up), which removes
+// ~10 tiny launches per level from every PCG iteration.
+#define MG_TAIL_MAX_LEVELS 8
+struct TailLevels {
+	LevelDev L[MG_TAIL_MAX_LEVELS];
+	int n;
+};
+
+__device__ __forceinline__ void tail_half_sweep(const LevelDev &L, int colour) {
 	for (long long own = threadIdx.x; own < L.nown; own += blockDim.x) {
-		L.x[own + L.sxy] = 0.f;
+		int x = (int)(own % L.nx);
+		long long rest = own / L.nx;
+		int y = (int)(rest % L.ny);
+		int lz = (int)(rest / L.ny) + 1;
+		if (((x + y + (lz - 1 + L.zpar) + colour) & 1) != 0) { continue; }
+		long long c = own + L.sxy;
+		float d = L.diag[c];
+		if (d > 0.f) {
+			L.x[c] = (L.b[c] + lv_offdiag_sum(L, L.x, c)) / d;
+		}
 	}
 	__syncthreads();
-	for (int s = 0; s < sweeps; ++s) {
-		for (int half = 0; half < 4; ++half) { // red, black, black, red
-			int colour = (half == 0 || half == 3) ? 0 : 1;
-			for (long long own = threadIdx.x; own < L.nown; own += blockDim.x) {
-				int x = (int)(own % L.nx);
-				long long rest = own / L.nx;
-				int y = (int)(rest % L.ny);
-				int lz = (int)(rest / L.ny) + 1;
-				if (((x + y + (lz - 1 + L.zpar) + colour) & 1) != 0) { continue; }
-				long long c = own + L.sxy;
-				float d = L.diag[c];
-				if (d > 0.f) {
-					L.x[c] = (L.b[c] + lv_offdiag_sum(L, L.x, c)) / d;
-				}
-			}
-			__syncthreads();
+}
+__device__ __forceinline__ void tail_restrict(const LevelDev &F, const LevelDev &C) {
+	for (long long own = threadIdx.x; own < C.nown; own += blockDim.x) {
+		int X_ = (int)(own % C.nx);
+		long long rest = own / C.nx;
+		int Y_ = (int)(rest % C.ny);
+		int LZ = (int)(rest / C.ny) + 1;
+		float acc = 0.f;
+		for (int k = 0; k < 8; ++k) {
+			int x = 2 * X_ + (k & 1), y = 2 * Y_ + ((k >> 1) & 1), lz = 2 * (LZ - 1) + ((k >> 2) & 1) + 1;
+			if (x >= F.nx || y >= F.ny || lz > F.nzl) { continue; }
+			long long c = x + (long long)F.nx * (y + (long long)F.ny * lz);
+			float d = F.diag[c];
+			if (d <= 0.f) { continue; }
+			acc += F.b[c] - (d * F.x[c] - lv_offdiag_sum(F, F.x, c));
+		}
+		C.b[own + C.sxy] = acc;
+		C.x[own + C.sxy] = 0.f;
+	}
+	__syncthreads();
+}
+__device__ __forceinline__ void tail_prolong(const LevelDev &F, const LevelDev &C) {
+	for (long long own = threadIdx.x; own < F.nown; own += blockDim.x) {
+		int x = (int)(own % F.nx);
+		long long rest = own / F.nx;
+		int y = (int)(rest % F.ny);
+		int lz = (int)(rest / F.ny) + 1;
+		long long c = own + F.sxy;
+		if (F.diag[c] <= 0.f) { continue; }
+		long long cc = (x >> 1) + (long long)C.nx * ((y >> 1) + (long long)C.ny * (((lz - 1) >> 1) + 1));
+		F.x[c] += MG_OMEGA * C.x[cc];
+	}
+	__syncthreads();
+}
+
+__global__ void __launch_bounds__(1024) k_mg_tail(TailLevels T, const PcgScalars *scal) {
+	if (scal->done) { return; }
+	const int last = T.n - 1;
+	for (int l = 0; l < last; ++l) { // down: x of the entry level was zeroed by the restriction that filled its b
+		for (int s = 0; s < MG_PRE; ++s) {
+			tail_half_sweep(T.L[l], 0);
+			tail_half_sweep(T.L[l], 1);
+		}
+		tail_restrict(T.L[l], T.L[l + 1]);
+	}
+	for (int s = 0; s < MG_COARSE_SWEEPS; ++s) { // coarsest: red, black, black, red
+		tail_half_sweep(T.L[last], 0);
+		tail_half_sweep(T.L[last], 1);
+		tail_half_sweep(T.L[last], 1);
+		tail_half_sweep(T.L[last], 0);
+	}
+	for (int l = last - 1; l >= 0; --l) { // up
+		tail_prolong(T.L[l], T.L[l + 1]);
+		for (int s = 0; s < MG_POST; ++s) {
+			tail_half_sweep(T.L[l], 1);
+			tail_half_sweep(T.L[l], 0);
 		}
 	}
 }
@@ -314,11 +370,9 @@ static int mg_alloc(lfk_ctx *c) {
 		}
 		c->mg.push_back(L);
 		c->mg_z0.push_back(z0);
-		long long cells = L.sxy * nzl;
-		bool small = cells <= MG_COARSE_MAX_CELLS && c->nranks == 1;
 		// slabs must stay aligned to the aggregates; stop coarsening when they would not (multi-GPU)
 		bool aligned = c->nranks == 1 || (z0 % 2 == 0 && nzl % 2 == 0 && nz % 2 == 0 && nzl >= 2);
-		if (small || !aligned || (nx <= 2 && ny <= 2 && nzl <= 2)) { break; }
+		if (!aligned || (nx <= 2 && ny <= 2 && nzl <= 2)) { break; }
 		nx = (nx + 1) / 2; ny = (ny + 1) / 2; nzl = (nzl + 1) / 2; z0 /= 2; nz = (nz + 1) / 2;
 	}
 	return 0;
@@ -384,13 +438,18 @@ static int vcycle(lfk_ctx *c, size_t l) {
 	size_t last = c->mg.size() - 1;
 	MgLevel &L = c->mg[l];
 	LevelDev Ld = level_dev(L, c->mg_z0[l]);
-	if (l == last) {
-		if (c->nranks == 1 && Ld.nown <= MG_COARSE_MAX_CELLS && l > 0) {
-			LFK_LAUNCH(c, k_mg_coarsest, 1, 1024, 0, Ld, MG_COARSE_SWEEPS, c->d_scal);
-		} else { // large coarsest level (multi-GPU alignment limit, or a tiny fine grid): symmetric sweeps
-			LFK_TRY(smooth(c, l, 0, MG_COARSE_SWEEPS));
-			LFK_TRY(smooth(c, l, 1, MG_COARSE_SWEEPS));
+	if (c->nranks == 1 && l > 0 && Ld.nown <= MG_COARSE_MAX_CELLS && last - l < MG_TAIL_MAX_LEVELS) {
+		TailLevels T; // this level and everything below it: one block, one launch
+		T.n = 0;
+		for (size_t k = l; k <= last; ++k) {
+			T.L[T.n++] = level_dev(c->mg[k], c->mg_z0[k]);
 		}
+		LFK_LAUNCH(c, k_mg_tail, 1, 1024, 0, T, c->d_scal);
+		return 0;
+	}
+	if (l == last) { // coarsest level reached outside the tail (multi-GPU alignment limit, or a tiny fine grid)
+		LFK_TRY(smooth(c, l, 0, MG_COARSE_SWEEPS));
+		LFK_TRY(smooth(c, l, 1, MG_COARSE_SWEEPS));
 		return 0;
 	}
 	LFK_TRY(smooth(c, l, 0, MG_PRE)); // red, black

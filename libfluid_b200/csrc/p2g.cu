@@ -9,6 +9,8 @@
 // order of the CPU restatement.
 #include "lfk_internal.cuh"
 
+#include <cstdlib>
+
 struct P2GParams {
 	double h, half;
 	double gdt[3];
@@ -59,10 +61,10 @@ template <int METHOD> __global__ void __launch_bounds__(128) k_p2g_gather(GridDe
 					w1 = hxc * hat(dyf) * hzc;
 					w2 = hxc * hyc * hat(dzf);
 				} else { // PIC / FLIP divide (src/simulation.cpp:313-315)
-					double hxc = hat(dxc / Q.h), hyc = hat(dyc / Q.h), hzc = hat(dzc / Q.h);
-					w0 = hat(dxf / Q.h) * hyc * hzc;
-					w1 = hxc * hat(dyf / Q.h) * hzc;
-					w2 = hxc * hyc * hat(dzf / Q.h);
+					double hxc = hat(div_h(dxc, G)), hyc = hat(div_h(dyc, G)), hzc = hat(div_h(dzc, G));
+					w0 = hat(div_h(dxf, G)) * hyc * hzc;
+					w1 = hxc * hat(div_h(dyf, G)) * hzc;
+					w2 = hxc * hyc * hat(div_h(dzf, G));
 				}
 				if (w0 == 0.0 && w1 == 0.0 && w2 == 0.0) { continue; } // adds exact zeros in the reference
 				double v0 = P.f[PF_VX][q], v1 = P.f[PF_VY][q], v2 = P.f[PF_VZ][q];
@@ -130,10 +132,19 @@ __global__ void k_gravity(GridDesc G, double g0, double g1, double g2, double *_
 	w[me] += g2;
 }
 
+int lfkg_p2g_brick(lfk_ctx *c, double gravity_dt, bool add_gravity); // p2g_brick.cu
+
 int lfkg_p2g(lfk_ctx *c, double gravity_dt, bool add_gravity) {
 	PhaseTimer T(c, LFK_PHASE_P2G);
 	LFK_REQUIRE(c, c->table_valid, LFK_E_STATE, "lfk_p2g needs the cell table of lfk_hash");
 	const GridDesc &G = c->g;
+	static const bool use_gather = getenv("LFK_P2G_GATHER") != nullptr; // A/B switch: the simple gather kernel below
+	if (!use_gather) {
+		LFK_TRY(lfkg_p2g_brick(c, gravity_dt, add_gravity));
+		c->system_valid = false;
+		c->pressure_valid = false;
+		return 0;
+	}
 	P2GParams Q;
 	Q.h = G.h;
 	Q.half = 0.5 * G.h;

@@ -1,0 +1,336 @@
+// P2G, production kernel: cell-owner scatter on bricks -- no atomics, fixed summation order (bit-reproducible),
+// each particle field read from global memory as coalesced 8-byte async copies.
+// Reference: simulation::_transfer_to_grid_{pic,flip,apic}, src/simulation.cpp:293-412, 428-445, 72-78.
+//
+// A block owns the +faces of a brick of BX x BY x BZ cells and visits every cell that can touch one of them (the
+// brick plus a one-cell halo: 32 x 10 x 10 cells).  A warp takes one row of 32 cells, lane <-> cell:
+//   1. the row's particles are staged into the warp's shared-memory slab with cp.async -- lanes <-> consecutive
+//      particles on the global side (coalesced), transposed to [cell][slot] on the shared side;
+//   2. each lane runs over the particles of ITS cell and accumulates, in registers, their contribution to the
+//      2 x 3 x 3 faces (per velocity component) the cell can reach;
+//   3. the lane adds its 18 partial sums into the block's accumulator tile one neighbour offset at a time.  For a
+//      fixed offset all lanes of a row hit distinct faces, and rows are scheduled in 9 colours (y mod 3, z mod 3)
+//      so that concurrently active warps never touch the same face: plain read-modify-write, no atomics, and the
+//      order of additions does not depend on timing.
+// After the last colour the tile holds sum(w) and sum(w v) of every face of the brick, complete: the block
+// normalises, classifies, zeroes boundary faces, takes the FLIP snapshot, adds gravity and writes the faces.
+// The halo is recomputed by the neighbouring bricks (1.67x redundant flops) -- that buys determinism and removes
+// the global accumulator arrays, their zeroing and a separate normalisation pass.
+//
+// This file is compiled WITH fused multiply-add (the summation order already differs from the reference's, P2G is
+// tolerance-checked: rel-L2 <= 1e-12 against the oracle).
+#include "lfk_internal.cuh"
+
+#define PB_BX 30
+#define PB_BY 8
+#define PB_BZ 8
+#define PB_RY (PB_BY + 2)
+#define PB_RZ (PB_BZ + 2)
+#define PB_WARPS 6
+#define PB_THREADS (PB_WARPS * 32)
+#define PB_WIN 8                 // particle slots per cell staged at a time
+#define PB_CSTRIDE (PB_WIN + 1)  // padded: lane stride of 9 doubles is bank-conflict free
+#define PB_FSTRIDE (32 * PB_CSTRIDE)
+#define PB_FIELDS 7              // pos(3) + v_k + c_k(3)
+#define PB_ACC_COMP (2 * PB_BZ * PB_BY * 32)
+
+struct PBParams {
+	double half, inv_h;
+	double gdt[3];
+	int add_gravity;
+	int hdiv; // PIC / FLIP: weights use (x_p - x_face) / h
+};
+
+__device__ __forceinline__ void cp_async8(double *smem, const double *gmem) {
+	unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+	asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(s), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() {
+	asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
+}
+__device__ __forceinline__ double hatw(double d) {
+	return fmax(0.0, 1.0 - fabs(d));
+}
+
+// Contributions of the staged particles of one cell to one velocity component.  COMP selects which axis is
+// staggered: the staggered axis has 2 reachable faces (cell - 1, cell), the other two axes 3 (cell - 1 .. cell + 1).
+template <int COMP, bool APIC> __device__ __forceinline__ void accumulate_cell(const double *__restrict__ st,
+	int lane, int nslots, const double *cc /* cell-centre coords of cell-1, cell, cell+1 per axis: [3][3] */,
+	double half, double inv_h, int hdiv, double *accw, double *accv) {
+	constexpr int NA = COMP == 0 ? 2 : 3, NB = COMP == 1 ? 2 : 3, NC = COMP == 2 ? 2 : 3;
+	// sample positions per axis: staggered axis -> +face of (cell - 1), +face of cell; others -> centres
+	double sx[NA], sy[NB], sz[NC];
+#pragma unroll
+	for (int a = 0; a < NA; ++a) { sx[a] = COMP == 0 ? cc[0 * 3 + a] + half : cc[0 * 3 + a]; }
+#pragma unroll
+	for (int b = 0; b < NB; ++b) { sy[b] = COMP == 1 ? cc[1 * 3 + b] + half : cc[1 * 3 + b]; }
+#pragma unroll
+	for (int c = 0; c < NC; ++c) { sz[c] = COMP == 2 ? cc[2 * 3 + c] + half : cc[2 * 3 + c]; }
+	const double *sp = st + lane * PB_CSTRIDE;
+	for (int s = 0; s < nslots; ++s) {
+		const double px = sp[0 * PB_FSTRIDE + s], py = sp[1 * PB_FSTRIDE + s], pz = sp[2 * PB_FSTRIDE + s];
+		const double vk = sp[3 * PB_FSTRIDE + s];
+		double c0 = 0.0, c1 = 0.0, c2 = 0.0;
+		if (APIC) {
+			c0 = sp[4 * PB_FSTRIDE + s];
+			c1 = sp[5 * PB_FSTRIDE + s];
+			c2 = sp[6 * PB_FSTRIDE + s];
+		}
+		double wx[NA], wy[NB], wz[NC], ax[NA], by[NB], cz[NC];
+#pragma unroll
+		for (int a = 0; a < NA; ++a) {
+			double d = px - sx[a];
+			wx[a] = hatw(hdiv ? d * inv_h : d);
+			ax[a] = vk - c0 * d; // v_k + c_k0 * (x_sample - x_p)
+		}
+#pragma unroll
+		for (int b = 0; b < NB; ++b) {
+			double d = py - sy[b];
+			wy[b] = hatw(hdiv ? d * inv_h : d);
+			by[b] = -c1 * d;
+		}
+#pragma unroll
+		for (int c = 0; c < NC; ++c) {
+			double d = pz - sz[c];
+			wz[c] = hatw(hdiv ? d * inv_h : d);
+			cz[c] = -c2 * d;
+		}
+#pragma unroll
+		for (int c = 0; c < NC; ++c) {
+#pragma unroll
+			for (int b = 0; b < NB; ++b) {
+				const double wyz = wy[b] * wz[c], bc = by[b] + cz[c];
+#pragma unroll
+				for (int a = 0; a < NA; ++a) {
+					const double w = wx[a] * wyz;
+					const int t = (c * NB + b) * NA + a;
+					accw[t] += w;
+					accv[t] = fma(w, ax[a] + bc, accv[t]);
+				}
+			}
+		}
+	}
+}
+
+// add the lane's 18 partial sums into the block tile, one neighbour offset at a time
+template <int COMP> __device__ __forceinline__ void flush_cell(double *__restrict__ acc, int fx0, int fy0, int fz0,
+	int nfx, const double *accw, const double *accv) {
+	constexpr int NA = COMP == 0 ? 2 : 3, NB = COMP == 1 ? 2 : 3, NC = COMP == 2 ? 2 : 3;
+	// fx0 / fy0 / fz0: tile coordinates of the face owned by (cell - 1) along each axis
+#pragma unroll
+	for (int c = 0; c < NC; ++c) {
+#pragma unroll
+		for (int b = 0; b < NB; ++b) {
+#pragma unroll
+			for (int a = 0; a < NA; ++a) {
+				const int fx = fx0 + a, fy = fy0 + b, fz = fz0 + c;
+				const int t = (c * NB + b) * NA + a;
+				if (fx >= 0 && fx < nfx && fy >= 0 && fy < PB_BY && fz >= 0 && fz < PB_BZ) {
+					double *p = acc + (fz * PB_BY + fy) * 32 + fx;
+					p[0] += accw[t];
+					p[PB_BZ * PB_BY * 32] += accv[t];
+				}
+				__syncwarp(); // lanes c (offset a) and c + 1 (offset a - 1) share a face: keep the steps ordered
+			}
+		}
+	}
+}
+
+template <int METHOD> __global__ void __launch_bounds__(PB_THREADS, 1) k_p2g_brick(GridDesc G, PBParams Q,
+	ParticleSoA P, const uint32_t *__restrict__ begin, const double *__restrict__ cxs,
+	const double *__restrict__ cys, const double *__restrict__ czs, double *__restrict__ u, double *__restrict__ v,
+	double *__restrict__ w, double *__restrict__ uo, double *__restrict__ vo, double *__restrict__ wo,
+	uint8_t *__restrict__ typ) {
+	constexpr bool APIC = METHOD == LFK_METHOD_APIC;
+	extern __shared__ double smem[];
+	double *acc = smem;                                  // [3][2][BZ][BY][32]
+	double *stage_all = smem + 3 * PB_ACC_COMP;          // [WARPS][FIELDS][32 * 9]
+	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+	double *st = stage_all + warp * (PB_FIELDS * PB_FSTRIDE);
+	const int x0 = blockIdx.x * PB_BX, y0 = blockIdx.y * PB_BY, lz0 = blockIdx.z * PB_BZ + 1;
+	const int nfx = min(PB_BX, G.nx - x0); // faces of this brick along x
+
+	for (int e = threadIdx.x; e < 3 * PB_ACC_COMP; e += PB_THREADS) { acc[e] = 0.0; }
+	__syncthreads();
+
+	const int x = x0 - 1 + lane; // this lane's cell column
+	const bool xin = x >= 0 && x < G.nx;
+	// cell-centre coordinates of x-1, x, x+1 (table built by repeated addition like the reference; edge entries are
+	// extrapolated by +-h, they only ever carry targets outside the grid)
+	double cc[9];
+	{
+		int xm = x - 1, xp = x + 1;
+		double xc = xin ? cxs[x] : (x < 0 ? cxs[0] - G.h : cxs[G.nx - 1] + G.h);
+		cc[0] = (xm >= 0 && xm < G.nx) ? cxs[xm] : xc - G.h;
+		cc[1] = xc;
+		cc[2] = (xp >= 0 && xp < G.nx) ? cxs[xp] : xc + G.h;
+	}
+	const double *fields[15];
+#pragma unroll
+	for (int f = 0; f < 15; ++f) { fields[f] = P.f[f]; }
+
+	for (int colour = 0; colour < 9; ++colour) {
+		const int cy = colour % 3, cz = colour / 3;
+		// rows of this colour: ry = cy, cy + 3, ...; rz = cz, cz + 3, ...
+		const int nry = (PB_RY - cy + 2) / 3, nrz = (PB_RZ - cz + 2) / 3;
+		for (int job = warp; job < nry * nrz; job += PB_WARPS) {
+			const int ry = cy + 3 * (job % nry), rz = cz + 3 * (job / nry);
+			const int y = y0 - 1 + ry, lz = lz0 - 1 + rz;
+			const int z = lz - 1 + G.z0;
+			if (y < 0 || y >= G.ny || lz < 0 || lz >= G.nlz || z < 0 || z >= G.nz) { continue; }
+			const long long row = (long long)G.nx * (y + (long long)G.ny * lz);
+			uint32_t pb = 0, pe = 0;
+			if (xin) {
+				pb = begin[row + x];
+				pe = begin[row + x + 1];
+			}
+			const int cnt = (int)(pe - pb);
+			int maxcnt = cnt;
+#pragma unroll
+			for (int o = 16; o > 0; o >>= 1) { maxcnt = max(maxcnt, __shfl_xor_sync(0xffffffffu, maxcnt, o)); }
+			if (maxcnt == 0) { continue; }
+			{
+				double yc = cys[y], zc = czs[z];
+				cc[3] = y > 0 ? cys[y - 1] : yc - G.h;
+				cc[4] = yc;
+				cc[5] = y + 1 < G.ny ? cys[y + 1] : yc + G.h;
+				cc[6] = z > 0 ? czs[z - 1] : zc - G.h;
+				cc[7] = zc;
+				cc[8] = z + 1 < G.nz ? czs[z + 1] : zc + G.h;
+			}
+			for (int win = 0; win < maxcnt; win += PB_WIN) {
+				const int nslots = max(0, min(PB_WIN, cnt - win));
+				// ---- positions: lanes <-> consecutive particles (coalesced), stored [cell][slot] ----
+#pragma unroll
+				for (int k = 0; k < PB_WIN; ++k) {
+					const int t = k * 32 + lane, sc = t / PB_WIN, ss = t % PB_WIN;
+					const uint32_t qb = __shfl_sync(0xffffffffu, pb, sc), qe = __shfl_sync(0xffffffffu, pe, sc);
+					const uint32_t q = qb + win + ss;
+					if (q < qe) {
+#pragma unroll
+						for (int f = 0; f < 3; ++f) { cp_async8(st + f * PB_FSTRIDE + sc * PB_CSTRIDE + ss, fields[f] + q); }
+					}
+				}
+#pragma unroll
+				for (int comp = 0; comp < 3; ++comp) {
+#pragma unroll
+					for (int k = 0; k < PB_WIN; ++k) {
+						const int t = k * 32 + lane, sc = t / PB_WIN, ss = t % PB_WIN;
+						const uint32_t qb = __shfl_sync(0xffffffffu, pb, sc), qe = __shfl_sync(0xffffffffu, pe, sc);
+						const uint32_t q = qb + win + ss;
+						if (q < qe) {
+							double *dst = st + sc * PB_CSTRIDE + ss;
+							cp_async8(dst + 3 * PB_FSTRIDE, fields[PF_VX + comp] + q);
+							if (APIC) {
+#pragma unroll
+								for (int f = 0; f < 3; ++f) {
+									cp_async8(dst + (4 + f) * PB_FSTRIDE, fields[PF_C0 + 3 * comp + f] + q);
+								}
+							}
+						}
+					}
+					cp_async_wait_all();
+					__syncwarp();
+					double accw[18], accv[18];
+#pragma unroll
+					for (int t = 0; t < 18; ++t) {
+						accw[t] = 0.0;
+						accv[t] = 0.0;
+					}
+					double *acck = acc + comp * PB_ACC_COMP;
+					// tile coordinates of the faces owned by (cell - 1): x: lane - 2, y: ry - 2, z: rz - 2
+					if (comp == 0) {
+						accumulate_cell<0, APIC>(st, lane, nslots, cc, Q.half, Q.inv_h, Q.hdiv, accw, accv);
+						__syncwarp();
+						flush_cell<0>(acck, lane - 2, ry - 2, rz - 2, nfx, accw, accv);
+					} else if (comp == 1) {
+						accumulate_cell<1, APIC>(st, lane, nslots, cc, Q.half, Q.inv_h, Q.hdiv, accw, accv);
+						__syncwarp();
+						flush_cell<1>(acck, lane - 2, ry - 2, rz - 2, nfx, accw, accv);
+					} else {
+						accumulate_cell<2, APIC>(st, lane, nslots, cc, Q.half, Q.inv_h, Q.hdiv, accw, accv);
+						__syncwarp();
+						flush_cell<2>(acck, lane - 2, ry - 2, rz - 2, nfx, accw, accv);
+					}
+				}
+			}
+		}
+		__syncthreads();
+	}
+
+	// ---- normalise + classify + boundary faces + FLIP snapshot + gravity, write the brick's faces ----
+	for (int e = threadIdx.x; e < PB_BZ * PB_BY * 32; e += PB_THREADS) {
+		const int fx = e & 31, fy = (e >> 5) % PB_BY, fz = (e >> 5) / PB_BY;
+		const int cx = x0 + fx, cyy = y0 + fy, lz = lz0 + fz;
+		if (fx >= nfx || cyy >= G.ny || lz > G.nzl) { continue; }
+		const int z = lz - 1 + G.z0;
+		const long long me = cx + (long long)G.nx * (cyy + (long long)G.ny * lz);
+		double r[3];
+#pragma unroll
+		for (int k = 0; k < 3; ++k) {
+			const double sw = acc[k * PB_ACC_COMP + e], sv = acc[k * PB_ACC_COMP + PB_BZ * PB_BY * 32 + e];
+			r[k] = sw > 1e-6 ? sv / sw : 0.0; // src/simulation.cpp:380-386
+		}
+		uint8_t t = typ[me];
+		if (t != LFK_CELL_SOLID) { // :388-393
+			t = (begin[me + 1] - begin[me]) > 0 ? LFK_CELL_FLUID : LFK_CELL_AIR;
+			typ[me] = t;
+		}
+		const bool bx = cx == G.nx - 1, by = cyy == G.ny - 1, bz = z == G.nz - 1;
+		if (METHOD == LFK_METHOD_FLIP) { // :340-344
+			uo[me] = bx ? 0.0 : r[0];
+			vo[me] = by ? 0.0 : r[1];
+			wo[me] = bz ? 0.0 : r[2];
+		}
+		if (APIC) { // :397
+			if (bx) { r[0] = 0.0; }
+			if (by) { r[1] = 0.0; }
+			if (bz) { r[2] = 0.0; }
+		}
+		if (Q.add_gravity) { // :72-78
+			r[0] += Q.gdt[0];
+			r[1] += Q.gdt[1];
+			r[2] += Q.gdt[2];
+		}
+		u[me] = r[0];
+		v[me] = r[1];
+		w[me] = r[2];
+	}
+}
+
+int lfkg_p2g_brick(lfk_ctx *c, double gravity_dt, bool add_gravity) {
+	const GridDesc &G = c->g;
+	PBParams Q;
+	Q.half = 0.5 * G.h;
+	Q.inv_h = 1.0 / G.h;
+	Q.add_gravity = add_gravity ? 1 : 0;
+	Q.hdiv = c->prm.method != LFK_METHOD_APIC && G.h != 1.0;
+	for (int d = 0; d < 3; ++d) {
+		Q.gdt[d] = c->prm.gravity[d] * gravity_dt;
+	}
+	dim3 grid((unsigned)((G.nx + PB_BX - 1) / PB_BX), (unsigned)((G.ny + PB_BY - 1) / PB_BY),
+		(unsigned)((G.nzl + PB_BZ - 1) / PB_BZ));
+	const size_t smem = (size_t)(3 * PB_ACC_COMP + PB_WARPS * PB_FIELDS * PB_FSTRIDE) * sizeof(double);
+	static bool attr_set = false;
+	if (!attr_set) {
+		LFK_CUDA(c, cudaFuncSetAttribute(k_p2g_brick<LFK_METHOD_PIC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+		LFK_CUDA(c, cudaFuncSetAttribute(k_p2g_brick<LFK_METHOD_FLIP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+		LFK_CUDA(c, cudaFuncSetAttribute(k_p2g_brick<LFK_METHOD_APIC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+		attr_set = true;
+	}
+	switch (c->prm.method) {
+	case LFK_METHOD_PIC:
+		LFK_LAUNCH(c, k_p2g_brick<LFK_METHOD_PIC>, grid, PB_THREADS, smem, G, Q, c->P, c->begin, c->ctr[0], c->ctr[1],
+			c->ctr[2], c->vel[0], c->vel[1], c->vel[2], c->vel_old[0], c->vel_old[1], c->vel_old[2], c->typ);
+		break;
+	case LFK_METHOD_FLIP:
+		LFK_LAUNCH(c, k_p2g_brick<LFK_METHOD_FLIP>, grid, PB_THREADS, smem, G, Q, c->P, c->begin, c->ctr[0], c->ctr[1],
+			c->ctr[2], c->vel[0], c->vel[1], c->vel[2], c->vel_old[0], c->vel_old[1], c->vel_old[2], c->typ);
+		break;
+	default:
+		LFK_LAUNCH(c, k_p2g_brick<LFK_METHOD_APIC>, grid, PB_THREADS, smem, G, Q, c->P, c->begin, c->ctr[0], c->ctr[1],
+			c->ctr[2], c->vel[0], c->vel[1], c->vel[2], c->vel_old[0], c->vel_old[1], c->vel_old[2], c->typ);
+		break;
+	}
+	return 0;
+}

@@ -93,8 +93,8 @@ int lfkp_positions_to_aos(lfk_ctx *c, double *d_xyz, uint64_t n) {
 // =========================================================================================================
 // K1: cell keys (reference src/simulation.cpp:251-261) -- must be bit-exact: IEEE sub, IEEE div, truncation
 // =========================================================================================================
-__device__ __forceinline__ int cell_coord_clamped(double pos, double off, double h, int n) {
-	double g = __ddiv_rn(__dsub_rn(pos, off), h);
+__device__ __forceinline__ int cell_coord_clamped(double pos, double off, const GridDesc &G, int n) {
+	double g = div_h(__dsub_rn(pos, off), G);
 	g = dmax_std(g, 0.0);
 	// static_cast<size_t>: truncation toward zero; cvt.rzi.u64.f64 saturates, and anything >= n clamps to n - 1
 	unsigned long long v = (unsigned long long)g;
@@ -108,9 +108,9 @@ __global__ void k_keys_hist(GridDesc G, const double *__restrict__ px, const dou
 	bool active = i < n;
 	unsigned amask = __ballot_sync(0xffffffffu, active);
 	if (!active) { return; }
-	int x = cell_coord_clamped(px[i], G.off[0], G.h, G.nx);
-	int y = cell_coord_clamped(py[i], G.off[1], G.h, G.ny);
-	int z = cell_coord_clamped(pz[i], G.off[2], G.h, G.nz);
+	int x = cell_coord_clamped(px[i], G.off[0], G, G.nx);
+	int y = cell_coord_clamped(py[i], G.off[1], G, G.ny);
+	int z = cell_coord_clamped(pz[i], G.off[2], G, G.nz);
 	int lz = z - G.z0 + 1;
 	lz = lz < 0 ? 0 : (lz > G.nlz - 1 ? G.nlz - 1 : lz); // migrants are handled by the exchange layer
 	uint32_t k = (uint32_t)(x + (long long)G.nx * (y + (long long)G.ny * lz));
@@ -412,8 +412,8 @@ __device__ void collide_one(const GridDesc &G, const MotionParams &M, const uint
 		int cur[3], tc[3], adv[3];
 #pragma unroll
 		for (int d = 0; d < 3; ++d) {
-			gf[d] = (from[d] - G.off[d]) / h;
-			double gt = (to[d] - G.off[d]) / h;
+			gf[d] = div_h(from[d] - G.off[d], G);
+			double gt = div_h(to[d] - G.off[d], G);
 			cur[d] = (int)floor(gf[d]);
 			tc[d] = (int)floor(gt);
 			double diff = gt - gf[d];
@@ -476,7 +476,7 @@ __device__ void collide_one(const GridDesc &G, const MotionParams &M, const uint
 #pragma unroll
 	for (int d = 0; d < 3; ++d) {
 		double gp = to[d] - G.off[d];
-		unsigned long long idx = (unsigned long long)(gp / h);
+		unsigned long long idx = (unsigned long long)div_h(gp, G);
 		ci[d] = (int)(idx < 0x7fffffffull ? idx : 0x7fffffffull);
 		cp[d] = gp - (double)idx * h;
 	}
@@ -614,7 +614,7 @@ template <bool COLLIDE> __global__ void __launch_bounds__(128) k_correct(GridDes
 	const int size[3] = { G.nx, G.ny, G.nz };
 #pragma unroll
 	for (int d = 0; d < 3; ++d) { // compute_cell_index (no clamp), then for_each_in_range_checked
-		unsigned long long ci = (unsigned long long)((p[d] - G.off[d]) / G.h);
+		unsigned long long ci = (unsigned long long)div_h(p[d] - G.off[d], G);
 		long long cl = ci > 0x7fffffffull ? 0x7fffffffll : (long long)ci;
 		lo[d] = (int)(cl < 1 ? 0 : cl - 1);
 		long long h2 = cl + 2;
@@ -668,19 +668,249 @@ template <bool COLLIDE> __global__ void __launch_bounds__(128) k_correct(GridDes
 	nz_[i] = np3[2];
 }
 
+// ---- tiled version ------------------------------------------------------------------------------------------
+// A block owns a tile of CT_TY x CT_TZ rows x CT_LX cells.  The positions of every particle in the tile plus its
+// one-cell halo are staged ONCE in shared memory as fp32 coordinates relative to the tile origin (16 B each, with
+// the particle's global index), so the ~100-200 candidate tests per particle run on fp32 data from shared memory
+// instead of fp64 data from L1/L2.  The fp32 test is only a conservative PRE-FILTER (its threshold carries a 10x
+// margin over the worst-case rounding error); candidates that pass are re-evaluated in fp64 from the original
+// positions, in the reference's order, so the result is bit-identical to the plain fp64 loop above.
+#define CT_LX 32
+#define CT_TY 2
+#define CT_TZ 2
+#define CT_SY (CT_TY + 2)
+#define CT_SZ (CT_TZ + 2)
+#define CT_ROWS (CT_SY * CT_SZ)
+#define CT_OWN (CT_TY * CT_TZ)
+#define CT_CAP 5120           // staged particles per tile (80 KB); denser tiles take the global-memory path
+#define CT_THREADS 256
+#define CT_LIST 24
+
+__device__ __forceinline__ void pair_exact(const MotionParams &M, const double *p, const double *o, double &sx,
+	double &sy, double &sz) {
+	double ox = p[0] - o[0], oy = p[1] - o[1], oz = p[2] - o[2];
+	double sq = 0.0;
+	sq += ox * ox;
+	sq += oy * oy;
+	sq += oz * oz;
+	if (sq < 1e-12) {
+		double kick[3];
+		degenerate_kick(p, o, kick);
+		sx += kick[0];
+		sy += kick[1];
+		sz += kick[2];
+	} else {
+		double kl = 1.0 - sq / M.re2;
+		if (kl > 0.0) {
+			double kern = kl * kl * kl;
+			double sc = kern / sqrt(sq);
+			sx += sc * ox;
+			sy += sc * oy;
+			sz += sc * oz;
+		}
+	}
+}
+
+// the plain fp64 neighbourhood loop (fallback for over-full tiles and for particles outside their key cell)
+__device__ void spring_global(const GridDesc &G, const MotionParams &M, const double *__restrict__ px,
+	const double *__restrict__ py, const double *__restrict__ pz, const uint32_t *__restrict__ begin,
+	unsigned long long i, const double *p, double &sx, double &sy, double &sz) {
+	int lo[3], hi[3];
+	const int size[3] = { G.nx, G.ny, G.nz };
+#pragma unroll
+	for (int d = 0; d < 3; ++d) {
+		unsigned long long ci = (unsigned long long)div_h(p[d] - G.off[d], G);
+		long long cl = ci > 0x7fffffffull ? 0x7fffffffll : (long long)ci;
+		lo[d] = (int)(cl < 1 ? 0 : cl - 1);
+		long long h2 = cl + 2;
+		hi[d] = (int)(h2 < size[d] ? h2 : size[d]);
+	}
+	for (int cz = lo[2]; cz < hi[2]; ++cz) {
+		int lz = cz - G.z0 + 1;
+		if (lz < 0 || lz >= G.nlz) { continue; }
+		for (int cy = lo[1]; cy < hi[1]; ++cy) {
+			if (lo[0] >= hi[0]) { continue; }
+			long long row = (long long)G.nx * (cy + (long long)G.ny * lz);
+			uint32_t qb = begin[row + lo[0]], qe = begin[row + hi[0]];
+			for (uint32_t q = qb; q < qe; ++q) {
+				if (q == i) { continue; }
+				double o[3] = { px[q], py[q], pz[q] };
+				pair_exact(M, p, o, sx, sy, sz);
+			}
+		}
+	}
+}
+
+template <bool COLLIDE> __global__ void __launch_bounds__(CT_THREADS) k_correct_tiled(GridDesc G, MotionParams M,
+	ParticleSoA P, double *__restrict__ nx_, double *__restrict__ ny_, double *__restrict__ nz_,
+	const uint32_t *__restrict__ begin, const uint8_t *__restrict__ typ) {
+	extern __shared__ float4 stage[];
+	__shared__ uint32_t rowstart[CT_ROWS], rowoff[CT_ROWS + 1], cellbeg[CT_ROWS][CT_LX + 3];
+	__shared__ uint32_t ownbeg[CT_OWN], ownpre[CT_OWN + 1];
+	const double *__restrict__ px = P.f[PF_PX], *__restrict__ py = P.f[PF_PY], *__restrict__ pz = P.f[PF_PZ];
+	const int x0 = blockIdx.x * CT_LX, y0 = blockIdx.y * CT_TY, lz0 = blockIdx.z * CT_TZ + 1;
+	const int tid = threadIdx.x;
+
+	// ---- table of the staged rows ----
+	for (int e = tid; e < CT_ROWS * (CT_LX + 3); e += CT_THREADS) {
+		int r = e / (CT_LX + 3), k = e % (CT_LX + 3);
+		int y = y0 - 1 + r % CT_SY, lz = lz0 - 1 + r / CT_SY;
+		uint32_t v = 0;
+		if (y >= 0 && y < G.ny && lz >= 0 && lz < G.nlz) {
+			long long row = (long long)G.nx * (y + (long long)G.ny * lz);
+			int xa = x0 - 1 < 0 ? 0 : x0 - 1;
+			int xk = x0 - 1 + k;
+			xk = xk < 0 ? 0 : (xk > G.nx ? G.nx : xk);
+			uint32_t base = begin[row + xa];
+			v = begin[row + xk] - base;
+			if (k == 0) { rowstart[r] = base; }
+		} else if (k == 0) {
+			rowstart[r] = 0;
+		}
+		cellbeg[r][k] = v;
+	}
+	__syncthreads();
+	if (tid == 0) {
+		uint32_t acc = 0;
+		for (int r = 0; r < CT_ROWS; ++r) {
+			rowoff[r] = acc;
+			acc += cellbeg[r][CT_LX + 2];
+		}
+		rowoff[CT_ROWS] = acc;
+		uint32_t oacc = 0;
+		for (int o = 0; o < CT_OWN; ++o) { // own rows: cells x0 .. x0 + LX - 1 (clipped) of the inner rows
+			int r = (o / CT_TY + 1) * CT_SY + (o % CT_TY + 1);
+			int y = y0 + o % CT_TY, lz = lz0 + o / CT_TY;
+			uint32_t nown = 0;
+			if (y < G.ny && lz <= G.nzl) {
+				nown = cellbeg[r][CT_LX + 1] - cellbeg[r][1];
+			}
+			ownbeg[o] = rowstart[r] + cellbeg[r][1];
+			ownpre[o] = oacc;
+			oacc += nown;
+		}
+		ownpre[CT_OWN] = oacc;
+	}
+	__syncthreads();
+	const uint32_t nown_total = ownpre[CT_OWN];
+	if (nown_total == 0) { return; }
+	const uint32_t staged = rowoff[CT_ROWS];
+	const bool use_stage = staged <= CT_CAP;
+	// tile origin (one cell below the tile in every axis), fp64; staged coordinates are relative to it
+	const double org[3] = { G.off[0] + (double)(x0 - 1) * G.h, G.off[1] + (double)(y0 - 1) * G.h,
+		G.off[2] + (double)(lz0 - 2 + G.z0) * G.h };
+	if (use_stage) {
+		for (int r = 0; r < CT_ROWS; ++r) {
+			uint32_t cnt = cellbeg[r][CT_LX + 2], gs = rowstart[r], so = rowoff[r];
+			for (uint32_t j = tid; j < cnt; j += CT_THREADS) {
+				uint32_t q = gs + j;
+				stage[so + j] = make_float4((float)(px[q] - org[0]), (float)(py[q] - org[1]), (float)(pz[q] - org[2]),
+					__uint_as_float(q));
+			}
+		}
+	}
+	__syncthreads();
+	const float thr = (float)(M.re2 + 1e-4 * G.h * G.h);
+
+	for (uint32_t t = tid; t < nown_total; t += CT_THREADS) {
+		int o = 0;
+#pragma unroll
+		for (int k = 1; k < CT_OWN; ++k) {
+			if (t >= ownpre[k]) { o = k; }
+		}
+		const unsigned long long i = (unsigned long long)ownbeg[o] + (t - ownpre[o]);
+		const int oy = o % CT_TY, oz = o / CT_TY;
+		double p[3] = { px[i], py[i], pz[i] };
+		double sx = 0.0, sy = 0.0, sz = 0.0;
+		// unclamped cell and in-cell fraction (compute_cell_index)
+		long long ci[3];
+		double fr[3];
+#pragma unroll
+		for (int d = 0; d < 3; ++d) {
+			double f = div_h(p[d] - G.off[d], G);
+			unsigned long long u = (unsigned long long)f;
+			ci[d] = u > 0x7fffffffull ? 0x7fffffffll : (long long)u;
+			fr[d] = f - (double)u;
+		}
+		const bool in_tile = use_stage && ci[0] >= x0 && ci[0] < x0 + CT_LX && ci[0] < G.nx && ci[1] == y0 + oy &&
+			ci[2] == lz0 + oz - 1 + G.z0;
+		if (!in_tile) {
+			spring_global(G, M, px, py, pz, begin, i, p, sx, sy, sz);
+		} else {
+			const float rx = (float)(p[0] - org[0]), ry = (float)(p[1] - org[1]), rz = (float)(p[2] - org[2]);
+			// cells (rows) farther than the kernel radius re = h / sqrt(2) = 0.7071 h cannot contribute
+			const int klo = (int)(ci[0] - x0) + (fr[0] > 0.7075 ? 1 : 0);
+			const int khi = (int)(ci[0] - x0) + 3 - (fr[0] < 0.2925 ? 1 : 0);
+			uint32_t cand[CT_LIST];
+			int nc = 0;
+			for (int dz = -1; dz <= 1; ++dz) {
+				if ((dz < 0 && fr[2] > 0.7075) || (dz > 0 && fr[2] < 0.2925)) { continue; }
+				for (int dy = -1; dy <= 1; ++dy) {
+					if ((dy < 0 && fr[1] > 0.7075) || (dy > 0 && fr[1] < 0.2925)) { continue; }
+					const int r = (oz + 1 + dz) * CT_SY + (oy + 1 + dy);
+					const uint32_t s0 = rowoff[r] + cellbeg[r][klo], s1 = rowoff[r] + cellbeg[r][khi];
+					for (uint32_t s = s0; s < s1; ++s) {
+						float4 q = stage[s];
+						float dx = rx - q.x, dyv = ry - q.y, dzv = rz - q.z;
+						float d2 = dx * dx + dyv * dyv + dzv * dzv;
+						if (d2 < thr) {
+							cand[nc++] = __float_as_uint(q.w);
+							if (nc == CT_LIST) { // flush: evaluate exactly, in order
+								for (int k = 0; k < CT_LIST; ++k) {
+									uint32_t j = cand[k];
+									if (j == i) { continue; }
+									double ov[3] = { px[j], py[j], pz[j] };
+									pair_exact(M, p, ov, sx, sy, sz);
+								}
+								nc = 0;
+							}
+						}
+					}
+				}
+			}
+			for (int k = 0; k < nc; ++k) {
+				uint32_t j = cand[k];
+				if (j == i) { continue; }
+				double ov[3] = { px[j], py[j], pz[j] };
+				pair_exact(M, p, ov, sx, sy, sz);
+			}
+		}
+		double np3[3] = { p[0] + sx * M.corr_factor, p[1] + sy * M.corr_factor, p[2] + sz * M.corr_factor };
+#pragma unroll
+		for (int d = 0; d < 3; ++d) {
+			np3[d] = dclamp_std(np3[d], M.gmin[d], M.gmax[d]);
+		}
+		if (COLLIDE) {
+			collide_one(G, M, typ, p, np3);
+		}
+		nx_[i] = np3[0];
+		ny_[i] = np3[1];
+		nz_[i] = np3[2];
+	}
+}
+
 static int correct_impl(lfk_ctx *c, double dt, bool fuse_collide) {
 	PhaseTimer T(c, LFK_PHASE_CORRECT_COLLIDE);
 	LFK_REQUIRE(c, c->table_valid, LFK_E_STATE, "lfk_correct needs the cell table of lfk_hash");
 	if (c->np == 0) { return 0; }
 	MotionParams M = motion_params(c, dt);
-	unsigned nb = lfk_blocks((long long)c->np, 128);
+	const GridDesc &G = c->g;
+	dim3 grid((unsigned)((G.nx + CT_LX - 1) / CT_LX), (unsigned)((G.ny + CT_TY - 1) / CT_TY),
+		(unsigned)((G.nzl + CT_TZ - 1) / CT_TZ));
+	const size_t smem = (size_t)CT_CAP * sizeof(float4);
+	static bool attr_set = false;
+	if (!attr_set) {
+		LFK_CUDA(c, cudaFuncSetAttribute(k_correct_tiled<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+		LFK_CUDA(c, cudaFuncSetAttribute(k_correct_tiled<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+		attr_set = true;
+	}
 	if (fuse_collide) {
-		LFK_LAUNCH(c, k_correct<true>, nb, 128, 0, c->g, M, c->P, c->Palt.f[PF_PX], c->Palt.f[PF_PY],
-			c->Palt.f[PF_PZ], c->begin, c->typ, (unsigned long long)c->np);
+		LFK_LAUNCH(c, k_correct_tiled<true>, grid, CT_THREADS, smem, G, M, c->P, c->Palt.f[PF_PX], c->Palt.f[PF_PY],
+			c->Palt.f[PF_PZ], c->begin, c->typ);
 	} else {
 		LFK_TRY(materialise_old(c));
-		LFK_LAUNCH(c, k_correct<false>, nb, 128, 0, c->g, M, c->P, c->Palt.f[PF_PX], c->Palt.f[PF_PY],
-			c->Palt.f[PF_PZ], c->begin, c->typ, (unsigned long long)c->np);
+		LFK_LAUNCH(c, k_correct_tiled<false>, grid, CT_THREADS, smem, G, M, c->P, c->Palt.f[PF_PX], c->Palt.f[PF_PY],
+			c->Palt.f[PF_PZ], c->begin, c->typ);
 	}
 	for (int d = 0; d < 3; ++d) {
 		double *t = c->P.f[PF_PX + d];
@@ -748,14 +978,14 @@ __device__ __forceinline__ double trilerp8(const double *v, double t1, double t2
 	return lerp1(b0, b1, t1);
 }
 // c = sum over the 8 corners of grad_kernel(corner) * sample, in the reference's corner order
-__device__ __forceinline__ void c_vector(double h, const double *v, double tx, double ty, double tz, double *out) {
+__device__ __forceinline__ void c_vector(const GridDesc &G, const double *v, double tx, double ty, double tz, double *out) {
 	double ax = 0.0, ay = 0.0, az = 0.0;
 #pragma unroll
 	for (int k = 0; k < 8; ++k) {
 		double px = (k & 1) ? tx - 1.0 : tx, py = (k & 2) ? ty - 1.0 : ty, pz = (k & 4) ? tz - 1.0 : tz;
 		double sx = px > 0.0 ? -1.0 : 1.0, sy = py > 0.0 ? -1.0 : 1.0, sz = pz > 0.0 ? -1.0 : 1.0;
 		double nx = 1.0 - fabs(px), ny = 1.0 - fabs(py), nz = 1.0 - fabs(pz);
-		double gx = sx * ny * nz / h, gy = nx * sy * nz / h, gz = nx * ny * sz / h;
+		double gx = div_h(sx * ny * nz, G), gy = div_h(nx * sy * nz, G), gz = div_h(nx * ny * sz, G);
 		if (k == 0) {
 			ax = gx * v[k];
 			ay = gy * v[k];
@@ -824,7 +1054,7 @@ template <int METHOD> __global__ void __launch_bounds__(128) k_g2p(GridDesc G, P
 	int dsel[3];
 #pragma unroll
 	for (int d = 0; d < 3; ++d) { // compute_cell_index_and_position: no clamping
-		double f = (p[d] - G.off[d]) / G.h;
+		double f = div_h(p[d] - G.off[d], G);
 		unsigned long long ci = (unsigned long long)f;
 		gi[d] = ci > 0x7fffffffull ? 0x7fffffffll : (long long)ci;
 		t[d] = f - (double)ci;
@@ -863,15 +1093,15 @@ template <int METHOD> __global__ void __launch_bounds__(128) k_g2p(GridDesc G, P
 		P.f[PF_VZ][i] = vn[2];
 		if (METHOD == LFK_METHOD_APIC) {
 			double cv[3];
-			c_vector(G.h, sx, t[0], tmid[1], tmid[2], cv);
+			c_vector(G, sx, t[0], tmid[1], tmid[2], cv);
 			P.f[PF_C0 + 0][i] = cv[0];
 			P.f[PF_C0 + 1][i] = cv[1];
 			P.f[PF_C0 + 2][i] = cv[2];
-			c_vector(G.h, sy, tmid[0], t[1], tmid[2], cv);
+			c_vector(G, sy, tmid[0], t[1], tmid[2], cv);
 			P.f[PF_C0 + 3][i] = cv[0];
 			P.f[PF_C0 + 4][i] = cv[1];
 			P.f[PF_C0 + 5][i] = cv[2];
-			c_vector(G.h, sz, tmid[0], tmid[1], t[2], cv);
+			c_vector(G, sz, tmid[0], tmid[1], t[2], cv);
 			P.f[PF_C0 + 6][i] = cv[0];
 			P.f[PF_C0 + 7][i] = cv[1];
 			P.f[PF_C0 + 8][i] = cv[2];
