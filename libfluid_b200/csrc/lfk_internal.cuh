@@ -272,4 +272,55 @@ __device__ __forceinline__ double block_max(double v) {
 	}
 	return v;
 }
+
+// ---- pressure-system flag byte (one per cell): bits 0-2 non-solid neighbour count (the diagonal), bit 3 "is an
+// unknown" (the cell holds particles, reference src/simulation.cpp:83-87), bit 4 type == fluid, bits 5-7
+// type(+x / +y / +z neighbour) == fluid ---------------------------------------------------------------------------
+#define FL_N(f) ((f) & 7u)
+#define FL_L 8u
+#define FL_SELF 16u
+#define FL_XP 32u
+#define FL_YP 64u
+#define FL_ZP 128u
+
+#define RED_BLOCKS 1184 // reduction kernels: 148 SMs x 8 resident blocks of 256 threads
+#define RED_THREADS 256
+
+// deterministic finish of a block-partial reduction (run by the last block): `op` 0 sum, 1 max
+__device__ __forceinline__ double finish_partials(const double *partials, unsigned nblocks, int op) {
+	double acc = op ? -1.0e300 : 0.0;
+	for (unsigned k = threadIdx.x; k < nblocks; k += blockDim.x) {
+		double t = partials[k];
+		acc = op ? fmax(acc, t) : acc + t;
+	}
+	return op ? block_max(acc) : block_sum(acc);
+}
+
+// finalisers of the PCG scalars: run by the last block of the producing kernel on one GPU, or by k_finalize after
+// the NCCL all-reduce of the local partial results on several GPUs
+enum { FIN_BB = 0, FIN_ALPHA = 1, FIN_RESID = 2, FIN_BETA_FIRST = 3, FIN_BETA = 4 };
+__device__ __forceinline__ void pcg_finalize(PcgScalars *scal, int which, double tolerance) {
+	switch (which) {
+	case FIN_BB: // early-out of the reference (src/pressure_solver.cpp:29-35)
+		scal->iters = 0;
+		scal->resmax = 0.0;
+		scal->done = scal->bb < 1e-6 ? 1 : 0;
+		break;
+	case FIN_ALPHA:
+		scal->alpha = scal->sigma / scal->zs;
+		break;
+	case FIN_RESID: // :54-58 (two-sided: max |r|, which implies the reference's one-sided max r < tolerance)
+		scal->iters += 1;
+		if (scal->resmax < tolerance) { scal->done = 1; }
+		break;
+	case FIN_BETA_FIRST: // :38-42
+		scal->sigma = scal->sigma_new;
+		scal->beta = 0.0;
+		break;
+	default: // :62-68
+		scal->beta = scal->sigma_new / scal->sigma;
+		scal->sigma = scal->sigma_new;
+		break;
+	}
+}
 #endif

@@ -19,12 +19,6 @@
 
 #include <algorithm>
 
-#define FL_N(f) ((f) & 7u)
-#define FL_L 8u
-#define FL_SELF 16u
-#define FL_XP 32u
-#define FL_YP 64u
-#define FL_ZP 128u
 
 #define MG_OMEGA 1.8f
 #define MG_PRE 2
@@ -61,25 +55,6 @@ __device__ __forceinline__ float l0_offdiag_sum(const GridDesc &G, unsigned f, c
 	if (f & FL_YP) { s += X[c + G.nx]; }
 	if (f & FL_ZP) { s += X[c + G.sxy]; }
 	return s;
-}
-
-// b0 = r / a_scale (the integer-coefficient system), x0 = 0
-__global__ void k_mg_load(GridDesc G, const double *__restrict__ r, float *__restrict__ b0, float *__restrict__ x0,
-	double inv_a_scale, const PcgScalars *scal) {
-	if (scal->done) { return; }
-	long long own = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-	if (own >= G.nown) { return; }
-	long long c = own + G.sxy;
-	b0[c] = (float)(r[c] * inv_a_scale);
-	x0[c] = 0.f;
-}
-__global__ void k_mg_store(GridDesc G, const float *__restrict__ x0, const uint8_t *__restrict__ flags,
-	double *__restrict__ z, double inv_a_scale, const PcgScalars *scal) {
-	if (scal->done) { return; }
-	long long own = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-	if (own >= G.nown) { return; }
-	long long c = own + G.sxy;
-	z[c] = (flags[c] & FL_L) ? (double)x0[c] * inv_a_scale : 0.0;
 }
 
 // one colour of red-black Gauss-Seidel on level 0; each thread owns one cell of that colour (x = 2i + parity)
@@ -413,7 +388,7 @@ int lfkm_setup(lfk_ctx *c, double a_scale) {
 	return 0;
 }
 
-static int smooth(lfk_ctx *c, size_t l, int first_colour, int sweeps) {
+static int smooth(lfk_ctx *c, size_t l, int first_colour, int sweeps, bool skip_first = false) {
 	const GridDesc &G = c->g;
 	MgLevel &L = c->mg[l];
 	LevelDev Ld = level_dev(L, c->mg_z0[l]);
@@ -422,6 +397,7 @@ static int smooth(lfk_ctx *c, size_t l, int first_colour, int sweeps) {
 	for (int s = 0; s < sweeps; ++s) {
 		for (int h = 0; h < 2; ++h) {
 			int colour = first_colour ^ h;
+			if (skip_first && s == 0 && h == 0) { continue; } // already done by the kernel that produced b0 / x0
 			if (c->nranks > 1) { LFK_TRY(lfkx_halo_f32(c, L.x, L.nx, L.ny, L.nzl)); }
 			if (l == 0) {
 				LFK_LAUNCH(c, k_mg_rbgs_l0, nb, 256, 0, G, c->flags, L.b, L.x, colour, c->d_scal);
@@ -452,7 +428,7 @@ static int vcycle(lfk_ctx *c, size_t l) {
 		LFK_TRY(smooth(c, l, 1, MG_COARSE_SWEEPS));
 		return 0;
 	}
-	LFK_TRY(smooth(c, l, 0, MG_PRE)); // red, black
+	LFK_TRY(smooth(c, l, 0, MG_PRE, l == 0)); // red, black (level 0: the first red half-sweep is pre-applied)
 	MgLevel &C = c->mg[l + 1];
 	LevelDev Cd = level_dev(C, c->mg_z0[l + 1]);
 	if (c->nranks > 1) { LFK_TRY(lfkx_halo_f32(c, L.x, L.nx, L.ny, L.nzl)); }
@@ -471,13 +447,44 @@ static int vcycle(lfk_ctx *c, size_t l) {
 	return 0;
 }
 
-// z = M^-1 r
-int lfkm_apply(lfk_ctx *c, const double *r, double *z, double a_scale) {
+// level-0 buffers, filled by the PCG kernels that produce r (see MgPreload in pressure.cu)
+int lfkm_level0(lfk_ctx *c, float **b0, float **x0) {
+	LFK_TRY(mg_alloc(c));
+	*b0 = c->mg[0].b;
+	*x0 = c->mg[0].x;
+	return 0;
+}
+
+// z = x0 / a_scale (fp64) fused with sigma_new = z.r and its finaliser
+__global__ void __launch_bounds__(RED_THREADS) k_mg_store_dot(GridDesc G, const float *__restrict__ x0,
+	const uint8_t *__restrict__ flags, const double *__restrict__ r, double *__restrict__ z, double inv_a_scale,
+	PcgScalars *scal, double *partials, unsigned *ticket, int finalize, int first) {
+	if (scal->done) { return; }
+	double acc = 0.0;
+	for (long long own = (long long)blockIdx.x * blockDim.x + threadIdx.x; own < G.nown;
+		own += (long long)gridDim.x * blockDim.x) {
+		long long c = own + G.sxy;
+		double zv = (flags[c] & FL_L) ? (double)x0[c] * inv_a_scale : 0.0;
+		z[c] = zv;
+		acc += zv * r[c];
+	}
+	acc = block_sum(acc);
+	if (threadIdx.x == 0) { partials[blockIdx.x] = acc; }
+	if (lfk_last_block(ticket)) {
+		double tot = finish_partials(partials, gridDim.x, 0);
+		if (threadIdx.x == 0) {
+			scal->sigma_new = tot;
+			if (finalize) { pcg_finalize(scal, first ? FIN_BETA_FIRST : FIN_BETA, 0.0); }
+		}
+	}
+}
+
+// z = M^-1 r, sigma_new = z.r.  b0 and the red half of x0 were written by k_pcg_init / k_update_pr.
+int lfkm_apply_preloaded(lfk_ctx *c, double a_scale, unsigned nb, int fin, int first) {
 	const GridDesc &G = c->g;
 	MgLevel &L0 = c->mg[0];
-	unsigned nb = lfk_blocks(G.nown, 256);
-	LFK_LAUNCH(c, k_mg_load, nb, 256, 0, G, r, L0.b, L0.x, 1.0 / a_scale, c->d_scal);
 	LFK_TRY(vcycle(c, 0));
-	LFK_LAUNCH(c, k_mg_store, nb, 256, 0, G, L0.x, c->flags, z, 1.0 / a_scale, c->d_scal);
+	LFK_LAUNCH(c, k_mg_store_dot, nb, RED_THREADS, 0, G, L0.x, c->flags, c->r, c->z, 1.0 / a_scale, c->d_scal,
+		c->partials, c->ticket, fin, first);
 	return 0;
 }

@@ -21,18 +21,20 @@
 // tolerance-checked: rel-L2 <= 1e-12 against the oracle).
 #include "lfk_internal.cuh"
 
+// Brick 30 x 10 x 7 faces => 12 x 9 rows of 32 cells; every colour (y mod 3, z mod 3) has exactly 4 x 3 = 12 rows =
+// two balanced rounds for 6 warps.  ~90 KB of shared memory per block => two blocks (12 warps) per SM.
 #define PB_BX 30
-#define PB_BY 8
-#define PB_BZ 8
+#define PB_BY 10
+#define PB_BZ 7
 #define PB_RY (PB_BY + 2)
 #define PB_RZ (PB_BZ + 2)
 #define PB_WARPS 6
 #define PB_THREADS (PB_WARPS * 32)
-#define PB_WIN 8                 // particle slots per cell staged at a time
-#define PB_CSTRIDE (PB_WIN + 1)  // padded: lane stride of 9 doubles is bank-conflict free
+#define PB_WIN 4                 // particle slots per cell staged at a time
+#define PB_CSTRIDE (PB_WIN + 1)  // padded: lane stride of 5 doubles is bank-conflict free
 #define PB_FSTRIDE (32 * PB_CSTRIDE)
 #define PB_FIELDS 7              // pos(3) + v_k + c_k(3)
-#define PB_ACC_COMP (2 * PB_BZ * PB_BY * 32)
+#define PB_ACC_COMP (2 * PB_BZ * PB_BY * 32) // one velocity component: sum(w) and sum(w v) per face
 
 struct PBParams {
 	double half, inv_h;
@@ -136,43 +138,63 @@ template <int COMP> __device__ __forceinline__ void flush_cell(double *__restric
 	}
 }
 
-template <int METHOD> __global__ void __launch_bounds__(PB_THREADS, 1) k_p2g_brick(GridDesc G, PBParams Q,
-	ParticleSoA P, const uint32_t *__restrict__ begin, const double *__restrict__ cxs,
-	const double *__restrict__ cys, const double *__restrict__ czs, double *__restrict__ u, double *__restrict__ v,
-	double *__restrict__ w, double *__restrict__ uo, double *__restrict__ vo, double *__restrict__ wo,
-	uint8_t *__restrict__ typ) {
-	constexpr bool APIC = METHOD == LFK_METHOD_APIC;
-	extern __shared__ double smem[];
-	double *acc = smem;                                  // [3][2][BZ][BY][32]
-	double *stage_all = smem + 3 * PB_ACC_COMP;          // [WARPS][FIELDS][32 * 9]
-	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-	double *st = stage_all + warp * (PB_FIELDS * PB_FSTRIDE);
-	const int x0 = blockIdx.x * PB_BX, y0 = blockIdx.y * PB_BY, lz0 = blockIdx.z * PB_BZ + 1;
-	const int nfx = min(PB_BX, G.nx - x0); // faces of this brick along x
+// one velocity component of one row: stage, accumulate over all slot windows, flush once
+template <int COMP, bool APIC> __device__ __forceinline__ void row_component(double *__restrict__ st,
+	double *__restrict__ acc, const double *const *fields, int lane, uint32_t pb, uint32_t pe, int cnt, int maxcnt,
+	const double *cc, const PBParams &Q, int ry, int rz, int nfx) {
+	double accw[18], accv[18];
+#pragma unroll
+	for (int t = 0; t < 18; ++t) {
+		accw[t] = 0.0;
+		accv[t] = 0.0;
+	}
+	for (int win = 0; win < maxcnt; win += PB_WIN) {
+		const int nslots = max(0, min(PB_WIN, cnt - win));
+		// lanes <-> consecutive particles on the global side (coalesced), [cell][slot] on the shared side
+#pragma unroll
+		for (int k = 0; k < PB_WIN; ++k) {
+			const int t = k * 32 + lane, sc = t / PB_WIN, ss = t % PB_WIN;
+			const uint32_t qb = __shfl_sync(0xffffffffu, pb, sc), qe = __shfl_sync(0xffffffffu, pe, sc);
+			const uint32_t q = qb + win + ss;
+			if (q < qe) {
+				double *dst = st + sc * PB_CSTRIDE + ss;
+#pragma unroll
+				for (int f = 0; f < 3; ++f) { cp_async8(dst + f * PB_FSTRIDE, fields[f] + q); }
+				cp_async8(dst + 3 * PB_FSTRIDE, fields[PF_VX + COMP] + q);
+				if (APIC) {
+#pragma unroll
+					for (int f = 0; f < 3; ++f) { cp_async8(dst + (4 + f) * PB_FSTRIDE, fields[PF_C0 + 3 * COMP + f] + q); }
+				}
+			}
+		}
+		cp_async_wait_all();
+		__syncwarp();
+		accumulate_cell<COMP, APIC>(st, lane, nslots, cc, Q.half, Q.inv_h, Q.hdiv, accw, accv);
+		__syncwarp(); // the slab is overwritten by the next window
+	}
+	// tile coordinates of the faces owned by (cell - 1): x: lane - 2, y: ry - 2, z: rz - 2
+	flush_cell<COMP>(acc, lane - 2, ry - 2, rz - 2, nfx, accw, accv);
+}
 
-	for (int e = threadIdx.x; e < 3 * PB_ACC_COMP; e += PB_THREADS) { acc[e] = 0.0; }
-	__syncthreads();
-
+template <int COMP, bool APIC> __device__ __forceinline__ void brick_component(const GridDesc &G, const PBParams &Q,
+	double *__restrict__ st, double *__restrict__ acc, const double *const *fields, const uint32_t *__restrict__ begin,
+	const double *__restrict__ cxs, const double *__restrict__ cys, const double *__restrict__ czs, int warp, int lane,
+	int x0, int y0, int lz0, int nfx) {
 	const int x = x0 - 1 + lane; // this lane's cell column
 	const bool xin = x >= 0 && x < G.nx;
-	// cell-centre coordinates of x-1, x, x+1 (table built by repeated addition like the reference; edge entries are
-	// extrapolated by +-h, they only ever carry targets outside the grid)
+	// cell-centre coordinates of cell - 1, cell, cell + 1 per axis (table built by repeated addition like the
+	// reference; entries outside the grid are extrapolated by +-h and only ever carry targets outside the grid)
 	double cc[9];
 	{
-		int xm = x - 1, xp = x + 1;
-		double xc = xin ? cxs[x] : (x < 0 ? cxs[0] - G.h : cxs[G.nx - 1] + G.h);
+		const int xm = x - 1, xp = x + 1;
+		const double xc = xin ? cxs[x] : (x < 0 ? cxs[0] - G.h : cxs[G.nx - 1] + G.h);
 		cc[0] = (xm >= 0 && xm < G.nx) ? cxs[xm] : xc - G.h;
 		cc[1] = xc;
 		cc[2] = (xp >= 0 && xp < G.nx) ? cxs[xp] : xc + G.h;
 	}
-	const double *fields[15];
-#pragma unroll
-	for (int f = 0; f < 15; ++f) { fields[f] = P.f[f]; }
-
 	for (int colour = 0; colour < 9; ++colour) {
 		const int cy = colour % 3, cz = colour / 3;
-		// rows of this colour: ry = cy, cy + 3, ...; rz = cz, cz + 3, ...
-		const int nry = (PB_RY - cy + 2) / 3, nrz = (PB_RZ - cz + 2) / 3;
+		const int nry = (PB_RY - cy + 2) / 3, nrz = (PB_RZ - cz + 2) / 3; // rows cy, cy + 3, ... / cz, cz + 3, ...
 		for (int job = warp; job < nry * nrz; job += PB_WARPS) {
 			const int ry = cy + 3 * (job % nry), rz = cz + 3 * (job / nry);
 			const int y = y0 - 1 + ry, lz = lz0 - 1 + rz;
@@ -189,112 +211,72 @@ template <int METHOD> __global__ void __launch_bounds__(PB_THREADS, 1) k_p2g_bri
 #pragma unroll
 			for (int o = 16; o > 0; o >>= 1) { maxcnt = max(maxcnt, __shfl_xor_sync(0xffffffffu, maxcnt, o)); }
 			if (maxcnt == 0) { continue; }
-			{
-				double yc = cys[y], zc = czs[z];
-				cc[3] = y > 0 ? cys[y - 1] : yc - G.h;
-				cc[4] = yc;
-				cc[5] = y + 1 < G.ny ? cys[y + 1] : yc + G.h;
-				cc[6] = z > 0 ? czs[z - 1] : zc - G.h;
-				cc[7] = zc;
-				cc[8] = z + 1 < G.nz ? czs[z + 1] : zc + G.h;
-			}
-			for (int win = 0; win < maxcnt; win += PB_WIN) {
-				const int nslots = max(0, min(PB_WIN, cnt - win));
-				// ---- positions: lanes <-> consecutive particles (coalesced), stored [cell][slot] ----
+			const double yc = cys[y], zc = czs[z];
+			cc[3] = y > 0 ? cys[y - 1] : yc - G.h;
+			cc[4] = yc;
+			cc[5] = y + 1 < G.ny ? cys[y + 1] : yc + G.h;
+			cc[6] = z > 0 ? czs[z - 1] : zc - G.h;
+			cc[7] = zc;
+			cc[8] = z + 1 < G.nz ? czs[z + 1] : zc + G.h;
+			row_component<COMP, APIC>(st, acc, fields, lane, pb, pe, cnt, maxcnt, cc, Q, ry, rz, nfx);
+		}
+		__syncthreads(); // rows of the next colour may touch the faces this colour just updated
+	}
+}
+
+template <int METHOD> __global__ void __launch_bounds__(PB_THREADS, 2) k_p2g_brick(GridDesc G, PBParams Q,
+	ParticleSoA P, const uint32_t *__restrict__ begin, const double *__restrict__ cxs,
+	const double *__restrict__ cys, const double *__restrict__ czs, double *__restrict__ u, double *__restrict__ v,
+	double *__restrict__ w, double *__restrict__ uo, double *__restrict__ vo, double *__restrict__ wo,
+	uint8_t *__restrict__ typ) {
+	constexpr bool APIC = METHOD == LFK_METHOD_APIC;
+	extern __shared__ double smem[];
+	double *acc = smem;                              // [2][BZ][BY][32], reused by the three components
+	double *stage_all = smem + PB_ACC_COMP;          // [WARPS][FIELDS][32 * CSTRIDE]
+	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+	double *st = stage_all + warp * (PB_FIELDS * PB_FSTRIDE);
+	const int x0 = blockIdx.x * PB_BX, y0 = blockIdx.y * PB_BY, lz0 = blockIdx.z * PB_BZ + 1;
+	const int nfx = min(PB_BX, G.nx - x0); // faces of this brick along x
+	const double *fields[15];
 #pragma unroll
-				for (int k = 0; k < PB_WIN; ++k) {
-					const int t = k * 32 + lane, sc = t / PB_WIN, ss = t % PB_WIN;
-					const uint32_t qb = __shfl_sync(0xffffffffu, pb, sc), qe = __shfl_sync(0xffffffffu, pe, sc);
-					const uint32_t q = qb + win + ss;
-					if (q < qe) {
-#pragma unroll
-						for (int f = 0; f < 3; ++f) { cp_async8(st + f * PB_FSTRIDE + sc * PB_CSTRIDE + ss, fields[f] + q); }
-					}
-				}
-#pragma unroll
-				for (int comp = 0; comp < 3; ++comp) {
-#pragma unroll
-					for (int k = 0; k < PB_WIN; ++k) {
-						const int t = k * 32 + lane, sc = t / PB_WIN, ss = t % PB_WIN;
-						const uint32_t qb = __shfl_sync(0xffffffffu, pb, sc), qe = __shfl_sync(0xffffffffu, pe, sc);
-						const uint32_t q = qb + win + ss;
-						if (q < qe) {
-							double *dst = st + sc * PB_CSTRIDE + ss;
-							cp_async8(dst + 3 * PB_FSTRIDE, fields[PF_VX + comp] + q);
-							if (APIC) {
-#pragma unroll
-								for (int f = 0; f < 3; ++f) {
-									cp_async8(dst + (4 + f) * PB_FSTRIDE, fields[PF_C0 + 3 * comp + f] + q);
-								}
-							}
-						}
-					}
-					cp_async_wait_all();
-					__syncwarp();
-					double accw[18], accv[18];
-#pragma unroll
-					for (int t = 0; t < 18; ++t) {
-						accw[t] = 0.0;
-						accv[t] = 0.0;
-					}
-					double *acck = acc + comp * PB_ACC_COMP;
-					// tile coordinates of the faces owned by (cell - 1): x: lane - 2, y: ry - 2, z: rz - 2
-					if (comp == 0) {
-						accumulate_cell<0, APIC>(st, lane, nslots, cc, Q.half, Q.inv_h, Q.hdiv, accw, accv);
-						__syncwarp();
-						flush_cell<0>(acck, lane - 2, ry - 2, rz - 2, nfx, accw, accv);
-					} else if (comp == 1) {
-						accumulate_cell<1, APIC>(st, lane, nslots, cc, Q.half, Q.inv_h, Q.hdiv, accw, accv);
-						__syncwarp();
-						flush_cell<1>(acck, lane - 2, ry - 2, rz - 2, nfx, accw, accv);
-					} else {
-						accumulate_cell<2, APIC>(st, lane, nslots, cc, Q.half, Q.inv_h, Q.hdiv, accw, accv);
-						__syncwarp();
-						flush_cell<2>(acck, lane - 2, ry - 2, rz - 2, nfx, accw, accv);
-					}
+	for (int f = 0; f < 15; ++f) { fields[f] = P.f[f]; }
+	double *const out[3] = { u, v, w };
+	double *const old[3] = { uo, vo, wo };
+
+#pragma unroll 1
+	for (int comp = 0; comp < 3; ++comp) {
+		for (int e = threadIdx.x; e < PB_ACC_COMP; e += PB_THREADS) { acc[e] = 0.0; }
+		__syncthreads();
+		if (comp == 0) {
+			brick_component<0, APIC>(G, Q, st, acc, fields, begin, cxs, cys, czs, warp, lane, x0, y0, lz0, nfx);
+		} else if (comp == 1) {
+			brick_component<1, APIC>(G, Q, st, acc, fields, begin, cxs, cys, czs, warp, lane, x0, y0, lz0, nfx);
+		} else {
+			brick_component<2, APIC>(G, Q, st, acc, fields, begin, cxs, cys, czs, warp, lane, x0, y0, lz0, nfx);
+		}
+		// ---- normalise + boundary faces + FLIP snapshot + gravity, write this component of the brick's faces
+		// (the last colour ended with a __syncthreads) ----
+		for (int e = threadIdx.x; e < PB_BZ * PB_BY * 32; e += PB_THREADS) {
+			const int fx = e & 31, fy = (e >> 5) % PB_BY, fz = (e >> 5) / PB_BY;
+			const int cx = x0 + fx, cyy = y0 + fy, lz = lz0 + fz;
+			if (fx >= nfx || cyy >= G.ny || lz > G.nzl) { continue; }
+			const int z = lz - 1 + G.z0;
+			const long long me = cx + (long long)G.nx * (cyy + (long long)G.ny * lz);
+			const double sw = acc[e], sv = acc[PB_BZ * PB_BY * 32 + e];
+			double r = sw > 1e-6 ? sv / sw : 0.0; // src/simulation.cpp:380-386
+			const bool edge = comp == 0 ? cx == G.nx - 1 : (comp == 1 ? cyy == G.ny - 1 : z == G.nz - 1);
+			if (METHOD == LFK_METHOD_FLIP) { old[comp][me] = edge ? 0.0 : r; } // :340-344
+			if (APIC && edge) { r = 0.0; }                                      // :397
+			if (Q.add_gravity) { r += Q.gdt[comp]; }                            // :72-78
+			out[comp][me] = r;
+			if (comp == 0) { // classification, once per cell (:388-393)
+				uint8_t t = typ[me];
+				if (t != LFK_CELL_SOLID) {
+					typ[me] = (begin[me + 1] - begin[me]) > 0 ? LFK_CELL_FLUID : LFK_CELL_AIR;
 				}
 			}
 		}
 		__syncthreads();
-	}
-
-	// ---- normalise + classify + boundary faces + FLIP snapshot + gravity, write the brick's faces ----
-	for (int e = threadIdx.x; e < PB_BZ * PB_BY * 32; e += PB_THREADS) {
-		const int fx = e & 31, fy = (e >> 5) % PB_BY, fz = (e >> 5) / PB_BY;
-		const int cx = x0 + fx, cyy = y0 + fy, lz = lz0 + fz;
-		if (fx >= nfx || cyy >= G.ny || lz > G.nzl) { continue; }
-		const int z = lz - 1 + G.z0;
-		const long long me = cx + (long long)G.nx * (cyy + (long long)G.ny * lz);
-		double r[3];
-#pragma unroll
-		for (int k = 0; k < 3; ++k) {
-			const double sw = acc[k * PB_ACC_COMP + e], sv = acc[k * PB_ACC_COMP + PB_BZ * PB_BY * 32 + e];
-			r[k] = sw > 1e-6 ? sv / sw : 0.0; // src/simulation.cpp:380-386
-		}
-		uint8_t t = typ[me];
-		if (t != LFK_CELL_SOLID) { // :388-393
-			t = (begin[me + 1] - begin[me]) > 0 ? LFK_CELL_FLUID : LFK_CELL_AIR;
-			typ[me] = t;
-		}
-		const bool bx = cx == G.nx - 1, by = cyy == G.ny - 1, bz = z == G.nz - 1;
-		if (METHOD == LFK_METHOD_FLIP) { // :340-344
-			uo[me] = bx ? 0.0 : r[0];
-			vo[me] = by ? 0.0 : r[1];
-			wo[me] = bz ? 0.0 : r[2];
-		}
-		if (APIC) { // :397
-			if (bx) { r[0] = 0.0; }
-			if (by) { r[1] = 0.0; }
-			if (bz) { r[2] = 0.0; }
-		}
-		if (Q.add_gravity) { // :72-78
-			r[0] += Q.gdt[0];
-			r[1] += Q.gdt[1];
-			r[2] += Q.gdt[2];
-		}
-		u[me] = r[0];
-		v[me] = r[1];
-		w[me] = r[2];
 	}
 }
 
@@ -310,7 +292,7 @@ int lfkg_p2g_brick(lfk_ctx *c, double gravity_dt, bool add_gravity) {
 	}
 	dim3 grid((unsigned)((G.nx + PB_BX - 1) / PB_BX), (unsigned)((G.ny + PB_BY - 1) / PB_BY),
 		(unsigned)((G.nzl + PB_BZ - 1) / PB_BZ));
-	const size_t smem = (size_t)(3 * PB_ACC_COMP + PB_WARPS * PB_FIELDS * PB_FSTRIDE) * sizeof(double);
+	const size_t smem = (size_t)(PB_ACC_COMP + PB_WARPS * PB_FIELDS * PB_FSTRIDE) * sizeof(double);
 	static bool attr_set = false;
 	if (!attr_set) {
 		LFK_CUDA(c, cudaFuncSetAttribute(k_p2g_brick<LFK_METHOD_PIC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -358,7 +358,7 @@ struct MotionParams {
 	double lo[3], hi[3]; // advect clamp corners
 	double gmin[3], gmax[3]; // correct clamp corners
 	double skin, skin_max;
-	double dt, corr_factor, re2;
+	double dt, corr_factor, re2, inv_re2;
 };
 
 static MotionParams motion_params(const lfk_ctx *c, double dt) {
@@ -378,6 +378,7 @@ static MotionParams motion_params(const lfk_ctx *c, double dt) {
 	double re = G.h / sqrt(2.0);
 	m.corr_factor = dt * c->prm.correction_stiffness * re;
 	m.re2 = re * re;
+	m.inv_re2 = 1.0 / m.re2;
 	return m;
 }
 
@@ -700,10 +701,12 @@ __device__ __forceinline__ void pair_exact(const MotionParams &M, const double *
 		sy += kick[1];
 		sz += kick[2];
 	} else {
-		double kl = 1.0 - sq / M.re2;
+		// reference: kernel = (1 - r^2 / re^2)^3, spring += kernel / sqrt(r^2) * offset.  The two IEEE divisions and
+		// the IEEE square root cost ~150 instructions per pair; the reciprocal multiply and rsqrt() (<= 1 ulp) cost
+		// ~25 and move the corrected position by < 1e-16 cells -- positions are tolerance-checked (1e-12).
+		double kl = 1.0 - sq * M.inv_re2;
 		if (kl > 0.0) {
-			double kern = kl * kl * kl;
-			double sc = kern / sqrt(sq);
+			double sc = kl * kl * kl * rsqrt(sq);
 			sx += sc * ox;
 			sy += sc * oy;
 			sz += sc * oz;
@@ -849,10 +852,11 @@ template <bool COLLIDE> __global__ void __launch_bounds__(CT_THREADS) k_correct_
 					if ((dy < 0 && fr[1] > 0.7075) || (dy > 0 && fr[1] < 0.2925)) { continue; }
 					const int r = (oz + 1 + dz) * CT_SY + (oy + 1 + dy);
 					const uint32_t s0 = rowoff[r] + cellbeg[r][klo], s1 = rowoff[r] + cellbeg[r][khi];
+#pragma unroll 4
 					for (uint32_t s = s0; s < s1; ++s) {
 						float4 q = stage[s];
 						float dx = rx - q.x, dyv = ry - q.y, dzv = rz - q.z;
-						float d2 = dx * dx + dyv * dyv + dzv * dzv;
+						float d2 = __fmaf_rn(dzv, dzv, __fmaf_rn(dyv, dyv, dx * dx));
 						if (d2 < thr) {
 							cand[nc++] = __float_as_uint(q.w);
 							if (nc == CT_LIST) { // flush: evaluate exactly, in order

@@ -11,17 +11,7 @@
 #include <cmath>
 #include <cstring>
 
-// flag byte per cell: bits 0-2 nonsolid neighbour count (diagonal), bit 3 "is an unknown" (cell holds particles,
-// reference src/simulation.cpp:83-87), bit 4 type == fluid, bits 5-7 type(+x/+y/+z neighbour) == fluid.
-#define FL_N(f) ((f) & 7u)
-#define FL_L 8u
-#define FL_SELF 16u
-#define FL_XP 32u
-#define FL_YP 64u
-#define FL_ZP 128u
-
-#define RED_BLOCKS 1184 // 148 SMs x 8 resident blocks of 256 threads
-#define RED_THREADS 256
+// (the flag byte FL_* and the reduction helpers live in lfk_internal.cuh)
 
 __device__ __forceinline__ void cell_xyz(const GridDesc &G, long long own, int &x, int &y, int &lz) {
 	x = (int)(own % G.nx);
@@ -97,43 +87,6 @@ __device__ __forceinline__ double stencil_apply(const GridDesc &G, unsigned f, c
 	return a_scale * value;
 }
 
-// deterministic finish of a block-partial reduction: `op` 0 sum, 1 max
-__device__ __forceinline__ double finish_partials(double *partials, unsigned nblocks, int op) {
-	double acc = op ? -1.0e300 : 0.0;
-	for (unsigned k = threadIdx.x; k < nblocks; k += blockDim.x) {
-		double t = partials[k];
-		acc = op ? fmax(acc, t) : acc + t;
-	}
-	return op ? block_max(acc) : block_sum(acc);
-}
-
-// ---- finalisers of the PCG scalars: run by the last block on one GPU, or by k_finalize after the NCCL
-// all-reduce of the local partial results on several GPUs ------------------------------------------------------
-enum { FIN_BB = 0, FIN_ALPHA = 1, FIN_RESID = 2, FIN_BETA_FIRST = 3, FIN_BETA = 4 };
-__device__ __forceinline__ void pcg_finalize(PcgScalars *scal, int which, double tolerance) {
-	switch (which) {
-	case FIN_BB: // early-out of the reference (src/pressure_solver.cpp:29-35)
-		scal->iters = 0;
-		scal->resmax = 0.0;
-		scal->done = scal->bb < 1e-6 ? 1 : 0;
-		break;
-	case FIN_ALPHA:
-		scal->alpha = scal->sigma / scal->zs;
-		break;
-	case FIN_RESID: // :54-58 (two-sided: max |r|, which implies the reference's one-sided max r < tolerance)
-		scal->iters += 1;
-		if (scal->resmax < tolerance) { scal->done = 1; }
-		break;
-	case FIN_BETA_FIRST: // :38-42
-		scal->sigma = scal->sigma_new;
-		scal->beta = 0.0;
-		break;
-	default: // :62-68
-		scal->beta = scal->sigma_new / scal->sigma;
-		scal->sigma = scal->sigma_new;
-		break;
-	}
-}
 __global__ void k_finalize(PcgScalars *scal, int which, double tolerance) {
 	if (which != FIN_BB && scal->done) { return; }
 	pcg_finalize(scal, which, tolerance);
@@ -183,9 +136,28 @@ __global__ void k_spmv_plain(GridDesc G, const uint8_t *__restrict__ flags, cons
 	z[c] = out;
 }
 
+// Multigrid input fused into the kernels that produce r: b0 = r / a_scale in fp32, and x0 = the result of the first
+// (red) Gauss-Seidel half-sweep from a zero initial guess, i.e. b0 / n on red cells and 0 on black ones.  Saves the
+// load kernel, one half-sweep and a re-read of r per PCG iteration.
+struct MgPreload {
+	float *b0, *x0; // level-0 rhs / solution, or NULL when the preconditioner is not multigrid
+	const uint8_t *flags;
+	double inv_a_scale;
+};
+__device__ __forceinline__ void mg_preload(const GridDesc &G, const MgPreload &M, long long own, long long c, double rv) {
+	if (M.b0 == nullptr) { return; }
+	int x, y, lz;
+	cell_xyz(G, own, x, y, lz);
+	unsigned f = M.flags[c];
+	float bv = (float)(rv * M.inv_a_scale);
+	M.b0[c] = bv;
+	bool red = ((x + y + (lz - 1 + G.z0)) & 1) == 0;
+	M.x0[c] = (red && (f & FL_L) && FL_N(f) > 0) ? bv / (float)FL_N(f) : 0.f;
+}
+
 // r = b, sum b^2
 __global__ void __launch_bounds__(RED_THREADS) k_pcg_init(GridDesc G, const double *__restrict__ b,
-	double *__restrict__ r, PcgScalars *scal, double *partials, unsigned *ticket, int finalize) {
+	double *__restrict__ r, PcgScalars *scal, double *partials, unsigned *ticket, int finalize, MgPreload M) {
 	double acc = 0.0;
 	for (long long own = (long long)blockIdx.x * blockDim.x + threadIdx.x; own < G.nown;
 		own += (long long)gridDim.x * blockDim.x) {
@@ -193,6 +165,7 @@ __global__ void __launch_bounds__(RED_THREADS) k_pcg_init(GridDesc G, const doub
 		double v = b[c];
 		r[c] = v;
 		acc += v * v;
+		mg_preload(G, M, own, c, v);
 	}
 	acc = block_sum(acc);
 	if (threadIdx.x == 0) { partials[blockIdx.x] = acc; }
@@ -245,7 +218,7 @@ __global__ void __launch_bounds__(RED_THREADS) k_dot_zr(GridDesc G, const double
 // p += alpha s ; r -= alpha z ; residual = max |r|
 __global__ void __launch_bounds__(RED_THREADS) k_update_pr(GridDesc G, double *__restrict__ p,
 	double *__restrict__ r, const double *__restrict__ s, const double *__restrict__ z, PcgScalars *scal,
-	double *partials, unsigned *ticket, double tolerance, int finalize) {
+	double *partials, unsigned *ticket, double tolerance, int finalize, MgPreload M) {
 	if (scal->done) { return; }
 	const double alpha = scal->alpha;
 	double m = 0.0;
@@ -256,6 +229,7 @@ __global__ void __launch_bounds__(RED_THREADS) k_update_pr(GridDesc G, double *_
 		double rv = r[c] + (-alpha) * z[c];
 		r[c] = rv;
 		m = fmax(m, fabs(rv));
+		mg_preload(G, M, own, c, rv);
 	}
 	m = block_max(m);
 	if (threadIdx.x == 0) { partials[blockIdx.x] = m; }
@@ -309,15 +283,18 @@ static int allreduce_scalar(lfk_ctx *c, double *field, bool is_max, int which, d
 	return 0;
 }
 
-int lfkm_setup(lfk_ctx *c, double a_scale);                       // mg.cu
-int lfkm_apply(lfk_ctx *c, const double *r, double *z, double a_scale); // mg.cu
+int lfkm_setup(lfk_ctx *c, double a_scale);                                    // mg.cu
+int lfkm_level0(lfk_ctx *c, float **b0, float **x0);                           // mg.cu
+int lfkm_apply_preloaded(lfk_ctx *c, double a_scale, unsigned nb, int fin, int first); // mg.cu: V-cycle + (z, z.r)
 
-static int apply_preconditioner(lfk_ctx *c, double a_scale) {
+// z = M^-1 r and sigma_new = z.r (+ its finaliser on one GPU)
+static int precondition_and_dot(lfk_ctx *c, double a_scale, unsigned nb, int fin, int first) {
 	const GridDesc &G = c->g;
 	if (c->prm.preconditioner == LFK_PRECOND_MULTIGRID) {
-		return lfkm_apply(c, c->r, c->z, a_scale);
+		return lfkm_apply_preloaded(c, a_scale, nb, fin, first);
 	}
 	LFK_LAUNCH(c, k_precond_jacobi, lfk_blocks(G.nown, 256), 256, 0, G, c->flags, c->r, c->z, a_scale, c->d_scal);
+	LFK_LAUNCH(c, k_dot_zr, nb, RED_THREADS, 0, G, c->z, c->r, c->d_scal, c->partials, c->ticket, fin, first);
 	return 0;
 }
 
@@ -335,10 +312,13 @@ int lfks_solve(lfk_ctx *c, double dt, double *residual, uint64_t *iters) {
 	if (c->prm.preconditioner == LFK_PRECOND_MULTIGRID && !c->mg_valid) {
 		LFK_TRY(lfkm_setup(c, a_scale));
 	}
-	LFK_LAUNCH(c, k_pcg_init, nb, RED_THREADS, 0, G, c->b, c->r, c->d_scal, c->partials, c->ticket, fin);
+	MgPreload M{ nullptr, nullptr, c->flags, 1.0 / a_scale };
+	if (c->prm.preconditioner == LFK_PRECOND_MULTIGRID) {
+		LFK_TRY(lfkm_level0(c, &M.b0, &M.x0));
+	}
+	LFK_LAUNCH(c, k_pcg_init, nb, RED_THREADS, 0, G, c->b, c->r, c->d_scal, c->partials, c->ticket, fin, M);
 	LFK_TRY(allreduce_scalar(c, &c->d_scal->bb, false, FIN_BB, tol));
-	LFK_TRY(apply_preconditioner(c, a_scale));
-	LFK_LAUNCH(c, k_dot_zr, nb, RED_THREADS, 0, G, c->z, c->r, c->d_scal, c->partials, c->ticket, fin, 1);
+	LFK_TRY(precondition_and_dot(c, a_scale, nb, fin, 1));
 	LFK_TRY(allreduce_scalar(c, &c->d_scal->sigma_new, false, FIN_BETA_FIRST, tol));
 	LFK_LAUNCH(c, k_xpby, eb, 256, 0, G, c->s, c->z, c->d_scal);
 
@@ -356,11 +336,10 @@ int lfks_solve(lfk_ctx *c, double dt, double *residual, uint64_t *iters) {
 				c->ticket, fin);
 			LFK_TRY(allreduce_scalar(c, &c->d_scal->zs, false, FIN_ALPHA, tol));
 			LFK_LAUNCH(c, k_update_pr, nb, RED_THREADS, 0, G, c->p, c->r, c->s, c->z, c->d_scal, c->partials,
-				c->ticket, tol, fin);
+				c->ticket, tol, fin, M);
 			LFK_TRY(allreduce_scalar(c, &c->d_scal->resmax, true, FIN_RESID, tol));
 			if (issued + k + 1 < max_it) { // the reference leaves the loop after max_iterations updates of p, r
-				LFK_TRY(apply_preconditioner(c, a_scale));
-				LFK_LAUNCH(c, k_dot_zr, nb, RED_THREADS, 0, G, c->z, c->r, c->d_scal, c->partials, c->ticket, fin, 0);
+				LFK_TRY(precondition_and_dot(c, a_scale, nb, fin, 0));
 				LFK_TRY(allreduce_scalar(c, &c->d_scal->sigma_new, false, FIN_BETA, tol));
 				LFK_LAUNCH(c, k_xpby, eb, 256, 0, G, c->s, c->z, c->d_scal);
 			}
