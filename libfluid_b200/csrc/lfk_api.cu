@@ -517,11 +517,12 @@ extern "C" int lfk_num_fluid_cells(lfk_ctx *c, uint64_t *nf) {
 }
 
 extern "C" int lfk_download_fluid_cells(lfk_ctx *c, uint64_t *raw, uint64_t capacity) {
-	if (!c || !raw) { return LFK_E_INVALID; }
+	if (!c) { return LFK_E_INVALID; }
 	uint64_t nf = 0;
 	LFK_TRY(fetch_num_fluid(c, &nf));
 	LFK_REQUIRE(c, capacity >= nf, LFK_E_CAPACITY, "fluid-cell buffer too small");
-	if (nf == 0) { return 0; }
+	if (nf == 0) { return 0; } // an empty list may come with a NULL buffer (std::vector::data())
+	LFK_REQUIRE(c, raw != nullptr, LFK_E_INVALID, "NULL fluid-cell buffer");
 	LFK_TRY(reserve_staging(c, (size_t)nf * 8));
 	LFK_TRY(lfks_fluid_cells(c, (uint64_t*)c->staging));
 	LFK_CUDA(c, cudaMemcpyAsync(raw, c->staging, (size_t)nf * 8, cudaMemcpyDeviceToHost, c->stream));
@@ -582,12 +583,13 @@ extern "C" int lfk_download_rhs(lfk_ctx *c, double dt, double *b, uint8_t *flags
 }
 
 extern "C" int lfk_download_pressure(lfk_ctx *c, double *p, uint64_t capacity) {
-	if (!c || !p) { return LFK_E_INVALID; }
+	if (!c) { return LFK_E_INVALID; }
 	LFK_REQUIRE(c, c->pressure_valid, LFK_E_STATE, "no pressure available (call lfk_pressure_solve)");
 	uint64_t nf = 0;
 	LFK_TRY(fetch_num_fluid(c, &nf));
 	LFK_REQUIRE(c, capacity >= nf, LFK_E_CAPACITY, "pressure buffer too small");
 	if (nf == 0) { return 0; }
+	LFK_REQUIRE(c, p != nullptr, LFK_E_INVALID, "NULL pressure buffer");
 	LFK_TRY(reserve_staging(c, (size_t)nf * 8));
 	LFK_TRY(lfks_compact(c, c->p, (double*)c->staging, nullptr, nullptr));
 	LFK_CUDA(c, cudaMemcpyAsync(p, c->staging, (size_t)nf * 8, cudaMemcpyDeviceToHost, c->stream));

@@ -685,7 +685,7 @@ template <bool COLLIDE> __global__ void __launch_bounds__(128) k_correct(GridDes
 #define CT_OWN (CT_TY * CT_TZ)
 #define CT_CAP 5120           // staged particles per tile (80 KB); denser tiles take the global-memory path
 #define CT_THREADS 256
-#define CT_LIST 24
+#define CT_LIST 40
 
 __device__ __forceinline__ void pair_exact(const MotionParams &M, const double *p, const double *o, double &sx,
 	double &sy, double &sz) {
@@ -844,39 +844,44 @@ template <bool COLLIDE> __global__ void __launch_bounds__(CT_THREADS) k_correct_
 			// cells (rows) farther than the kernel radius re = h / sqrt(2) = 0.7071 h cannot contribute
 			const int klo = (int)(ci[0] - x0) + (fr[0] > 0.7075 ? 1 : 0);
 			const int khi = (int)(ci[0] - x0) + 3 - (fr[0] < 0.2925 ? 1 : 0);
+			// Phase 1: fp32 scan of the staged candidates, four at a time (four independent LDS.128 in flight); the
+			// survivors' particle indices go to a small per-thread list.  Phase 2 evaluates them in fp64, in order.
 			uint32_t cand[CT_LIST];
 			int nc = 0;
+			const float4 *__restrict__ sbase = stage;
+#define CT_TEST(q) do { float dx_ = rx - (q).x, dy_ = ry - (q).y, dz_ = rz - (q).z; \
+	float d2_ = __fmaf_rn(dz_, dz_, __fmaf_rn(dy_, dy_, dx_ * dx_)); \
+	if (d2_ < thr) { cand[nc < CT_LIST ? nc : CT_LIST - 1] = __float_as_uint((q).w); ++nc; } } while (0)
 			for (int dz = -1; dz <= 1; ++dz) {
 				if ((dz < 0 && fr[2] > 0.7075) || (dz > 0 && fr[2] < 0.2925)) { continue; }
 				for (int dy = -1; dy <= 1; ++dy) {
 					if ((dy < 0 && fr[1] > 0.7075) || (dy > 0 && fr[1] < 0.2925)) { continue; }
 					const int r = (oz + 1 + dz) * CT_SY + (oy + 1 + dy);
-					const uint32_t s0 = rowoff[r] + cellbeg[r][klo], s1 = rowoff[r] + cellbeg[r][khi];
-#pragma unroll 4
-					for (uint32_t s = s0; s < s1; ++s) {
-						float4 q = stage[s];
-						float dx = rx - q.x, dyv = ry - q.y, dzv = rz - q.z;
-						float d2 = __fmaf_rn(dzv, dzv, __fmaf_rn(dyv, dyv, dx * dx));
-						if (d2 < thr) {
-							cand[nc++] = __float_as_uint(q.w);
-							if (nc == CT_LIST) { // flush: evaluate exactly, in order
-								for (int k = 0; k < CT_LIST; ++k) {
-									uint32_t j = cand[k];
-									if (j == i) { continue; }
-									double ov[3] = { px[j], py[j], pz[j] };
-									pair_exact(M, p, ov, sx, sy, sz);
-								}
-								nc = 0;
-							}
-						}
+					uint32_t s = rowoff[r] + cellbeg[r][klo];
+					const uint32_t s1 = rowoff[r] + cellbeg[r][khi];
+					for (; s + 4 <= s1; s += 4) {
+						const float4 q0 = sbase[s], q1 = sbase[s + 1], q2 = sbase[s + 2], q3 = sbase[s + 3];
+						CT_TEST(q0);
+						CT_TEST(q1);
+						CT_TEST(q2);
+						CT_TEST(q3);
+					}
+					for (; s < s1; ++s) {
+						const float4 q0 = sbase[s];
+						CT_TEST(q0);
 					}
 				}
 			}
-			for (int k = 0; k < nc; ++k) {
-				uint32_t j = cand[k];
-				if (j == i) { continue; }
-				double ov[3] = { px[j], py[j], pz[j] };
-				pair_exact(M, p, ov, sx, sy, sz);
+#undef CT_TEST
+			if (nc > CT_LIST) { // more neighbours within reach than the list holds (a clump): plain fp64 loop instead
+				spring_global(G, M, px, py, pz, begin, i, p, sx, sy, sz);
+			} else {
+				for (int k = 0; k < nc; ++k) {
+					uint32_t j = cand[k];
+					if (j == i) { continue; }
+					double ov[3] = { px[j], py[j], pz[j] };
+					pair_exact(M, p, ov, sx, sy, sz);
+				}
 			}
 		}
 		double np3[3] = { p[0] + sx * M.corr_factor, p[1] + sy * M.corr_factor, p[2] + sz * M.corr_factor };
