@@ -45,6 +45,7 @@ template <typename T> static void dev_free(T *&p) {
 
 int lfkp_reserve_particles(lfk_ctx *c, uint64_t n) {
 	if (n <= c->cap) { return 0; }
+	if (c->np > 0) { LFK_TRY(lfkp_materialise_vc(c)); } // the permutation buffer is reallocated below
 	uint64_t ncap = std::max<uint64_t>(n, c->cap + c->cap / 4);
 	ncap = (ncap + 1023) / 1024 * 1024;
 	ParticleSoA nP{}, nA{};
@@ -352,6 +353,8 @@ extern "C" int lfk_upload_particles(lfk_ctx *c, const void *aos152, uint64_t n) 
 	PhaseTimer T(c, LFK_PHASE_TRANSFER);
 	LFK_CUDA(c, cudaSetDevice(c->device));
 	c->np = 0;
+	c->v_deferred = false;
+	c->c_deferred = false;
 	LFK_TRY(lfkp_reserve_particles(c, n));
 	if (n > 0) {
 		LFK_TRY(reserve_staging(c, (size_t)n * 152));
@@ -363,6 +366,8 @@ extern "C" int lfk_upload_particles(lfk_ctx *c, const void *aos152, uint64_t n) 
 	c->old_valid = true;
 	c->table_valid = false;
 	c->keys_valid = true;
+	c->v_deferred = false;
+	c->c_deferred = false;
 	return 0;
 }
 
@@ -379,6 +384,7 @@ extern "C" int lfk_download_particles(lfk_ctx *c, void *aos152, uint64_t capacit
 	LFK_REQUIRE(c, capacity >= c->np, LFK_E_CAPACITY, "particle buffer too small");
 	if (c->np == 0) { return 0; }
 	LFK_REQUIRE(c, aos152 != nullptr, LFK_E_INVALID, "NULL particle buffer");
+	LFK_TRY(lfkp_materialise_vc(c));
 	LFK_TRY(reserve_staging(c, (size_t)c->np * 152));
 	LFK_TRY(lfkp_soa_to_aos(c, c->staging, c->np));
 	LFK_CUDA(c, cudaMemcpyAsync(aos152, c->staging, (size_t)c->np * 152, cudaMemcpyDeviceToHost, c->stream));
@@ -534,7 +540,7 @@ extern "C" int lfk_download_fluid_cells(lfk_ctx *c, uint64_t *raw, uint64_t capa
 extern "C" int lfk_hash(lfk_ctx *c) {
 	if (!c) { return LFK_E_INVALID; }
 	NEED_PARAMS(c);
-	return lfkp_hash(c);
+	return lfkp_hash(c, false);
 }
 extern "C" int lfk_advect(lfk_ctx *c, double dt) {
 	if (!c) { return LFK_E_INVALID; }
@@ -664,7 +670,7 @@ extern "C" int lfk_time_step(lfk_ctx *c, double dt) {
 	if (!c) { return LFK_E_INVALID; }
 	NEED_PARAMS(c);
 	LFK_TRY(lfkp_advect_collide(c, dt));            // :50-60
-	LFK_TRY(lfkp_hash(c));                          // :62-64
+	LFK_TRY(lfkp_hash(c, true));                    // :62-64 (lean: v / c are read through the permutation)
 	LFK_TRY(lfkg_p2g(c, dt, true));                 // :66-78 (gravity fused)
 	LFK_TRY(lfks_solve(c, dt, nullptr, nullptr));   // :83-99
 	LFK_TRY(lfks_apply_pressure(c, dt));            // :104

@@ -77,6 +77,8 @@ struct lfk_ctx {
 	bool old_valid = false;   // false: old_position == position (not materialised)
 	bool table_valid = false;
 	bool keys_valid = false;
+	// lean sort: velocity / c rows are still in the order before the last sort; perm[i] = their index for particle i
+	bool v_deferred = false, c_deferred = false;
 
 	// grid (local cells incl. ghosts)
 	double *vel[3] = { nullptr, nullptr, nullptr };
@@ -97,6 +99,7 @@ struct lfk_ctx {
 	uint32_t *ordinal = nullptr;    // exclusive scan of (cnt > 0) over local cells, ncl + 1 entries
 	bool ordinal_valid = false;
 	std::vector<MgLevel> mg;
+	uint16_t *mg_mask = nullptr;   // level-0 coupling mask (mg.cu)
 	std::vector<int> mg_z0;        // global z of the first owned layer, per level (red-black parity)
 	bool mg_valid = false;
 
@@ -159,7 +162,9 @@ struct PhaseTimer { // accumulates device time of a phase into stats.phase_ms wh
 int lfkp_aos_to_soa(lfk_ctx *c, const void *d_aos, uint64_t n);
 int lfkp_soa_to_aos(lfk_ctx *c, void *d_aos, uint64_t n);
 int lfkp_positions_to_aos(lfk_ctx *c, double *d_xyz, uint64_t n);
-int lfkp_hash(lfk_ctx *c);
+int lfkp_hash(lfk_ctx *c, bool lean);
+int lfkp_materialise_vc(lfk_ctx *c);
+int lfkp_permute_c(lfk_ctx *c);
 int lfkp_advect(lfk_ctx *c, double dt);
 int lfkp_collide(lfk_ctx *c);
 int lfkp_advect_collide(lfk_ctx *c, double dt);       // fused, no old_position traffic
@@ -271,6 +276,27 @@ __device__ __forceinline__ double block_max(double v) {
 		v = warp_max(v);
 	}
 	return v;
+}
+
+// ---- iteration over the owned cells without 64-bit div/mod: a warp takes one x-row at a time (lanes <-> 32
+// consecutive cells: coalesced), rows are dealt round-robin to the warps of the grid.  f(x, y, lz, c) with c the
+// local raw index.  Works for any 1-D block whose size is a multiple of 32 and any grid size.
+template <typename F> __device__ __forceinline__ void for_own_cells(const GridDesc &G, F f) {
+	const int wpb = (int)(blockDim.x >> 5), rows = G.ny * G.nzl;
+	for (int row = (int)blockIdx.x * wpb + (int)(threadIdx.x >> 5); row < rows; row += (int)gridDim.x * wpb) {
+		const int y = row % G.ny, lz = row / G.ny + 1;
+		const long long base = (long long)G.nx * (y + (long long)G.ny * lz);
+		for (int x = (int)(threadIdx.x & 31); x < G.nx; x += 32) {
+			f(x, y, lz, base + x);
+		}
+	}
+}
+// grid size for a for_own_cells kernel with `threads` threads per block that should run as ONE wave
+static inline unsigned lfk_row_blocks(const GridDesc &G, int threads, unsigned cap) {
+	long long rows = (long long)G.ny * G.nzl, wpb = threads / 32;
+	long long nb = (rows + wpb - 1) / wpb;
+	if (nb < 1) { nb = 1; }
+	return (unsigned)(nb > cap ? cap : nb);
 }
 
 // ---- pressure-system flag byte (one per cell): bits 0-2 non-solid neighbour count (the diagonal), bit 3 "is an

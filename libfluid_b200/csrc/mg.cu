@@ -14,17 +14,36 @@
 //   * the whole cycle runs in fp32 (the preconditioner only shapes the search directions; CG itself stays fp64),
 //     which halves its memory traffic.
 //
-// Level 0 reads the solver's flag byte (1 B/cell) instead of coefficient arrays.
+// Pass fusion (every pass over level 0 costs ~13 B/cell of HBM traffic, so passes are what is minimised):
+//   * the first red half-sweep from the zero initial guess is produced by the PCG kernel that writes r (MgPreload);
+//   * the prolongation is folded into the first post-smoothing half-sweep: a Gauss-Seidel update overwrites its
+//     cell without reading it, so `x += omega P e` only matters for the RED neighbours that the first (black)
+//     post-sweep reads -- it adds omega * e_coarse to them on the fly -- and the red cells themselves are
+//     overwritten by the red sweep that follows.  No prolongation pass exists;
+//   * the last (red) half-sweep also converts the result to fp64 z, and accumulates z.r (k_mg_final_l0).
+//
+// Level 0 reads a 2-byte-per-cell coupling mask (built from the solver's flag byte once per solve) instead of
+// coefficient arrays.
 #include "lfk_internal.cuh"
 
 #include <algorithm>
-
 
 #define MG_OMEGA 1.8f
 #define MG_PRE 2
 #define MG_POST 2
 #define MG_COARSE_SWEEPS 8
 #define MG_COARSE_MAX_CELLS 4096 // a level this small is smoothed to convergence by one block
+
+// level-0 coupling mask: bits 0-2 diagonal (non-solid neighbour count), bit 3 "is an unknown", bits 4-9 "the
+// -x, +x, -y, +y, -z, +z neighbour is an unknown coupled to this cell"
+#define MF_N(m) ((m) & 7u)
+#define MF_L 8u
+#define MF_XM 16u
+#define MF_XP 32u
+#define MF_YM 64u
+#define MF_YP 128u
+#define MF_ZM 256u
+#define MF_ZP 512u
 
 struct LevelDev { // by-value kernel argument
 	int nx, ny, nzl;   // owned size
@@ -42,40 +61,152 @@ static LevelDev level_dev(const MgLevel &L, int z0) {
 	return d;
 }
 
-// ---- level-0 operator from the flag byte ----------------------------------------------------------------------
-__device__ __forceinline__ float l0_offdiag_sum(const GridDesc &G, unsigned f, const float *__restrict__ X,
-	long long c, int x, int y) {
-	float s = 0.f;
-	if (f & FL_SELF) {
-		if (x > 0) { s += X[c - 1]; }
-		if (y > 0) { s += X[c - G.nx]; }
-		s += X[c - G.sxy];
+// warp-per-row iteration over the owned cells of a level (no 64-bit div/mod); lanes <-> consecutive x
+template <typename F> __device__ __forceinline__ void for_rows(int nx, int ny, int nzl, F f) {
+	const int wpb = (int)(blockDim.x >> 5), rows = ny * nzl;
+	for (int row = (int)blockIdx.x * wpb + (int)(threadIdx.x >> 5); row < rows; row += (int)gridDim.x * wpb) {
+		const int y = row % ny, lz = row / ny + 1;
+		const long long base = (long long)nx * (y + (long long)ny * lz);
+		for (int x = (int)(threadIdx.x & 31); x < nx; x += 32) {
+			f(x, y, lz, base + x);
+		}
 	}
-	if (f & FL_XP) { s += X[c + 1]; }
-	if (f & FL_YP) { s += X[c + G.nx]; }
-	if (f & FL_ZP) { s += X[c + G.sxy]; }
+}
+// same, but only the cells of one colour: lane <-> every second cell of the row
+template <typename F> __device__ __forceinline__ void for_rows_colour(int nx, int ny, int nzl, int zpar, int colour, F f) {
+	const int wpb = (int)(blockDim.x >> 5), rows = ny * nzl;
+	for (int row = (int)blockIdx.x * wpb + (int)(threadIdx.x >> 5); row < rows; row += (int)gridDim.x * wpb) {
+		const int y = row % ny, lz = row / ny + 1;
+		const long long base = (long long)nx * (y + (long long)ny * lz);
+		for (int x = 2 * (int)(threadIdx.x & 31) + ((y + (lz - 1 + zpar) + colour) & 1); x < nx; x += 64) {
+			f(x, y, lz, base + x);
+		}
+	}
+}
+static inline unsigned row_blocks(int ny, int nzl, int threads, unsigned cap) {
+	long long rows = (long long)ny * nzl, wpb = threads / 32;
+	long long nb = (rows + wpb - 1) / wpb;
+	if (nb < 1) { nb = 1; }
+	return (unsigned)(nb > cap ? cap : nb);
+}
+
+// ---- level 0 ------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_mg_mask_l0(GridDesc G, const uint8_t *__restrict__ flags,
+	uint16_t *__restrict__ mask) {
+	for_own_cells(G, [&](int x, int y, int, long long c) {
+		unsigned f = flags[c], m = 0;
+		if (f & FL_L) {
+			m = FL_N(f) | MF_L;
+			if (f & FL_SELF) { // coupled to the -neighbours that are unknowns (their "+ neighbour is fluid" == this cell)
+				if (x > 0 && (flags[c - 1] & FL_L)) { m |= MF_XM; }
+				if (y > 0 && (flags[c - G.nx] & FL_L)) { m |= MF_YM; }
+				if (flags[c - G.sxy] & FL_L) { m |= MF_ZM; }
+			}
+			if ((f & FL_XP) && (flags[c + 1] & FL_L)) { m |= MF_XP; }
+			if ((f & FL_YP) && (flags[c + G.nx] & FL_L)) { m |= MF_YP; }
+			if ((f & FL_ZP) && (flags[c + G.sxy] & FL_L)) { m |= MF_ZP; }
+		}
+		mask[c] = (uint16_t)m;
+	});
+}
+
+// All six neighbour loads are issued unconditionally (the arrays carry a ghost layer in z and rows are contiguous,
+// so every address is inside the allocation) and masked afterwards: one memory round trip per cell instead of
+// "mask, then the neighbours the mask selects".
+__device__ __forceinline__ float l0_offdiag_sum(const GridDesc &G, unsigned m, const float *__restrict__ X, long long c) {
+	const float xm = X[c - 1], xp = X[c + 1], ym = X[c - G.nx], yp = X[c + G.nx], zm = X[c - G.sxy], zp = X[c + G.sxy];
+	float s = 0.f;
+	s += (m & MF_XM) ? xm : 0.f;
+	s += (m & MF_XP) ? xp : 0.f;
+	s += (m & MF_YM) ? ym : 0.f;
+	s += (m & MF_YP) ? yp : 0.f;
+	s += (m & MF_ZM) ? zm : 0.f;
+	s += (m & MF_ZP) ? zp : 0.f;
 	return s;
 }
 
-// one colour of red-black Gauss-Seidel on level 0; each thread owns one cell of that colour (x = 2i + parity)
-__global__ void __launch_bounds__(256) k_mg_rbgs_l0(GridDesc G, const uint8_t *__restrict__ flags,
-	const float *__restrict__ b, float *__restrict__ X, int colour, const PcgScalars *scal) {
+// omega * (sum over the coupled neighbours of the coarse correction of THEIR aggregate)
+__device__ __forceinline__ float l0_prolong_sum(unsigned m, const LevelDev &C, int x, int y, int lz) {
+	const int X_ = x >> 1, Y_ = y >> 1, LZ = ((lz - 1) >> 1) + 1;
+	const long long cc = X_ + (long long)C.nx * (Y_ + (long long)C.ny * LZ);
+	// the neighbour across the aggregate boundary belongs to the adjacent aggregate, the other one to this one
+	const float e = C.x[cc];
+	const float ex = C.x[cc + ((x & 1) ? 1 : -1)], ey = C.x[cc + ((y & 1) ? C.nx : -C.nx)];
+	const float ez = C.x[cc + (((lz - 1) & 1) ? C.sxy : -C.sxy)];
+	float s = 0.f;
+	s += (m & MF_XM) ? ((x & 1) ? e : ex) : 0.f;
+	s += (m & MF_XP) ? ((x & 1) ? ex : e) : 0.f;
+	s += (m & MF_YM) ? ((y & 1) ? e : ey) : 0.f;
+	s += (m & MF_YP) ? ((y & 1) ? ey : e) : 0.f;
+	s += (m & MF_ZM) ? (((lz - 1) & 1) ? e : ez) : 0.f;
+	s += (m & MF_ZP) ? (((lz - 1) & 1) ? ez : e) : 0.f;
+	return MG_OMEGA * s;
+}
+
+// one colour of red-black Gauss-Seidel on level 0.  PROLONG: the neighbours carry a pending coarse correction.
+template <bool PROLONG> __global__ void __launch_bounds__(256) k_mg_rbgs_l0(GridDesc G,
+	const uint16_t *__restrict__ mask, const float *__restrict__ b, float *__restrict__ X, int colour, LevelDev C,
+	const PcgScalars *scal) {
 	if (scal->done) { return; }
-	int hx = (G.nx + 1) >> 1;
-	long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-	long long total = (long long)hx * G.ny * G.nzl;
-	if (t >= total) { return; }
-	int xi = (int)(t % hx);
-	long long rest = t / hx;
-	int y = (int)(rest % G.ny);
-	int lz = (int)(rest / G.ny) + 1;
-	int x = 2 * xi + ((y + (lz - 1 + G.z0) + colour) & 1);
-	if (x >= G.nx) { return; }
-	long long c = x + (long long)G.nx * (y + (long long)G.ny * lz);
-	unsigned f = flags[c];
-	if (!(f & FL_L) || FL_N(f) == 0) { return; }
-	float s = b[c] + l0_offdiag_sum(G, f, X, c, x, y);
-	X[c] = s / (float)FL_N(f);
+	for_rows_colour(G.nx, G.ny, G.nzl, G.z0, colour, [&](int x, int y, int lz, long long c) {
+		const unsigned m = mask[c];
+		float s = b[c] + l0_offdiag_sum(G, m, X, c);
+		if (PROLONG) { s += l0_prolong_sum(m, C, x, y, lz); }
+		if ((m & MF_L) && MF_N(m) > 0) { X[c] = s / (float)MF_N(m); }
+	});
+}
+
+// last half-sweep of the cycle (colour `colour`) fused with z = x0 / a_scale (fp64), sigma_new = z.r and its finaliser
+__global__ void __launch_bounds__(RED_THREADS) k_mg_final_l0(GridDesc G, const uint16_t *__restrict__ mask,
+	const float *__restrict__ b, const float *__restrict__ X, int colour, const double *__restrict__ r,
+	double *__restrict__ z, double inv_a_scale, PcgScalars *scal, double *partials, unsigned *ticket, int finalize,
+	int first) {
+	if (scal->done) { return; }
+	double acc = 0.0;
+	for_own_cells(G, [&](int x, int y, int lz, long long c) {
+		const unsigned m = mask[c];
+		const float xc = X[c], bv = b[c];
+		const double rv = r[c];
+		const float upd = (bv + l0_offdiag_sum(G, m, X, c)) / (float)(MF_N(m) > 0 ? MF_N(m) : 1u);
+		double zv = 0.0;
+		if (m & MF_L) {
+			const bool mine = (((x + y + (lz - 1 + G.z0)) & 1) == colour) && MF_N(m) > 0;
+			zv = (double)(mine ? upd : xc) * inv_a_scale;
+			acc += zv * rv;
+		}
+		z[c] = zv;
+	});
+	acc = block_sum(acc);
+	if (threadIdx.x == 0) { partials[blockIdx.x] = acc; }
+	if (lfk_last_block(ticket)) {
+		double tot = finish_partials(partials, gridDim.x, 0);
+		if (threadIdx.x == 0) {
+			scal->sigma_new = tot;
+			if (finalize) { pcg_finalize(scal, first ? FIN_BETA_FIRST : FIN_BETA, 0.0); }
+		}
+	}
+}
+
+// coarse b = P^T (b - A x) of level 0, coarse x = 0.  One thread per coarse cell.
+__global__ void __launch_bounds__(128) k_mg_restrict_l0(GridDesc G, const uint16_t *__restrict__ mask,
+	const float *__restrict__ b, const float *__restrict__ X, LevelDev C, const PcgScalars *scal) {
+	if (scal->done) { return; }
+	for_rows(C.nx, C.ny, C.nzl, [&](int X_, int Y_, int LZ, long long cc) {
+		float acc = 0.f;
+#pragma unroll
+		for (int k = 0; k < 8; ++k) {
+			int x = 2 * X_ + (k & 1), y = 2 * Y_ + ((k >> 1) & 1), lz = 2 * (LZ - 1) + ((k >> 2) & 1) + 1;
+			if (x >= G.nx || y >= G.ny || lz > G.nzl) { continue; }
+			// the pre-smoothing ended with a black half-sweep: black residuals are zero (to rounding), only red ones count
+			if (((x + y + (lz - 1 + G.z0)) & 1) != 0) { continue; }
+			long long c = x + (long long)G.nx * (y + (long long)G.ny * lz);
+			unsigned m = mask[c];
+			float res = b[c] - ((float)MF_N(m) * X[c] - l0_offdiag_sum(G, m, X, c));
+			acc += (m & MF_L) ? res : 0.f;
+		}
+		C.b[cc] = acc;
+		C.x[cc] = 0.f;
+	});
 }
 
 // ---- generic level: coefficient arrays ------------------------------------------------------------------------
@@ -84,23 +215,46 @@ __device__ __forceinline__ float lv_offdiag_sum(const LevelDev &L, const float *
 	return L.cx[c] * X[c + 1] + L.cx[c - 1] * X[c - 1] + L.cy[c] * X[c + L.nx] + L.cy[c - L.nx] * X[c - L.nx] +
 		L.cz[c] * X[c + L.sxy] + L.cz[c - L.sxy] * X[c - L.sxy];
 }
+// sum over the neighbours of coupling * (omega * coarse correction of the neighbour's aggregate)
+__device__ __forceinline__ float lv_prolong_sum(const LevelDev &L, const LevelDev &C, long long c, int x, int y, int lz) {
+	const int X_ = x >> 1, Y_ = y >> 1, LZ = ((lz - 1) >> 1) + 1;
+	const long long cc = X_ + (long long)C.nx * (Y_ + (long long)C.ny * LZ);
+	const float e = C.x[cc];
+	// a zero coupling multiplies a finite value: the coarse arrays carry a ghost shell of zeros around the domain
+	float s = L.cx[c - 1] * ((x & 1) ? e : C.x[cc - 1]) + L.cx[c] * ((x & 1) ? C.x[cc + 1] : e);
+	s += L.cy[c - L.nx] * ((y & 1) ? e : C.x[cc - C.nx]) + L.cy[c] * ((y & 1) ? C.x[cc + C.nx] : e);
+	s += L.cz[c - L.sxy] * (((lz - 1) & 1) ? e : C.x[cc - C.sxy]) + L.cz[c] * (((lz - 1) & 1) ? C.x[cc + C.sxy] : e);
+	return MG_OMEGA * s;
+}
 
-__global__ void __launch_bounds__(256) k_mg_rbgs(LevelDev L, int colour, const PcgScalars *scal) {
+template <bool PROLONG> __global__ void __launch_bounds__(256) k_mg_rbgs(LevelDev L, int colour, LevelDev C,
+	const PcgScalars *scal) {
 	if (scal->done) { return; }
-	int hx = (L.nx + 1) >> 1;
-	long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-	long long total = (long long)hx * L.ny * L.nzl;
-	if (t >= total) { return; }
-	int xi = (int)(t % hx);
-	long long rest = t / hx;
-	int y = (int)(rest % L.ny);
-	int lz = (int)(rest / L.ny) + 1;
-	int x = 2 * xi + ((y + (lz - 1 + L.zpar) + colour) & 1);
-	if (x >= L.nx) { return; }
-	long long c = x + (long long)L.nx * (y + (long long)L.ny * lz);
-	float d = L.diag[c];
-	if (d <= 0.f) { return; }
-	L.x[c] = (L.b[c] + lv_offdiag_sum(L, L.x, c)) / d;
+	for_rows_colour(L.nx, L.ny, L.nzl, L.zpar, colour, [&](int x, int y, int lz, long long c) {
+		float d = L.diag[c];
+		if (d <= 0.f) { return; }
+		float s = L.b[c] + lv_offdiag_sum(L, L.x, c);
+		if (PROLONG) { s += lv_prolong_sum(L, C, c, x, y, lz); }
+		L.x[c] = s / d;
+	});
+}
+
+__global__ void __launch_bounds__(128) k_mg_restrict(LevelDev F, LevelDev C, const PcgScalars *scal) {
+	if (scal->done) { return; }
+	for_rows(C.nx, C.ny, C.nzl, [&](int X_, int Y_, int LZ, long long cc) {
+		float acc = 0.f;
+#pragma unroll
+		for (int k = 0; k < 8; ++k) {
+			int x = 2 * X_ + (k & 1), y = 2 * Y_ + ((k >> 1) & 1), lz = 2 * (LZ - 1) + ((k >> 2) & 1) + 1;
+			if (x >= F.nx || y >= F.ny || lz > F.nzl) { continue; }
+			long long c = x + (long long)F.nx * (y + (long long)F.ny * lz);
+			float d = F.diag[c];
+			if (d <= 0.f) { continue; }
+			acc += F.b[c] - (d * F.x[c] - lv_offdiag_sum(F, F.x, c));
+		}
+		C.b[cc] = acc;
+		C.x[cc] = 0.f;
+	});
 }
 
 // ---- the coarse tail: every level with at most MG_COARSE_MAX_CELLS cells is handled by ONE block in ONE launch
@@ -112,27 +266,26 @@ struct TailLevels {
 	int n;
 };
 
+// block-wide loop over the owned cells of a small level (int arithmetic only)
+template <typename F> __device__ __forceinline__ void tail_cells(const LevelDev &L, F f) {
+	const int n = (int)L.nown;
+	for (int own = (int)threadIdx.x; own < n; own += (int)blockDim.x) {
+		const int x = own % L.nx, rest = own / L.nx;
+		f(x, rest % L.ny, rest / L.ny + 1, (long long)own + L.sxy);
+	}
+}
 __device__ __forceinline__ void tail_half_sweep(const LevelDev &L, int colour) {
-	for (long long own = threadIdx.x; own < L.nown; own += blockDim.x) {
-		int x = (int)(own % L.nx);
-		long long rest = own / L.nx;
-		int y = (int)(rest % L.ny);
-		int lz = (int)(rest / L.ny) + 1;
-		if (((x + y + (lz - 1 + L.zpar) + colour) & 1) != 0) { continue; }
-		long long c = own + L.sxy;
+	tail_cells(L, [&](int x, int y, int lz, long long c) {
+		if (((x + y + (lz - 1 + L.zpar) + colour) & 1) != 0) { return; }
 		float d = L.diag[c];
 		if (d > 0.f) {
 			L.x[c] = (L.b[c] + lv_offdiag_sum(L, L.x, c)) / d;
 		}
-	}
+	});
 	__syncthreads();
 }
 __device__ __forceinline__ void tail_restrict(const LevelDev &F, const LevelDev &C) {
-	for (long long own = threadIdx.x; own < C.nown; own += blockDim.x) {
-		int X_ = (int)(own % C.nx);
-		long long rest = own / C.nx;
-		int Y_ = (int)(rest % C.ny);
-		int LZ = (int)(rest / C.ny) + 1;
+	tail_cells(C, [&](int X_, int Y_, int LZ, long long cc) {
 		float acc = 0.f;
 		for (int k = 0; k < 8; ++k) {
 			int x = 2 * X_ + (k & 1), y = 2 * Y_ + ((k >> 1) & 1), lz = 2 * (LZ - 1) + ((k >> 2) & 1) + 1;
@@ -142,22 +295,17 @@ __device__ __forceinline__ void tail_restrict(const LevelDev &F, const LevelDev 
 			if (d <= 0.f) { continue; }
 			acc += F.b[c] - (d * F.x[c] - lv_offdiag_sum(F, F.x, c));
 		}
-		C.b[own + C.sxy] = acc;
-		C.x[own + C.sxy] = 0.f;
-	}
+		C.b[cc] = acc;
+		C.x[cc] = 0.f;
+	});
 	__syncthreads();
 }
 __device__ __forceinline__ void tail_prolong(const LevelDev &F, const LevelDev &C) {
-	for (long long own = threadIdx.x; own < F.nown; own += blockDim.x) {
-		int x = (int)(own % F.nx);
-		long long rest = own / F.nx;
-		int y = (int)(rest % F.ny);
-		int lz = (int)(rest / F.ny) + 1;
-		long long c = own + F.sxy;
-		if (F.diag[c] <= 0.f) { continue; }
+	tail_cells(F, [&](int x, int y, int lz, long long c) {
+		if (F.diag[c] <= 0.f) { return; }
 		long long cc = (x >> 1) + (long long)C.nx * ((y >> 1) + (long long)C.ny * (((lz - 1) >> 1) + 1));
 		F.x[c] += MG_OMEGA * C.x[cc];
-	}
+	});
 	__syncthreads();
 }
 
@@ -186,144 +334,58 @@ __global__ void __launch_bounds__(1024) k_mg_tail(TailLevels T, const PcgScalars
 	}
 }
 
-// ---- transfer operators -----------------------------------------------------------------------------------------
-// coarse b = P^T (b - A x) of the finer level, coarse x = 0.  One thread per coarse cell.
-__global__ void __launch_bounds__(128) k_mg_restrict_l0(GridDesc G, const uint8_t *__restrict__ flags,
-	const float *__restrict__ b, const float *__restrict__ X, LevelDev C, const PcgScalars *scal) {
-	if (scal->done) { return; }
-	long long own = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-	if (own >= C.nown) { return; }
-	int X_ = (int)(own % C.nx);
-	long long rest = own / C.nx;
-	int Y_ = (int)(rest % C.ny);
-	int LZ = (int)(rest / C.ny) + 1;
-	float acc = 0.f;
-#pragma unroll
-	for (int k = 0; k < 8; ++k) {
-		int x = 2 * X_ + (k & 1), y = 2 * Y_ + ((k >> 1) & 1), lz = 2 * (LZ - 1) + ((k >> 2) & 1) + 1;
-		if (x >= G.nx || y >= G.ny || lz > G.nzl) { continue; }
-		long long c = x + (long long)G.nx * (y + (long long)G.ny * lz);
-		unsigned f = flags[c];
-		if (!(f & FL_L)) { continue; }
-		acc += b[c] - ((float)FL_N(f) * X[c] - l0_offdiag_sum(G, f, X, c, x, y));
-	}
-	long long cc = own + C.sxy;
-	C.b[cc] = acc;
-	C.x[cc] = 0.f;
-}
-__global__ void __launch_bounds__(128) k_mg_restrict(LevelDev F, LevelDev C, const PcgScalars *scal) {
-	if (scal->done) { return; }
-	long long own = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-	if (own >= C.nown) { return; }
-	int X_ = (int)(own % C.nx);
-	long long rest = own / C.nx;
-	int Y_ = (int)(rest % C.ny);
-	int LZ = (int)(rest / C.ny) + 1;
-	float acc = 0.f;
-#pragma unroll
-	for (int k = 0; k < 8; ++k) {
-		int x = 2 * X_ + (k & 1), y = 2 * Y_ + ((k >> 1) & 1), lz = 2 * (LZ - 1) + ((k >> 2) & 1) + 1;
-		if (x >= F.nx || y >= F.ny || lz > F.nzl) { continue; }
-		long long c = x + (long long)F.nx * (y + (long long)F.ny * lz);
-		float d = F.diag[c];
-		if (d <= 0.f) { continue; }
-		acc += F.b[c] - (d * F.x[c] - lv_offdiag_sum(F, F.x, c));
-	}
-	long long cc = own + C.sxy;
-	C.b[cc] = acc;
-	C.x[cc] = 0.f;
-}
-// x_fine += omega * P x_coarse
-__global__ void k_mg_prolong_l0(GridDesc G, const uint8_t *__restrict__ flags, float *__restrict__ X, LevelDev C,
-	const PcgScalars *scal) {
-	if (scal->done) { return; }
-	long long own = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-	if (own >= G.nown) { return; }
-	int x = (int)(own % G.nx);
-	long long rest = own / G.nx;
-	int y = (int)(rest % G.ny);
-	int lz = (int)(rest / G.ny) + 1;
-	long long c = own + G.sxy;
-	if (!(flags[c] & FL_L)) { return; }
-	long long cc = (x >> 1) + (long long)C.nx * ((y >> 1) + (long long)C.ny * (((lz - 1) >> 1) + 1));
-	X[c] += MG_OMEGA * C.x[cc];
-}
-__global__ void k_mg_prolong(LevelDev F, LevelDev C, const PcgScalars *scal) {
-	if (scal->done) { return; }
-	long long own = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-	if (own >= F.nown) { return; }
-	int x = (int)(own % F.nx);
-	long long rest = own / F.nx;
-	int y = (int)(rest % F.ny);
-	int lz = (int)(rest / F.ny) + 1;
-	long long c = own + F.sxy;
-	if (F.diag[c] <= 0.f) { return; }
-	long long cc = (x >> 1) + (long long)C.nx * ((y >> 1) + (long long)C.ny * (((lz - 1) >> 1) + 1));
-	F.x[c] += MG_OMEGA * C.x[cc];
-}
-
 // ---- Galerkin coarse operators ----------------------------------------------------------------------------------
 struct LevelOut {
 	float *diag, *cx, *cy, *cz;
 };
-__global__ void __launch_bounds__(128) k_mg_build_l1(GridDesc G, const uint8_t *__restrict__ flags, LevelDev C,
+__global__ void __launch_bounds__(128) k_mg_build_l1(GridDesc G, const uint16_t *__restrict__ mask, LevelDev C,
 	LevelOut O) {
-	long long own = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-	if (own >= C.nown) { return; }
-	int X_ = (int)(own % C.nx);
-	long long rest = own / C.nx;
-	int Y_ = (int)(rest % C.ny);
-	int LZ = (int)(rest / C.ny) + 1;
-	float diag = 0.f, cxp = 0.f, cyp = 0.f, czp = 0.f;
+	for_rows(C.nx, C.ny, C.nzl, [&](int X_, int Y_, int LZ, long long cc) {
+		float diag = 0.f, cxp = 0.f, cyp = 0.f, czp = 0.f;
 #pragma unroll
-	for (int k = 0; k < 8; ++k) {
-		int dx = k & 1, dy = (k >> 1) & 1, dz = (k >> 2) & 1;
-		int x = 2 * X_ + dx, y = 2 * Y_ + dy, lz = 2 * (LZ - 1) + dz + 1;
-		if (x >= G.nx || y >= G.ny || lz > G.nzl) { continue; }
-		long long c = x + (long long)G.nx * (y + (long long)G.ny * lz);
-		unsigned f = flags[c];
-		if (!(f & FL_L)) { continue; }
-		diag += (float)FL_N(f);
-		// coupling(c, c + e) exists iff both are unknowns and the + neighbour's type is fluid
-		if ((f & FL_XP) && (flags[c + 1] & FL_L)) { if (dx == 0) { diag -= 2.f; } else { cxp += 1.f; } }
-		if ((f & FL_YP) && (flags[c + G.nx] & FL_L)) { if (dy == 0) { diag -= 2.f; } else { cyp += 1.f; } }
-		if ((f & FL_ZP) && (flags[c + G.sxy] & FL_L)) {
-			if (dz == 0 && lz + 1 <= G.nzl) { diag -= 2.f; } else { czp += 1.f; }
+		for (int k = 0; k < 8; ++k) {
+			int dx = k & 1, dy = (k >> 1) & 1, dz = (k >> 2) & 1;
+			int x = 2 * X_ + dx, y = 2 * Y_ + dy, lz = 2 * (LZ - 1) + dz + 1;
+			if (x >= G.nx || y >= G.ny || lz > G.nzl) { continue; }
+			long long c = x + (long long)G.nx * (y + (long long)G.ny * lz);
+			unsigned m = mask[c];
+			if (!(m & MF_L)) { continue; }
+			diag += (float)MF_N(m);
+			// a coupling inside the aggregate folds into the diagonal (-1 from each side), one across it stays a coupling
+			if (m & MF_XP) { if (dx == 0) { diag -= 2.f; } else { cxp += 1.f; } }
+			if (m & MF_YP) { if (dy == 0) { diag -= 2.f; } else { cyp += 1.f; } }
+			if (m & MF_ZP) {
+				if (dz == 0 && lz + 1 <= G.nzl) { diag -= 2.f; } else { czp += 1.f; }
+			}
 		}
-	}
-	long long cc = own + C.sxy;
-	O.diag[cc] = diag;
-	O.cx[cc] = cxp;
-	O.cy[cc] = cyp;
-	O.cz[cc] = czp;
+		O.diag[cc] = diag;
+		O.cx[cc] = cxp;
+		O.cy[cc] = cyp;
+		O.cz[cc] = czp;
+	});
 }
 __global__ void __launch_bounds__(128) k_mg_build(LevelDev F, LevelDev C, LevelOut O) {
-	long long own = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-	if (own >= C.nown) { return; }
-	int X_ = (int)(own % C.nx);
-	long long rest = own / C.nx;
-	int Y_ = (int)(rest % C.ny);
-	int LZ = (int)(rest / C.ny) + 1;
-	float diag = 0.f, cxp = 0.f, cyp = 0.f, czp = 0.f;
+	for_rows(C.nx, C.ny, C.nzl, [&](int X_, int Y_, int LZ, long long cc) {
+		float diag = 0.f, cxp = 0.f, cyp = 0.f, czp = 0.f;
 #pragma unroll
-	for (int k = 0; k < 8; ++k) {
-		int dx = k & 1, dy = (k >> 1) & 1, dz = (k >> 2) & 1;
-		int x = 2 * X_ + dx, y = 2 * Y_ + dy, lz = 2 * (LZ - 1) + dz + 1;
-		if (x >= F.nx || y >= F.ny || lz > F.nzl) { continue; }
-		long long c = x + (long long)F.nx * (y + (long long)F.ny * lz);
-		float d = F.diag[c];
-		if (d <= 0.f) { continue; }
-		diag += d;
-		float a = F.cx[c], bq = F.cy[c], cq = F.cz[c];
-		if (dx == 0) { diag -= 2.f * a; } else { cxp += a; }
-		if (dy == 0) { diag -= 2.f * bq; } else { cyp += bq; }
-		if (dz == 0 && lz + 1 <= F.nzl) { diag -= 2.f * cq; } else { czp += cq; }
-	}
-	long long cc = own + C.sxy;
-	O.diag[cc] = diag;
-	O.cx[cc] = cxp;
-	O.cy[cc] = cyp;
-	O.cz[cc] = czp;
+		for (int k = 0; k < 8; ++k) {
+			int dx = k & 1, dy = (k >> 1) & 1, dz = (k >> 2) & 1;
+			int x = 2 * X_ + dx, y = 2 * Y_ + dy, lz = 2 * (LZ - 1) + dz + 1;
+			if (x >= F.nx || y >= F.ny || lz > F.nzl) { continue; }
+			long long c = x + (long long)F.nx * (y + (long long)F.ny * lz);
+			float d = F.diag[c];
+			if (d <= 0.f) { continue; }
+			diag += d;
+			float a = F.cx[c], bq = F.cy[c], cq = F.cz[c];
+			if (dx == 0) { diag -= 2.f * a; } else { cxp += a; }
+			if (dy == 0) { diag -= 2.f * bq; } else { cyp += bq; }
+			if (dz == 0 && lz + 1 <= F.nzl) { diag -= 2.f * cq; } else { czp += cq; }
+		}
+		O.diag[cc] = diag;
+		O.cx[cc] = cxp;
+		O.cy[cc] = cyp;
+		O.cz[cc] = czp;
+	});
 }
 
 // ---- host side ---------------------------------------------------------------------------------------------------
@@ -331,6 +393,8 @@ static int mg_alloc(lfk_ctx *c) {
 	if (!c->mg.empty()) { return 0; }
 	const GridDesc &G = c->g;
 	int nx = G.nx, ny = G.ny, nzl = G.nzl, z0 = G.z0, nz = G.nz;
+	LFK_CUDA(c, cudaMalloc((void**)&c->mg_mask, ((size_t)G.ncl + 2) * sizeof(uint16_t)));
+	LFK_CUDA(c, cudaMemsetAsync(c->mg_mask, 0, ((size_t)G.ncl + 2) * sizeof(uint16_t), c->stream));
 	for (int l = 0; l < 16; ++l) {
 		MgLevel L{};
 		L.nx = nx; L.ny = ny; L.nzl = nzl; L.nlz = nzl + 2;
@@ -360,6 +424,7 @@ int lfkm_free(lfk_ctx *c) {
 			if (p) { cudaFree(p); }
 		}
 	}
+	if (c->mg_mask) { cudaFree(c->mg_mask); c->mg_mask = nullptr; }
 	c->mg.clear();
 	c->mg_z0.clear();
 	return 0;
@@ -369,13 +434,15 @@ int lfkm_setup(lfk_ctx *c, double a_scale) {
 	(void)a_scale;
 	LFK_TRY(mg_alloc(c));
 	const GridDesc &G = c->g;
+	// the flag byte's ghost layers are valid here (lfks_build_system exchanged them)
+	LFK_LAUNCH(c, k_mg_mask_l0, lfk_row_blocks(G, 256, 1u << 20), 256, 0, G, c->flags, c->mg_mask);
 	for (size_t l = 1; l < c->mg.size(); ++l) {
 		MgLevel &C = c->mg[l];
 		LevelDev Cd = level_dev(C, c->mg_z0[l]);
 		LevelOut O{ C.diag, C.cx, C.cy, C.cz };
-		unsigned nb = lfk_blocks(Cd.nown, 128);
+		unsigned nb = row_blocks(Cd.ny, Cd.nzl, 128, 1u << 20);
 		if (l == 1) {
-			LFK_LAUNCH(c, k_mg_build_l1, nb, 128, 0, G, c->flags, Cd, O);
+			LFK_LAUNCH(c, k_mg_build_l1, nb, 128, 0, G, c->mg_mask, Cd, O);
 		} else {
 			LFK_LAUNCH(c, k_mg_build, nb, 128, 0, level_dev(c->mg[l - 1], c->mg_z0[l - 1]), Cd, O);
 		}
@@ -388,27 +455,35 @@ int lfkm_setup(lfk_ctx *c, double a_scale) {
 	return 0;
 }
 
-static int smooth(lfk_ctx *c, size_t l, int first_colour, int sweeps, bool skip_first = false) {
+// one half-sweep of colour `colour` on level l; `prolong`: the neighbours carry the pending correction of level l + 1
+static int half_sweep(lfk_ctx *c, size_t l, int colour, bool prolong) {
 	const GridDesc &G = c->g;
 	MgLevel &L = c->mg[l];
 	LevelDev Ld = level_dev(L, c->mg_z0[l]);
-	long long half = (long long)((L.nx + 1) / 2) * L.ny * L.nzl;
-	unsigned nb = lfk_blocks(half, 256);
-	for (int s = 0; s < sweeps; ++s) {
-		for (int h = 0; h < 2; ++h) {
-			int colour = first_colour ^ h;
-			if (skip_first && s == 0 && h == 0) { continue; } // already done by the kernel that produced b0 / x0
-			if (c->nranks > 1) { LFK_TRY(lfkx_halo_f32(c, L.x, L.nx, L.ny, L.nzl)); }
-			if (l == 0) {
-				LFK_LAUNCH(c, k_mg_rbgs_l0, nb, 256, 0, G, c->flags, L.b, L.x, colour, c->d_scal);
-			} else {
-				LFK_LAUNCH(c, k_mg_rbgs, nb, 256, 0, Ld, colour, c->d_scal);
-			}
+	LevelDev Cd = prolong ? level_dev(c->mg[l + 1], c->mg_z0[l + 1]) : Ld;
+	unsigned nb = row_blocks(L.ny, L.nzl, 256, 1u << 20);
+	if (c->nranks > 1) {
+		LFK_TRY(lfkx_halo_f32(c, L.x, L.nx, L.ny, L.nzl));
+		if (prolong) { LFK_TRY(lfkx_halo_f32(c, c->mg[l + 1].x, Cd.nx, Cd.ny, Cd.nzl)); }
+	}
+	if (l == 0) {
+		if (prolong) {
+			LFK_LAUNCH(c, k_mg_rbgs_l0<true>, nb, 256, 0, G, c->mg_mask, L.b, L.x, colour, Cd, c->d_scal);
+		} else {
+			LFK_LAUNCH(c, k_mg_rbgs_l0<false>, nb, 256, 0, G, c->mg_mask, L.b, L.x, colour, Cd, c->d_scal);
+		}
+	} else {
+		if (prolong) {
+			LFK_LAUNCH(c, k_mg_rbgs<true>, nb, 256, 0, Ld, colour, Cd, c->d_scal);
+		} else {
+			LFK_LAUNCH(c, k_mg_rbgs<false>, nb, 256, 0, Ld, colour, Cd, c->d_scal);
 		}
 	}
 	return 0;
 }
 
+// V-cycle on levels >= l.  At level 0 the first red half-sweep was pre-applied by the kernel that produced b0 / x0,
+// and the very last (red) half-sweep is left to k_mg_final_l0.
 static int vcycle(lfk_ctx *c, size_t l) {
 	const GridDesc &G = c->g;
 	size_t last = c->mg.size() - 1;
@@ -424,26 +499,34 @@ static int vcycle(lfk_ctx *c, size_t l) {
 		return 0;
 	}
 	if (l == last) { // coarsest level reached outside the tail (multi-GPU alignment limit, or a tiny fine grid)
-		LFK_TRY(smooth(c, l, 0, MG_COARSE_SWEEPS));
-		LFK_TRY(smooth(c, l, 1, MG_COARSE_SWEEPS));
+		for (int s = 0; s < MG_COARSE_SWEEPS; ++s) {
+			if (!(l == 0 && s == 0)) { LFK_TRY(half_sweep(c, l, 0, false)); }
+			LFK_TRY(half_sweep(c, l, 1, false));
+		}
+		for (int s = 0; s < MG_COARSE_SWEEPS; ++s) {
+			LFK_TRY(half_sweep(c, l, 1, false));
+			if (!(l == 0 && s == MG_COARSE_SWEEPS - 1)) { LFK_TRY(half_sweep(c, l, 0, false)); }
+		}
 		return 0;
 	}
-	LFK_TRY(smooth(c, l, 0, MG_PRE, l == 0)); // red, black (level 0: the first red half-sweep is pre-applied)
+	for (int s = 0; s < MG_PRE; ++s) { // red, black
+		if (!(l == 0 && s == 0)) { LFK_TRY(half_sweep(c, l, 0, false)); }
+		LFK_TRY(half_sweep(c, l, 1, false));
+	}
 	MgLevel &C = c->mg[l + 1];
 	LevelDev Cd = level_dev(C, c->mg_z0[l + 1]);
 	if (c->nranks > 1) { LFK_TRY(lfkx_halo_f32(c, L.x, L.nx, L.ny, L.nzl)); }
+	unsigned rb = row_blocks(Cd.ny, Cd.nzl, 128, 1u << 20);
 	if (l == 0) {
-		LFK_LAUNCH(c, k_mg_restrict_l0, lfk_blocks(Cd.nown, 128), 128, 0, G, c->flags, L.b, L.x, Cd, c->d_scal);
+		LFK_LAUNCH(c, k_mg_restrict_l0, rb, 128, 0, G, c->mg_mask, L.b, L.x, Cd, c->d_scal);
 	} else {
-		LFK_LAUNCH(c, k_mg_restrict, lfk_blocks(Cd.nown, 128), 128, 0, Ld, Cd, c->d_scal);
+		LFK_LAUNCH(c, k_mg_restrict, rb, 128, 0, Ld, Cd, c->d_scal);
 	}
 	LFK_TRY(vcycle(c, l + 1));
-	if (l == 0) {
-		LFK_LAUNCH(c, k_mg_prolong_l0, lfk_blocks(G.nown, 256), 256, 0, G, c->flags, L.x, Cd, c->d_scal);
-	} else {
-		LFK_LAUNCH(c, k_mg_prolong, lfk_blocks(Ld.nown, 256), 256, 0, Ld, Cd, c->d_scal);
+	for (int s = 0; s < MG_POST; ++s) { // black (the first one applies the prolongation on the fly), red
+		LFK_TRY(half_sweep(c, l, 1, s == 0));
+		if (!(l == 0 && s == MG_POST - 1)) { LFK_TRY(half_sweep(c, l, 0, false)); }
 	}
-	LFK_TRY(smooth(c, l, 1, MG_POST)); // black, red
 	return 0;
 }
 
@@ -455,36 +538,13 @@ int lfkm_level0(lfk_ctx *c, float **b0, float **x0) {
 	return 0;
 }
 
-// z = x0 / a_scale (fp64) fused with sigma_new = z.r and its finaliser
-__global__ void __launch_bounds__(RED_THREADS) k_mg_store_dot(GridDesc G, const float *__restrict__ x0,
-	const uint8_t *__restrict__ flags, const double *__restrict__ r, double *__restrict__ z, double inv_a_scale,
-	PcgScalars *scal, double *partials, unsigned *ticket, int finalize, int first) {
-	if (scal->done) { return; }
-	double acc = 0.0;
-	for (long long own = (long long)blockIdx.x * blockDim.x + threadIdx.x; own < G.nown;
-		own += (long long)gridDim.x * blockDim.x) {
-		long long c = own + G.sxy;
-		double zv = (flags[c] & FL_L) ? (double)x0[c] * inv_a_scale : 0.0;
-		z[c] = zv;
-		acc += zv * r[c];
-	}
-	acc = block_sum(acc);
-	if (threadIdx.x == 0) { partials[blockIdx.x] = acc; }
-	if (lfk_last_block(ticket)) {
-		double tot = finish_partials(partials, gridDim.x, 0);
-		if (threadIdx.x == 0) {
-			scal->sigma_new = tot;
-			if (finalize) { pcg_finalize(scal, first ? FIN_BETA_FIRST : FIN_BETA, 0.0); }
-		}
-	}
-}
-
 // z = M^-1 r, sigma_new = z.r.  b0 and the red half of x0 were written by k_pcg_init / k_update_pr.
 int lfkm_apply_preloaded(lfk_ctx *c, double a_scale, unsigned nb, int fin, int first) {
 	const GridDesc &G = c->g;
 	MgLevel &L0 = c->mg[0];
 	LFK_TRY(vcycle(c, 0));
-	LFK_LAUNCH(c, k_mg_store_dot, nb, RED_THREADS, 0, G, L0.x, c->flags, c->r, c->z, 1.0 / a_scale, c->d_scal,
-		c->partials, c->ticket, fin, first);
+	if (c->nranks > 1) { LFK_TRY(lfkx_halo_f32(c, L0.x, L0.nx, L0.ny, L0.nzl)); }
+	LFK_LAUNCH(c, k_mg_final_l0, nb, RED_THREADS, 0, G, c->mg_mask, L0.b, L0.x, 0, c->r, c->z, 1.0 / a_scale,
+		c->d_scal, c->partials, c->ticket, fin, first);
 	return 0;
 }

@@ -145,6 +145,7 @@ int lfkg_p2g(lfk_ctx *c, double gravity_dt, bool add_gravity) {
 		c->pressure_valid = false;
 		return 0;
 	}
+	LFK_TRY(lfkp_materialise_vc(c));
 	P2GParams Q;
 	Q.h = G.h;
 	Q.half = 0.5 * G.h;

@@ -140,7 +140,8 @@ template <int COMP> __device__ __forceinline__ void flush_cell(double *__restric
 
 // one velocity component of one row: stage, accumulate over all slot windows, flush once
 template <int COMP, bool APIC> __device__ __forceinline__ void row_component(double *__restrict__ st,
-	double *__restrict__ acc, const double *const *fields, int lane, uint32_t pb, uint32_t pe, int cnt, int maxcnt,
+	double *__restrict__ acc, const double *const *fields, const uint32_t *__restrict__ permv,
+	const uint32_t *__restrict__ permc, int lane, uint32_t pb, uint32_t pe, int cnt, int maxcnt,
 	const double *cc, const PBParams &Q, int ry, int rz, int nfx) {
 	double accw[18], accv[18];
 #pragma unroll
@@ -160,10 +161,13 @@ template <int COMP, bool APIC> __device__ __forceinline__ void row_component(dou
 				double *dst = st + sc * PB_CSTRIDE + ss;
 #pragma unroll
 				for (int f = 0; f < 3; ++f) { cp_async8(dst + f * PB_FSTRIDE, fields[f] + q); }
-				cp_async8(dst + 3 * PB_FSTRIDE, fields[PF_VX + COMP] + q);
+				// lean sort: velocity / c rows may still be in the pre-sort order (index perm[q])
+				const uint32_t qv = permv ? permv[q] : q;
+				cp_async8(dst + 3 * PB_FSTRIDE, fields[PF_VX + COMP] + qv);
 				if (APIC) {
+					const uint32_t qc = permc ? permc[q] : q;
 #pragma unroll
-					for (int f = 0; f < 3; ++f) { cp_async8(dst + (4 + f) * PB_FSTRIDE, fields[PF_C0 + 3 * COMP + f] + q); }
+					for (int f = 0; f < 3; ++f) { cp_async8(dst + (4 + f) * PB_FSTRIDE, fields[PF_C0 + 3 * COMP + f] + qc); }
 				}
 			}
 		}
@@ -177,7 +181,8 @@ template <int COMP, bool APIC> __device__ __forceinline__ void row_component(dou
 }
 
 template <int COMP, bool APIC> __device__ __forceinline__ void brick_component(const GridDesc &G, const PBParams &Q,
-	double *__restrict__ st, double *__restrict__ acc, const double *const *fields, const uint32_t *__restrict__ begin,
+	double *__restrict__ st, double *__restrict__ acc, const double *const *fields,
+	const uint32_t *__restrict__ permv, const uint32_t *__restrict__ permc, const uint32_t *__restrict__ begin,
 	const double *__restrict__ cxs, const double *__restrict__ cys, const double *__restrict__ czs, int warp, int lane,
 	int x0, int y0, int lz0, int nfx) {
 	const int x = x0 - 1 + lane; // this lane's cell column
@@ -218,14 +223,15 @@ template <int COMP, bool APIC> __device__ __forceinline__ void brick_component(c
 			cc[6] = z > 0 ? czs[z - 1] : zc - G.h;
 			cc[7] = zc;
 			cc[8] = z + 1 < G.nz ? czs[z + 1] : zc + G.h;
-			row_component<COMP, APIC>(st, acc, fields, lane, pb, pe, cnt, maxcnt, cc, Q, ry, rz, nfx);
+			row_component<COMP, APIC>(st, acc, fields, permv, permc, lane, pb, pe, cnt, maxcnt, cc, Q, ry, rz, nfx);
 		}
 		__syncthreads(); // rows of the next colour may touch the faces this colour just updated
 	}
 }
 
 template <int METHOD> __global__ void __launch_bounds__(PB_THREADS, 2) k_p2g_brick(GridDesc G, PBParams Q,
-	ParticleSoA P, const uint32_t *__restrict__ begin, const double *__restrict__ cxs,
+	ParticleSoA P, const uint32_t *__restrict__ permv, const uint32_t *__restrict__ permc,
+	const uint32_t *__restrict__ begin, const double *__restrict__ cxs,
 	const double *__restrict__ cys, const double *__restrict__ czs, double *__restrict__ u, double *__restrict__ v,
 	double *__restrict__ w, double *__restrict__ uo, double *__restrict__ vo, double *__restrict__ wo,
 	uint8_t *__restrict__ typ) {
@@ -248,11 +254,11 @@ template <int METHOD> __global__ void __launch_bounds__(PB_THREADS, 2) k_p2g_bri
 		for (int e = threadIdx.x; e < PB_ACC_COMP; e += PB_THREADS) { acc[e] = 0.0; }
 		__syncthreads();
 		if (comp == 0) {
-			brick_component<0, APIC>(G, Q, st, acc, fields, begin, cxs, cys, czs, warp, lane, x0, y0, lz0, nfx);
+			brick_component<0, APIC>(G, Q, st, acc, fields, permv, permc, begin, cxs, cys, czs, warp, lane, x0, y0, lz0, nfx);
 		} else if (comp == 1) {
-			brick_component<1, APIC>(G, Q, st, acc, fields, begin, cxs, cys, czs, warp, lane, x0, y0, lz0, nfx);
+			brick_component<1, APIC>(G, Q, st, acc, fields, permv, permc, begin, cxs, cys, czs, warp, lane, x0, y0, lz0, nfx);
 		} else {
-			brick_component<2, APIC>(G, Q, st, acc, fields, begin, cxs, cys, czs, warp, lane, x0, y0, lz0, nfx);
+			brick_component<2, APIC>(G, Q, st, acc, fields, permv, permc, begin, cxs, cys, czs, warp, lane, x0, y0, lz0, nfx);
 		}
 		// ---- normalise + boundary faces + FLIP snapshot + gravity, write this component of the brick's faces
 		// (the last colour ended with a __syncthreads) ----
@@ -292,6 +298,7 @@ int lfkg_p2g_brick(lfk_ctx *c, double gravity_dt, bool add_gravity) {
 	}
 	dim3 grid((unsigned)((G.nx + PB_BX - 1) / PB_BX), (unsigned)((G.ny + PB_BY - 1) / PB_BY),
 		(unsigned)((G.nzl + PB_BZ - 1) / PB_BZ));
+	const uint32_t *permv = c->v_deferred ? c->perm : nullptr, *permc = c->c_deferred ? c->perm : nullptr;
 	const size_t smem = (size_t)(PB_ACC_COMP + PB_WARPS * PB_FIELDS * PB_FSTRIDE) * sizeof(double);
 	static bool attr_set = false;
 	if (!attr_set) {
@@ -302,15 +309,15 @@ int lfkg_p2g_brick(lfk_ctx *c, double gravity_dt, bool add_gravity) {
 	}
 	switch (c->prm.method) {
 	case LFK_METHOD_PIC:
-		LFK_LAUNCH(c, k_p2g_brick<LFK_METHOD_PIC>, grid, PB_THREADS, smem, G, Q, c->P, c->begin, c->ctr[0], c->ctr[1],
+		LFK_LAUNCH(c, k_p2g_brick<LFK_METHOD_PIC>, grid, PB_THREADS, smem, G, Q, c->P, permv, permc, c->begin, c->ctr[0], c->ctr[1],
 			c->ctr[2], c->vel[0], c->vel[1], c->vel[2], c->vel_old[0], c->vel_old[1], c->vel_old[2], c->typ);
 		break;
 	case LFK_METHOD_FLIP:
-		LFK_LAUNCH(c, k_p2g_brick<LFK_METHOD_FLIP>, grid, PB_THREADS, smem, G, Q, c->P, c->begin, c->ctr[0], c->ctr[1],
+		LFK_LAUNCH(c, k_p2g_brick<LFK_METHOD_FLIP>, grid, PB_THREADS, smem, G, Q, c->P, permv, permc, c->begin, c->ctr[0], c->ctr[1],
 			c->ctr[2], c->vel[0], c->vel[1], c->vel[2], c->vel_old[0], c->vel_old[1], c->vel_old[2], c->typ);
 		break;
 	default:
-		LFK_LAUNCH(c, k_p2g_brick<LFK_METHOD_APIC>, grid, PB_THREADS, smem, G, Q, c->P, c->begin, c->ctr[0], c->ctr[1],
+		LFK_LAUNCH(c, k_p2g_brick<LFK_METHOD_APIC>, grid, PB_THREADS, smem, G, Q, c->P, permv, permc, c->begin, c->ctr[0], c->ctr[1],
 			c->ctr[2], c->vel[0], c->vel[1], c->vel[2], c->vel_old[0], c->vel_old[1], c->vel_old[2], c->typ);
 		break;
 	}

@@ -302,26 +302,68 @@ __global__ void __launch_bounds__(256) k_sort_big_cells(const uint32_t *__restri
 	}
 }
 
-__global__ void k_gather_particles(ParticleSoA dst, ParticleSoA src, uint32_t *__restrict__ key_dst,
-	const uint32_t *__restrict__ key_src, const uint32_t *__restrict__ perm, unsigned long long n, int nfields) {
+// dst[i] = src[perm[i]] for the field groups selected by `groups` (bit g <-> fields 3g .. 3g + 2: position, velocity,
+// cx, cy, cz, old_position) and, with_key, the cell key
+__global__ void __launch_bounds__(256) k_gather_particles(ParticleSoA dst, ParticleSoA src,
+	uint32_t *__restrict__ key_dst, const uint32_t *__restrict__ key_src, const uint32_t *__restrict__ perm,
+	unsigned long long n, unsigned groups, int with_key) {
 	unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
 	if (i >= n) { return; }
-	uint32_t s = perm[i];
-	key_dst[i] = key_src[s];
-#pragma unroll 5
-	for (int f = 0; f < 15; ++f) {
-		dst.f[f][i] = src.f[f][s];
-	}
-	if (nfields > 15) {
-		for (int f = 15; f < 18; ++f) {
-			dst.f[f][i] = src.f[f][s];
+	const uint32_t s = perm[i];
+	if (with_key) { key_dst[i] = key_src[s]; }
+#pragma unroll
+	for (int g = 0; g < 6; ++g) {
+		if (groups & (1u << g)) {
+			const double a = src.f[3 * g][s], b = src.f[3 * g + 1][s], c = src.f[3 * g + 2][s];
+			dst.f[3 * g][i] = a;
+			dst.f[3 * g + 1][i] = b;
+			dst.f[3 * g + 2][i] = c;
 		}
 	}
 }
 
-int lfkp_hash(lfk_ctx *c) {
+// gathers the selected field groups through c->perm into the alternate buffers and makes those current
+static int permute_groups(lfk_ctx *c, unsigned groups, bool with_key) {
+	if (c->np == 0 || (groups == 0 && !with_key)) { return 0; }
+	LFK_LAUNCH(c, k_gather_particles, lfk_blocks((long long)c->np, 256), 256, 0, c->Palt, c->P, c->key_alt, c->key,
+		c->perm, (unsigned long long)c->np, groups, with_key ? 1 : 0);
+	for (int g = 0; g < 6; ++g) {
+		if (groups & (1u << g)) {
+			for (int f = 3 * g; f < 3 * g + 3; ++f) {
+				double *t = c->P.f[f]; c->P.f[f] = c->Palt.f[f]; c->Palt.f[f] = t;
+			}
+		}
+	}
+	if (with_key) {
+		uint32_t *kt = c->key; c->key = c->key_alt; c->key_alt = kt;
+	}
+	return 0;
+}
+
+#define GROUP_POS 1u
+#define GROUP_VEL 2u
+#define GROUP_C (4u | 8u | 16u)
+#define GROUP_OLD 32u
+
+// brings a velocity / c payload that a lean sort left in the pre-sort order (see lfkp_hash) into particle order
+int lfkp_materialise_vc(lfk_ctx *c) {
+	unsigned groups = (c->v_deferred ? GROUP_VEL : 0u) | (c->c_deferred ? GROUP_C : 0u);
+	c->v_deferred = false;
+	c->c_deferred = false;
+	return permute_groups(c, groups, false);
+}
+int lfkp_permute_c(lfk_ctx *c) {
+	c->c_deferred = false;
+	return permute_groups(c, GROUP_C, false);
+}
+
+// K1 + K2.  lean: only the positions (and keys) are physically permuted.  The velocity -- and for APIC the c rows --
+// stay where they are and are read through `perm` by the one kernel that still needs them (P2G; FLIP's G2P), because
+// G2P overwrites them in the new order anyway: that removes 192 of the 240 B/particle the full permutation moves.
+int lfkp_hash(lfk_ctx *c, bool lean) {
 	PhaseTimer T(c, LFK_PHASE_SORT);
 	const GridDesc &G = c->g;
+	LFK_TRY(lfkp_materialise_vc(c)); // a pending permutation cannot be composed with a new one
 	LFK_CUDA(c, cudaMemsetAsync(c->cnt, 0, (size_t)G.ncl * sizeof(uint32_t), c->stream));
 	uint64_t n = c->np;
 	if (n > 0) {
@@ -339,10 +381,15 @@ int lfkp_hash(lfk_ctx *c) {
 		if (n > SMALL_CELL) {
 			LFK_LAUNCH(c, k_sort_big_cells, 296, 256, 0, c->begin, c->perm, c->bigcells, c->bigcount, c->bigcap);
 		}
-		LFK_LAUNCH(c, k_gather_particles, lfk_blocks((long long)n, 256), 256, 0, c->Palt, c->P, c->key_alt, c->key,
-			c->perm, (unsigned long long)n, c->old_valid ? 18 : 15);
-		ParticleSoA t = c->P; c->P = c->Palt; c->Palt = t;
-		uint32_t *kt = c->key; c->key = c->key_alt; c->key_alt = kt;
+		unsigned groups = GROUP_POS | (c->old_valid ? GROUP_OLD : 0u);
+		if (lean) {
+			c->v_deferred = true;
+			c->c_deferred = c->prm.method == LFK_METHOD_APIC;
+			if (!c->c_deferred) { groups |= GROUP_C; }
+		} else {
+			groups |= GROUP_VEL | GROUP_C;
+		}
+		LFK_TRY(permute_groups(c, groups, true));
 	}
 	c->table_valid = true;
 	c->keys_valid = true;
@@ -409,15 +456,21 @@ __device__ void collide_one(const GridDesc &G, const MotionParams &M, const uint
 	const double h = G.h;
 	for (int j = 0; j < 3; ++j) {
 		bool into_wall = false;
-		double gf[3], inv[3], normal[3], t[3];
+		double gf[3], gt[3], inv[3], normal[3], t[3];
 		int cur[3], tc[3], adv[3];
 #pragma unroll
 		for (int d = 0; d < 3; ++d) {
 			gf[d] = div_h(from[d] - G.off[d], G);
-			double gt = div_h(to[d] - G.off[d], G);
+			gt[d] = div_h(to[d] - G.off[d], G);
 			cur[d] = (int)floor(gf[d]);
-			tc[d] = (int)floor(gt);
-			double diff = gt - gf[d];
+			tc[d] = (int)floor(gt[d]);
+		}
+		if (cur[0] == tc[0] && cur[1] == tc[1] && cur[2] == tc[2]) {
+			break; // no cell boundary is crossed: the march below would not take a single step
+		}
+#pragma unroll
+		for (int d = 0; d < 3; ++d) {
+			double diff = gt[d] - gf[d];
 			int face;
 			if (diff > 0.0) {
 				adv[d] = 1;
@@ -556,6 +609,7 @@ static int materialise_old(lfk_ctx *c) {
 
 int lfkp_advect(lfk_ctx *c, double dt) {
 	PhaseTimer T(c, LFK_PHASE_ADVECT_COLLIDE);
+	LFK_TRY(lfkp_materialise_vc(c));
 	LFK_TRY(materialise_old(c));
 	if (c->np == 0) { return 0; }
 	LFK_LAUNCH(c, k_advect, lfk_blocks((long long)c->np, 256), 256, 0, motion_params(c, dt), c->P,
@@ -580,6 +634,7 @@ int lfkp_advect_collide(lfk_ctx *c, double dt) {
 		LFK_TRY(lfkp_advect(c, dt));
 		return lfkp_collide(c);
 	}
+	LFK_TRY(lfkp_materialise_vc(c));
 	if (c->np > 0) {
 		LFK_LAUNCH(c, k_advect_collide, lfk_blocks((long long)c->np, 128), 128, 0, c->g, motion_params(c, dt), c->P,
 			c->typ, (unsigned long long)c->np);
@@ -604,78 +659,13 @@ __device__ __forceinline__ void degenerate_kick(const double *p, const double *o
 	}
 }
 
-template <bool COLLIDE> __global__ void __launch_bounds__(128) k_correct(GridDesc G, MotionParams M, ParticleSoA P,
-	double *__restrict__ nx_, double *__restrict__ ny_, double *__restrict__ nz_,
-	const uint32_t *__restrict__ begin, const uint8_t *__restrict__ typ, unsigned long long n) {
-	unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
-	if (i >= n) { return; }
-	const double *__restrict__ px = P.f[PF_PX], *__restrict__ py = P.f[PF_PY], *__restrict__ pz = P.f[PF_PZ];
-	double p[3] = { px[i], py[i], pz[i] };
-	int lo[3], hi[3];
-	const int size[3] = { G.nx, G.ny, G.nz };
-#pragma unroll
-	for (int d = 0; d < 3; ++d) { // compute_cell_index (no clamp), then for_each_in_range_checked
-		unsigned long long ci = (unsigned long long)div_h(p[d] - G.off[d], G);
-		long long cl = ci > 0x7fffffffull ? 0x7fffffffll : (long long)ci;
-		lo[d] = (int)(cl < 1 ? 0 : cl - 1);
-		long long h2 = cl + 2;
-		hi[d] = (int)(h2 < size[d] ? h2 : size[d]);
-	}
-	double sx = 0.0, sy = 0.0, sz = 0.0;
-	for (int cz = lo[2]; cz < hi[2]; ++cz) {
-		int lz = cz - G.z0 + 1;
-		for (int cy = lo[1]; cy < hi[1]; ++cy) {
-			if (lo[0] >= hi[0]) { continue; }
-			// cells lo[0]..hi[0]-1 of one row are contiguous in the sorted particle array
-			long long row = (long long)G.nx * (cy + (long long)G.ny * lz);
-			uint32_t qb = begin[row + lo[0]], qe = begin[row + hi[0]];
-			for (uint32_t q = qb; q < qe; ++q) {
-				if (q == i) { continue; }
-				double o[3] = { px[q], py[q], pz[q] };
-				double ox = p[0] - o[0], oy = p[1] - o[1], oz = p[2] - o[2];
-				double sq = 0.0;
-				sq += ox * ox;
-				sq += oy * oy;
-				sq += oz * oz;
-				if (sq < 1e-12) {
-					double kick[3];
-					degenerate_kick(p, o, kick);
-					sx += kick[0];
-					sy += kick[1];
-					sz += kick[2];
-				} else {
-					double kl = 1.0 - sq / M.re2;
-					if (kl > 0.0) { // kernel == 0 otherwise: adds +-0 in the reference, a no-op
-						double kern = kl * kl * kl;
-						double sc = kern / sqrt(sq);
-						sx += sc * ox;
-						sy += sc * oy;
-						sz += sc * oz;
-					}
-				}
-			}
-		}
-	}
-	double np3[3] = { p[0] + sx * M.corr_factor, p[1] + sy * M.corr_factor, p[2] + sz * M.corr_factor };
-#pragma unroll
-	for (int d = 0; d < 3; ++d) {
-		np3[d] = dclamp_std(np3[d], M.gmin[d], M.gmax[d]);
-	}
-	if (COLLIDE) { // second _detect_collisions of the step: old_position == pre-correction position
-		collide_one(G, M, typ, p, np3);
-	}
-	nx_[i] = np3[0];
-	ny_[i] = np3[1];
-	nz_[i] = np3[2];
-}
-
-// ---- tiled version ------------------------------------------------------------------------------------------
 // A block owns a tile of CT_TY x CT_TZ rows x CT_LX cells.  The positions of every particle in the tile plus its
 // one-cell halo are staged ONCE in shared memory as fp32 coordinates relative to the tile origin (16 B each, with
-// the particle's global index), so the ~100-200 candidate tests per particle run on fp32 data from shared memory
-// instead of fp64 data from L1/L2.  The fp32 test is only a conservative PRE-FILTER (its threshold carries a 10x
-// margin over the worst-case rounding error); candidates that pass are re-evaluated in fp64 from the original
-// positions, in the reference's order, so the result is bit-identical to the plain fp64 loop above.
+// the particle's global index), so the candidate tests per particle run on fp32 data from shared memory instead of
+// fp64 data from L1/L2.  The fp32 test is only a conservative PRE-FILTER (its threshold carries a 10x margin over
+// the worst-case rounding error); candidates that pass are re-evaluated in fp64 from the original positions, in the
+// reference's order.  Per neighbouring row only the cells that the kernel radius can reach are scanned
+// (re^2 - dy_min^2 - dz_min^2 leaves an x window of 0..3 cells).
 #define CT_LX 32
 #define CT_TY 2
 #define CT_TZ 2
@@ -684,8 +674,18 @@ template <bool COLLIDE> __global__ void __launch_bounds__(128) k_correct(GridDes
 #define CT_ROWS (CT_SY * CT_SZ)
 #define CT_OWN (CT_TY * CT_TZ)
 #define CT_CAP 5120           // staged particles per tile (80 KB); denser tiles take the global-memory path
-#define CT_THREADS 256
+#define CT_THREADS 512
 #define CT_LIST 40
+
+// 1 / sqrt(x) for x in the normal range: hardware seed (rel. error 2^-22) + two Newton steps (~1 ulp)
+__device__ __forceinline__ double fast_rsqrt(double x) {
+	double y;
+	asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+	const double hx = 0.5 * x;
+	y = fma(y, fma(-hx * y, y, 0.5), y);
+	y = fma(y, fma(-hx * y, y, 0.5), y);
+	return y;
+}
 
 __device__ __forceinline__ void pair_exact(const MotionParams &M, const double *p, const double *o, double &sx,
 	double &sy, double &sz) {
@@ -702,11 +702,11 @@ __device__ __forceinline__ void pair_exact(const MotionParams &M, const double *
 		sz += kick[2];
 	} else {
 		// reference: kernel = (1 - r^2 / re^2)^3, spring += kernel / sqrt(r^2) * offset.  The two IEEE divisions and
-		// the IEEE square root cost ~150 instructions per pair; the reciprocal multiply and rsqrt() (<= 1 ulp) cost
-		// ~25 and move the corrected position by < 1e-16 cells -- positions are tolerance-checked (1e-12).
+		// the IEEE square root cost ~200 instructions per pair; the reciprocal multiply and the Newton rsqrt (~1 ulp)
+		// cost ~25 and move the corrected position by < 1e-16 cells -- positions are tolerance-checked (1e-12).
 		double kl = 1.0 - sq * M.inv_re2;
 		if (kl > 0.0) {
-			double sc = kl * kl * kl * rsqrt(sq);
+			double sc = kl * kl * kl * fast_rsqrt(sq);
 			sx += sc * ox;
 			sy += sc * oy;
 			sz += sc * oz;
@@ -744,7 +744,7 @@ __device__ void spring_global(const GridDesc &G, const MotionParams &M, const do
 	}
 }
 
-template <bool COLLIDE> __global__ void __launch_bounds__(CT_THREADS) k_correct_tiled(GridDesc G, MotionParams M,
+template <bool COLLIDE> __global__ void __launch_bounds__(CT_THREADS, 2) k_correct_tiled(GridDesc G, MotionParams M,
 	ParticleSoA P, double *__restrict__ nx_, double *__restrict__ ny_, double *__restrict__ nz_,
 	const uint32_t *__restrict__ begin, const uint8_t *__restrict__ typ) {
 	extern __shared__ float4 stage[];
@@ -827,13 +827,13 @@ template <bool COLLIDE> __global__ void __launch_bounds__(CT_THREADS) k_correct_
 		double sx = 0.0, sy = 0.0, sz = 0.0;
 		// unclamped cell and in-cell fraction (compute_cell_index)
 		long long ci[3];
-		double fr[3];
+		float fr[3];
 #pragma unroll
 		for (int d = 0; d < 3; ++d) {
 			double f = div_h(p[d] - G.off[d], G);
 			unsigned long long u = (unsigned long long)f;
 			ci[d] = u > 0x7fffffffull ? 0x7fffffffll : (long long)u;
-			fr[d] = f - (double)u;
+			fr[d] = (float)(f - (double)u);
 		}
 		const bool in_tile = use_stage && ci[0] >= x0 && ci[0] < x0 + CT_LX && ci[0] < G.nx && ci[1] == y0 + oy &&
 			ci[2] == lz0 + oz - 1 + G.z0;
@@ -841,9 +841,7 @@ template <bool COLLIDE> __global__ void __launch_bounds__(CT_THREADS) k_correct_
 			spring_global(G, M, px, py, pz, begin, i, p, sx, sy, sz);
 		} else {
 			const float rx = (float)(p[0] - org[0]), ry = (float)(p[1] - org[1]), rz = (float)(p[2] - org[2]);
-			// cells (rows) farther than the kernel radius re = h / sqrt(2) = 0.7071 h cannot contribute
-			const int klo = (int)(ci[0] - x0) + (fr[0] > 0.7075 ? 1 : 0);
-			const int khi = (int)(ci[0] - x0) + 3 - (fr[0] < 0.2925 ? 1 : 0);
+			const int kown = (int)(ci[0] - x0) + 1; // index of the particle's own cell in cellbeg[r][]
 			// Phase 1: fp32 scan of the staged candidates, four at a time (four independent LDS.128 in flight); the
 			// survivors' particle indices go to a small per-thread list.  Phase 2 evaluates them in fp64, in order.
 			uint32_t cand[CT_LIST];
@@ -853,9 +851,17 @@ template <bool COLLIDE> __global__ void __launch_bounds__(CT_THREADS) k_correct_
 	float d2_ = __fmaf_rn(dz_, dz_, __fmaf_rn(dy_, dy_, dx_ * dx_)); \
 	if (d2_ < thr) { cand[nc < CT_LIST ? nc : CT_LIST - 1] = __float_as_uint((q).w); ++nc; } } while (0)
 			for (int dz = -1; dz <= 1; ++dz) {
-				if ((dz < 0 && fr[2] > 0.7075) || (dz > 0 && fr[2] < 0.2925)) { continue; }
+				// distance (in cells) from the particle to the nearest point of the neighbouring layer / row
+				const float zmin = dz < 0 ? fr[2] : (dz > 0 ? 1.f - fr[2] : 0.f);
+				const float remz = 0.501f - zmin * zmin; // (re / h)^2 = 1/2, plus the pre-filter's margin
+				if (remz <= 0.f) { continue; }
 				for (int dy = -1; dy <= 1; ++dy) {
-					if ((dy < 0 && fr[1] > 0.7075) || (dy > 0 && fr[1] < 0.2925)) { continue; }
+					const float ymin = dy < 0 ? fr[1] : (dy > 0 ? 1.f - fr[1] : 0.f);
+					const float rem = remz - ymin * ymin;
+					if (rem <= 0.f) { continue; }
+					const float xr = sqrtf(rem); // reach along x within this row: < 0.708 cells
+					const int klo = kown + (fr[0] - xr < 0.f ? -1 : 0);
+					const int khi = kown + (fr[0] + xr >= 1.f ? 2 : 1);
 					const int r = (oz + 1 + dz) * CT_SY + (oy + 1 + dy);
 					uint32_t s = rowoff[r] + cellbeg[r][klo];
 					const uint32_t s1 = rowoff[r] + cellbeg[r][khi];
@@ -876,11 +882,17 @@ template <bool COLLIDE> __global__ void __launch_bounds__(CT_THREADS) k_correct_
 			if (nc > CT_LIST) { // more neighbours within reach than the list holds (a clump): plain fp64 loop instead
 				spring_global(G, M, px, py, pz, begin, i, p, sx, sy, sz);
 			} else {
+				// candidate positions are fetched one iteration ahead of their use
+				uint32_t j = nc > 0 ? cand[0] : (uint32_t)i;
+				double ov[3] = { px[j], py[j], pz[j] };
 				for (int k = 0; k < nc; ++k) {
-					uint32_t j = cand[k];
-					if (j == i) { continue; }
-					double ov[3] = { px[j], py[j], pz[j] };
-					pair_exact(M, p, ov, sx, sy, sz);
+					const uint32_t jn = k + 1 < nc ? cand[k + 1] : j;
+					const double on[3] = { px[jn], py[jn], pz[jn] };
+					if (j != i) { pair_exact(M, p, ov, sx, sy, sz); }
+					j = jn;
+					ov[0] = on[0];
+					ov[1] = on[1];
+					ov[2] = on[2];
 				}
 			}
 		}
@@ -976,171 +988,6 @@ int lfkp_cfl(lfk_ctx *c, double *value) {
 }
 
 // =========================================================================================================
-// G1-G4: grid -> particle (reference src/mac_grid.cpp:40-112, src/simulation.cpp:447-560)
-// =========================================================================================================
-__device__ __forceinline__ double lerp1(double a, double b, double t) {
-	return a * (1.0 - t) + b * t;
-}
-__device__ __forceinline__ double trilerp8(const double *v, double t1, double t2, double t3) {
-	double b0 = lerp1(lerp1(v[0], v[1], t3), lerp1(v[2], v[3], t3), t2);
-	double b1 = lerp1(lerp1(v[4], v[5], t3), lerp1(v[6], v[7], t3), t2);
-	return lerp1(b0, b1, t1);
-}
-// c = sum over the 8 corners of grad_kernel(corner) * sample, in the reference's corner order
-__device__ __forceinline__ void c_vector(const GridDesc &G, const double *v, double tx, double ty, double tz, double *out) {
-	double ax = 0.0, ay = 0.0, az = 0.0;
-#pragma unroll
-	for (int k = 0; k < 8; ++k) {
-		double px = (k & 1) ? tx - 1.0 : tx, py = (k & 2) ? ty - 1.0 : ty, pz = (k & 4) ? tz - 1.0 : tz;
-		double sx = px > 0.0 ? -1.0 : 1.0, sy = py > 0.0 ? -1.0 : 1.0, sz = pz > 0.0 ? -1.0 : 1.0;
-		double nx = 1.0 - fabs(px), ny = 1.0 - fabs(py), nz = 1.0 - fabs(pz);
-		double gx = div_h(sx * ny * nz, G), gy = div_h(nx * sy * nz, G), gz = div_h(nx * ny * sz, G);
-		if (k == 0) {
-			ax = gx * v[k];
-			ay = gy * v[k];
-			az = gz * v[k];
-		} else {
-			ax += gx * v[k];
-			ay += gy * v[k];
-			az += gz * v[k];
-		}
-	}
-	out[0] = ax;
-	out[1] = ay;
-	out[2] = az;
-}
-
-struct FaceFetch { // the 3 clamped cell coordinates per axis of get_face_samples, and their "clamped" bits
-	int ci[3][3];
-	bool cl[3][3];
-};
-
-__device__ __forceinline__ void face_fetch_setup(const GridDesc &G, const long long *gi, FaceFetch &F) {
-	const int size[3] = { G.nx, G.ny, G.nz };
-#pragma unroll
-	for (int a = 0; a < 3; ++a) {
-#pragma unroll
-		for (int d = 0; d < 3; ++d) {
-			long long val = gi[a] + d; // _clamp(val, 1, max) then -1
-			if (val < 1) {
-				F.ci[a][d] = 0;
-				F.cl[a][d] = true;
-			} else if (val >= size[a]) {
-				F.ci[a][d] = size[a] - 1;
-				F.cl[a][d] = true;
-			} else {
-				F.ci[a][d] = (int)val - 1;
-				F.cl[a][d] = false;
-			}
-		}
-	}
-}
-
-template <int K> __device__ __forceinline__ void face_samples_comp(const GridDesc &G, const FaceFetch &F,
-	const double *__restrict__ comp, const int *dsel, double *s) {
-#pragma unroll
-	for (int k = 0; k < 8; ++k) {
-		int bx = k & 1, by = (k >> 1) & 1, bz = (k >> 2) & 1;
-		int dx = K == 0 ? bx : dsel[0] + bx;
-		int dy = K == 1 ? by : dsel[1] + by;
-		int dz = K == 2 ? bz : dsel[2] + bz;
-		bool clamped = K == 0 ? F.cl[0][dx] : (K == 1 ? F.cl[1][dy] : F.cl[2][dz]);
-		int lz = F.ci[2][dz] - G.z0 + 1;
-		long long idx = F.ci[0][dx] + (long long)G.nx * (F.ci[1][dy] + (long long)G.ny * lz);
-		s[k] = clamped ? 0.0 : __ldg(comp + idx);
-	}
-}
-
-template <int METHOD> __global__ void __launch_bounds__(128) k_g2p(GridDesc G, ParticleSoA P,
-	const double *__restrict__ u, const double *__restrict__ v, const double *__restrict__ w,
-	const double *__restrict__ uo, const double *__restrict__ vo, const double *__restrict__ wo,
-	double blend, unsigned long long n) {
-	unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
-	if (i >= n) { return; }
-	double p[3] = { P.f[PF_PX][i], P.f[PF_PY][i], P.f[PF_PZ][i] };
-	long long gi[3];
-	double t[3], tmid[3];
-	int dsel[3];
-#pragma unroll
-	for (int d = 0; d < 3; ++d) { // compute_cell_index_and_position: no clamping
-		double f = div_h(p[d] - G.off[d], G);
-		unsigned long long ci = (unsigned long long)f;
-		gi[d] = ci > 0x7fffffffull ? 0x7fffffffll : (long long)ci;
-		t[d] = f - (double)ci;
-		tmid[d] = t[d] - 0.5;
-		dsel[d] = 1;
-		if (tmid[d] < 0.0) {
-			dsel[d] = 0;
-			tmid[d] += 1.0;
-		}
-	}
-	FaceFetch F;
-	face_fetch_setup(G, gi, F);
-	double sx[8], sy[8], sz[8];
-	face_samples_comp<0>(G, F, u, dsel, sx);
-	face_samples_comp<1>(G, F, v, dsel, sy);
-	face_samples_comp<2>(G, F, w, dsel, sz);
-	double vn[3];
-	vn[0] = trilerp8(sx, tmid[2], tmid[1], t[0]);
-	vn[1] = trilerp8(sy, tmid[2], t[1], tmid[0]);
-	vn[2] = trilerp8(sz, t[2], tmid[1], tmid[0]);
-	if (METHOD == LFK_METHOD_FLIP) {
-		double ox[8], oy[8], oz[8];
-		face_samples_comp<0>(G, F, uo, dsel, ox);
-		face_samples_comp<1>(G, F, vo, dsel, oy);
-		face_samples_comp<2>(G, F, wo, dsel, oz);
-		double vold[3];
-		vold[0] = trilerp8(ox, tmid[2], tmid[1], t[0]);
-		vold[1] = trilerp8(oy, tmid[2], t[1], tmid[0]);
-		vold[2] = trilerp8(oz, t[2], tmid[1], tmid[0]);
-		P.f[PF_VX][i] = vn[0] + (P.f[PF_VX][i] - vold[0]) * blend;
-		P.f[PF_VY][i] = vn[1] + (P.f[PF_VY][i] - vold[1]) * blend;
-		P.f[PF_VZ][i] = vn[2] + (P.f[PF_VZ][i] - vold[2]) * blend;
-	} else {
-		P.f[PF_VX][i] = vn[0];
-		P.f[PF_VY][i] = vn[1];
-		P.f[PF_VZ][i] = vn[2];
-		if (METHOD == LFK_METHOD_APIC) {
-			double cv[3];
-			c_vector(G, sx, t[0], tmid[1], tmid[2], cv);
-			P.f[PF_C0 + 0][i] = cv[0];
-			P.f[PF_C0 + 1][i] = cv[1];
-			P.f[PF_C0 + 2][i] = cv[2];
-			c_vector(G, sy, tmid[0], t[1], tmid[2], cv);
-			P.f[PF_C0 + 3][i] = cv[0];
-			P.f[PF_C0 + 4][i] = cv[1];
-			P.f[PF_C0 + 5][i] = cv[2];
-			c_vector(G, sz, tmid[0], tmid[1], t[2], cv);
-			P.f[PF_C0 + 6][i] = cv[0];
-			P.f[PF_C0 + 7][i] = cv[1];
-			P.f[PF_C0 + 8][i] = cv[2];
-		}
-	}
-}
-
-int lfkp_g2p(lfk_ctx *c) {
-	PhaseTimer T(c, LFK_PHASE_G2P);
-	if (c->np == 0) { return 0; }
-	unsigned nb = lfk_blocks((long long)c->np, 128);
-	unsigned long long n = c->np;
-	switch (c->prm.method) {
-	case LFK_METHOD_PIC:
-		LFK_LAUNCH(c, k_g2p<LFK_METHOD_PIC>, nb, 128, 0, c->g, c->P, c->vel[0], c->vel[1], c->vel[2],
-			c->vel_old[0], c->vel_old[1], c->vel_old[2], c->prm.blending_factor, n);
-		break;
-	case LFK_METHOD_FLIP:
-		LFK_LAUNCH(c, k_g2p<LFK_METHOD_FLIP>, nb, 128, 0, c->g, c->P, c->vel[0], c->vel[1], c->vel[2],
-			c->vel_old[0], c->vel_old[1], c->vel_old[2], c->prm.blending_factor, n);
-		break;
-	default:
-		LFK_LAUNCH(c, k_g2p<LFK_METHOD_APIC>, nb, 128, 0, c->g, c->P, c->vel[0], c->vel[1], c->vel[2],
-			c->vel_old[0], c->vel_old[1], c->vel_old[2], c->prm.blending_factor, n);
-		break;
-	}
-	return 0;
-}
-
-// =========================================================================================================
 // Synthetic seeding (bench scenes): jittered sub-cell sampling like simulation::seed_func
 // (reference include/fluid/simulation.h:80-115), with a counter-based hash RNG instead of pcg32.
 // =========================================================================================================
@@ -1186,7 +1033,12 @@ __global__ void k_seed_box(GridDesc G, ParticleSoA P, uint32_t *__restrict__ key
 int lfkp_seed_box(lfk_ctx *c, const double *start, const double *size, const double *vel, uint32_t dens,
 	uint64_t seed, int append) {
 	const GridDesc &G = c->g;
-	if (!append) { c->np = 0; }
+	if (!append) {
+		c->np = 0;
+		c->v_deferred = false;
+		c->c_deferred = false;
+	}
+	LFK_TRY(lfkp_materialise_vc(c));
 	double end[3] = { start[0] + size[0], start[1] + size[1], start[2] + size[2] };
 	int c0[3], c1[3];
 	const int gsz[3] = { G.nx, G.ny, G.nz };

@@ -21,69 +21,71 @@ __device__ __forceinline__ void cell_xyz(const GridDesc &G, long long own, int &
 }
 
 // ---- S1-S3: flags + b (src/pressure_solver.cpp:150-242) ---------------------------------------------------
-__global__ void k_build_system(GridDesc G, const uint32_t *__restrict__ cnt, const uint8_t *__restrict__ typ,
-	const double *__restrict__ u, const double *__restrict__ v, const double *__restrict__ w,
-	uint8_t *__restrict__ flags, double *__restrict__ b, double *__restrict__ p, double inv_h) {
-	long long own = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-	if (own >= G.nown) { return; }
-	int x, y, lz;
-	cell_xyz(G, own, x, y, lz);
-	long long c = own + G.sxy;
-	p[c] = 0.0;
-	if (cnt[c] == 0) {
-		flags[c] = 0;
-		b[c] = 0.0;
-		return;
-	}
-	const uint8_t S = LFK_CELL_SOLID, F = LFK_CELL_FLUID;
-	// out-of-grid neighbours read as solid (mac_grid::get_cell_and_type); the z ghost layers carry that already
-	uint8_t txp = x + 1 < G.nx ? typ[c + 1] : S, txn = x > 0 ? typ[c - 1] : S;
-	uint8_t typ_ = y + 1 < G.ny ? typ[c + G.nx] : S, tyn = y > 0 ? typ[c - G.nx] : S;
-	uint8_t tzp = typ[c + G.sxy], tzn = typ[c - G.sxy];
-	unsigned n = (txp != S) + (typ_ != S) + (tzp != S) + (txn != S) + (tyn != S) + (tzn != S);
-	unsigned f = n | FL_L;
-	if (typ[c] == F) { f |= FL_SELF; }
-	if (txp == F) { f |= FL_XP; }
-	if (typ_ == F) { f |= FL_YP; }
-	if (tzp == F) { f |= FL_ZP; }
-	flags[c] = (uint8_t)f;
+__global__ void __launch_bounds__(256) k_build_system(GridDesc G, const uint32_t *__restrict__ cnt,
+	const uint8_t *__restrict__ typ, const double *__restrict__ u, const double *__restrict__ v,
+	const double *__restrict__ w, uint8_t *__restrict__ flags, double *__restrict__ b, double *__restrict__ p,
+	double inv_h) {
+	for_own_cells(G, [&](int x, int y, int lz, long long c) {
+		p[c] = 0.0;
+		if (cnt[c] == 0) {
+			flags[c] = 0;
+			b[c] = 0.0;
+			return;
+		}
+		const uint8_t S = LFK_CELL_SOLID, F = LFK_CELL_FLUID;
+		// out-of-grid neighbours read as solid (mac_grid::get_cell_and_type); the z ghost layers carry that already
+		uint8_t txp = x + 1 < G.nx ? typ[c + 1] : S, txn = x > 0 ? typ[c - 1] : S;
+		uint8_t typ_ = y + 1 < G.ny ? typ[c + G.nx] : S, tyn = y > 0 ? typ[c - G.nx] : S;
+		uint8_t tzp = typ[c + G.sxy], tzn = typ[c - G.sxy];
+		unsigned n = (txp != S) + (typ_ != S) + (tzp != S) + (txn != S) + (tyn != S) + (tzn != S);
+		unsigned f = n | FL_L;
+		if (typ[c] == F) { f |= FL_SELF; }
+		if (txp == F) { f |= FL_XP; }
+		if (typ_ == F) { f |= FL_YP; }
+		if (tzp == F) { f |= FL_ZP; }
+		flags[c] = (uint8_t)f;
 
-	double vx = u[c], vy = v[c], vz = w[c];
-	double value = -(vx + vy + vz);
-	int z = lz - 1 + G.z0;
-	if (x > 0) {
-		double q = u[c - 1];
-		value += q;
-		if (txn == S) { value -= q; }
-	}
-	if (y > 0) {
-		double q = v[c - G.nx];
-		value += q;
-		if (tyn == S) { value -= q; }
-	}
-	if (z > 0) {
-		double q = w[c - G.sxy];
-		value += q;
-		if (tzn == S) { value -= q; }
-	}
-	if (txp == S) { value += vx; }
-	if (typ_ == S) { value += vy; }
-	if (tzp == S) { value += vz; }
-	b[c] = inv_h * value;
+		double vx = u[c], vy = v[c], vz = w[c];
+		double value = -(vx + vy + vz);
+		int z = lz - 1 + G.z0;
+		if (x > 0) {
+			double q = u[c - 1];
+			value += q;
+			if (txn == S) { value -= q; }
+		}
+		if (y > 0) {
+			double q = v[c - G.nx];
+			value += q;
+			if (tyn == S) { value -= q; }
+		}
+		if (z > 0) {
+			double q = w[c - G.sxy];
+			value += q;
+			if (tzn == S) { value -= q; }
+		}
+		if (txp == S) { value += vx; }
+		if (typ_ == S) { value += vy; }
+		if (tzp == S) { value += vz; }
+		b[c] = inv_h * value;
+	});
 }
 
 // ---- S6: out = a_scale * A v (src/pressure_solver.cpp:334-362), same subtraction order as the reference ------
+// The six neighbour loads are unconditional (ghost layers / contiguous rows keep every address inside the allocation)
+// and masked afterwards, so they are all in flight together with the flag byte; subtracting 0.0 is exact, so the
+// result is bit-identical to the reference's conditional form.
 __device__ __forceinline__ double stencil_apply(const GridDesc &G, unsigned f, const double *__restrict__ s,
 	long long c, int x, int y, double a_scale) {
-	double value = (double)FL_N(f) * s[c];
-	if (f & FL_SELF) { // coupling to -neighbours is the neighbour's "fluid_pos" flag == type(self) == fluid
-		if (x > 0) { value -= s[c - 1]; }
-		if (y > 0) { value -= s[c - G.nx]; }
-		value -= s[c - G.sxy];
-	}
-	if (f & FL_XP) { value -= s[c + 1]; }
-	if (f & FL_YP) { value -= s[c + G.nx]; }
-	if (f & FL_ZP) { value -= s[c + G.sxy]; }
+	const double sc = s[c], xm = s[c - 1], xp = s[c + 1], ym = s[c - G.nx], yp = s[c + G.nx], zm = s[c - G.sxy],
+		zp = s[c + G.sxy];
+	const bool self = f & FL_SELF; // coupling to -neighbours is the neighbour's "fluid_pos" flag == type(self) == fluid
+	double value = (double)FL_N(f) * sc;
+	value -= (self && x > 0) ? xm : 0.0;
+	value -= (self && y > 0) ? ym : 0.0;
+	value -= self ? zm : 0.0;
+	value -= (f & FL_XP) ? xp : 0.0;
+	value -= (f & FL_YP) ? yp : 0.0;
+	value -= (f & FL_ZP) ? zp : 0.0;
 	return a_scale * value;
 }
 
@@ -97,19 +99,16 @@ __global__ void __launch_bounds__(RED_THREADS) k_spmv_dot(GridDesc G, const uint
 	double *partials, unsigned *ticket, int finalize) {
 	if (scal->done) { return; }
 	double acc = 0.0;
-	for (long long own = (long long)blockIdx.x * blockDim.x + threadIdx.x; own < G.nown;
-		own += (long long)gridDim.x * blockDim.x) {
-		long long c = own + G.sxy;
-		unsigned f = flags[c];
+	for_own_cells(G, [&](int x, int y, int lz, long long c) {
+		const unsigned f = flags[c];
+		const double av = stencil_apply(G, f, s, c, x, y, a_scale);
 		double out = 0.0;
 		if (f & FL_L) {
-			int x, y, lz;
-			cell_xyz(G, own, x, y, lz);
-			out = stencil_apply(G, f, s, c, x, y, a_scale);
+			out = av;
 			acc += out * s[c];
 		}
 		z[c] = out;
-	}
+	});
 	acc = block_sum(acc);
 	if (threadIdx.x == 0) { partials[blockIdx.x] = acc; }
 	if (lfk_last_block(ticket)) {
@@ -121,19 +120,13 @@ __global__ void __launch_bounds__(RED_THREADS) k_spmv_dot(GridDesc G, const uint
 	}
 }
 
-__global__ void k_spmv_plain(GridDesc G, const uint8_t *__restrict__ flags, const double *__restrict__ s,
-	double *__restrict__ z, double a_scale) {
-	long long own = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-	if (own >= G.nown) { return; }
-	long long c = own + G.sxy;
-	unsigned f = flags[c];
-	double out = 0.0;
-	if (f & FL_L) {
-		int x, y, lz;
-		cell_xyz(G, own, x, y, lz);
-		out = stencil_apply(G, f, s, c, x, y, a_scale);
-	}
-	z[c] = out;
+__global__ void __launch_bounds__(256) k_spmv_plain(GridDesc G, const uint8_t *__restrict__ flags,
+	const double *__restrict__ s, double *__restrict__ z, double a_scale) {
+	for_own_cells(G, [&](int x, int y, int lz, long long c) {
+		const unsigned f = flags[c];
+		const double av = stencil_apply(G, f, s, c, x, y, a_scale);
+		z[c] = (f & FL_L) ? av : 0.0;
+	});
 }
 
 // Multigrid input fused into the kernels that produce r: b0 = r / a_scale in fp32, and x0 = the result of the first
@@ -144,10 +137,9 @@ struct MgPreload {
 	const uint8_t *flags;
 	double inv_a_scale;
 };
-__device__ __forceinline__ void mg_preload(const GridDesc &G, const MgPreload &M, long long own, long long c, double rv) {
+__device__ __forceinline__ void mg_preload(const GridDesc &G, const MgPreload &M, int x, int y, int lz, long long c,
+	double rv) {
 	if (M.b0 == nullptr) { return; }
-	int x, y, lz;
-	cell_xyz(G, own, x, y, lz);
 	unsigned f = M.flags[c];
 	float bv = (float)(rv * M.inv_a_scale);
 	M.b0[c] = bv;
@@ -159,14 +151,12 @@ __device__ __forceinline__ void mg_preload(const GridDesc &G, const MgPreload &M
 __global__ void __launch_bounds__(RED_THREADS) k_pcg_init(GridDesc G, const double *__restrict__ b,
 	double *__restrict__ r, PcgScalars *scal, double *partials, unsigned *ticket, int finalize, MgPreload M) {
 	double acc = 0.0;
-	for (long long own = (long long)blockIdx.x * blockDim.x + threadIdx.x; own < G.nown;
-		own += (long long)gridDim.x * blockDim.x) {
-		long long c = own + G.sxy;
+	for_own_cells(G, [&](int x, int y, int lz, long long c) {
 		double v = b[c];
 		r[c] = v;
 		acc += v * v;
-		mg_preload(G, M, own, c, v);
-	}
+		mg_preload(G, M, x, y, lz, c, v);
+	});
 	acc = block_sum(acc);
 	if (threadIdx.x == 0) { partials[blockIdx.x] = acc; }
 	if (lfk_last_block(ticket)) {
@@ -199,11 +189,7 @@ __global__ void __launch_bounds__(RED_THREADS) k_dot_zr(GridDesc G, const double
 	const double *__restrict__ r, PcgScalars *scal, double *partials, unsigned *ticket, int finalize, int first) {
 	if (scal->done) { return; }
 	double acc = 0.0;
-	for (long long own = (long long)blockIdx.x * blockDim.x + threadIdx.x; own < G.nown;
-		own += (long long)gridDim.x * blockDim.x) {
-		long long c = own + G.sxy;
-		acc += z[c] * r[c];
-	}
+	for_own_cells(G, [&](int, int, int, long long c) { acc += z[c] * r[c]; });
 	acc = block_sum(acc);
 	if (threadIdx.x == 0) { partials[blockIdx.x] = acc; }
 	if (lfk_last_block(ticket)) {
@@ -222,15 +208,13 @@ __global__ void __launch_bounds__(RED_THREADS) k_update_pr(GridDesc G, double *_
 	if (scal->done) { return; }
 	const double alpha = scal->alpha;
 	double m = 0.0;
-	for (long long own = (long long)blockIdx.x * blockDim.x + threadIdx.x; own < G.nown;
-		own += (long long)gridDim.x * blockDim.x) {
-		long long c = own + G.sxy;
+	for_own_cells(G, [&](int x, int y, int lz, long long c) {
 		p[c] = p[c] + alpha * s[c];
 		double rv = r[c] + (-alpha) * z[c];
 		r[c] = rv;
 		m = fmax(m, fabs(rv));
-		mg_preload(G, M, own, c, rv);
-	}
+		mg_preload(G, M, x, y, lz, c, rv);
+	});
 	m = block_max(m);
 	if (threadIdx.x == 0) { partials[blockIdx.x] = m; }
 	if (lfk_last_block(ticket)) {
@@ -259,7 +243,7 @@ int lfks_build_system(lfk_ctx *c, double dt) {
 		LFK_TRY(lfkx_halo_u8(c, c->typ));
 		for (int d = 0; d < 3; ++d) { LFK_TRY(lfkx_halo_f64(c, c->vel[d])); }
 	}
-	LFK_LAUNCH(c, k_build_system, lfk_blocks(G.nown, 256), 256, 0, G, c->cnt, c->typ, c->vel[0], c->vel[1],
+	LFK_LAUNCH(c, k_build_system, lfk_row_blocks(G, 256, 1u << 20), 256, 0, G, c->cnt, c->typ, c->vel[0], c->vel[1],
 		c->vel[2], c->flags, c->b, c->p, 1.0 / G.h);
 	if (c->nranks > 1) {
 		LFK_TRY(lfkx_halo_u8(c, c->flags));
@@ -270,9 +254,8 @@ int lfks_build_system(lfk_ctx *c, double dt) {
 	return 0;
 }
 
-static inline unsigned red_blocks(long long n) {
-	unsigned nb = lfk_blocks(n, RED_THREADS);
-	return nb > RED_BLOCKS ? RED_BLOCKS : nb;
+static inline unsigned red_blocks(const GridDesc &G) {
+	return lfk_row_blocks(G, RED_THREADS, RED_BLOCKS);
 }
 
 static int allreduce_scalar(lfk_ctx *c, double *field, bool is_max, int which, double tol) {
@@ -308,7 +291,7 @@ int lfks_solve(lfk_ctx *c, double dt, double *residual, uint64_t *iters) {
 	const double a_scale = dt / (c->prm.density * G.h * G.h);
 	const double tol = c->prm.tolerance;
 	const int fin = c->nranks == 1 ? 1 : 0;
-	const unsigned nb = red_blocks(G.nown), eb = lfk_blocks(G.nown, 256);
+	const unsigned nb = red_blocks(G), eb = lfk_blocks(G.nown, 256);
 	if (c->prm.preconditioner == LFK_PRECOND_MULTIGRID && !c->mg_valid) {
 		LFK_TRY(lfkm_setup(c, a_scale));
 	}
@@ -365,7 +348,7 @@ int lfks_apply_a(lfk_ctx *c, double dt, const double *d_v_dense, double *d_out_d
 		LFK_TRY(lfks_build_system(c, dt));
 	}
 	const double a_scale = dt / (c->prm.density * G.h * G.h);
-	LFK_LAUNCH(c, k_spmv_plain, lfk_blocks(G.nown, 256), 256, 0, G, c->flags, d_v_dense, d_out_dense, a_scale);
+	LFK_LAUNCH(c, k_spmv_plain, lfk_row_blocks(G, 256, 1u << 20), 256, 0, G, c->flags, d_v_dense, d_out_dense, a_scale);
 	return 0;
 }
 
@@ -392,38 +375,36 @@ __device__ __forceinline__ double face_update(double val, bool Lc, bool Ld, uint
 	return val;
 }
 
-__global__ void k_apply_pressure(GridDesc G, const uint8_t *__restrict__ flags, const uint8_t *__restrict__ typ,
-	const double *__restrict__ p, double *__restrict__ u, double *__restrict__ v, double *__restrict__ w,
-	double coeff) {
-	long long own = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-	if (own >= G.nown) { return; }
-	int x, y, lz;
-	cell_xyz(G, own, x, y, lz);
-	long long c = own + G.sxy;
-	const bool Lc = flags[c] & FL_L;
-	const uint8_t tc = typ[c];
-	const double pc = p[c];
-	{
-		bool in = x + 1 < G.nx;
-		bool Ld = in && (flags[c + 1] & FL_L);
-		if (Lc || Ld) {
-			u[c] = face_update(u[c], Lc, Ld, tc, in ? typ[c + 1] : (uint8_t)LFK_CELL_SOLID, pc, in ? p[c + 1] : 0.0, coeff);
+__global__ void __launch_bounds__(256) k_apply_pressure(GridDesc G, const uint8_t *__restrict__ flags,
+	const uint8_t *__restrict__ typ, const double *__restrict__ p, double *__restrict__ u, double *__restrict__ v,
+	double *__restrict__ w, double coeff) {
+	for_own_cells(G, [&](int x, int y, int lz, long long c) {
+		const bool Lc = flags[c] & FL_L;
+		const uint8_t tc = typ[c];
+		const double pc = p[c];
+		{
+			bool in = x + 1 < G.nx;
+			bool Ld = in && (flags[c + 1] & FL_L);
+			if (Lc || Ld) {
+				u[c] = face_update(u[c], Lc, Ld, tc, in ? typ[c + 1] : (uint8_t)LFK_CELL_SOLID, pc, in ? p[c + 1] : 0.0,
+					coeff);
+			}
 		}
-	}
-	{
-		bool in = y + 1 < G.ny;
-		bool Ld = in && (flags[c + G.nx] & FL_L);
-		if (Lc || Ld) {
-			v[c] = face_update(v[c], Lc, Ld, tc, in ? typ[c + G.nx] : (uint8_t)LFK_CELL_SOLID, pc,
-				in ? p[c + G.nx] : 0.0, coeff);
+		{
+			bool in = y + 1 < G.ny;
+			bool Ld = in && (flags[c + G.nx] & FL_L);
+			if (Lc || Ld) {
+				v[c] = face_update(v[c], Lc, Ld, tc, in ? typ[c + G.nx] : (uint8_t)LFK_CELL_SOLID, pc,
+					in ? p[c + G.nx] : 0.0, coeff);
+			}
 		}
-	}
-	{ // z: the ghost layer is solid / not an unknown at the domain boundary, the neighbour's cells otherwise
-		bool Ld = flags[c + G.sxy] & FL_L;
-		if (Lc || Ld) {
-			w[c] = face_update(w[c], Lc, Ld, tc, typ[c + G.sxy], pc, p[c + G.sxy], coeff);
+		{ // z: the ghost layer is solid / not an unknown at the domain boundary, the neighbour's cells otherwise
+			bool Ld = flags[c + G.sxy] & FL_L;
+			if (Lc || Ld) {
+				w[c] = face_update(w[c], Lc, Ld, tc, typ[c + G.sxy], pc, p[c + G.sxy], coeff);
+			}
 		}
-	}
+	});
 }
 
 int lfks_apply_pressure(lfk_ctx *c, double dt) {
@@ -433,7 +414,7 @@ int lfks_apply_pressure(lfk_ctx *c, double dt) {
 	const GridDesc &G = c->g;
 	if (c->nranks > 1) { LFK_TRY(lfkx_halo_f64(c, c->p)); }
 	double coeff = dt / (c->prm.density * G.h);
-	LFK_LAUNCH(c, k_apply_pressure, lfk_blocks(G.nown, 256), 256, 0, G, c->flags, c->typ, c->p, c->vel[0],
+	LFK_LAUNCH(c, k_apply_pressure, lfk_row_blocks(G, 256, 1u << 20), 256, 0, G, c->flags, c->typ, c->p, c->vel[0],
 		c->vel[1], c->vel[2], coeff);
 	c->system_valid = false; // b was built from the pre-projection velocities
 	return 0;

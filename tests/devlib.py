@@ -161,8 +161,12 @@ def check_device_against_record(ctx, rec, orc, exact=False):
     out = ctx.download_particles()
     refg = rec["g2p/particles"]
     close("g2p_velocity", out["velocity"], refg["velocity"], TOL_PARTICLE)
+    # c rows are velocity GRADIENTS: where the grid velocity is (nearly) uniform the reference's corner-by-corner sum
+    # leaves cancellation noise of ~1e-16 |v| / h, so the error is measured against max(|c|, |v| / h)
+    vscale = np.linalg.norm(refg["velocity"]) / float(ctx.params.cell_size)
     for f in ("cx", "cy", "cz"):
-        close("g2p_" + f, out[f], refg[f], TOL_PARTICLE)
+        err, scale = np.linalg.norm(out[f] - refg[f]), max(np.linalg.norm(refg[f]), vscale)
+        need("g2p_" + f, err <= TOL_PARTICLE * scale, "|err| %.3e > %.1e * %.3e" % (err, TOL_PARTICLE, scale))
     cfl = ctx.cfl()
     need("cfl", abs(cfl - float(rec["g2p/cfl"])) <= 1e-14 * abs(cfl), "%r vs %r" % (cfl, float(rec["g2p/cfl"])))
     return bad

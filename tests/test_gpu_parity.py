@@ -154,3 +154,39 @@ def test_projection_roundtrip_properties_large():
     b2, _ = ctx.download_rhs(dt)  # rhs of the projected field == -div/h
     assert np.abs(b2).max() < 5e-6
     ctx.close()
+
+
+@pytest.mark.parametrize("scene", ["dam_break", "flip_obstacle", "pic_sphere"])
+def test_fused_step_equals_staged_step_on_device(scene):
+    """lfk_time_step (lean sort: velocity / c rows read through the permutation, fused advect+collide and
+    correct+collide, gravity folded into P2G) against the same step issued stage by stage through the C ABI."""
+    orc, rec = load_golden(scene)
+    outs = []
+    for fused in (True, False):
+        ctx = DL.context_for(rec, max_iterations=2000)
+        ctx.upload_cells(rec["hash0/cells"])
+        ctx.upload_particles(rec["collide1/particles"])  # old_position == position, as after a completed step
+        for step in range(3):
+            dt = 0.004 + 0.001 * step
+            if fused:
+                ctx.time_step(dt)
+            else:
+                ctx.advect(dt)
+                ctx.collide()
+                ctx.hash()
+                ctx.p2g()
+                ctx.gravity(dt)
+                ctx.pressure_solve(dt)
+                ctx.apply_pressure(dt)
+                ctx.correct(dt)
+                ctx.collide()
+                ctx.extrapolate()
+                ctx.g2p()
+        outs.append((ctx.download_particles().copy(), ctx.download_cells().copy()))
+        ctx.close()
+    (pa, ca), (pb, cb) = outs
+    assert np.array_equal(pa["raw_cell_index"], pb["raw_cell_index"])
+    for f in ("position", "velocity", "cx", "cy", "cz"):
+        assert PL.rel_l2(pa[f], pb[f]) < 1e-13, f
+    assert np.array_equal(ca["type"], cb["type"])
+    assert PL.rel_l2(ca["vel"], cb["vel"]) < 1e-13
