@@ -113,33 +113,55 @@ __global__ void __launch_bounds__(256) k_mg_mask_l0(GridDesc G, const uint8_t *_
 // All six neighbour loads are issued unconditionally (the arrays carry a ghost layer in z and rows are contiguous,
 // so every address is inside the allocation) and masked afterwards: one memory round trip per cell instead of
 // "mask, then the neighbours the mask selects".
-__device__ __forceinline__ float l0_offdiag_sum(const GridDesc &G, unsigned m, const float *__restrict__ X, long long c) {
-	const float xm = X[c - 1], xp = X[c + 1], ym = X[c - G.nx], yp = X[c + G.nx], zm = X[c - G.sxy], zp = X[c + G.sxy];
+struct L0Raw {
+	float b, xc, xm, xp, ym, yp, zm, zp;
+	float e, ex, ey, ez; // coarse corrections (PROLONG only)
+	unsigned m;
+};
+template <bool PROLONG> __device__ __forceinline__ L0Raw l0_load(const GridDesc &G, const uint16_t *__restrict__ mask,
+	const float *__restrict__ b, const float *__restrict__ X, const LevelDev &C, int x, int y, int lz, long long c) {
+	L0Raw r;
+	r.m = mask[c];
+	r.b = b[c];
+	r.xc = X[c];
+	r.xm = X[c - 1];
+	r.xp = X[c + 1];
+	r.ym = X[c - G.nx];
+	r.yp = X[c + G.nx];
+	r.zm = X[c - G.sxy];
+	r.zp = X[c + G.sxy];
+	if (PROLONG) {
+		const int X_ = x >> 1, Y_ = y >> 1, LZ = ((lz - 1) >> 1) + 1;
+		const long long cc = X_ + (long long)C.nx * (Y_ + (long long)C.ny * LZ);
+		// the neighbour across the aggregate boundary belongs to the adjacent aggregate, the other one to this one
+		r.e = C.x[cc];
+		r.ex = C.x[cc + ((x & 1) ? 1 : -1)];
+		r.ey = C.x[cc + ((y & 1) ? C.nx : -C.nx)];
+		r.ez = C.x[cc + (((lz - 1) & 1) ? C.sxy : -C.sxy)];
+	}
+	return r;
+}
+__device__ __forceinline__ float l0_offdiag_sum(const L0Raw &r) {
+	const unsigned m = r.m;
 	float s = 0.f;
-	s += (m & MF_XM) ? xm : 0.f;
-	s += (m & MF_XP) ? xp : 0.f;
-	s += (m & MF_YM) ? ym : 0.f;
-	s += (m & MF_YP) ? yp : 0.f;
-	s += (m & MF_ZM) ? zm : 0.f;
-	s += (m & MF_ZP) ? zp : 0.f;
+	s += (m & MF_XM) ? r.xm : 0.f;
+	s += (m & MF_XP) ? r.xp : 0.f;
+	s += (m & MF_YM) ? r.ym : 0.f;
+	s += (m & MF_YP) ? r.yp : 0.f;
+	s += (m & MF_ZM) ? r.zm : 0.f;
+	s += (m & MF_ZP) ? r.zp : 0.f;
 	return s;
 }
-
 // omega * (sum over the coupled neighbours of the coarse correction of THEIR aggregate)
-__device__ __forceinline__ float l0_prolong_sum(unsigned m, const LevelDev &C, int x, int y, int lz) {
-	const int X_ = x >> 1, Y_ = y >> 1, LZ = ((lz - 1) >> 1) + 1;
-	const long long cc = X_ + (long long)C.nx * (Y_ + (long long)C.ny * LZ);
-	// the neighbour across the aggregate boundary belongs to the adjacent aggregate, the other one to this one
-	const float e = C.x[cc];
-	const float ex = C.x[cc + ((x & 1) ? 1 : -1)], ey = C.x[cc + ((y & 1) ? C.nx : -C.nx)];
-	const float ez = C.x[cc + (((lz - 1) & 1) ? C.sxy : -C.sxy)];
+__device__ __forceinline__ float l0_prolong_sum(const L0Raw &r, int x, int y, int lz) {
+	const unsigned m = r.m;
 	float s = 0.f;
-	s += (m & MF_XM) ? ((x & 1) ? e : ex) : 0.f;
-	s += (m & MF_XP) ? ((x & 1) ? ex : e) : 0.f;
-	s += (m & MF_YM) ? ((y & 1) ? e : ey) : 0.f;
-	s += (m & MF_YP) ? ((y & 1) ? ey : e) : 0.f;
-	s += (m & MF_ZM) ? (((lz - 1) & 1) ? e : ez) : 0.f;
-	s += (m & MF_ZP) ? (((lz - 1) & 1) ? ez : e) : 0.f;
+	s += (m & MF_XM) ? ((x & 1) ? r.e : r.ex) : 0.f;
+	s += (m & MF_XP) ? ((x & 1) ? r.ex : r.e) : 0.f;
+	s += (m & MF_YM) ? ((y & 1) ? r.e : r.ey) : 0.f;
+	s += (m & MF_YP) ? ((y & 1) ? r.ey : r.e) : 0.f;
+	s += (m & MF_ZM) ? (((lz - 1) & 1) ? r.e : r.ez) : 0.f;
+	s += (m & MF_ZP) ? (((lz - 1) & 1) ? r.ez : r.e) : 0.f;
 	return MG_OMEGA * s;
 }
 
@@ -148,12 +170,13 @@ template <bool PROLONG> __global__ void __launch_bounds__(256) k_mg_rbgs_l0(Grid
 	const uint16_t *__restrict__ mask, const float *__restrict__ b, float *__restrict__ X, int colour, LevelDev C,
 	const PcgScalars *scal) {
 	if (scal->done) { return; }
-	for_rows_colour(G.nx, G.ny, G.nzl, G.z0, colour, [&](int x, int y, int lz, long long c) {
-		const unsigned m = mask[c];
-		float s = b[c] + l0_offdiag_sum(G, m, X, c);
-		if (PROLONG) { s += l0_prolong_sum(m, C, x, y, lz); }
-		if ((m & MF_L) && MF_N(m) > 0) { X[c] = s / (float)MF_N(m); }
-	});
+	rows_pipelined<4, L0Raw>(G.nx, G.ny, G.nzl, G.z0, colour,
+		[&](int x, int y, int lz, long long c) { return l0_load<PROLONG>(G, mask, b, X, C, x, y, lz, c); },
+		[&](int x, int y, int lz, long long c, const L0Raw &r) {
+			float s = r.b + l0_offdiag_sum(r);
+			if (PROLONG) { s += l0_prolong_sum(r, x, y, lz); }
+			if ((r.m & MF_L) && MF_N(r.m) > 0) { X[c] = __fdividef(s, (float)MF_N(r.m)); }
+		});
 }
 
 // last half-sweep of the cycle (colour `colour`) fused with z = x0 / a_scale (fp64), sigma_new = z.r and its finaliser
@@ -163,19 +186,23 @@ __global__ void __launch_bounds__(RED_THREADS) k_mg_final_l0(GridDesc G, const u
 	int first) {
 	if (scal->done) { return; }
 	double acc = 0.0;
-	for_own_cells(G, [&](int x, int y, int lz, long long c) {
-		const unsigned m = mask[c];
-		const float xc = X[c], bv = b[c];
-		const double rv = r[c];
-		const float upd = (bv + l0_offdiag_sum(G, m, X, c)) / (float)(MF_N(m) > 0 ? MF_N(m) : 1u);
-		double zv = 0.0;
-		if (m & MF_L) {
+	struct FinRaw { L0Raw l; double r; };
+	LevelDev none{};
+	rows_pipelined<4, FinRaw>(G.nx, G.ny, G.nzl, 0, -1,
+		[&](int x, int y, int lz, long long c) {
+			FinRaw v;
+			v.l = l0_load<false>(G, mask, b, X, none, x, y, lz, c);
+			v.r = r[c];
+			return v;
+		},
+		[&](int x, int y, int lz, long long c, const FinRaw &v) {
+			const unsigned m = v.l.m;
+			const float upd = __fdividef(v.l.b + l0_offdiag_sum(v.l), (float)(MF_N(m) > 0 ? MF_N(m) : 1u));
 			const bool mine = (((x + y + (lz - 1 + G.z0)) & 1) == colour) && MF_N(m) > 0;
-			zv = (double)(mine ? upd : xc) * inv_a_scale;
-			acc += zv * rv;
-		}
-		z[c] = zv;
-	});
+			const double zv = (m & MF_L) ? (double)(mine ? upd : v.l.xc) * inv_a_scale : 0.0;
+			acc += zv * v.r; // zv == 0 on cells that are not unknowns
+			z[c] = zv;
+		});
 	acc = block_sum(acc);
 	if (threadIdx.x == 0) { partials[blockIdx.x] = acc; }
 	if (lfk_last_block(ticket)) {
@@ -191,22 +218,38 @@ __global__ void __launch_bounds__(RED_THREADS) k_mg_final_l0(GridDesc G, const u
 __global__ void __launch_bounds__(128) k_mg_restrict_l0(GridDesc G, const uint16_t *__restrict__ mask,
 	const float *__restrict__ b, const float *__restrict__ X, LevelDev C, const PcgScalars *scal) {
 	if (scal->done) { return; }
-	for_rows(C.nx, C.ny, C.nzl, [&](int X_, int Y_, int LZ, long long cc) {
-		float acc = 0.f;
+	// the pre-smoothing ended with a black half-sweep: black residuals are zero (to rounding), so only the 4 red
+	// cells of each aggregate are visited; (dy, dz) in {0,1}^2, dx fixed by the colour
+	struct Raw4 { L0Raw q[4]; };
+	LevelDev none{};
+	rows_pipelined<1, Raw4>(C.nx, C.ny, C.nzl, 0, -1,
+		[&](int X_, int Y_, int LZ, long long) {
+			Raw4 v;
 #pragma unroll
-		for (int k = 0; k < 8; ++k) {
-			int x = 2 * X_ + (k & 1), y = 2 * Y_ + ((k >> 1) & 1), lz = 2 * (LZ - 1) + ((k >> 2) & 1) + 1;
-			if (x >= G.nx || y >= G.ny || lz > G.nzl) { continue; }
-			// the pre-smoothing ended with a black half-sweep: black residuals are zero (to rounding), only red ones count
-			if (((x + y + (lz - 1 + G.z0)) & 1) != 0) { continue; }
-			long long c = x + (long long)G.nx * (y + (long long)G.ny * lz);
-			unsigned m = mask[c];
-			float res = b[c] - ((float)MF_N(m) * X[c] - l0_offdiag_sum(G, m, X, c));
-			acc += (m & MF_L) ? res : 0.f;
-		}
-		C.b[cc] = acc;
-		C.x[cc] = 0.f;
-	});
+			for (int k = 0; k < 4; ++k) {
+				int y = 2 * Y_ + (k & 1), lz = 2 * (LZ - 1) + ((k >> 1) & 1) + 1;
+				int x = 2 * X_ + ((y + (lz - 1 + G.z0)) & 1);
+				// cells beyond an odd-sized grid: clamp the address (any valid cell), the contribution is dropped below
+				x = x < G.nx ? x : G.nx - 1;
+				y = y < G.ny ? y : G.ny - 1;
+				lz = lz <= G.nzl ? lz : G.nzl;
+				v.q[k] = l0_load<false>(G, mask, b, X, none, x, y, lz, x + (long long)G.nx * (y + (long long)G.ny * lz));
+			}
+			return v;
+		},
+		[&](int X_, int Y_, int LZ, long long cc, const Raw4 &v) {
+			float acc = 0.f;
+#pragma unroll
+			for (int k = 0; k < 4; ++k) {
+				const int y = 2 * Y_ + (k & 1), lz = 2 * (LZ - 1) + ((k >> 1) & 1) + 1;
+				const int x = 2 * X_ + ((y + (lz - 1 + G.z0)) & 1);
+				const L0Raw &q = v.q[k];
+				const float res = q.b - ((float)MF_N(q.m) * q.xc - l0_offdiag_sum(q));
+				acc += ((q.m & MF_L) && x < G.nx && y < G.ny && lz <= G.nzl) ? res : 0.f;
+			}
+			C.b[cc] = acc;
+			C.x[cc] = 0.f;
+		});
 }
 
 // ---- generic level: coefficient arrays ------------------------------------------------------------------------
@@ -215,28 +258,45 @@ __device__ __forceinline__ float lv_offdiag_sum(const LevelDev &L, const float *
 	return L.cx[c] * X[c + 1] + L.cx[c - 1] * X[c - 1] + L.cy[c] * X[c + L.nx] + L.cy[c - L.nx] * X[c - L.nx] +
 		L.cz[c] * X[c + L.sxy] + L.cz[c - L.sxy] * X[c - L.sxy];
 }
-// sum over the neighbours of coupling * (omega * coarse correction of the neighbour's aggregate)
-__device__ __forceinline__ float lv_prolong_sum(const LevelDev &L, const LevelDev &C, long long c, int x, int y, int lz) {
-	const int X_ = x >> 1, Y_ = y >> 1, LZ = ((lz - 1) >> 1) + 1;
-	const long long cc = X_ + (long long)C.nx * (Y_ + (long long)C.ny * LZ);
-	const float e = C.x[cc];
-	// a zero coupling multiplies a finite value: the coarse arrays carry a ghost shell of zeros around the domain
-	float s = L.cx[c - 1] * ((x & 1) ? e : C.x[cc - 1]) + L.cx[c] * ((x & 1) ? C.x[cc + 1] : e);
-	s += L.cy[c - L.nx] * ((y & 1) ? e : C.x[cc - C.nx]) + L.cy[c] * ((y & 1) ? C.x[cc + C.nx] : e);
-	s += L.cz[c - L.sxy] * (((lz - 1) & 1) ? e : C.x[cc - C.sxy]) + L.cz[c] * (((lz - 1) & 1) ? C.x[cc + C.sxy] : e);
-	return MG_OMEGA * s;
-}
-
 template <bool PROLONG> __global__ void __launch_bounds__(256) k_mg_rbgs(LevelDev L, int colour, LevelDev C,
 	const PcgScalars *scal) {
 	if (scal->done) { return; }
-	for_rows_colour(L.nx, L.ny, L.nzl, L.zpar, colour, [&](int x, int y, int lz, long long c) {
-		float d = L.diag[c];
-		if (d <= 0.f) { return; }
-		float s = L.b[c] + lv_offdiag_sum(L, L.x, c);
-		if (PROLONG) { s += lv_prolong_sum(L, C, c, x, y, lz); }
-		L.x[c] = s / d;
-	});
+	struct Raw {
+		float d, b, cxm, cxp, cym, cyp, czm, czp, xm, xp, ym, yp, zm, zp, e, ex, ey, ez;
+	};
+	rows_pipelined<2, Raw>(L.nx, L.ny, L.nzl, L.zpar, colour,
+		[&](int x, int y, int lz, long long c) {
+			Raw r;
+			r.d = L.diag[c];
+			r.b = L.b[c];
+			// couplings across the domain boundary are 0, so the wrapped neighbour reads are harmless (0 * finite)
+			r.cxm = L.cx[c - 1]; r.cxp = L.cx[c];
+			r.cym = L.cy[c - L.nx]; r.cyp = L.cy[c];
+			r.czm = L.cz[c - L.sxy]; r.czp = L.cz[c];
+			r.xm = L.x[c - 1]; r.xp = L.x[c + 1];
+			r.ym = L.x[c - L.nx]; r.yp = L.x[c + L.nx];
+			r.zm = L.x[c - L.sxy]; r.zp = L.x[c + L.sxy];
+			if (PROLONG) {
+				const int X_ = x >> 1, Y_ = y >> 1, LZ = ((lz - 1) >> 1) + 1;
+				const long long cc = X_ + (long long)C.nx * (Y_ + (long long)C.ny * LZ);
+				r.e = C.x[cc];
+				r.ex = C.x[cc + ((x & 1) ? 1 : -1)];
+				r.ey = C.x[cc + ((y & 1) ? C.nx : -C.nx)];
+				r.ez = C.x[cc + (((lz - 1) & 1) ? C.sxy : -C.sxy)];
+			}
+			return r;
+		},
+		[&](int x, int y, int lz, long long c, const Raw &r) {
+			float s = r.b + (r.cxp * r.xp + r.cxm * r.xm + r.cyp * r.yp + r.cym * r.ym + r.czp * r.zp + r.czm * r.zm);
+			if (PROLONG) {
+				// a zero coupling multiplies a finite value: the coarse arrays carry a ghost shell of zeros
+				float t = r.cxm * ((x & 1) ? r.e : r.ex) + r.cxp * ((x & 1) ? r.ex : r.e);
+				t += r.cym * ((y & 1) ? r.e : r.ey) + r.cyp * ((y & 1) ? r.ey : r.e);
+				t += r.czm * (((lz - 1) & 1) ? r.e : r.ez) + r.czp * (((lz - 1) & 1) ? r.ez : r.e);
+				s += MG_OMEGA * t;
+			}
+			if (r.d > 0.f) { L.x[c] = __fdividef(s, r.d); }
+		});
 }
 
 __global__ void __launch_bounds__(128) k_mg_restrict(LevelDev F, LevelDev C, const PcgScalars *scal) {

@@ -74,18 +74,33 @@ __global__ void __launch_bounds__(256) k_build_system(GridDesc G, const uint32_t
 // The six neighbour loads are unconditional (ghost layers / contiguous rows keep every address inside the allocation)
 // and masked afterwards, so they are all in flight together with the flag byte; subtracting 0.0 is exact, so the
 // result is bit-identical to the reference's conditional form.
-__device__ __forceinline__ double stencil_apply(const GridDesc &G, unsigned f, const double *__restrict__ s,
-	long long c, int x, int y, double a_scale) {
-	const double sc = s[c], xm = s[c - 1], xp = s[c + 1], ym = s[c - G.nx], yp = s[c + G.nx], zm = s[c - G.sxy],
-		zp = s[c + G.sxy];
+struct Stencil7 {
+	double c, xm, xp, ym, yp, zm, zp;
+	unsigned f;
+};
+__device__ __forceinline__ Stencil7 stencil_load(const GridDesc &G, const uint8_t *__restrict__ flags,
+	const double *__restrict__ s, long long c) {
+	Stencil7 v;
+	v.f = flags[c];
+	v.c = s[c];
+	v.xm = s[c - 1];
+	v.xp = s[c + 1];
+	v.ym = s[c - G.nx];
+	v.yp = s[c + G.nx];
+	v.zm = s[c - G.sxy];
+	v.zp = s[c + G.sxy];
+	return v;
+}
+__device__ __forceinline__ double stencil_apply(const Stencil7 &v, int x, int y, double a_scale) {
+	const unsigned f = v.f;
 	const bool self = f & FL_SELF; // coupling to -neighbours is the neighbour's "fluid_pos" flag == type(self) == fluid
-	double value = (double)FL_N(f) * sc;
-	value -= (self && x > 0) ? xm : 0.0;
-	value -= (self && y > 0) ? ym : 0.0;
-	value -= self ? zm : 0.0;
-	value -= (f & FL_XP) ? xp : 0.0;
-	value -= (f & FL_YP) ? yp : 0.0;
-	value -= (f & FL_ZP) ? zp : 0.0;
+	double value = (double)FL_N(f) * v.c;
+	value -= (self && x > 0) ? v.xm : 0.0;
+	value -= (self && y > 0) ? v.ym : 0.0;
+	value -= self ? v.zm : 0.0;
+	value -= (f & FL_XP) ? v.xp : 0.0;
+	value -= (f & FL_YP) ? v.yp : 0.0;
+	value -= (f & FL_ZP) ? v.zp : 0.0;
 	return a_scale * value;
 }
 
@@ -99,16 +114,13 @@ __global__ void __launch_bounds__(RED_THREADS) k_spmv_dot(GridDesc G, const uint
 	double *partials, unsigned *ticket, int finalize) {
 	if (scal->done) { return; }
 	double acc = 0.0;
-	for_own_cells(G, [&](int x, int y, int lz, long long c) {
-		const unsigned f = flags[c];
-		const double av = stencil_apply(G, f, s, c, x, y, a_scale);
-		double out = 0.0;
-		if (f & FL_L) {
-			out = av;
-			acc += out * s[c];
-		}
-		z[c] = out;
-	});
+	rows_pipelined<4, Stencil7>(G.nx, G.ny, G.nzl, 0, -1,
+		[&](int, int, int, long long c) { return stencil_load(G, flags, s, c); },
+		[&](int x, int y, int, long long c, const Stencil7 &v) {
+			const double out = (v.f & FL_L) ? stencil_apply(v, x, y, a_scale) : 0.0;
+			acc += out * v.c; // out == 0 on cells that are not unknowns
+			z[c] = out;
+		});
 	acc = block_sum(acc);
 	if (threadIdx.x == 0) { partials[blockIdx.x] = acc; }
 	if (lfk_last_block(ticket)) {
@@ -123,9 +135,8 @@ __global__ void __launch_bounds__(RED_THREADS) k_spmv_dot(GridDesc G, const uint
 __global__ void __launch_bounds__(256) k_spmv_plain(GridDesc G, const uint8_t *__restrict__ flags,
 	const double *__restrict__ s, double *__restrict__ z, double a_scale) {
 	for_own_cells(G, [&](int x, int y, int lz, long long c) {
-		const unsigned f = flags[c];
-		const double av = stencil_apply(G, f, s, c, x, y, a_scale);
-		z[c] = (f & FL_L) ? av : 0.0;
+		const Stencil7 v = stencil_load(G, flags, s, c);
+		z[c] = (v.f & FL_L) ? stencil_apply(v, x, y, a_scale) : 0.0;
 	});
 }
 
@@ -138,9 +149,8 @@ struct MgPreload {
 	double inv_a_scale;
 };
 __device__ __forceinline__ void mg_preload(const GridDesc &G, const MgPreload &M, int x, int y, int lz, long long c,
-	double rv) {
+	double rv, unsigned f) {
 	if (M.b0 == nullptr) { return; }
-	unsigned f = M.flags[c];
 	float bv = (float)(rv * M.inv_a_scale);
 	M.b0[c] = bv;
 	bool red = ((x + y + (lz - 1 + G.z0)) & 1) == 0;
@@ -155,7 +165,7 @@ __global__ void __launch_bounds__(RED_THREADS) k_pcg_init(GridDesc G, const doub
 		double v = b[c];
 		r[c] = v;
 		acc += v * v;
-		mg_preload(G, M, x, y, lz, c, v);
+		mg_preload(G, M, x, y, lz, c, v, M.flags[c]);
 	});
 	acc = block_sum(acc);
 	if (threadIdx.x == 0) { partials[blockIdx.x] = acc; }
@@ -208,13 +218,24 @@ __global__ void __launch_bounds__(RED_THREADS) k_update_pr(GridDesc G, double *_
 	if (scal->done) { return; }
 	const double alpha = scal->alpha;
 	double m = 0.0;
-	for_own_cells(G, [&](int x, int y, int lz, long long c) {
-		p[c] = p[c] + alpha * s[c];
-		double rv = r[c] + (-alpha) * z[c];
-		r[c] = rv;
-		m = fmax(m, fabs(rv));
-		mg_preload(G, M, x, y, lz, c, rv);
-	});
+	struct PR { double p, s, r, z; unsigned f; };
+	rows_pipelined<4, PR>(G.nx, G.ny, G.nzl, 0, -1,
+		[&](int, int, int, long long c) {
+			PR v;
+			v.p = p[c];
+			v.s = s[c];
+			v.r = r[c];
+			v.z = z[c];
+			v.f = M.flags[c];
+			return v;
+		},
+		[&](int x, int y, int lz, long long c, const PR &v) {
+			const double rv = v.r + (-alpha) * v.z;
+			p[c] = v.p + alpha * v.s;
+			r[c] = rv;
+			m = fmax(m, fabs(rv));
+			mg_preload(G, M, x, y, lz, c, rv, v.f);
+		});
 	m = block_max(m);
 	if (threadIdx.x == 0) { partials[blockIdx.x] = m; }
 	if (lfk_last_block(ticket)) {
