@@ -73,6 +73,7 @@ typedef struct lfk_stats {
 	double phase_ms[16];        /* accumulated per LFK_PHASE_* since the last reset (only when timing is on) */
 	uint64_t num_particles;
 	uint64_t num_fluid_cells;
+	uint64_t exchanged_particles; /* multi-GPU: particles sent to the z neighbours by the last sort */
 } lfk_stats;
 enum {
 	LFK_PHASE_ADVECT_COLLIDE = 0, LFK_PHASE_SORT = 1, LFK_PHASE_P2G = 2, LFK_PHASE_SOLVE_SETUP = 3,

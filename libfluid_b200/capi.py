@@ -36,7 +36,8 @@ class Params(C.Structure):
 
 class Stats(C.Structure):
     _fields_ = [("kernel_launches", C.c_uint64), ("pcg_iterations", C.c_uint64), ("pcg_residual", C.c_double),
-                ("phase_ms", C.c_double * 16), ("num_particles", C.c_uint64), ("num_fluid_cells", C.c_uint64)]
+                ("phase_ms", C.c_double * 16), ("num_particles", C.c_uint64), ("num_fluid_cells", C.c_uint64),
+                ("exchanged_particles", C.c_uint64)]
 
 
 class LfkError(RuntimeError):
@@ -349,7 +350,8 @@ class Context:
         s = Stats()
         self._ck(self.L.lfk_get_stats(self.ptr, C.byref(s)))
         d = dict(kernel_launches=s.kernel_launches, pcg_iterations=s.pcg_iterations, pcg_residual=s.pcg_residual,
-                 num_particles=s.num_particles, num_fluid_cells=s.num_fluid_cells)
+                 num_particles=s.num_particles, num_fluid_cells=s.num_fluid_cells,
+                 exchanged_particles=s.exchanged_particles)
         d["phase_ms"] = {PHASES[i]: s.phase_ms[i] for i in range(len(PHASES))}
         return d
 

@@ -101,6 +101,23 @@ static int halo_bytes(lfk_ctx *c, void *field, size_t layer_elems, int nzl, nccl
 	return 0;
 }
 
+// my second-to-top owned layer (z0 + nzl - 2) goes to the upper rank, which sees it as layer z0 - 2
+int lfkx_layer_below(lfk_ctx *c, const double *field, double *dst) {
+	if (c->nranks == 1) { return 0; }
+	PhaseTimer T(c, LFK_PHASE_EXCHANGE);
+	ncclComm_t comm = (ncclComm_t)c->comm;
+	const size_t L = (size_t)c->g.sxy;
+	LFK_NCCL(c, g_nccl.GroupStart());
+	if (c->rank + 1 < c->nranks) {
+		LFK_NCCL(c, g_nccl.Send(field + (size_t)(c->g.nzl - 1) * L, L, ncclDouble, c->rank + 1, comm, c->stream));
+	}
+	if (c->rank > 0) {
+		LFK_NCCL(c, g_nccl.Recv(dst, L, ncclDouble, c->rank - 1, comm, c->stream));
+	}
+	LFK_NCCL(c, g_nccl.GroupEnd());
+	return 0;
+}
+
 int lfkx_halo_f64(lfk_ctx *c, double *field) {
 	return halo_bytes(c, field, (size_t)c->g.sxy, c->g.nzl, ncclDouble, 8);
 }
@@ -118,5 +135,173 @@ int lfkx_allreduce_sum(lfk_ctx *c, double *d_vals, int n) {
 int lfkx_allreduce_max(lfk_ctx *c, double *d_vals, int n) {
 	if (c->nranks == 1) { return 0; }
 	LFK_NCCL(c, g_nccl.AllReduce(d_vals, d_vals, (size_t)n, ncclDouble, ncclMax, (ncclComm_t)c->comm, c->stream));
+	return 0;
+}
+
+// =========================================================================================================
+// Particle exchange (once per step, between advection and the cell sort).
+//
+// Rank r owns the cells z in [z0, z0 + nzl).  After advection every own particle is classified by its z cell zc:
+//   zc <  z0 - 1        left the slab for good        -> sent DOWN, marked dead (dropped by the sort)
+//   zc == z0 - 1        now belongs to the lower rank -> sent DOWN, kept here as a ghost copy (the ghost layer)
+//   zc == z0            own, bottom boundary layer    -> a ghost copy is sent DOWN
+//   zc == z0 + nzl - 1  own, top boundary layer       -> a ghost copy is sent UP
+//   zc == z0 + nzl      now belongs to the upper rank -> sent UP, kept here as a ghost copy
+//   zc >  z0 + nzl      left the slab for good        -> sent UP, marked dead
+// What arrives is appended behind the own particles; the sort's keys then sort immigrants into owned cells and
+// ghost copies into the ghost layers with no further distinction.  P2G and the position correction read the ghost
+// layers' particles exactly like the reference reads the neighbouring cells (src/simulation.cpp:300-330, 572-600).
+// The order of every message is the order of the sender's array (block counts -> scan -> offsets), so the result
+// does not depend on timing.
+// =========================================================================================================
+#define XCH_THREADS 1024
+#define XCH_FIELDS 15 // position, velocity, cx, cy, cz
+
+__device__ __forceinline__ void xch_classify(const GridDesc &G, double z, int has_up, int has_dn, bool &up, bool &dn,
+	bool &dead) {
+	const int zc = cell_coord_clamped(z, G.off[2], G, G.nz);
+	const int top = G.z0 + G.nzl;
+	up = has_up && zc >= top - 1;
+	dn = has_dn && zc <= G.z0;
+	dead = zc > top || zc < G.z0 - 1;
+}
+
+__global__ void __launch_bounds__(XCH_THREADS) k_xch_count(GridDesc G, const double *__restrict__ pz,
+	unsigned long long n, int has_up, int has_dn, uint32_t *__restrict__ cnt_up, uint32_t *__restrict__ cnt_dn) {
+	unsigned long long i = (unsigned long long)blockIdx.x * XCH_THREADS + threadIdx.x;
+	bool up = false, dn = false, dead = false;
+	if (i < n) { xch_classify(G, pz[i], has_up, has_dn, up, dn, dead); }
+	int nu = __syncthreads_count(up), nd = __syncthreads_count(dn);
+	if (threadIdx.x == 0) {
+		cnt_up[blockIdx.x] = (uint32_t)nu;
+		cnt_dn[blockIdx.x] = (uint32_t)nd;
+	}
+}
+
+// exclusive position of this thread among the threads of the block whose flag is set (deterministic)
+__device__ __forceinline__ uint32_t block_rank(bool flag, uint32_t *warp_tot /* [32] shared */) {
+	const unsigned b = __ballot_sync(0xffffffffu, flag);
+	const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+	__syncthreads();
+	if (lane == 0) { warp_tot[w] = (uint32_t)__popc(b); }
+	__syncthreads();
+	uint32_t before = 0;
+	for (int k = 0; k < w; ++k) { before += warp_tot[k]; }
+	return before + (uint32_t)__popc(b & ((1u << lane) - 1u));
+}
+
+__global__ void __launch_bounds__(XCH_THREADS) k_xch_pack(GridDesc G, ParticleSoA P, unsigned long long n, int has_up,
+	int has_dn, const uint32_t *__restrict__ off_up, const uint32_t *__restrict__ off_dn, double *__restrict__ send_up,
+	double *__restrict__ send_dn) {
+	__shared__ uint32_t wt[32];
+	unsigned long long i = (unsigned long long)blockIdx.x * XCH_THREADS + threadIdx.x;
+	bool up = false, dn = false, dead = false;
+	if (i < n) { xch_classify(G, P.f[PF_PZ][i], has_up, has_dn, up, dn, dead); }
+	const uint32_t ru = block_rank(up, wt), rd = block_rank(dn, wt);
+	if (up) {
+		double *rec = send_up + (size_t)(off_up[blockIdx.x] + ru) * XCH_FIELDS;
+		for (int f = 0; f < XCH_FIELDS; ++f) { rec[f] = P.f[f][i]; }
+	}
+	if (dn) {
+		double *rec = send_dn + (size_t)(off_dn[blockIdx.x] + rd) * XCH_FIELDS;
+		for (int f = 0; f < XCH_FIELDS; ++f) { rec[f] = P.f[f][i]; }
+	}
+	if (dead) { P.f[PF_PZ][i] = __longlong_as_double(0x7ff8000000000000ll); } // NaN: the sort drops it
+}
+
+__global__ void k_xch_unpack(ParticleSoA P, unsigned long long at, const double *__restrict__ recv,
+	unsigned long long n, int with_old) {
+	unsigned long long j = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+	if (j >= n) { return; }
+	const double *rec = recv + j * XCH_FIELDS;
+	for (int f = 0; f < XCH_FIELDS; ++f) { P.f[f][at + j] = rec[f]; }
+	if (with_old) { // old_position == position for a particle in flight between two steps
+		for (int d = 0; d < 3; ++d) { P.f[PF_OX + d][at + j] = rec[d]; }
+	}
+}
+
+static int grow(lfk_ctx *c, double **buf, size_t *cap, size_t need) {
+	if (need <= *cap) { return 0; }
+	if (*buf) { cudaFree(*buf); *buf = nullptr; *cap = 0; }
+	size_t ncap = need + need / 4 + 1024;
+	LFK_CUDA(c, cudaMalloc((void**)buf, ncap * XCH_FIELDS * sizeof(double)));
+	*cap = ncap;
+	return 0;
+}
+
+int lfkx_exchange_particles(lfk_ctx *c, uint64_t *n_in) {
+	*n_in = c->np;
+	if (c->nranks == 1) { return 0; }
+	PhaseTimer T(c, LFK_PHASE_EXCHANGE);
+	const GridDesc &G = c->g;
+	ncclComm_t comm = (ncclComm_t)c->comm;
+	const int has_up = c->rank + 1 < c->nranks ? 1 : 0, has_dn = c->rank > 0 ? 1 : 0;
+	const uint64_t n = c->np;
+	const unsigned nb = lfk_blocks((long long)n, XCH_THREADS);
+	// per-block counts, their scans (nb + 1 entries each): [cnt_up | cnt_dn | off_up | off_dn]
+	const size_t need = 4 * ((size_t)nb + 1);
+	if (need > c->xcnt_n) {
+		if (c->xcnt) { cudaFree(c->xcnt); c->xcnt = nullptr; }
+		LFK_CUDA(c, cudaMalloc((void**)&c->xcnt, need * sizeof(uint32_t)));
+		c->xcnt_n = need;
+	}
+	uint32_t *cnt_up = c->xcnt, *cnt_dn = cnt_up + nb + 1, *off_up = cnt_dn + nb + 1, *off_dn = off_up + nb + 1;
+	ParticleSoA V = lfk_own_view(c);
+	uint32_t *hc = c->h_xcounts;
+	hc[0] = hc[1] = hc[2] = hc[3] = 0;
+	if (n > 0) {
+		LFK_LAUNCH(c, k_xch_count, nb, XCH_THREADS, 0, G, V.f[PF_PZ], (unsigned long long)n, has_up, has_dn, cnt_up, cnt_dn);
+		LFK_TRY(lfkp_exclusive_scan_u32(c, cnt_up, off_up, nb, 0));
+		LFK_TRY(lfkp_exclusive_scan_u32(c, cnt_dn, off_dn, nb, 0));
+		LFK_CUDA(c, cudaMemcpyAsync(hc + 0, off_up + nb, sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+		LFK_CUDA(c, cudaMemcpyAsync(hc + 1, off_dn + nb, sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+		LFK_CUDA(c, cudaStreamSynchronize(c->stream));
+	}
+	const uint32_t send_up = hc[0], send_dn = hc[1];
+	LFK_TRY(grow(c, &c->xsend[0], &c->xsend_cap[0], send_up));
+	LFK_TRY(grow(c, &c->xsend[1], &c->xsend_cap[1], send_dn));
+	if (n > 0) {
+		LFK_LAUNCH(c, k_xch_pack, nb, XCH_THREADS, 0, G, V, (unsigned long long)n, has_up, has_dn, off_up, off_dn,
+			c->xsend[0], c->xsend[1]);
+	}
+	// message sizes
+	LFK_CUDA(c, cudaMemcpyAsync(c->xcounts, hc, 2 * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
+	LFK_CUDA(c, cudaMemsetAsync(c->xcounts + 2, 0, 2 * sizeof(uint32_t), c->stream));
+	LFK_NCCL(c, g_nccl.GroupStart());
+	if (has_up) {
+		LFK_NCCL(c, g_nccl.Send(c->xcounts + 0, 1, ncclUint32, c->rank + 1, comm, c->stream));
+		LFK_NCCL(c, g_nccl.Recv(c->xcounts + 2, 1, ncclUint32, c->rank + 1, comm, c->stream));
+	}
+	if (has_dn) {
+		LFK_NCCL(c, g_nccl.Send(c->xcounts + 1, 1, ncclUint32, c->rank - 1, comm, c->stream));
+		LFK_NCCL(c, g_nccl.Recv(c->xcounts + 3, 1, ncclUint32, c->rank - 1, comm, c->stream));
+	}
+	LFK_NCCL(c, g_nccl.GroupEnd());
+	LFK_CUDA(c, cudaMemcpyAsync(hc + 2, c->xcounts + 2, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+	LFK_CUDA(c, cudaStreamSynchronize(c->stream));
+	const uint32_t recv_up = hc[2], recv_dn = hc[3];
+	// payload: what the lower neighbour sent goes first (deterministic append order)
+	const size_t nrecv = (size_t)recv_up + recv_dn;
+	LFK_TRY(grow(c, &c->xrecv, &c->xrecv_cap, nrecv));
+	LFK_NCCL(c, g_nccl.GroupStart());
+	if (has_up) {
+		if (send_up) { LFK_NCCL(c, g_nccl.Send(c->xsend[0], (size_t)send_up * XCH_FIELDS, ncclDouble, c->rank + 1, comm, c->stream)); }
+		if (recv_up) {
+			LFK_NCCL(c, g_nccl.Recv(c->xrecv + (size_t)recv_dn * XCH_FIELDS, (size_t)recv_up * XCH_FIELDS, ncclDouble,
+				c->rank + 1, comm, c->stream));
+		}
+	}
+	if (has_dn) {
+		if (send_dn) { LFK_NCCL(c, g_nccl.Send(c->xsend[1], (size_t)send_dn * XCH_FIELDS, ncclDouble, c->rank - 1, comm, c->stream)); }
+		if (recv_dn) { LFK_NCCL(c, g_nccl.Recv(c->xrecv, (size_t)recv_dn * XCH_FIELDS, ncclDouble, c->rank - 1, comm, c->stream)); }
+	}
+	LFK_NCCL(c, g_nccl.GroupEnd());
+	if (nrecv > 0) {
+		LFK_TRY(lfkp_reserve_particles(c, n + nrecv)); // may move the own particles to the front (first = 0)
+		LFK_LAUNCH(c, k_xch_unpack, lfk_blocks((long long)nrecv, 256), 256, 0, c->P, (unsigned long long)(c->first + n),
+			c->xrecv, (unsigned long long)nrecv, c->old_valid ? 1 : 0);
+	}
+	c->stats.exchanged_particles = (uint64_t)send_up + send_dn;
+	*n_in = n + nrecv;
 	return 0;
 }

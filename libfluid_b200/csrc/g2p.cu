@@ -20,6 +20,9 @@ struct G2PArgs {
 	const double *u, *v, *w;     // face velocities
 	const double *uo, *vo, *wo;  // FLIP: the pre-projection snapshot
 	const uint32_t *perm;    // FLIP: vs is still in the order before the last sort (NULL: already permuted)
+	// multi-GPU: w / wo of the layer BELOW the lower ghost layer (z0 - 2), or NULL.  The position correction can nudge
+	// an own particle of the bottom layer into the ghost layer; its z-faces then reach one layer further down.
+	const double *w_below, *wo_below;
 	double blend;
 };
 
@@ -51,7 +54,7 @@ __device__ __forceinline__ void face_fetch_setup(const GridDesc &G, const long l
 
 // the 8 samples of component K: index bit 0 <-> x, bit 1 <-> y, bit 2 <-> z
 template <int K> __device__ __forceinline__ void face_samples_comp(const GridDesc &G, const FaceFetch &F,
-	const double *__restrict__ comp, const int *dsel, double *s) {
+	const double *__restrict__ comp, const double *__restrict__ below, const int *dsel, double *s) {
 #pragma unroll
 	for (int k = 0; k < 8; ++k) {
 		int bx = k & 1, by = (k >> 1) & 1, bz = (k >> 2) & 1;
@@ -60,8 +63,16 @@ template <int K> __device__ __forceinline__ void face_samples_comp(const GridDes
 		int dz = K == 2 ? bz : dsel[2] + bz;
 		bool clamped = K == 0 ? F.cl[0][dx] : (K == 1 ? F.cl[1][dy] : F.cl[2][dz]);
 		int lz = F.ci[2][dz] - G.z0 + 1;
+		// multi-GPU: position correction can nudge a boundary particle into the ghost layer, whose far neighbours are
+		// not held by this rank -- the nearest held layer stands in (single GPU: never clamps)
+		const double *src = comp;
+		if (K == 2 && lz < 0 && below != nullptr) { // the extra layer lives in its own one-layer array
+			src = below;
+			lz = 0;
+		}
+		lz = lz < 0 ? 0 : (lz > G.nlz - 1 ? G.nlz - 1 : lz);
 		long long idx = F.ci[0][dx] + (long long)G.nx * (F.ci[1][dy] + (long long)G.ny * lz);
-		s[k] = clamped ? 0.0 : __ldg(comp + idx);
+		s[k] = clamped ? 0.0 : __ldg(src + idx);
 	}
 }
 
@@ -121,21 +132,21 @@ template <int METHOD> __global__ void __launch_bounds__(128) k_g2p(GridDesc G, G
 	face_fetch_setup(G, gi, F);
 	double s[8], vn[3], g[3];
 	// x component: weights (t.x, tmid.y, tmid.z)
-	face_samples_comp<0>(G, F, A.u, dsel, s);
+	face_samples_comp<0>(G, F, A.u, nullptr, dsel, s);
 	trilinear<APIC>(s, t[0], tmid[1], tmid[2], vn[0], g);
 	if (APIC) {
 		A.cd[0][i] = div_h(g[0], G);
 		A.cd[1][i] = div_h(g[1], G);
 		A.cd[2][i] = div_h(g[2], G);
 	}
-	face_samples_comp<1>(G, F, A.v, dsel, s);
+	face_samples_comp<1>(G, F, A.v, nullptr, dsel, s);
 	trilinear<APIC>(s, tmid[0], t[1], tmid[2], vn[1], g);
 	if (APIC) {
 		A.cd[3][i] = div_h(g[0], G);
 		A.cd[4][i] = div_h(g[1], G);
 		A.cd[5][i] = div_h(g[2], G);
 	}
-	face_samples_comp<2>(G, F, A.w, dsel, s);
+	face_samples_comp<2>(G, F, A.w, A.w_below, dsel, s);
 	trilinear<APIC>(s, tmid[0], tmid[1], t[2], vn[2], g);
 	if (APIC) {
 		A.cd[6][i] = div_h(g[0], G);
@@ -144,11 +155,11 @@ template <int METHOD> __global__ void __launch_bounds__(128) k_g2p(GridDesc G, G
 	}
 	if (METHOD == LFK_METHOD_FLIP) { // v = v_new + (v_p - v_old) * blend (:463-505)
 		double vold[3], dummy[3];
-		face_samples_comp<0>(G, F, A.uo, dsel, s);
+		face_samples_comp<0>(G, F, A.uo, nullptr, dsel, s);
 		trilinear<false>(s, t[0], tmid[1], tmid[2], vold[0], dummy);
-		face_samples_comp<1>(G, F, A.vo, dsel, s);
+		face_samples_comp<1>(G, F, A.vo, nullptr, dsel, s);
 		trilinear<false>(s, tmid[0], t[1], tmid[2], vold[1], dummy);
-		face_samples_comp<2>(G, F, A.wo, dsel, s);
+		face_samples_comp<2>(G, F, A.wo, A.wo_below, dsel, s);
 		trilinear<false>(s, tmid[0], tmid[1], t[2], vold[2], dummy);
 		const unsigned long long src = A.perm ? (unsigned long long)A.perm[i] : i;
 #pragma unroll
@@ -169,19 +180,27 @@ int lfkp_g2p(lfk_ctx *c) {
 	// permutation and writes the result to the alternate buffers, which then become current.
 	if (c->c_deferred && method != LFK_METHOD_APIC) { LFK_TRY(lfkp_permute_c(c)); }
 	const bool indirect = c->v_deferred && method == LFK_METHOD_FLIP;
+	if (c->nranks > 1) { // the samples reach into the ghost layers and, for z-faces, one layer below the lower one
+		for (int d = 0; d < 3; ++d) { LFK_TRY(lfkx_halo_f64(c, c->vel[d])); }
+		LFK_TRY(lfkx_layer_below(c, c->vel[2], c->wlow[0]));
+	}
 	if (c->np > 0) {
 		G2PArgs A;
-		A.px = c->P.f[PF_PX];
-		A.py = c->P.f[PF_PY];
-		A.pz = c->P.f[PF_PZ];
+		// own particles are entries [first, first + np); the permutation holds absolute source indices
+		const uint64_t o = c->first;
+		A.px = c->P.f[PF_PX] + o;
+		A.py = c->P.f[PF_PY] + o;
+		A.pz = c->P.f[PF_PZ] + o;
 		for (int d = 0; d < 3; ++d) {
-			A.vs[d] = c->P.f[PF_VX + d];
-			A.vd[d] = indirect ? c->Palt.f[PF_VX + d] : c->P.f[PF_VX + d];
+			A.vs[d] = indirect ? c->P.f[PF_VX + d] : c->P.f[PF_VX + d] + o;
+			A.vd[d] = (indirect ? c->Palt.f[PF_VX + d] : c->P.f[PF_VX + d]) + o;
 		}
-		for (int k = 0; k < 9; ++k) { A.cd[k] = c->P.f[PF_C0 + k]; }
+		for (int k = 0; k < 9; ++k) { A.cd[k] = c->P.f[PF_C0 + k] + o; }
 		A.u = c->vel[0]; A.v = c->vel[1]; A.w = c->vel[2];
 		A.uo = c->vel_old[0]; A.vo = c->vel_old[1]; A.wo = c->vel_old[2];
-		A.perm = indirect ? c->perm : nullptr;
+		A.perm = indirect ? c->perm + o : nullptr;
+		A.w_below = c->rank > 0 ? c->wlow[0] : nullptr;
+		A.wo_below = c->rank > 0 ? c->wlow[1] : nullptr;
 		A.blend = c->prm.blending_factor;
 		unsigned nb = lfk_blocks((long long)c->np, 128);
 		unsigned long long n = c->np;

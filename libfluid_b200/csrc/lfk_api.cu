@@ -44,7 +44,7 @@ template <typename T> static void dev_free(T *&p) {
 }
 
 int lfkp_reserve_particles(lfk_ctx *c, uint64_t n) {
-	if (n <= c->cap) { return 0; }
+	if (c->first + n <= c->cap) { return 0; }
 	if (c->np > 0) { LFK_TRY(lfkp_materialise_vc(c)); } // the permutation buffer is reallocated below
 	uint64_t ncap = std::max<uint64_t>(n, c->cap + c->cap / 4);
 	ncap = (ncap + 1023) / 1024 * 1024;
@@ -58,14 +58,18 @@ int lfkp_reserve_particles(lfk_ctx *c, uint64_t n) {
 	LFK_TRY(dev_alloc(c, &nkalt, ncap));
 	LFK_TRY(dev_alloc(c, &nslot, ncap));
 	LFK_TRY(dev_alloc(c, &nperm, ncap));
-	if (c->np > 0) { // keep what is there
+	if (c->np > 0) { // keep the own particles, now from index 0 (the cell table, if any, becomes invalid)
 		int nf = c->old_valid ? PF_COUNT : 15;
 		for (int f = 0; f < nf; ++f) {
-			LFK_CUDA(c, cudaMemcpyAsync(nP.f[f], c->P.f[f], c->np * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+			LFK_CUDA(c, cudaMemcpyAsync(nP.f[f], c->P.f[f] + c->first, c->np * sizeof(double), cudaMemcpyDeviceToDevice,
+				c->stream));
 		}
-		LFK_CUDA(c, cudaMemcpyAsync(nkey, c->key, c->np * sizeof(uint32_t), cudaMemcpyDeviceToDevice, c->stream));
+		LFK_CUDA(c, cudaMemcpyAsync(nkey, c->key + c->first, c->np * sizeof(uint32_t), cudaMemcpyDeviceToDevice, c->stream));
 		LFK_CUDA(c, cudaStreamSynchronize(c->stream));
 	}
+	if (c->first != 0) { c->table_valid = false; }
+	c->first = 0;
+	c->ntot = c->np;
 	for (int f = 0; f < PF_COUNT; ++f) {
 		dev_free(c->P.f[f]);
 		dev_free(c->Palt.f[f]);
@@ -156,6 +160,8 @@ static int free_all(lfk_ctx *c) {
 	dev_free(c->begin);
 	dev_free(c->valid[0]);
 	dev_free(c->valid[1]);
+	dev_free(c->wlow[0]);
+	dev_free(c->wlow[1]);
 	dev_free(c->flags);
 	dev_free(c->b);
 	dev_free(c->p);
@@ -170,6 +176,12 @@ static int free_all(lfk_ctx *c) {
 	dev_free(c->bigcells);
 	dev_free(c->bigcount);
 	dev_free(c->d_reduce);
+	dev_free(c->xsend[0]);
+	dev_free(c->xsend[1]);
+	dev_free(c->xrecv);
+	dev_free(c->xcnt);
+	dev_free(c->xcounts);
+	if (c->h_xcounts) { cudaFreeHost(c->h_xcounts); c->h_xcounts = nullptr; }
 	if (c->staging) { cudaFree(c->staging); c->staging = nullptr; }
 	if (c->h_scal) { cudaFreeHost(c->h_scal); c->h_scal = nullptr; }
 	if (c->h_reduce) { cudaFreeHost(c->h_reduce); c->h_reduce = nullptr; }
@@ -185,8 +197,10 @@ extern "C" int lfk_create(lfk_ctx **out, uint64_t nx, uint64_t ny, uint64_t nz, 
 	if (nx < 1 || ny < 1 || nz < 1 || nx > 4096 || ny > 4096 || nz > 4096) {
 		return lfk_fail(nullptr, LFK_E_INVALID, "grid size out of range", __FILE__, __LINE__);
 	}
-	if (nranks < 1 || rank < 0 || rank >= nranks || (nranks > 1 && nz < 3 * (uint64_t)nranks)) {
-		return lfk_fail(nullptr, LFK_E_INVALID, "bad rank layout (slabs must be >= 3 cells thick)", __FILE__, __LINE__);
+	// a particle moves at most cfl_number (3) cells per step: with slabs >= 4 cells thick an immigrant cannot reach
+	// the far boundary layer of its new slab within the step it arrives in (one exchange per step suffices)
+	if (nranks < 1 || rank < 0 || rank >= nranks || (nranks > 1 && nz < 4 * (uint64_t)nranks)) {
+		return lfk_fail(nullptr, LFK_E_INVALID, "bad rank layout (slabs must be >= 4 cells thick)", __FILE__, __LINE__);
 	}
 	int ndev = 0;
 	cudaError_t e = cudaGetDeviceCount(&ndev);
@@ -238,10 +252,16 @@ extern "C" int lfk_create(lfk_ctx **out, uint64_t nx, uint64_t ny, uint64_t nz, 
 	CREATE_TRY(dev_alloc(c, &c->ctr[1], (size_t)ny));
 	CREATE_TRY(dev_alloc(c, &c->ctr[2], (size_t)nz));
 	CREATE_TRY(dev_alloc(c, &c->typ, ncl));
-	CREATE_TRY(dev_alloc(c, &c->cnt, ncl));
-	CREATE_TRY(dev_alloc(c, &c->begin, ncl + 1));
+	CREATE_TRY(dev_alloc(c, &c->cnt, ncl + 1));   // + the graveyard bin of the cell sort
+	CREATE_TRY(dev_alloc(c, &c->begin, ncl + 2));
 	CREATE_TRY(dev_alloc(c, &c->valid[0], ncl));
 	CREATE_TRY(dev_alloc(c, &c->valid[1], ncl));
+	if (nranks > 1) {
+		for (int k = 0; k < 2; ++k) {
+			CREATE_TRY(dev_alloc(c, &c->wlow[k], (size_t)G.sxy));
+			CREATE_CUDA(cudaMemsetAsync(c->wlow[k], 0, (size_t)G.sxy * sizeof(double), c->stream));
+		}
+	}
 	CREATE_TRY(dev_alloc(c, &c->flags, ncl));
 	CREATE_TRY(dev_alloc(c, &c->b, ncl));
 	CREATE_TRY(dev_alloc(c, &c->p, ncl));
@@ -258,8 +278,10 @@ extern "C" int lfk_create(lfk_ctx **out, uint64_t nx, uint64_t ny, uint64_t nz, 
 	CREATE_TRY(dev_alloc(c, &c->d_reduce, 16));
 	CREATE_CUDA(cudaMallocHost((void**)&c->h_scal, sizeof(PcgScalars)));
 	CREATE_CUDA(cudaMallocHost((void**)&c->h_reduce, 16 * sizeof(double)));
-	CREATE_CUDA(cudaMemsetAsync(c->cnt, 0, ncl * sizeof(uint32_t), c->stream));
-	CREATE_CUDA(cudaMemsetAsync(c->begin, 0, (ncl + 1) * sizeof(uint32_t), c->stream));
+	CREATE_TRY(dev_alloc(c, &c->xcounts, 8));
+	CREATE_CUDA(cudaMallocHost((void**)&c->h_xcounts, 8 * sizeof(uint32_t)));
+	CREATE_CUDA(cudaMemsetAsync(c->cnt, 0, (ncl + 1) * sizeof(uint32_t), c->stream));
+	CREATE_CUDA(cudaMemsetAsync(c->begin, 0, (ncl + 2) * sizeof(uint32_t), c->stream));
 	CREATE_CUDA(cudaMemsetAsync(c->flags, 0, ncl, c->stream));
 	CREATE_CUDA(cudaMemsetAsync(c->ticket, 0, 4 * sizeof(unsigned), c->stream));
 	CREATE_CUDA(cudaMemsetAsync(c->d_scal, 0, sizeof(PcgScalars), c->stream));
@@ -353,6 +375,8 @@ extern "C" int lfk_upload_particles(lfk_ctx *c, const void *aos152, uint64_t n) 
 	PhaseTimer T(c, LFK_PHASE_TRANSFER);
 	LFK_CUDA(c, cudaSetDevice(c->device));
 	c->np = 0;
+	c->first = 0;
+	c->ntot = 0;
 	c->v_deferred = false;
 	c->c_deferred = false;
 	LFK_TRY(lfkp_reserve_particles(c, n));
@@ -363,6 +387,7 @@ extern "C" int lfk_upload_particles(lfk_ctx *c, const void *aos152, uint64_t n) 
 		LFK_TRY(lfkp_aos_to_soa(c, c->staging, n));
 	}
 	c->np = n;
+	c->ntot = n;
 	c->old_valid = true;
 	c->table_valid = false;
 	c->keys_valid = true;
@@ -483,13 +508,13 @@ extern "C" int lfk_download_old_cells(lfk_ctx *c, void *aos32) {
 }
 
 __global__ void k_table_to_u64(GridDesc G, const uint32_t *__restrict__ begin, unsigned long long *__restrict__ out_b,
-	unsigned long long *__restrict__ out_c) {
+	unsigned long long *__restrict__ out_c, uint32_t first) {
 	long long own = (long long)blockIdx.x * blockDim.x + threadIdx.x;
 	if (own >= G.nown) { return; }
 	long long i = own + G.sxy;
 	uint32_t b = begin[i], n = begin[i + 1] - b;
 	out_c[own] = n;
-	out_b[own] = n ? b : 0; // the reference leaves begin = 0 in empty cells (reset_space_hash)
+	out_b[own] = n ? b - first : 0; // the reference leaves begin = 0 in empty cells (reset_space_hash)
 }
 
 extern "C" int lfk_download_table(lfk_ctx *c, uint64_t *begin, uint64_t *count) {
@@ -499,7 +524,7 @@ extern "C" int lfk_download_table(lfk_ctx *c, uint64_t *begin, uint64_t *count) 
 	size_t nown = (size_t)G.nown;
 	LFK_TRY(reserve_staging(c, nown * 16));
 	unsigned long long *db = (unsigned long long*)c->staging, *dc = db + nown;
-	LFK_LAUNCH(c, k_table_to_u64, lfk_blocks(G.nown, 256), 256, 0, G, c->begin, db, dc);
+	LFK_LAUNCH(c, k_table_to_u64, lfk_blocks(G.nown, 256), 256, 0, G, c->begin, db, dc, (uint32_t)c->first);
 	size_t off = (size_t)G.z0 * G.sxy;
 	LFK_CUDA(c, cudaMemcpyAsync(begin + off, db, nown * 8, cudaMemcpyDeviceToHost, c->stream));
 	LFK_CUDA(c, cudaMemcpyAsync(count + off, dc, nown * 8, cudaMemcpyDeviceToHost, c->stream));

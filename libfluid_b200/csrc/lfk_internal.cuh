@@ -70,8 +70,10 @@ struct lfk_ctx {
 	lfk_params prm{};
 	std::string err;
 
-	// particles
-	uint64_t np = 0, cap = 0;
+	// particles: the rank's OWN particles are entries [first, first + np) of the SoA arrays.  first != 0 only between a
+	// multi-GPU sort and the next one: the sorted array then reads [ghost copies of the lower neighbour's top layer |
+	// own | ghost copies of the upper neighbour's bottom layer], ntot entries in all, addressed by the cell table.
+	uint64_t np = 0, cap = 0, first = 0, ntot = 0;
 	ParticleSoA P{}, Palt{};
 	uint32_t *key = nullptr, *key_alt = nullptr, *slot = nullptr, *perm = nullptr;
 	bool old_valid = false;   // false: old_position == position (not materialised)
@@ -87,6 +89,7 @@ struct lfk_ctx {
 	uint32_t *cnt = nullptr, *begin = nullptr; // begin has ncl + 1 entries
 	double *ctr[3] = { nullptr, nullptr, nullptr }; // cell-centre coordinates per axis (reference: repeated addition)
 	uint8_t *valid[2] = { nullptr, nullptr };
+	double *wlow[2] = { nullptr, nullptr }; // multi-GPU: w (and FLIP's snapshot) of layer z0 - 2, for G2P (g2p.cu)
 
 	// solver
 	uint8_t *flags = nullptr;
@@ -102,6 +105,12 @@ struct lfk_ctx {
 	uint16_t *mg_mask = nullptr;   // level-0 coupling mask (mg.cu)
 	std::vector<int> mg_z0;        // global z of the first owned layer, per level (red-black parity)
 	bool mg_valid = false;
+
+	// multi-GPU particle exchange (exchange.cu)
+	double *xsend[2] = { nullptr, nullptr }, *xrecv = nullptr; // [0] to / from the upper neighbour, [1] the lower one
+	size_t xsend_cap[2] = { 0, 0 }, xrecv_cap = 0;             // in particles (15 doubles each)
+	uint32_t *xcnt = nullptr; size_t xcnt_n = 0;               // per-block emigrant counts + their scans
+	uint32_t *xcounts = nullptr, *h_xcounts = nullptr;         // the 4 message sizes (device / pinned host)
 
 	// scratch
 	void *staging = nullptr; size_t staging_bytes = 0;
@@ -175,7 +184,12 @@ int lfkp_cfl(lfk_ctx *c, double *value);
 int lfkp_seed_box(lfk_ctx *c, const double *start, const double *size, const double *vel, uint32_t dens,
 	uint64_t seed, int append);
 int lfkp_exclusive_scan_u32(lfk_ctx *c, const uint32_t *in, uint32_t *out, long long n, int from_flags);
-int lfkp_reserve_particles(lfk_ctx *c, uint64_t n);
+int lfkp_reserve_particles(lfk_ctx *c, uint64_t n); // room for n entries behind `first` (may compact to first = 0)
+static inline ParticleSoA lfk_own_view(const lfk_ctx *c) { // the own particles as arrays indexed from 0
+	ParticleSoA v = c->P;
+	for (int f = 0; f < PF_COUNT; ++f) { v.f[f] += c->first; }
+	return v;
+}
 
 // ---- implemented in p2g.cu ----
 int lfkg_p2g(lfk_ctx *c, double gravity_dt, bool add_gravity);
@@ -200,6 +214,10 @@ int lfkx_destroy(lfk_ctx *c);
 int lfkx_halo_f64(lfk_ctx *c, double *field);          // fill both z ghost layers of a cell array from the neighbours
 int lfkx_halo_f32(lfk_ctx *c, float *field, int nx, int ny, int nzl);
 int lfkx_halo_u8(lfk_ctx *c, uint8_t *field);
+int lfkx_layer_below(lfk_ctx *c, const double *field, double *dst); // dst <- the lower rank's layer z0 - 2 of field
+// migrates particles that left the slab to the z neighbours and imports ghost copies of the neighbours' boundary
+// layers; appends what arrives behind the own particles and returns the number of entries to sort
+int lfkx_exchange_particles(lfk_ctx *c, uint64_t *n_in);
 int lfkx_allreduce_sum(lfk_ctx *c, double *d_vals, int n);
 int lfkx_allreduce_max(lfk_ctx *c, double *d_vals, int n);
 
@@ -215,6 +233,15 @@ __device__ __forceinline__ double dmax_std(double a, double b) { // std::max(a, 
 }
 __device__ __forceinline__ double dclamp_std(double v, double lo, double hi) { // std::clamp
 	return (v < lo) ? lo : (hi < v) ? hi : v;
+}
+// K1: cell coordinate of a position along one axis (reference src/simulation.cpp:251-261) -- must be bit-exact:
+// IEEE subtraction, IEEE division, truncation toward zero, clamp to [0, n - 1]
+__device__ __forceinline__ int cell_coord_clamped(double pos, double off, const GridDesc &G, int n) {
+	double g = div_h(__dsub_rn(pos, off), G);
+	g = dmax_std(g, 0.0);
+	// static_cast<size_t>: truncation toward zero; cvt.rzi.u64.f64 saturates, and anything >= n clamps to n - 1
+	unsigned long long v = (unsigned long long)g;
+	return (int)(v < (unsigned long long)(n - 1) ? v : (unsigned long long)(n - 1));
 }
 __device__ __forceinline__ unsigned long long mix64(unsigned long long x) {
 	x ^= x >> 30;

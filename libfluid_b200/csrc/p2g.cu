@@ -141,6 +141,10 @@ int lfkg_p2g(lfk_ctx *c, double gravity_dt, bool add_gravity) {
 	static const bool use_gather = getenv("LFK_P2G_GATHER") != nullptr; // A/B switch: the simple gather kernel below
 	if (!use_gather) {
 		LFK_TRY(lfkg_p2g_brick(c, gravity_dt, add_gravity));
+		if (c->nranks > 1 && c->prm.method == LFK_METHOD_FLIP) { // FLIP's G2P samples the snapshot in the ghost layers
+			for (int d = 0; d < 3; ++d) { LFK_TRY(lfkx_halo_f64(c, c->vel_old[d])); }
+			LFK_TRY(lfkx_layer_below(c, c->vel_old[2], c->wlow[1]));
+		}
 		c->system_valid = false;
 		c->pressure_valid = false;
 		return 0;

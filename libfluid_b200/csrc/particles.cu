@@ -73,34 +73,26 @@ int lfkp_aos_to_soa(lfk_ctx *c, const void *d_aos, uint64_t n) {
 	// raw_cell_index is a whole-grid raw index; device keys are local (one ghost layer below the slab)
 	long long shift = ((long long)1 - c->g.z0) * c->g.sxy;
 	LFK_LAUNCH(c, k_aos_to_soa, lfk_blocks((long long)n, AOS_TILE), AOS_TILE, 0,
-		(const unsigned long long*)d_aos, c->P, c->key, (unsigned long long)n, shift);
+		(const unsigned long long*)d_aos, lfk_own_view(c), c->key + c->first, (unsigned long long)n, shift);
 	return 0;
 }
 int lfkp_soa_to_aos(lfk_ctx *c, void *d_aos, uint64_t n) {
 	if (n == 0) { return 0; }
 	long long shift = ((long long)1 - c->g.z0) * c->g.sxy;
 	LFK_LAUNCH(c, k_soa_to_aos, lfk_blocks((long long)n, AOS_TILE), AOS_TILE, 0,
-		(unsigned long long*)d_aos, c->P, c->key, (unsigned long long)n, c->old_valid ? 1 : 0, shift);
+		(unsigned long long*)d_aos, lfk_own_view(c), c->key + c->first, (unsigned long long)n, c->old_valid ? 1 : 0, shift);
 	return 0;
 }
 int lfkp_positions_to_aos(lfk_ctx *c, double *d_xyz, uint64_t n) {
 	if (n == 0) { return 0; }
 	LFK_LAUNCH(c, k_positions_interleave, lfk_blocks((long long)n, 256), 256, 0,
-		d_xyz, c->P.f[PF_PX], c->P.f[PF_PY], c->P.f[PF_PZ], (unsigned long long)n);
+		d_xyz, c->P.f[PF_PX] + c->first, c->P.f[PF_PY] + c->first, c->P.f[PF_PZ] + c->first, (unsigned long long)n);
 	return 0;
 }
 
 // =========================================================================================================
 // K1: cell keys (reference src/simulation.cpp:251-261) -- must be bit-exact: IEEE sub, IEEE div, truncation
 // =========================================================================================================
-__device__ __forceinline__ int cell_coord_clamped(double pos, double off, const GridDesc &G, int n) {
-	double g = div_h(__dsub_rn(pos, off), G);
-	g = dmax_std(g, 0.0);
-	// static_cast<size_t>: truncation toward zero; cvt.rzi.u64.f64 saturates, and anything >= n clamps to n - 1
-	unsigned long long v = (unsigned long long)g;
-	return (int)(v < (unsigned long long)(n - 1) ? v : (unsigned long long)(n - 1));
-}
-
 __global__ void k_keys_hist(GridDesc G, const double *__restrict__ px, const double *__restrict__ py,
 	const double *__restrict__ pz, uint32_t *__restrict__ key, uint32_t *__restrict__ slot,
 	uint32_t *__restrict__ cnt, unsigned long long n) {
@@ -112,8 +104,12 @@ __global__ void k_keys_hist(GridDesc G, const double *__restrict__ px, const dou
 	int y = cell_coord_clamped(py[i], G.off[1], G, G.ny);
 	int z = cell_coord_clamped(pz[i], G.off[2], G, G.nz);
 	int lz = z - G.z0 + 1;
-	lz = lz < 0 ? 0 : (lz > G.nlz - 1 ? G.nlz - 1 : lz); // migrants are handled by the exchange layer
+	lz = lz < 0 ? 0 : (lz > G.nlz - 1 ? G.nlz - 1 : lz);
 	uint32_t k = (uint32_t)(x + (long long)G.nx * (y + (long long)G.ny * lz));
+	// multi-GPU: a particle that left for a neighbour beyond the ghost layer was marked (z = NaN) by the exchange; it
+	// goes to the graveyard bin behind the last cell and drops off the end of the sorted array
+	const double zz = pz[i];
+	if (zz != zz) { k = (uint32_t)G.ncl; }
 	key[i] = k;
 	// warp-aggregated histogram: particles arrive nearly sorted, so a warp touches only a handful of cells
 	unsigned peers = __match_any_sync(amask, k);
@@ -241,11 +237,12 @@ int lfkp_exclusive_scan_u32(lfk_ctx *c, const uint32_t *in, uint32_t *out, long 
 }
 
 // ---- K2: counting sort by cell, made stable by canonicalising the order inside each cell -------------------
+// perm holds ABSOLUTE source indices (entry i of the input view is element first + i of the arrays)
 __global__ void k_scatter_perm(const uint32_t *__restrict__ key, const uint32_t *__restrict__ slot,
-	const uint32_t *__restrict__ begin, uint32_t *__restrict__ perm, unsigned long long n) {
+	const uint32_t *__restrict__ begin, uint32_t *__restrict__ perm, unsigned long long n, uint32_t first) {
 	unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
 	if (i < n) {
-		perm[begin[key[i]] + slot[i]] = (uint32_t)i;
+		perm[begin[key[i]] + slot[i]] = first + (uint32_t)i;
 	}
 }
 
@@ -323,10 +320,10 @@ __global__ void __launch_bounds__(256) k_gather_particles(ParticleSoA dst, Parti
 }
 
 // gathers the selected field groups through c->perm into the alternate buffers and makes those current
-static int permute_groups(lfk_ctx *c, unsigned groups, bool with_key) {
-	if (c->np == 0 || (groups == 0 && !with_key)) { return 0; }
-	LFK_LAUNCH(c, k_gather_particles, lfk_blocks((long long)c->np, 256), 256, 0, c->Palt, c->P, c->key_alt, c->key,
-		c->perm, (unsigned long long)c->np, groups, with_key ? 1 : 0);
+static int permute_groups(lfk_ctx *c, unsigned groups, bool with_key, uint64_t n) {
+	if (n == 0 || (groups == 0 && !with_key)) { return 0; }
+	LFK_LAUNCH(c, k_gather_particles, lfk_blocks((long long)n, 256), 256, 0, c->Palt, c->P, c->key_alt, c->key,
+		c->perm, (unsigned long long)n, groups, with_key ? 1 : 0);
 	for (int g = 0; g < 6; ++g) {
 		if (groups & (1u << g)) {
 			for (int f = 3 * g; f < 3 * g + 3; ++f) {
@@ -350,11 +347,11 @@ int lfkp_materialise_vc(lfk_ctx *c) {
 	unsigned groups = (c->v_deferred ? GROUP_VEL : 0u) | (c->c_deferred ? GROUP_C : 0u);
 	c->v_deferred = false;
 	c->c_deferred = false;
-	return permute_groups(c, groups, false);
+	return permute_groups(c, groups, false, c->ntot);
 }
 int lfkp_permute_c(lfk_ctx *c) {
 	c->c_deferred = false;
-	return permute_groups(c, GROUP_C, false);
+	return permute_groups(c, GROUP_C, false, c->ntot);
 }
 
 // K1 + K2.  lean: only the positions (and keys) are physically permuted.  The velocity -- and for APIC the c rows --
@@ -363,17 +360,23 @@ int lfkp_permute_c(lfk_ctx *c) {
 int lfkp_hash(lfk_ctx *c, bool lean) {
 	PhaseTimer T(c, LFK_PHASE_SORT);
 	const GridDesc &G = c->g;
+	const bool multi = c->nranks > 1;
 	LFK_TRY(lfkp_materialise_vc(c)); // a pending permutation cannot be composed with a new one
-	LFK_CUDA(c, cudaMemsetAsync(c->cnt, 0, (size_t)G.ncl * sizeof(uint32_t), c->stream));
+	// entries to sort: the own particles, plus -- multi-GPU -- what the neighbours sent (immigrants and ghost copies of
+	// their boundary layers), appended behind them
 	uint64_t n = c->np;
+	if (multi) { LFK_TRY(lfkx_exchange_particles(c, &n)); }
+	const size_t nbins = (size_t)G.ncl + 1; // + the graveyard bin
+	LFK_CUDA(c, cudaMemsetAsync(c->cnt, 0, nbins * sizeof(uint32_t), c->stream));
 	if (n > 0) {
-		LFK_LAUNCH(c, k_keys_hist, lfk_blocks((long long)n, 256), 256, 0, G, c->P.f[PF_PX], c->P.f[PF_PY],
-			c->P.f[PF_PZ], c->key, c->slot, c->cnt, (unsigned long long)n);
-	}
-	LFK_TRY(lfkp_exclusive_scan_u32(c, c->cnt, c->begin, G.ncl, 0));
-	if (n > 0) {
-		LFK_LAUNCH(c, k_scatter_perm, lfk_blocks((long long)n, 256), 256, 0, c->key, c->slot, c->begin, c->perm,
+		LFK_LAUNCH(c, k_keys_hist, lfk_blocks((long long)n, 256), 256, 0, G, c->P.f[PF_PX] + c->first,
+			c->P.f[PF_PY] + c->first, c->P.f[PF_PZ] + c->first, c->key + c->first, c->slot, c->cnt,
 			(unsigned long long)n);
+	}
+	LFK_TRY(lfkp_exclusive_scan_u32(c, c->cnt, c->begin, (long long)nbins, 0));
+	if (n > 0) {
+		LFK_LAUNCH(c, k_scatter_perm, lfk_blocks((long long)n, 256), 256, 0, c->key + c->first, c->slot, c->begin,
+			c->perm, (unsigned long long)n, (uint32_t)c->first);
 		LFK_CUDA(c, cudaMemsetAsync(c->bigcount, 0, sizeof(unsigned), c->stream));
 		LFK_LAUNCH(c, k_sort_within_cells, lfk_blocks(G.ncl, 128), 128, 0, c->begin, c->perm, G.ncl, c->bigcells,
 			c->bigcount, c->bigcap);
@@ -389,7 +392,24 @@ int lfkp_hash(lfk_ctx *c, bool lean) {
 		} else {
 			groups |= GROUP_VEL | GROUP_C;
 		}
-		LFK_TRY(permute_groups(c, groups, true));
+		LFK_TRY(permute_groups(c, groups, true, n));
+	}
+	if (multi) { // own range of the sorted array = the owned layers; ghosts sit before / behind it, the dead at the end
+		const uint32_t *src[3] = { c->begin + G.sxy, c->begin + G.sxy * (G.nzl + 1), c->begin + G.ncl };
+		for (int k = 0; k < 3; ++k) {
+			LFK_CUDA(c, cudaMemcpyAsync(c->h_xcounts + 4 + k, src[k], sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+		}
+		LFK_CUDA(c, cudaStreamSynchronize(c->stream));
+		c->first = c->h_xcounts[4];
+		c->np = (uint64_t)c->h_xcounts[5] - c->h_xcounts[4];
+		c->ntot = c->h_xcounts[6];
+		// from here on `cnt` means "own particles per cell" (solver unknowns, fluid-cell list); the ghost layers'
+		// particles stay reachable through `begin`
+		LFK_CUDA(c, cudaMemsetAsync(c->cnt, 0, (size_t)G.sxy * sizeof(uint32_t), c->stream));
+		LFK_CUDA(c, cudaMemsetAsync(c->cnt + (G.ncl - G.sxy), 0, (size_t)G.sxy * sizeof(uint32_t), c->stream));
+	} else {
+		c->first = 0;
+		c->ntot = n;
 	}
 	c->table_valid = true;
 	c->keys_valid = true;
@@ -599,7 +619,7 @@ __global__ void k_advect_collide(GridDesc G, MotionParams M, ParticleSoA P, cons
 static int materialise_old(lfk_ctx *c) {
 	if (!c->old_valid && c->np > 0) {
 		for (int d = 0; d < 3; ++d) {
-			LFK_CUDA(c, cudaMemcpyAsync(c->P.f[PF_OX + d], c->P.f[PF_PX + d], c->np * sizeof(double),
+			LFK_CUDA(c, cudaMemcpyAsync(c->P.f[PF_OX + d] + c->first, c->P.f[PF_PX + d] + c->first, c->np * sizeof(double),
 				cudaMemcpyDeviceToDevice, c->stream));
 		}
 	}
@@ -612,7 +632,7 @@ int lfkp_advect(lfk_ctx *c, double dt) {
 	LFK_TRY(lfkp_materialise_vc(c));
 	LFK_TRY(materialise_old(c));
 	if (c->np == 0) { return 0; }
-	LFK_LAUNCH(c, k_advect, lfk_blocks((long long)c->np, 256), 256, 0, motion_params(c, dt), c->P,
+	LFK_LAUNCH(c, k_advect, lfk_blocks((long long)c->np, 256), 256, 0, motion_params(c, dt), lfk_own_view(c),
 		(unsigned long long)c->np);
 	c->table_valid = false;
 	return 0;
@@ -621,7 +641,7 @@ int lfkp_advect(lfk_ctx *c, double dt) {
 int lfkp_collide(lfk_ctx *c) {
 	PhaseTimer T(c, LFK_PHASE_ADVECT_COLLIDE);
 	if (c->np > 0) {
-		LFK_LAUNCH(c, k_collide, lfk_blocks((long long)c->np, 128), 128, 0, c->g, motion_params(c, 0.0), c->P, c->typ,
+		LFK_LAUNCH(c, k_collide, lfk_blocks((long long)c->np, 128), 128, 0, c->g, motion_params(c, 0.0), lfk_own_view(c), c->typ,
 			(unsigned long long)c->np, c->old_valid ? 1 : 0);
 	}
 	c->old_valid = false; // old_position = position (reference src/simulation.cpp:57-59,115-117)
@@ -636,8 +656,8 @@ int lfkp_advect_collide(lfk_ctx *c, double dt) {
 	}
 	LFK_TRY(lfkp_materialise_vc(c));
 	if (c->np > 0) {
-		LFK_LAUNCH(c, k_advect_collide, lfk_blocks((long long)c->np, 128), 128, 0, c->g, motion_params(c, dt), c->P,
-			c->typ, (unsigned long long)c->np);
+		LFK_LAUNCH(c, k_advect_collide, lfk_blocks((long long)c->np, 128), 128, 0, c->g, motion_params(c, dt),
+			lfk_own_view(c), c->typ, (unsigned long long)c->np);
 	}
 	c->table_valid = false;
 	return 0;
@@ -975,8 +995,11 @@ int lfkp_cfl(lfk_ctx *c, double *value) {
 	if (c->np > 0) {
 		unsigned nb = lfk_blocks((long long)c->np, 256);
 		if (nb > 148 * 8) { nb = 148 * 8; }
-		LFK_LAUNCH(c, k_max_speed2, nb, 256, 0, c->P.f[PF_VX], c->P.f[PF_VY], c->P.f[PF_VZ],
-			(unsigned long long)c->np, (unsigned long long*)c->d_reduce);
+		// (the maximum does not depend on the order, so a velocity payload still in pre-sort order is fine -- but then it
+		// lives at the pre-sort indices, hence materialise first when a permutation is pending)
+		LFK_TRY(lfkp_materialise_vc(c));
+		LFK_LAUNCH(c, k_max_speed2, nb, 256, 0, c->P.f[PF_VX] + c->first, c->P.f[PF_VY] + c->first,
+			c->P.f[PF_VZ] + c->first, (unsigned long long)c->np, (unsigned long long*)c->d_reduce);
 	}
 	if (c->nranks > 1) {
 		LFK_TRY(lfkx_allreduce_max(c, c->d_reduce, 1));
@@ -1035,6 +1058,8 @@ int lfkp_seed_box(lfk_ctx *c, const double *start, const double *size, const dou
 	const GridDesc &G = c->g;
 	if (!append) {
 		c->np = 0;
+		c->first = 0;
+		c->ntot = 0;
 		c->v_deferred = false;
 		c->c_deferred = false;
 	}
@@ -1060,9 +1085,9 @@ int lfkp_seed_box(lfk_ctx *c, const double *start, const double *size, const dou
 	LFK_TRY(lfkp_reserve_particles(c, c->np + total));
 	unsigned long long *counter = (unsigned long long*)c->d_reduce;
 	LFK_CUDA(c, cudaMemsetAsync(counter, 0, sizeof(unsigned long long), c->stream));
-	LFK_LAUNCH(c, k_seed_box, lfk_blocks((long long)total, 256), 256, 0, G, c->P, c->key, c0[0], c0[1], c0[2],
+	LFK_LAUNCH(c, k_seed_box, lfk_blocks((long long)total, 256), 256, 0, G, lfk_own_view(c), c->key + c->first, c0[0], c0[1], c0[2],
 		(int)ex, (int)ey, (int)ez, start[0], start[1], start[2], end[0], end[1], end[2], vel[0], vel[1], vel[2],
-		dens, (unsigned long long)seed, (unsigned long long)c->np, counter, (unsigned long long)c->cap);
+		dens, (unsigned long long)seed, (unsigned long long)c->np, counter, (unsigned long long)(c->cap - c->first));
 	LFK_CUDA(c, cudaMemcpyAsync(c->h_reduce, counter, sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
 	LFK_CUDA(c, cudaStreamSynchronize(c->stream));
 	unsigned long long added;

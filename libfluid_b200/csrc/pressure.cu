@@ -584,6 +584,8 @@ int lfks_synthetic_projection(lfk_ctx *c, uint64_t seed) {
 	LFK_LAUNCH(c, k_synthetic_projection, lfk_blocks(G.nown, 256), 256, 0, G, c->typ, c->cnt, c->vel[0], c->vel[1],
 		c->vel[2], (unsigned long long)seed);
 	c->np = 0;
+	c->first = 0;
+	c->ntot = 0;
 	c->table_valid = false;
 	c->ordinal_valid = false;
 	c->system_valid = false;

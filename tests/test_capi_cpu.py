@@ -36,9 +36,9 @@ def test_library_exports_every_declared_symbol(lib):
 
 
 def test_struct_layouts_match_header():
-    # lfk_params: 3+1+1+3+1+1+1+1+1 doubles, then 4 int32 ; lfk_stats: u64,u64,f64,16 f64,u64,u64
+    # lfk_params: 3+1+1+3+1+1+1+1+1 doubles, then 4 int32 ; lfk_stats: u64,u64,f64,16 f64,u64,u64,u64
     assert C.sizeof(capi.Params) == 13 * 8 + 4 * 4
-    assert C.sizeof(capi.Stats) == (3 + 16 + 2) * 8
+    assert C.sizeof(capi.Stats) == (3 + 16 + 3) * 8
     assert capi.PARTICLE_DTYPE.itemsize == 152 and capi.CELL_DTYPE.itemsize == 32
 
 
@@ -55,6 +55,6 @@ def test_no_cpu_fallback(lib):
 def test_create_rejects_bad_arguments(lib):
     ptr = C.c_void_p()
     assert lib.lfk_create(C.byref(ptr), 0, 8, 8, 0, None, 1, 0, None) == -2000
-    assert lib.lfk_create(C.byref(ptr), 8, 8, 8, 0, None, 4, 0, None) == -2000   # slabs thinner than 3 cells
+    assert lib.lfk_create(C.byref(ptr), 8, 8, 8, 0, None, 4, 0, None) == -2000   # slabs thinner than 4 cells
     assert lib.lfk_create(None, 8, 8, 8, 0, None, 1, 0, None) == -2000
     assert lib.lfk_set_params(None, None) == -2000

@@ -190,3 +190,17 @@ def test_fused_step_equals_staged_step_on_device(scene):
         assert PL.rel_l2(pa[f], pb[f]) < 1e-13, f
     assert np.array_equal(ca["type"], cb["type"])
     assert PL.rel_l2(ca["vel"], cb["vel"]) < 1e-13
+
+
+def test_two_gpu_slabs_match_single_gpu():
+    """z-slab decomposition with particle migration, ghost copies and NCCL halos against the single-GPU run of the
+    same scene (tests/mgpu_check.py under torchrun; needs >= 2 GPUs)."""
+    import subprocess
+    import sys
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
+           "127.0.0.1", "--master-port", "29517", os.path.join(os.path.dirname(__file__), "mgpu_check.py")]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
