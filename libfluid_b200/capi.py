@@ -56,7 +56,7 @@ SYMBOLS = (
     "lfk_pressure_solve", "lfk_download_rhs", "lfk_download_pressure", "lfk_upload_pressure", "lfk_apply_a",
     "lfk_apply_pressure", "lfk_correct", "lfk_extrapolate", "lfk_g2p", "lfk_cfl", "lfk_time_step",
     "lfk_time_step_cfl", "lfk_update", "lfk_seed_box_device", "lfk_synthetic_projection_device", "lfk_set_timing",
-    "lfk_get_stats", "lfk_reset_stats",
+    "lfk_set_tuning", "lfk_get_stats", "lfk_reset_stats",
 )
 
 _lib = None
@@ -104,6 +104,7 @@ def load_library():
     L.lfk_seed_box_device.argtypes = [vp, vp, vp, vp, C.c_uint32, u64, ci]
     L.lfk_synthetic_projection_device.argtypes = [vp, u64]
     L.lfk_set_timing.argtypes = [vp, ci]
+    L.lfk_set_tuning.argtypes = [vp, C.c_char_p, ci]
     L.lfk_get_stats.argtypes = [vp, C.POINTER(Stats)]
     _lib = L
     return L
@@ -345,6 +346,10 @@ class Context:
     # -- instrumentation --
     def set_timing(self, on):
         self._ck(self.L.lfk_set_timing(self.ptr, int(bool(on))))
+
+    def set_tuning(self, key, value):
+        """A/B switch between kernel variants computing the same result (lfk_set_tuning)."""
+        self._ck(self.L.lfk_set_tuning(self.ptr, key.encode(), int(value)))
 
     def stats(self):
         s = Stats()

@@ -190,6 +190,8 @@ static int free_all(lfk_ctx *c) {
 
 int lfkm_free(lfk_ctx *c); // mg.cu
 
+extern "C" int lfk_set_tuning(lfk_ctx *c, const char *key, int value);
+
 extern "C" int lfk_create(lfk_ctx **out, uint64_t nx, uint64_t ny, uint64_t nz, int device, void *stream,
 	int nranks, int rank, const void *nccl_id128) {
 	if (!out) { return lfk_fail(nullptr, LFK_E_INVALID, "out is NULL", __FILE__, __LINE__); }
@@ -297,6 +299,19 @@ extern "C" int lfk_create(lfk_ctx **out, uint64_t nx, uint64_t ny, uint64_t nz, 
 	CREATE_CUDA(cudaStreamSynchronize(c->stream));
 #undef CREATE_CUDA
 #undef CREATE_TRY
+	// LFK_TUNE="key=value,key=value": lfk_set_tuning for every context of the process (A/B runs of unmodified callers)
+	if (const char *env = getenv("LFK_TUNE")) {
+		std::string spec(env);
+		size_t pos = 0;
+		while (pos < spec.size()) {
+			size_t end = spec.find(',', pos);
+			if (end == std::string::npos) { end = spec.size(); }
+			const std::string item = spec.substr(pos, end - pos);
+			const size_t eq = item.find('=');
+			if (eq != std::string::npos) { lfk_set_tuning(c, item.substr(0, eq).c_str(), atoi(item.c_str() + eq + 1)); }
+			pos = end + 1;
+		}
+	}
 	*out = c;
 	return 0;
 }
@@ -697,7 +712,7 @@ extern "C" int lfk_time_step(lfk_ctx *c, double dt) {
 	LFK_TRY(lfkp_advect_collide(c, dt));            // :50-60
 	LFK_TRY(lfkp_hash(c, true));                    // :62-64 (lean: v / c are read through the permutation)
 	LFK_TRY(lfkg_p2g(c, dt, true));                 // :66-78 (gravity fused)
-	LFK_TRY(lfks_solve(c, dt, nullptr, nullptr));   // :83-99
+	LFK_TRY(lfks_solve(c, dt, nullptr, nullptr, true)); // :83-99 (initial guess: the previous step's pressure)
 	LFK_TRY(lfks_apply_pressure(c, dt));            // :104
 	LFK_TRY(lfkp_correct_collide(c, dt));           // :110-117
 	LFK_TRY(lfks_extrapolate(c));                   // :119
@@ -751,6 +766,18 @@ extern "C" int lfk_synthetic_projection_device(lfk_ctx *c, uint64_t seed) {
 extern "C" int lfk_set_timing(lfk_ctx *c, int enabled) {
 	if (!c) { return LFK_E_INVALID; }
 	c->timing = enabled != 0;
+	return 0;
+}
+extern "C" int lfk_set_tuning(lfk_ctx *c, const char *key, int value) {
+	if (!c || !key) { return LFK_E_INVALID; }
+	const std::string k(key);
+	if (k == "p2g") { c->tune.p2g = value; }
+	else if (k == "correct") { c->tune.correct = value; }
+	else if (k == "mg_tail") { c->tune.mg_tail = value; }
+	else if (k == "spmv") { c->tune.spmv = value; }
+	else if (k == "warm_start") { c->tune.warm_start = value; }
+	else if (k == "red_blocks") { c->tune.red_blocks = value; }
+	else { return lfk_fail(c, LFK_E_INVALID, "lfk_set_tuning: unknown key", __FILE__, __LINE__); }
 	return 0;
 }
 extern "C" int lfk_get_stats(lfk_ctx *c, lfk_stats *out) {

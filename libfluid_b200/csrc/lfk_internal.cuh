@@ -60,8 +60,20 @@ struct MgLevel {
 	float *x, *b, *r;        // solution / rhs / residual scratch (fp32)
 };
 
+// A/B switches and tuning knobs (lfk_set_tuning; the defaults are the production path)
+enum { LFK_TUNE_P2G_MARCH = 0, LFK_TUNE_P2G_BRICK = 1, LFK_TUNE_P2G_GATHER = 2 };
+struct lfk_tuning {
+	int p2g = LFK_TUNE_P2G_MARCH;
+	int correct = 0;  // 0: production position-correction kernel, 1: the previous one (A/B)
+	int mg_tail = 0;  // 0: shared-memory coarse tail, 1: the global-memory one (A/B)
+	int spmv = 0;     // 0: production SpMV + dot, 1: the previous one (A/B)
+	int warm_start = 1; // fused step: start PCG from the previous step's pressure (0: from p = 0 like the reference)
+	int red_blocks = 0; // > 0: cap on the grid of the PCG reduction kernels (default RED_BLOCKS)
+};
+
 struct lfk_ctx {
 	int device = 0;
+	lfk_tuning tune;
 	cudaStream_t stream = nullptr;
 	bool own_stream = false;
 	int nranks = 1, rank = 0;
@@ -96,6 +108,9 @@ struct lfk_ctx {
 	double *b = nullptr, *p = nullptr, *r = nullptr, *z = nullptr, *s = nullptr;
 	bool system_valid = false; double system_dt = 0.0;
 	bool pressure_valid = false;
+	double warm_scale = 0.0;        // != 0: lfks_build_system seeds p with warm_scale * (previous p)
+	bool warm_applied = false;
+	double last_solve_dt = 0.0; bool last_solve_ok = false; uint64_t last_iters = 0;
 	PcgScalars *d_scal = nullptr, *h_scal = nullptr;
 	double *partials = nullptr;     // [4][MAX_PARTIAL_BLOCKS]
 	unsigned *ticket = nullptr;     // last-block counters
@@ -197,7 +212,7 @@ int lfkg_gravity(lfk_ctx *c, double dt);
 
 // ---- implemented in pressure.cu ----
 int lfks_build_system(lfk_ctx *c, double dt);
-int lfks_solve(lfk_ctx *c, double dt, double *residual, uint64_t *iters);
+int lfks_solve(lfk_ctx *c, double dt, double *residual, uint64_t *iters, bool warm = false);
 int lfks_apply_pressure(lfk_ctx *c, double dt);
 int lfks_extrapolate(lfk_ctx *c);
 int lfks_apply_a(lfk_ctx *c, double dt, const double *d_v_dense, double *d_out_dense);

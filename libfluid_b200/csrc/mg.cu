@@ -369,8 +369,43 @@ __device__ __forceinline__ void tail_prolong(const LevelDev &F, const LevelDev &
 	__syncthreads();
 }
 
+__device__ __forceinline__ void tail_cycle(const TailLevels &T);
+
 __global__ void __launch_bounds__(1024) k_mg_tail(TailLevels T, const PcgScalars *scal) {
 	if (scal->done) { return; }
+	tail_cycle(T);
+}
+
+// Production variant: the tail levels (a few thousand cells in all) are copied into shared memory first, so the ~70
+// dependent half-sweeps / transfers of the tail run at shared-memory latency instead of L2 latency.
+__global__ void __launch_bounds__(1024) k_mg_tail_smem(TailLevels T, const PcgScalars *scal) {
+	if (scal->done) { return; }
+	extern __shared__ float tail_sm[];
+	TailLevels S = T;
+	float *ptr = tail_sm;
+	for (int l = 0; l < T.n; ++l) {
+		const LevelDev &L = T.L[l];
+		const int n = (int)(L.sxy * (L.nzl + 2)) + 2;
+		float *d = ptr, *cx = ptr + n, *cy = ptr + 2 * n, *cz = ptr + 3 * n, *x = ptr + 4 * n, *b = ptr + 5 * n;
+		ptr += 6 * n;
+		for (int i = (int)threadIdx.x; i < n; i += (int)blockDim.x) {
+			d[i] = L.diag[i];
+			cx[i] = L.cx[i];
+			cy[i] = L.cy[i];
+			cz[i] = L.cz[i];
+			x[i] = l == 0 ? L.x[i] : 0.f; // deeper levels are filled by the restrictions below; ghost entries stay 0
+			b[i] = l == 0 ? L.b[i] : 0.f;
+		}
+		S.L[l].diag = d; S.L[l].cx = cx; S.L[l].cy = cy; S.L[l].cz = cz; S.L[l].x = x; S.L[l].b = b;
+	}
+	__syncthreads();
+	tail_cycle(S);
+	const LevelDev &L0 = T.L[0];
+	const int n0 = (int)(L0.sxy * (L0.nzl + 2)) + 2;
+	for (int i = (int)threadIdx.x; i < n0; i += (int)blockDim.x) { L0.x[i] = S.L[0].x[i]; }
+}
+
+__device__ __forceinline__ void tail_cycle(const TailLevels &T) {
 	const int last = T.n - 1;
 	for (int l = 0; l < last; ++l) { // down: x of the entry level was zeroed by the restriction that filled its b
 		for (int s = 0; s < MG_PRE; ++s) {
@@ -555,7 +590,18 @@ static int vcycle(lfk_ctx *c, size_t l) {
 		for (size_t k = l; k <= last; ++k) {
 			T.L[T.n++] = level_dev(c->mg[k], c->mg_z0[k]);
 		}
-		LFK_LAUNCH(c, k_mg_tail, 1, 1024, 0, T, c->d_scal);
+		size_t smem = 0;
+		for (int k = 0; k < T.n; ++k) { smem += 6 * ((size_t)(T.L[k].sxy * (T.L[k].nzl + 2)) + 2) * sizeof(float); }
+		if (c->tune.mg_tail == 0 && smem <= 200 * 1024) {
+			static bool attr_set = false;
+			if (!attr_set) {
+				LFK_CUDA(c, cudaFuncSetAttribute(k_mg_tail_smem, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+				attr_set = true;
+			}
+			LFK_LAUNCH(c, k_mg_tail_smem, 1, 1024, smem, T, c->d_scal);
+		} else {
+			LFK_LAUNCH(c, k_mg_tail, 1, 1024, 0, T, c->d_scal);
+		}
 		return 0;
 	}
 	if (l == last) { // coarsest level reached outside the tail (multi-GPU alignment limit, or a tiny fine grid)

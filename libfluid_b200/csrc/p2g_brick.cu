@@ -20,6 +20,7 @@
 // This file is compiled WITH fused multiply-add (the summation order already differs from the reference's, P2G is
 // tolerance-checked: rel-L2 <= 1e-12 against the oracle).
 #include "lfk_internal.cuh"
+#include "p2g_accum.cuh"
 
 // Brick 30 x 10 x 7 faces => 12 x 9 rows of 32 cells; every colour (y mod 3, z mod 3) has exactly 4 x 3 = 12 rows =
 // two balanced rounds for 6 warps.  ~90 KB of shared memory per block => two blocks (12 warps) per SM.
@@ -30,89 +31,7 @@
 #define PB_RZ (PB_BZ + 2)
 #define PB_WARPS 6
 #define PB_THREADS (PB_WARPS * 32)
-#define PB_WIN 4                 // particle slots per cell staged at a time
-#define PB_CSTRIDE (PB_WIN + 1)  // padded: lane stride of 5 doubles is bank-conflict free
-#define PB_FSTRIDE (32 * PB_CSTRIDE)
-#define PB_FIELDS 7              // pos(3) + v_k + c_k(3)
 #define PB_ACC_COMP (2 * PB_BZ * PB_BY * 32) // one velocity component: sum(w) and sum(w v) per face
-
-struct PBParams {
-	double half, inv_h;
-	double gdt[3];
-	int add_gravity;
-	int hdiv; // PIC / FLIP: weights use (x_p - x_face) / h
-};
-
-__device__ __forceinline__ void cp_async8(double *smem, const double *gmem) {
-	unsigned s = (unsigned)__cvta_generic_to_shared(smem);
-	asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(s), "l"(gmem) : "memory");
-}
-__device__ __forceinline__ void cp_async_wait_all() {
-	asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;" ::: "memory");
-}
-__device__ __forceinline__ double hatw(double d) {
-	return fmax(0.0, 1.0 - fabs(d));
-}
-
-// Contributions of the staged particles of one cell to one velocity component.  COMP selects which axis is
-// staggered: the staggered axis has 2 reachable faces (cell - 1, cell), the other two axes 3 (cell - 1 .. cell + 1).
-template <int COMP, bool APIC> __device__ __forceinline__ void accumulate_cell(const double *__restrict__ st,
-	int lane, int nslots, const double *cc /* cell-centre coords of cell-1, cell, cell+1 per axis: [3][3] */,
-	double half, double inv_h, int hdiv, double *accw, double *accv) {
-	constexpr int NA = COMP == 0 ? 2 : 3, NB = COMP == 1 ? 2 : 3, NC = COMP == 2 ? 2 : 3;
-	// sample positions per axis: staggered axis -> +face of (cell - 1), +face of cell; others -> centres
-	double sx[NA], sy[NB], sz[NC];
-#pragma unroll
-	for (int a = 0; a < NA; ++a) { sx[a] = COMP == 0 ? cc[0 * 3 + a] + half : cc[0 * 3 + a]; }
-#pragma unroll
-	for (int b = 0; b < NB; ++b) { sy[b] = COMP == 1 ? cc[1 * 3 + b] + half : cc[1 * 3 + b]; }
-#pragma unroll
-	for (int c = 0; c < NC; ++c) { sz[c] = COMP == 2 ? cc[2 * 3 + c] + half : cc[2 * 3 + c]; }
-	const double *sp = st + lane * PB_CSTRIDE;
-	for (int s = 0; s < nslots; ++s) {
-		const double px = sp[0 * PB_FSTRIDE + s], py = sp[1 * PB_FSTRIDE + s], pz = sp[2 * PB_FSTRIDE + s];
-		const double vk = sp[3 * PB_FSTRIDE + s];
-		double c0 = 0.0, c1 = 0.0, c2 = 0.0;
-		if (APIC) {
-			c0 = sp[4 * PB_FSTRIDE + s];
-			c1 = sp[5 * PB_FSTRIDE + s];
-			c2 = sp[6 * PB_FSTRIDE + s];
-		}
-		double wx[NA], wy[NB], wz[NC], ax[NA], by[NB], cz[NC];
-#pragma unroll
-		for (int a = 0; a < NA; ++a) {
-			double d = px - sx[a];
-			wx[a] = hatw(hdiv ? d * inv_h : d);
-			ax[a] = vk - c0 * d; // v_k + c_k0 * (x_sample - x_p)
-		}
-#pragma unroll
-		for (int b = 0; b < NB; ++b) {
-			double d = py - sy[b];
-			wy[b] = hatw(hdiv ? d * inv_h : d);
-			by[b] = -c1 * d;
-		}
-#pragma unroll
-		for (int c = 0; c < NC; ++c) {
-			double d = pz - sz[c];
-			wz[c] = hatw(hdiv ? d * inv_h : d);
-			cz[c] = -c2 * d;
-		}
-#pragma unroll
-		for (int c = 0; c < NC; ++c) {
-#pragma unroll
-			for (int b = 0; b < NB; ++b) {
-				const double wyz = wy[b] * wz[c], bc = by[b] + cz[c];
-#pragma unroll
-				for (int a = 0; a < NA; ++a) {
-					const double w = wx[a] * wyz;
-					const int t = (c * NB + b) * NA + a;
-					accw[t] += w;
-					accv[t] = fma(w, ax[a] + bc, accv[t]);
-				}
-			}
-		}
-	}
-}
 
 // add the lane's 18 partial sums into the block tile, one neighbour offset at a time
 template <int COMP> __device__ __forceinline__ void flush_cell(double *__restrict__ acc, int fx0, int fy0, int fz0,

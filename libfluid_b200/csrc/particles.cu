@@ -930,6 +930,240 @@ template <bool COLLIDE> __global__ void __launch_bounds__(CT_THREADS, 2) k_corre
 	}
 }
 
+// ---- production variant of the tiled kernel: packed-fp32 pre-filter --------------------------------------------
+// Same tiling, same culling, same fp64 evaluation in the reference's order; what changes is the candidate test, which
+// is where the instructions go (~100 candidates per particle, ~12 of them within the kernel radius):
+//   * staged coordinates are in CELL units relative to the tile centre, stored as PAIRS of candidates
+//     {x0 x1 y0 y1} {z0 z1 w0 w1} with w = |q|^2, so that d^2 - T = w - 2 r.q - T (T = radius^2 + margin - |r|^2) of
+//     two candidates costs three packed FMAs and one packed add (sm_100 FFMA2 / FADD2), and its SIGN is the test;
+//   * the sign bytes of four candidates are gathered with three byte-permutes into one word; one mask test decides
+//     whether the group is recorded (the word plus the pair index), so a miss costs no predicated bookkeeping.
+// ~4.75 instructions per candidate against ~10 for the scalar d^2 test of k_correct_tiled (kept as the A/B kernel).
+// Rounding: |coordinates| <= 17.1 cells, so every intermediate is below 620 and carries an error below 4e-5; the
+// margin of 2e-3 cells^2 covers the sum of all of them 10x over, so the filter never drops a true neighbour.
+#define CT2_MARGIN 2e-3f
+#define CT2_LIST 32 // recorded groups per particle (each holds up to 4 neighbours)
+
+__device__ __forceinline__ unsigned long long f32x2_fma(unsigned long long a, unsigned long long b,
+	unsigned long long c) {
+	unsigned long long d;
+	asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+	return d;
+}
+__device__ __forceinline__ unsigned long long f32x2_add(unsigned long long a, unsigned long long b) {
+	unsigned long long d;
+	asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+	return d;
+}
+__device__ __forceinline__ unsigned long long f32x2_splat(float v) {
+	const unsigned long long u = (unsigned long long)__float_as_uint(v);
+	return (u << 32) | u;
+}
+
+template <bool COLLIDE> __global__ void __launch_bounds__(CT_THREADS, 2) k_correct_tiled2(GridDesc G, MotionParams M,
+	ParticleSoA P, double *__restrict__ nx_, double *__restrict__ ny_, double *__restrict__ nz_,
+	const uint32_t *__restrict__ begin, const uint8_t *__restrict__ typ) {
+	extern __shared__ ulonglong2 stage2[]; // pair g: stage2[2 g] = {x0 x1 | y0 y1}, stage2[2 g + 1] = {z0 z1 | w0 w1}
+	__shared__ uint32_t rowstart[CT_ROWS], rowoff[CT_ROWS + 1], cellbeg[CT_ROWS][CT_LX + 3];
+	__shared__ uint32_t ownbeg[CT_OWN], ownpre[CT_OWN + 1];
+	const double *__restrict__ px = P.f[PF_PX], *__restrict__ py = P.f[PF_PY], *__restrict__ pz = P.f[PF_PZ];
+	const int x0 = blockIdx.x * CT_LX, y0 = blockIdx.y * CT_TY, lz0 = blockIdx.z * CT_TZ + 1;
+	const int tid = threadIdx.x;
+
+	// ---- table of the staged rows ----
+	for (int e = tid; e < CT_ROWS * (CT_LX + 3); e += CT_THREADS) {
+		int r = e / (CT_LX + 3), k = e % (CT_LX + 3);
+		int y = y0 - 1 + r % CT_SY, lz = lz0 - 1 + r / CT_SY;
+		uint32_t v = 0;
+		if (y >= 0 && y < G.ny && lz >= 0 && lz < G.nlz) {
+			long long row = (long long)G.nx * (y + (long long)G.ny * lz);
+			int xa = x0 - 1 < 0 ? 0 : x0 - 1;
+			int xk = x0 - 1 + k;
+			xk = xk < 0 ? 0 : (xk > G.nx ? G.nx : xk);
+			uint32_t base = begin[row + xa];
+			v = begin[row + xk] - base;
+			if (k == 0) { rowstart[r] = base; }
+		} else if (k == 0) {
+			rowstart[r] = 0;
+		}
+		cellbeg[r][k] = v;
+	}
+	__syncthreads();
+	if (tid == 0) {
+		uint32_t acc = 0;
+		for (int r = 0; r < CT_ROWS; ++r) { // every row starts on a pair boundary
+			rowoff[r] = acc;
+			acc += (cellbeg[r][CT_LX + 2] + 1u) & ~1u;
+		}
+		rowoff[CT_ROWS] = acc;
+		uint32_t oacc = 0;
+		for (int o = 0; o < CT_OWN; ++o) { // own rows: cells x0 .. x0 + LX - 1 (clipped) of the inner rows
+			int r = (o / CT_TY + 1) * CT_SY + (o % CT_TY + 1);
+			int y = y0 + o % CT_TY, lz = lz0 + o / CT_TY;
+			uint32_t nown = 0;
+			if (y < G.ny && lz <= G.nzl) {
+				nown = cellbeg[r][CT_LX + 1] - cellbeg[r][1];
+			}
+			ownbeg[o] = rowstart[r] + cellbeg[r][1];
+			ownpre[o] = oacc;
+			oacc += nown;
+		}
+		ownpre[CT_OWN] = oacc;
+	}
+	__syncthreads();
+	const uint32_t nown_total = ownpre[CT_OWN];
+	if (nown_total == 0) { return; }
+	const uint32_t staged = rowoff[CT_ROWS];
+	const bool use_stage = staged <= CT_CAP;
+	// tile centre, fp64; staged coordinates are relative to it, in cells
+	const double ctr[3] = { G.off[0] + ((double)x0 + 0.5 * CT_LX) * G.h, G.off[1] + ((double)y0 + 0.5 * CT_TY) * G.h,
+		G.off[2] + ((double)(lz0 - 1 + G.z0) + 0.5 * CT_TZ) * G.h };
+	if (use_stage) {
+		float *sf = reinterpret_cast<float *>(stage2); // pair g: floats 8 g + {0 1 | 2 3 | 4 5 | 6 7} = x x y y z z w w
+		for (int r = 0; r < CT_ROWS; ++r) {
+			const uint32_t cnt = cellbeg[r][CT_LX + 2], gs = rowstart[r], so = rowoff[r];
+			const uint32_t padded = (cnt + 1u) & ~1u;
+			for (uint32_t j = tid; j < padded; j += CT_THREADS) {
+				float fx = 0.f, fy = 0.f, fz = 0.f, fw = 1e30f; // padding: never within reach
+				if (j < cnt) {
+					const uint32_t q = gs + j;
+					fx = (float)((px[q] - ctr[0]) * G.inv_h);
+					fy = (float)((py[q] - ctr[1]) * G.inv_h);
+					fz = (float)((pz[q] - ctr[2]) * G.inv_h);
+					fw = __fmaf_rn(fz, fz, __fmaf_rn(fy, fy, fx * fx));
+				}
+				const uint32_t s = so + j;
+				float *dst = sf + (s >> 1) * 8 + (s & 1u);
+				dst[0] = fx;
+				dst[2] = fy;
+				dst[4] = fz;
+				dst[6] = fw;
+			}
+		}
+	}
+	__syncthreads();
+
+	for (uint32_t t = tid; t < nown_total; t += CT_THREADS) {
+		int o = 0;
+#pragma unroll
+		for (int k = 1; k < CT_OWN; ++k) {
+			if (t >= ownpre[k]) { o = k; }
+		}
+		const unsigned long long i = (unsigned long long)ownbeg[o] + (t - ownpre[o]);
+		const int oy = o % CT_TY, oz = o / CT_TY;
+		double p[3] = { px[i], py[i], pz[i] };
+		double sx = 0.0, sy = 0.0, sz = 0.0;
+		// unclamped cell and in-cell fraction (compute_cell_index)
+		long long ci[3];
+		float fr[3];
+#pragma unroll
+		for (int d = 0; d < 3; ++d) {
+			double f = div_h(p[d] - G.off[d], G);
+			unsigned long long u = (unsigned long long)f;
+			ci[d] = u > 0x7fffffffull ? 0x7fffffffll : (long long)u;
+			fr[d] = (float)(f - (double)u);
+		}
+		const bool in_tile = use_stage && ci[0] >= x0 && ci[0] < x0 + CT_LX && ci[0] < G.nx && ci[1] == y0 + oy &&
+			ci[2] == lz0 + oz - 1 + G.z0;
+		if (!in_tile) {
+			spring_global(G, M, px, py, pz, begin, i, p, sx, sy, sz);
+		} else {
+			const float rx = (float)((p[0] - ctr[0]) * G.inv_h), ry = (float)((p[1] - ctr[1]) * G.inv_h),
+				rz = (float)((p[2] - ctr[2]) * G.inv_h);
+			const unsigned long long NRX = f32x2_splat(-2.f * rx), NRY = f32x2_splat(-2.f * ry),
+				NRZ = f32x2_splat(-2.f * rz);
+			// d^2 < 1/2 + margin  <=>  w - 2 r.q - T < 0,  T = 1/2 + margin - |r|^2
+			const unsigned long long NT = f32x2_splat(__fmaf_rn(rz, rz, __fmaf_rn(ry, ry, rx * rx)) - (0.5f + CT2_MARGIN));
+			const int kown = (int)(ci[0] - x0) + 1; // index of the particle's own cell in cellbeg[r][]
+			// Phase 1: packed fp32 scan of the staged candidates; groups with a hit are recorded (sign bytes + pair index)
+			uint2 rec[CT2_LIST];
+			int nr = 0;
+			for (int dz = -1; dz <= 1; ++dz) {
+				// distance (in cells) from the particle to the nearest point of the neighbouring layer / row
+				const float zmin = dz < 0 ? fr[2] : (dz > 0 ? 1.f - fr[2] : 0.f);
+				const float remz = 0.501f - zmin * zmin; // (re / h)^2 = 1/2, plus a margin
+				if (remz <= 0.f) { continue; }
+				for (int dy = -1; dy <= 1; ++dy) {
+					const float ymin = dy < 0 ? fr[1] : (dy > 0 ? 1.f - fr[1] : 0.f);
+					const float rem = remz - ymin * ymin;
+					if (rem <= 0.f) { continue; }
+					const float xr = sqrtf(rem); // reach along x within this row: < 0.708 cells
+					const int klo = kown + (fr[0] - xr < 0.f ? -1 : 0);
+					const int khi = kown + (fr[0] + xr >= 1.f ? 2 : 1);
+					const int r = (oz + 1 + dz) * CT_SY + (oy + 1 + dy);
+					// pairs [g, g1): the window rounded outwards to pair boundaries -- the extra candidates are particles
+					// of the same row outside the window (farther than the radius) or the row's padding entry
+					uint32_t g = (rowoff[r] + cellbeg[r][klo]) >> 1;
+					const uint32_t g1 = (rowoff[r] + cellbeg[r][khi] + 1u) >> 1;
+					for (; g + 2 <= g1; g += 2) {
+						const ulonglong2 a0 = stage2[2 * g], b0 = stage2[2 * g + 1], a1 = stage2[2 * g + 2], b1 = stage2[2 * g + 3];
+						unsigned long long c0 = f32x2_fma(NRX, a0.x, b0.y);
+						unsigned long long c1 = f32x2_fma(NRX, a1.x, b1.y);
+						c0 = f32x2_fma(NRY, a0.y, c0);
+						c1 = f32x2_fma(NRY, a1.y, c1);
+						c0 = f32x2_fma(NRZ, b0.x, c0);
+						c1 = f32x2_fma(NRZ, b1.x, c1);
+						c0 = f32x2_add(c0, NT);
+						c1 = f32x2_add(c1, NT);
+						const unsigned t01 = __byte_perm((unsigned)c0, (unsigned)(c0 >> 32), 0x0073);
+						const unsigned t23 = __byte_perm((unsigned)c1, (unsigned)(c1 >> 32), 0x0073);
+						const unsigned sg = __byte_perm(t01, t23, 0x5410);
+						if (sg & 0x80808080u) {
+							rec[nr < CT2_LIST ? nr : CT2_LIST - 1] = make_uint2(sg & 0x80808080u, g);
+							++nr;
+						}
+					}
+					if (g < g1) {
+						const ulonglong2 a0 = stage2[2 * g], b0 = stage2[2 * g + 1];
+						unsigned long long c0 = f32x2_fma(NRX, a0.x, b0.y);
+						c0 = f32x2_fma(NRY, a0.y, c0);
+						c0 = f32x2_fma(NRZ, b0.x, c0);
+						c0 = f32x2_add(c0, NT);
+						const unsigned sg = __byte_perm((unsigned)c0, (unsigned)(c0 >> 32), 0x0073) & 0x8080u;
+						if (sg) {
+							rec[nr < CT2_LIST ? nr : CT2_LIST - 1] = make_uint2(sg, g);
+							++nr;
+						}
+					}
+				}
+			}
+			if (nr > CT2_LIST) { // more neighbour groups than the list holds (a clump): plain fp64 loop instead
+				spring_global(G, M, px, py, pz, begin, i, p, sx, sy, sz);
+			} else {
+				// Phase 2: the recorded candidates in staging order (= the reference's order: rows by z then y, cells by
+				// x, particles in sorted order), evaluated in fp64 from the original positions
+				int row = 0;
+				for (int k = 0; k < nr; ++k) {
+					const uint2 rc = rec[k];
+					unsigned m = rc.x;
+					while (m) {
+						const int b = __ffs((int)m) - 1; // bit 8 j + 7 <-> candidate j of the group
+						m &= m - 1u;
+						const uint32_t s = 2u * rc.y + (uint32_t)(b >> 3);
+						while (s >= rowoff[row + 1]) { ++row; }
+						const uint32_t j = rowstart[row] + (s - rowoff[row]);
+						if (j != (uint32_t)i) {
+							const double ov[3] = { px[j], py[j], pz[j] };
+							pair_exact(M, p, ov, sx, sy, sz);
+						}
+					}
+				}
+			}
+		}
+		double np3[3] = { p[0] + sx * M.corr_factor, p[1] + sy * M.corr_factor, p[2] + sz * M.corr_factor };
+#pragma unroll
+		for (int d = 0; d < 3; ++d) {
+			np3[d] = dclamp_std(np3[d], M.gmin[d], M.gmax[d]);
+		}
+		if (COLLIDE) {
+			collide_one(G, M, typ, p, np3);
+		}
+		nx_[i] = np3[0];
+		ny_[i] = np3[1];
+		nz_[i] = np3[2];
+	}
+}
+
 static int correct_impl(lfk_ctx *c, double dt, bool fuse_collide) {
 	PhaseTimer T(c, LFK_PHASE_CORRECT_COLLIDE);
 	LFK_REQUIRE(c, c->table_valid, LFK_E_STATE, "lfk_correct needs the cell table of lfk_hash");
@@ -943,13 +1177,24 @@ static int correct_impl(lfk_ctx *c, double dt, bool fuse_collide) {
 	if (!attr_set) {
 		LFK_CUDA(c, cudaFuncSetAttribute(k_correct_tiled<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
 		LFK_CUDA(c, cudaFuncSetAttribute(k_correct_tiled<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+		LFK_CUDA(c, cudaFuncSetAttribute(k_correct_tiled2<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+		LFK_CUDA(c, cudaFuncSetAttribute(k_correct_tiled2<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
 		attr_set = true;
 	}
-	if (fuse_collide) {
+	const bool packed = c->tune.correct == 0; // production: packed-fp32 pre-filter; 1: the scalar one (A/B)
+	if (!fuse_collide) { LFK_TRY(materialise_old(c)); }
+	if (packed) {
+		if (fuse_collide) {
+			LFK_LAUNCH(c, k_correct_tiled2<true>, grid, CT_THREADS, smem, G, M, c->P, c->Palt.f[PF_PX], c->Palt.f[PF_PY],
+				c->Palt.f[PF_PZ], c->begin, c->typ);
+		} else {
+			LFK_LAUNCH(c, k_correct_tiled2<false>, grid, CT_THREADS, smem, G, M, c->P, c->Palt.f[PF_PX], c->Palt.f[PF_PY],
+				c->Palt.f[PF_PZ], c->begin, c->typ);
+		}
+	} else if (fuse_collide) {
 		LFK_LAUNCH(c, k_correct_tiled<true>, grid, CT_THREADS, smem, G, M, c->P, c->Palt.f[PF_PX], c->Palt.f[PF_PY],
 			c->Palt.f[PF_PZ], c->begin, c->typ);
 	} else {
-		LFK_TRY(materialise_old(c));
 		LFK_LAUNCH(c, k_correct_tiled<false>, grid, CT_THREADS, smem, G, M, c->P, c->Palt.f[PF_PX], c->Palt.f[PF_PY],
 			c->Palt.f[PF_PZ], c->begin, c->typ);
 	}

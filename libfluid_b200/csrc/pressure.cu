@@ -24,14 +24,22 @@ __device__ __forceinline__ void cell_xyz(const GridDesc &G, long long own, int &
 __global__ void __launch_bounds__(256) k_build_system(GridDesc G, const uint32_t *__restrict__ cnt,
 	const uint8_t *__restrict__ typ, const double *__restrict__ u, const double *__restrict__ v,
 	const double *__restrict__ w, uint8_t *__restrict__ flags, double *__restrict__ b, double *__restrict__ p,
-	double inv_h) {
+	double inv_h, double warm_scale) {
 	for_own_cells(G, [&](int x, int y, int lz, long long c) {
-		p[c] = 0.0;
 		if (cnt[c] == 0) {
+			p[c] = 0.0;
 			flags[c] = 0;
 			b[c] = 0.0;
 			return;
 		}
+		// initial guess: 0 like the reference (src/pressure_solver.cpp:24), or -- fused step only -- the previous
+		// step's pressure rescaled to this step's dt (p ~ 1 / dt); any finite start converges to the same tolerance
+		double p0 = 0.0;
+		if (warm_scale != 0.0) {
+			p0 = p[c] * warm_scale;
+			if (!(fabs(p0) < 1e300)) { p0 = 0.0; }
+		}
+		p[c] = p0;
 		const uint8_t S = LFK_CELL_SOLID, F = LFK_CELL_FLUID;
 		// out-of-grid neighbours read as solid (mac_grid::get_cell_and_type); the z ghost layers carry that already
 		uint8_t txp = x + 1 < G.nx ? typ[c + 1] : S, txn = x > 0 ? typ[c - 1] : S;
@@ -179,6 +187,31 @@ __global__ void __launch_bounds__(RED_THREADS) k_pcg_init(GridDesc G, const doub
 	}
 }
 
+// warm start: r = b - A p, sum b^2 (the early-out of the reference is decided on b, as there)
+__global__ void __launch_bounds__(RED_THREADS) k_pcg_init_warm(GridDesc G, const uint8_t *__restrict__ flags,
+	const double *__restrict__ b, const double *__restrict__ p, double *__restrict__ r, double a_scale,
+	PcgScalars *scal, double *partials, unsigned *ticket, int finalize, MgPreload M) {
+	double acc = 0.0;
+	for_own_cells(G, [&](int x, int y, int lz, long long c) {
+		const Stencil7 v = stencil_load(G, flags, p, c);
+		const double bv = b[c];
+		const double rv = (v.f & FL_L) ? bv - stencil_apply(v, x, y, a_scale) : bv; // b == 0 off the unknowns
+		r[c] = rv;
+		acc += bv * bv;
+		mg_preload(G, M, x, y, lz, c, rv, v.f);
+	});
+	acc = block_sum(acc);
+	if (threadIdx.x == 0) { partials[blockIdx.x] = acc; }
+	if (lfk_last_block(ticket)) {
+		double tot = finish_partials(partials, gridDim.x, 0);
+		if (threadIdx.x == 0) {
+			scal->bb = tot;
+			scal->sigma = 0.0;
+			if (finalize) { pcg_finalize(scal, FIN_BB, 0.0); }
+		}
+	}
+}
+
 // Jacobi: z = r / (a_scale * n)
 __global__ void k_precond_jacobi(GridDesc G, const uint8_t *__restrict__ flags, const double *__restrict__ r,
 	double *__restrict__ z, double a_scale, const PcgScalars *scal) {
@@ -265,7 +298,9 @@ int lfks_build_system(lfk_ctx *c, double dt) {
 		for (int d = 0; d < 3; ++d) { LFK_TRY(lfkx_halo_f64(c, c->vel[d])); }
 	}
 	LFK_LAUNCH(c, k_build_system, lfk_row_blocks(G, 256, 1u << 20), 256, 0, G, c->cnt, c->typ, c->vel[0], c->vel[1],
-		c->vel[2], c->flags, c->b, c->p, 1.0 / G.h);
+		c->vel[2], c->flags, c->b, c->p, 1.0 / G.h, c->warm_scale);
+	c->warm_applied = c->warm_scale != 0.0;
+	c->warm_scale = 0.0;
 	if (c->nranks > 1) {
 		LFK_TRY(lfkx_halo_u8(c, c->flags));
 	}
@@ -275,8 +310,9 @@ int lfks_build_system(lfk_ctx *c, double dt) {
 	return 0;
 }
 
-static inline unsigned red_blocks(const GridDesc &G) {
-	return lfk_row_blocks(G, RED_THREADS, RED_BLOCKS);
+static inline unsigned red_blocks(const lfk_ctx *c) {
+	const unsigned cap = c->tune.red_blocks > 0 ? (unsigned)c->tune.red_blocks : RED_BLOCKS;
+	return lfk_row_blocks(c->g, RED_THREADS, cap < RED_BLOCKS ? cap : RED_BLOCKS);
 }
 
 static int allreduce_scalar(lfk_ctx *c, double *field, bool is_max, int which, double tol) {
@@ -303,16 +339,26 @@ static int precondition_and_dot(lfk_ctx *c, double a_scale, unsigned nb, int fin
 }
 
 // pressure_solver::solve (src/pressure_solver.cpp:19-71)
-int lfks_solve(lfk_ctx *c, double dt, double *residual, uint64_t *iters) {
+int lfks_solve(lfk_ctx *c, double dt, double *residual, uint64_t *iters, bool warm) {
 	const GridDesc &G = c->g;
+	// warm start (fused step only): the previous solve's pressure, rescaled by dt_prev / dt, is the initial guess
+	c->warm_applied = false;
+	if (warm && c->tune.warm_start && c->last_solve_dt > 0.0 && dt > 0.0 && c->last_solve_ok) {
+		c->warm_scale = c->last_solve_dt / dt;
+		c->system_valid = false; // the initial guess is written by the kernel that builds the system
+	}
 	if (!c->system_valid || c->system_dt != dt) {
 		LFK_TRY(lfks_build_system(c, dt));
+	} else if (c->pressure_valid) { // the system is reused and p holds the previous solution: start from 0 again
+		LFK_CUDA(c, cudaMemsetAsync(c->p, 0, (size_t)G.ncl * sizeof(double), c->stream));
 	}
+	c->warm_scale = 0.0;
+	const bool warmed = c->warm_applied;
 	PhaseTimer T(c, LFK_PHASE_PCG);
 	const double a_scale = dt / (c->prm.density * G.h * G.h);
 	const double tol = c->prm.tolerance;
 	const int fin = c->nranks == 1 ? 1 : 0;
-	const unsigned nb = red_blocks(G), eb = lfk_blocks(G.nown, 256);
+	const unsigned nb = red_blocks(c), eb = lfk_blocks(G.nown, 256);
 	if (c->prm.preconditioner == LFK_PRECOND_MULTIGRID && !c->mg_valid) {
 		LFK_TRY(lfkm_setup(c, a_scale));
 	}
@@ -320,7 +366,13 @@ int lfks_solve(lfk_ctx *c, double dt, double *residual, uint64_t *iters) {
 	if (c->prm.preconditioner == LFK_PRECOND_MULTIGRID) {
 		LFK_TRY(lfkm_level0(c, &M.b0, &M.x0));
 	}
-	LFK_LAUNCH(c, k_pcg_init, nb, RED_THREADS, 0, G, c->b, c->r, c->d_scal, c->partials, c->ticket, fin, M);
+	if (warmed) {
+		if (c->nranks > 1) { LFK_TRY(lfkx_halo_f64(c, c->p)); }
+		LFK_LAUNCH(c, k_pcg_init_warm, nb, RED_THREADS, 0, G, c->flags, c->b, c->p, c->r, a_scale, c->d_scal, c->partials,
+			c->ticket, fin, M);
+	} else {
+		LFK_LAUNCH(c, k_pcg_init, nb, RED_THREADS, 0, G, c->b, c->r, c->d_scal, c->partials, c->ticket, fin, M);
+	}
 	LFK_TRY(allreduce_scalar(c, &c->d_scal->bb, false, FIN_BB, tol));
 	LFK_TRY(precondition_and_dot(c, a_scale, nb, fin, 1));
 	LFK_TRY(allreduce_scalar(c, &c->d_scal->sigma_new, false, FIN_BETA_FIRST, tol));
@@ -332,8 +384,12 @@ int lfks_solve(lfk_ctx *c, double dt, double *residual, uint64_t *iters) {
 	int poll = G.nown >= (1ll << 22) ? 2 : (G.nown >= (1ll << 18) ? 8 : 16);
 	int issued = 0;
 	bool done = false;
+	// first burst: one short of what the previous solve of this context needed (consecutive steps need about the same
+	// number of iterations), so that at most a couple of no-op iterations are issued past convergence
+	int first_burst = (int)c->last_iters - 1;
 	while (!done) {
-		int burst = max_it - issued < poll ? max_it - issued : poll;
+		int want = issued == 0 && first_burst > poll ? first_burst : poll;
+		int burst = max_it - issued < want ? max_it - issued : want;
 		for (int k = 0; k < burst; ++k) {
 			if (c->nranks > 1) { LFK_TRY(lfkx_halo_f64(c, c->s)); }
 			LFK_LAUNCH(c, k_spmv_dot, nb, RED_THREADS, 0, G, c->flags, c->s, c->z, a_scale, c->d_scal, c->partials,
@@ -352,8 +408,14 @@ int lfks_solve(lfk_ctx *c, double dt, double *residual, uint64_t *iters) {
 		LFK_CUDA(c, cudaMemcpyAsync(c->h_scal, c->d_scal, sizeof(PcgScalars), cudaMemcpyDeviceToHost, c->stream));
 		LFK_CUDA(c, cudaStreamSynchronize(c->stream));
 		done = c->h_scal->done != 0 || issued >= max_it;
-		if (poll < 8) { poll *= 2; }
+		if (poll < 8 && first_burst <= 2) { poll *= 2; }
 	}
+	if (warmed && c->h_scal->iters == 0 && c->h_scal->bb < 1e-6) { // early-out of the reference: p = 0 (:29-35)
+		LFK_CUDA(c, cudaMemsetAsync(c->p, 0, (size_t)G.ncl * sizeof(double), c->stream));
+	}
+	c->last_iters = c->h_scal->iters;
+	c->last_solve_dt = dt;
+	c->last_solve_ok = c->h_scal->done != 0 && c->h_scal->resmax < 1e300;
 	c->stats.pcg_iterations = c->h_scal->iters;
 	c->stats.pcg_residual = c->h_scal->resmax;
 	if (residual) { *residual = c->h_scal->resmax; }

@@ -164,6 +164,7 @@ def test_fused_step_equals_staged_step_on_device(scene):
     outs = []
     for fused in (True, False):
         ctx = DL.context_for(rec, max_iterations=2000)
+        ctx.set_tuning("warm_start", 0)  # same initial guess (p = 0) on both sides: the comparison is to rounding
         ctx.upload_cells(rec["hash0/cells"])
         ctx.upload_particles(rec["collide1/particles"])  # old_position == position, as after a completed step
         for step in range(3):
@@ -190,6 +191,97 @@ def test_fused_step_equals_staged_step_on_device(scene):
         assert PL.rel_l2(pa[f], pb[f]) < 1e-13, f
     assert np.array_equal(ca["type"], cb["type"])
     assert PL.rel_l2(ca["vel"], cb["vel"]) < 1e-13
+
+
+def _device_scene(n=40, method=capi.APIC, **kw):
+    """a sloshing block that fills ~half of an n^3 box, stepped a few times so that cells hold 0..20 particles"""
+    ctx = capi.Context((n, n, n), cell_size=1.0, gravity=(0.0, -981.0, 0.0), method=method, max_iterations=2000, **kw)
+    ctx.seed_box_device((0.0, 0.0, 0.0), (n * 0.55, n * 0.8, float(n)), density=2, seed=11)
+    return ctx
+
+
+@pytest.mark.parametrize("method", [capi.APIC, capi.FLIP, capi.PIC])
+def test_p2g_kernel_variants_agree(method):
+    """the z-marching P2G kernel (production) against the brick kernel and the plain gather kernel on the same
+    sorted state, through the staged call (velocity rows in place) and inside the fused step (lean sort: rows read
+    through the permutation); cell types exact, faces to summation-order rounding"""
+    ctx = _device_scene(method=method, blending_factor=0.95)
+    for _ in range(4):
+        ctx.time_step()
+    ctx.hash()
+    outs = {}
+    for name, v in (("march", 0), ("brick", 1), ("gather", 2)):
+        ctx.set_tuning("p2g", v)
+        ctx.p2g()
+        outs[name] = ctx.download_cells().copy()
+        if method == capi.FLIP:
+            outs[name + "/old"] = ctx.download_old_cells().copy()
+    for other in ("brick", "gather"):
+        assert np.array_equal(outs["march"]["type"], outs[other]["type"])
+        assert PL.rel_l2(outs["march"]["vel"], outs[other]["vel"]) < 1e-13, other
+        if method == capi.FLIP:
+            assert PL.rel_l2(outs["march/old"]["vel"], outs[other + "/old"]["vel"]) < 1e-13, other
+    assert np.abs(outs["march"]["vel"]).max() > 1.0  # a moving fluid, not an empty comparison
+    # fused steps: march against brick from the same state
+    parts, cells = ctx.download_particles().copy(), outs["march"]
+    res = []
+    for v in (0, 1):
+        ctx.set_tuning("p2g", v)
+        ctx.set_tuning("warm_start", 0)
+        ctx.upload_cells(cells)
+        ctx.upload_particles(parts)
+        for _ in range(2):
+            ctx.time_step(0.002)
+        res.append((ctx.download_particles().copy(), ctx.download_cells().copy()))
+    (pa, ca), (pb, cb) = res
+    assert np.array_equal(pa["raw_cell_index"], pb["raw_cell_index"])
+    assert np.array_equal(ca["type"], cb["type"])
+    for f in ("position", "velocity", "cx", "cy", "cz"):
+        assert PL.rel_l2(pa[f], pb[f]) < 1e-9, f  # two solves in between: agreement to solver tolerance
+    ctx.close()
+
+
+def test_position_correction_variants_agree():
+    """packed-fp32 pre-filter (production) against the scalar pre-filter: both only select candidates for the same
+    fp64 evaluation in the same order, so the corrected positions are bit-identical"""
+    ctx = _device_scene()
+    for _ in range(4):
+        ctx.time_step()
+    ctx.hash()
+    parts = ctx.download_particles().copy()
+    outs = []
+    for v in (0, 1):
+        ctx.set_tuning("correct", v)
+        ctx.upload_particles(parts)
+        ctx.hash()
+        ctx.correct(0.004)
+        outs.append(ctx.download_particles().copy())
+    assert np.array_equal(outs[0]["position"].view("u8"), outs[1]["position"].view("u8"))
+    moved = np.abs(outs[0]["position"] - parts[np.argsort(parts["raw_cell_index"], kind="stable")]["position"]).max()
+    assert moved > 1e-6
+    ctx.close()
+
+
+def test_warm_started_solve_reaches_the_same_tolerance():
+    """fused step with the previous pressure as initial guess against the reference's p = 0 start: same residual
+    tolerance, states agree to solver accuracy, and the warm start does not cost iterations"""
+    res = []
+    for warm in (1, 0):
+        ctx = _device_scene()
+        ctx.set_tuning("warm_start", warm)
+        its = 0
+        for _ in range(6):
+            ctx.time_step(0.002)
+            st = ctx.stats()
+            assert st["pcg_residual"] < 1e-6
+            its += st["pcg_iterations"]
+        res.append((ctx.download_particles().copy(), its))
+        ctx.close()
+    (pa, ia), (pb, ib) = res
+    assert np.array_equal(pa["raw_cell_index"], pb["raw_cell_index"])
+    assert PL.rel_l2(pa["position"], pb["position"]) < 1e-8
+    assert PL.rel_l2(pa["velocity"], pb["velocity"]) < 1e-4
+    assert ia <= ib + 6, (ia, ib)
 
 
 def test_two_gpu_slabs_match_single_gpu():

@@ -1,0 +1,97 @@
+#!/usr/bin/env python
+"""A/B timing of kernel variants on the bench scene (runs ON the GPU box).
+
+One process, one resident scene: after a warm-up, every configuration in CONFIGS is applied with lfk_set_tuning and
+timed over a few steps with the per-phase CUDA-event timers (lfk_set_timing).  Prints one JSON object per
+configuration and writes them all to gpurun_out/<tag>_sweep.json.  Not a bench number: the phase timers serialise
+the phases; bench.py is the measurement of record.
+
+  python tools/variant_sweep.py --grid 256 --tag r1c
+"""
+import argparse
+import json
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+OLD = {"p2g": 1, "correct": 1, "mg_tail": 1, "warm_start": 0, "red_blocks": 0}
+NEW = {"p2g": 0, "correct": 0, "mg_tail": 0, "warm_start": 1, "red_blocks": 0}
+CONFIGS = [
+    ("old", dict(OLD)),
+    ("old+p2g_march", dict(OLD, p2g=0)),
+    ("old+correct_packed", dict(OLD, correct=0)),
+    ("old+mg_tail_smem", dict(OLD, mg_tail=0)),
+    ("old+warm_start", dict(OLD, warm_start=1)),
+    ("old+red_blocks_1184", dict(OLD, red_blocks=1184)),
+    ("old+red_blocks_4736", dict(OLD, red_blocks=4736)),
+    ("new", dict(NEW)),
+]
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--grid", type=int, default=256)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=4)
+    ap.add_argument("--tag", default="sweep")
+    ap.add_argument("--only", default="")
+    args = ap.parse_args()
+    import torch
+    from libfluid_b200 import capi
+    import bench as B
+
+    torch.cuda.set_device(0)
+    n = args.grid
+    ctx = capi.Context((n, n, n), device=0, cell_size=1.0, gravity=B.GRAVITY, method=capi.APIC,
+                       max_iterations=1000, preconditioner=capi.PRECOND_MULTIGRID)
+    for k, (start, size) in enumerate(B.scene_boxes(n, n)):
+        ctx.seed_box_device(start, size, density=2, seed=20261017, append=k > 0)
+    npart = ctx.num_particles()
+    for key, val in OLD.items():
+        ctx.set_tuning(key, val)
+    for _ in range(args.warmup):
+        ctx.time_step()
+    out = []
+    for name, cfg in CONFIGS:
+        if args.only and name not in args.only.split(","):
+            continue
+        for key, val in cfg.items():
+            ctx.set_tuning(key, val)
+        try:
+            ctx.time_step()  # settle (first warm start, kernel attributes)
+            ctx.sync()
+            import time
+            t0 = time.perf_counter()
+            iters = 0
+            for _ in range(args.steps):
+                ctx.time_step()
+                iters += ctx.stats()["pcg_iterations"]
+            ctx.sync()
+            wall = (time.perf_counter() - t0) * 1e3 / args.steps
+            ctx.set_timing(True)
+            ctx.reset_stats()
+            piters = 0
+            for _ in range(args.steps):
+                ctx.time_step()
+                piters += ctx.stats()["pcg_iterations"]
+            st = ctx.stats()
+            ctx.set_timing(False)
+            phase = {k: round(v / args.steps, 3) for k, v in st["phase_ms"].items() if v > 0}
+            row = {"config": name, "ms_per_step_wall": round(wall, 3), "pcg_iters_per_step": iters / args.steps,
+                   "phase_ms": phase, "phase_sum": round(sum(phase.values()), 3),
+                   "pcg_ms_per_iter": round(phase.get("pcg", 0.0) * args.steps / max(piters, 1), 4),
+                   "particles": npart, "residual": st["pcg_residual"]}
+        except Exception as ex:  # keep going: the other variants are still worth measuring
+            row = {"config": name, "error": repr(ex)}
+        print(json.dumps(row), flush=True)
+        out.append(row)
+    os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+    with open(os.path.join(ROOT, "gpurun_out", args.tag + "_sweep.json"), "w") as f:
+        json.dump(out, f, indent=1)
+    ctx.close()
+
+
+if __name__ == "__main__":
+    main()
