@@ -292,7 +292,7 @@ extern "C" int lfk_create(lfk_ctx **out, uint64_t nx, uint64_t ny, uint64_t nz, 
 		CREATE_CUDA(cudaMemsetAsync(ptr, 0, ncl * sizeof(double), c->stream));
 	}
 	k_init_types<<<lfk_blocks(G.ncl, 256), 256, 0, c->stream>>>(G, c->typ);
-	CREATE_CUDA(cudaPeekAtLastError());
+	CREATE_CUDA(cudaGetLastError());
 	CREATE_CUDA(cudaEventCreate(&c->ev[0]));
 	CREATE_CUDA(cudaEventCreate(&c->ev[1]));
 	CREATE_TRY(lfkx_init(c, nccl_id128));

@@ -64,11 +64,11 @@ struct MgLevel {
 enum { LFK_TUNE_P2G_MARCH = 0, LFK_TUNE_P2G_BRICK = 1, LFK_TUNE_P2G_GATHER = 2 };
 struct lfk_tuning {
 	int p2g = LFK_TUNE_P2G_MARCH;
-	int correct = 0;  // 0: production position-correction kernel, 1: the previous one (A/B)
+	int correct = 0;  // 0: production position-correction kernel (scalar fp32 pre-filter), 1: packed-fp32 variant (A/B; slower)
 	int mg_tail = 0;  // 0: shared-memory coarse tail, 1: the global-memory one (A/B)
 	int spmv = 0;     // 0: production SpMV + dot, 1: the previous one (A/B)
 	int warm_start = 1; // fused step: start PCG from the previous step's pressure (0: from p = 0 like the reference)
-	int red_blocks = 0; // > 0: cap on the grid of the PCG reduction kernels (default RED_BLOCKS)
+	int red_blocks = 0; // > 0: cap on the grid of the PCG reduction kernels (default 8 x SM count)
 };
 
 struct lfk_ctx {
@@ -155,7 +155,7 @@ const char *lfk_cuda_err_name(cudaError_t e);
 #define LFK_LAUNCH(ctx, kernel, grid, block, smem, ...) do { \
 	kernel<<<(grid), (block), (smem), (ctx)->stream>>>(__VA_ARGS__); \
 	++(ctx)->stats.kernel_launches; \
-	LFK_CUDA((ctx), cudaPeekAtLastError()); } while (0)
+	LFK_CUDA((ctx), cudaGetLastError()); } while (0)
 
 static inline unsigned lfk_blocks(long long n, int block) {
 	long long b = (n + block - 1) / block;

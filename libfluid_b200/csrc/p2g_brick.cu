@@ -92,7 +92,7 @@ template <int COMP, bool APIC> __device__ __forceinline__ void row_component(dou
 		}
 		cp_async_wait_all();
 		__syncwarp();
-		accumulate_cell<COMP, APIC>(st, lane, nslots, cc, Q.half, Q.inv_h, Q.hdiv, accw, accv);
+		accumulate_cell<COMP, APIC>(st, lane, nslots, cc, Q.half, Q.inv_h, accw, accv);
 		__syncwarp(); // the slab is overwritten by the next window
 	}
 	// tile coordinates of the faces owned by (cell - 1): x: lane - 2, y: ry - 2, z: rz - 2
@@ -211,7 +211,6 @@ int lfkg_p2g_brick(lfk_ctx *c, double gravity_dt, bool add_gravity) {
 	Q.half = 0.5 * G.h;
 	Q.inv_h = 1.0 / G.h;
 	Q.add_gravity = add_gravity ? 1 : 0;
-	Q.hdiv = c->prm.method != LFK_METHOD_APIC && G.h != 1.0;
 	for (int d = 0; d < 3; ++d) {
 		Q.gdt[d] = c->prm.gravity[d] * gravity_dt;
 	}

@@ -29,7 +29,7 @@
 #include "p2g_accum.cuh"
 
 #define PM_BX 30
-#define PM_WARPS 10
+#define PM_WARPS 8 // warps are placed on the 4 SM sub-partitions (16 K registers each): ceil(warps / 4) * 32 * 200 regs must fit
 #define PM_BY (PM_WARPS - 2)
 #define PM_THREADS (PM_WARPS * 32)
 #define PM_STAGE (PB_FIELDS * PB_FSTRIDE)       // doubles per staging buffer
@@ -285,7 +285,7 @@ template <int COMP, int METHOD> __device__ __forceinline__ void pm_march(const G
 		}
 		const int cnt = (int)(D0.pe - D0.pb);
 		const int nslots = max(0, min(PB_WIN, cnt - D0.win));
-		accumulate_cell<COMP, APIC>(st + cur * PM_STAGE, lane, nslots, cc, Q.half, Q.inv_h, Q.hdiv, accw, accv);
+		accumulate_cell<COMP, APIC>(st + cur * PM_STAGE, lane, nslots, cc, Q.half, Q.inv_h, accw, accv);
 		__syncwarp(); // st[cur] is overwritten by the window after next
 		D0 = D1;
 		D1 = D2;
@@ -336,7 +336,6 @@ int lfkg_p2g_march(lfk_ctx *c, double gravity_dt, bool add_gravity) {
 	Q.half = 0.5 * G.h;
 	Q.inv_h = 1.0 / G.h;
 	Q.add_gravity = add_gravity ? 1 : 0;
-	Q.hdiv = c->prm.method != LFK_METHOD_APIC && G.h != 1.0;
 	for (int d = 0; d < 3; ++d) {
 		Q.gdt[d] = c->prm.gravity[d] * gravity_dt;
 	}

@@ -710,10 +710,9 @@ __device__ __forceinline__ double fast_rsqrt(double x) {
 __device__ __forceinline__ void pair_exact(const MotionParams &M, const double *p, const double *o, double &sx,
 	double &sy, double &sz) {
 	double ox = p[0] - o[0], oy = p[1] - o[1], oz = p[2] - o[2];
-	double sq = 0.0;
-	sq += ox * ox;
-	sq += oy * oy;
-	sq += oz * oz;
+	// explicit fused multiply-adds (the file is compiled --fmad=false for the bit-exact stages): 11 fp64 instructions
+	// less per pair than the separate multiplies and adds; the summation order is the reference's
+	const double sq = fma(oz, oz, fma(oy, oy, ox * ox));
 	if (sq < 1e-12) {
 		double kick[3];
 		degenerate_kick(p, o, kick);
@@ -724,12 +723,12 @@ __device__ __forceinline__ void pair_exact(const MotionParams &M, const double *
 		// reference: kernel = (1 - r^2 / re^2)^3, spring += kernel / sqrt(r^2) * offset.  The two IEEE divisions and
 		// the IEEE square root cost ~200 instructions per pair; the reciprocal multiply and the Newton rsqrt (~1 ulp)
 		// cost ~25 and move the corrected position by < 1e-16 cells -- positions are tolerance-checked (1e-12).
-		double kl = 1.0 - sq * M.inv_re2;
+		const double kl = fma(-sq, M.inv_re2, 1.0);
 		if (kl > 0.0) {
-			double sc = kl * kl * kl * fast_rsqrt(sq);
-			sx += sc * ox;
-			sy += sc * oy;
-			sz += sc * oz;
+			const double sc = kl * kl * kl * fast_rsqrt(sq);
+			sx = fma(sc, ox, sx);
+			sy = fma(sc, oy, sy);
+			sz = fma(sc, oz, sz);
 		}
 	}
 }
@@ -1181,7 +1180,7 @@ static int correct_impl(lfk_ctx *c, double dt, bool fuse_collide) {
 		LFK_CUDA(c, cudaFuncSetAttribute(k_correct_tiled2<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
 		attr_set = true;
 	}
-	const bool packed = c->tune.correct == 0; // production: packed-fp32 pre-filter; 1: the scalar one (A/B)
+	const bool packed = c->tune.correct == 1; // A/B: packed-fp32 pre-filter (42.6 ms at 256^3 against 30.6 for the scalar one)
 	if (!fuse_collide) { LFK_TRY(materialise_old(c)); }
 	if (packed) {
 		if (fuse_collide) {

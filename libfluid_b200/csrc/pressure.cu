@@ -310,8 +310,15 @@ int lfks_build_system(lfk_ctx *c, double dt) {
 	return 0;
 }
 
+// Grid of the PCG reduction kernels (SpMV + dot, p / r update, final sweep + dot): persistent-style, 8 blocks per SM,
+// rows strided over the warps -- measured at 256^3 (profiles/r1c_sweep.json): 1.01 ms / iteration against 1.11 with one
+// row per warp (16384 blocks: more block partials for the last block to reduce, a longer tail).
 static inline unsigned red_blocks(const lfk_ctx *c) {
-	const unsigned cap = c->tune.red_blocks > 0 ? (unsigned)c->tune.red_blocks : RED_BLOCKS;
+	static int sms = 0;
+	if (sms == 0) {
+		if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device) != cudaSuccess || sms <= 0) { sms = 148; }
+	}
+	const unsigned cap = c->tune.red_blocks > 0 ? (unsigned)c->tune.red_blocks : 8u * (unsigned)sms;
 	return lfk_row_blocks(c->g, RED_THREADS, cap < RED_BLOCKS ? cap : RED_BLOCKS);
 }
 

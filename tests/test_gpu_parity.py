@@ -242,7 +242,7 @@ def test_p2g_kernel_variants_agree(method):
 
 
 def test_position_correction_variants_agree():
-    """packed-fp32 pre-filter (production) against the scalar pre-filter: both only select candidates for the same
+    """scalar fp32 pre-filter (production) against the packed-fp32 variant: both only select candidates for the same
     fp64 evaluation in the same order, so the corrected positions are bit-identical"""
     ctx = _device_scene()
     for _ in range(4):

@@ -1,0 +1,101 @@
+#!/usr/bin/env python
+"""Projection-only sweep (BASELINE.json configs[4], SURVEY.md 8(d) "Config 5"); runs ON the GPU box.
+
+All-fluid n^3 box with solid domain walls and an air layer on top (non-singular system), face velocities i.i.d.
+uniform(-1, 1) from a counter-based seed, dt = 1/60, rho = 1, h = 1 => a_scale = 1/60.  For every grid size:
+assemble (flags + b), solve with PCG to |r|_inf < 1e-6, apply the pressure gradient, and check the divergence of the
+projected field.  Reports iterations, device time to tolerance, iterations/s and the credited HBM rate
+(105 B x fluid cells per iteration) against MEASURED_PEAKS.json.
+
+  python tools/projection_sweep.py --grids 128,256,512,1024 --tag r1c
+  torchrun --nproc-per-node 2 tools/projection_sweep.py --grids 256,512      (z-slabs, one rank per GPU)
+"""
+import argparse
+import json
+import os
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--grids", default="128,256,512")
+    ap.add_argument("--repeats", type=int, default=3)
+    ap.add_argument("--tag", default="projection")
+    ap.add_argument("--tune", default="", help="key=value,... passed to lfk_set_tuning")
+    args = ap.parse_args()
+    import numpy as np
+    import torch
+    from libfluid_b200 import capi
+    import bench as B
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    torch.cuda.set_device(local_rank)
+    dist, nccl_id = None, None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        box = [capi.nccl_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(box, src=0)
+        nccl_id = box[0]
+    peak, peak_src = B.measured_peak()
+    dt = 1.0 / 60.0
+    rows = []
+    for n in [int(g) for g in args.grids.split(",") if g]:
+        row = {"grid": n, "n_gpus": world}
+        try:
+            ctx = capi.Context((n, n, n), device=local_rank, nranks=world, rank=rank, nccl_id=nccl_id, cell_size=1.0,
+                               max_iterations=5000, preconditioner=capi.PRECOND_MULTIGRID)
+            for item in [t for t in args.tune.split(",") if t]:
+                k, v = item.split("=")
+                ctx.set_tuning(k, int(v))
+            best = None
+            for rep in range(args.repeats + 1):  # first pass = warm-up (allocations, multigrid set-up buffers)
+                ctx.synthetic_projection_device(seed=20261017)
+                ctx.set_timing(True)
+                ctx.reset_stats()
+                t0 = time.perf_counter()
+                res, iters = ctx.pressure_solve(dt)
+                ctx.sync()
+                wall = (time.perf_counter() - t0) * 1e3
+                st = ctx.stats()
+                ctx.set_timing(False)
+                ph = st["phase_ms"]
+                dev_ms = ph.get("pcg", 0.0) + ph.get("solve_setup", 0.0)
+                if rep > 0 and (best is None or dev_ms < best["device_ms"]):
+                    best = {"device_ms": dev_ms, "pcg_ms": ph.get("pcg", 0.0), "setup_ms": ph.get("solve_setup", 0.0),
+                            "wall_ms": wall, "iterations": int(iters), "residual": res,
+                            "launches": st["kernel_launches"]}
+            nf = ctx.num_fluid_cells()
+            ctx.apply_pressure(dt)
+            div = None
+            if world == 1 and n <= 512:  # the rhs of the projected field is -div/h: must be below the tolerance scale
+                b2, _ = ctx.download_rhs(dt)
+                div = float(np.abs(b2).max())
+            ctx.close()
+            it_ms = best["pcg_ms"] / max(best["iterations"], 1)
+            gbs = 105.0 * nf / (it_ms * 1e-3) / 1e9
+            row.update(best)
+            row.update({"fluid_cells_rank0": int(nf), "ms_per_iteration": it_ms, "iterations_per_s": 1e3 / it_ms,
+                        "credited_GBps_rank0": gbs, "frac_of_peak": gbs / peak, "peak_GBps": peak,
+                        "peak_source": peak_src, "max_abs_rhs_after_projection": div, "tolerance": 1e-6})
+        except Exception as ex:  # out of memory at the largest size must not lose the smaller rows
+            row["error"] = repr(ex)
+        if rank == 0:
+            print(json.dumps(row), flush=True)
+        rows.append(row)
+    if rank == 0:
+        os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+        with open(os.path.join(ROOT, "gpurun_out", "%s_projection_n%d.json" % (args.tag, world)), "w") as f:
+            json.dump(rows, f, indent=1)
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

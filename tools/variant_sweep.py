@@ -16,17 +16,16 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
-OLD = {"p2g": 1, "correct": 1, "mg_tail": 1, "warm_start": 0, "red_blocks": 0}
-NEW = {"p2g": 0, "correct": 0, "mg_tail": 0, "warm_start": 1, "red_blocks": 0}
+NEW = {"p2g": 0, "correct": 0, "mg_tail": 0, "warm_start": 1, "red_blocks": 0}  # the library defaults
+OLD = {"p2g": 1, "correct": 0, "mg_tail": 1, "warm_start": 0, "red_blocks": 16384}  # round r1b
 CONFIGS = [
-    ("old", dict(OLD)),
-    ("old+p2g_march", dict(OLD, p2g=0)),
-    ("old+correct_packed", dict(OLD, correct=0)),
-    ("old+mg_tail_smem", dict(OLD, mg_tail=0)),
-    ("old+warm_start", dict(OLD, warm_start=1)),
-    ("old+red_blocks_1184", dict(OLD, red_blocks=1184)),
-    ("old+red_blocks_4736", dict(OLD, red_blocks=4736)),
-    ("new", dict(NEW)),
+    ("defaults", dict(NEW)),
+    ("defaults+p2g_brick", dict(NEW, p2g=1)),
+    ("defaults+red_blocks_592", dict(NEW, red_blocks=592)),
+    ("defaults+red_blocks_2368", dict(NEW, red_blocks=2368)),
+    ("defaults+cold_start", dict(NEW, warm_start=0)),
+    ("defaults+mg_tail_global", dict(NEW, mg_tail=1)),
+    ("r1b", dict(OLD)),
 ]
 
 
@@ -49,7 +48,7 @@ def main():
     for k, (start, size) in enumerate(B.scene_boxes(n, n)):
         ctx.seed_box_device(start, size, density=2, seed=20261017, append=k > 0)
     npart = ctx.num_particles()
-    for key, val in OLD.items():
+    for key, val in NEW.items():
         ctx.set_tuning(key, val)
     for _ in range(args.warmup):
         ctx.time_step()
