@@ -488,6 +488,13 @@ static int mg_alloc(lfk_ctx *c) {
 	if (!c->mg.empty()) { return 0; }
 	const GridDesc &G = c->g;
 	int nx = G.nx, ny = G.ny, nzl = G.nzl, z0 = G.z0, nz = G.nz;
+	// the slab layout of every rank (same rule as lfk_create)
+	std::vector<int> all_z0((size_t)c->nranks), all_nzl((size_t)c->nranks);
+	for (int r = 0; r < c->nranks; ++r) {
+		const int base = G.nz / c->nranks, rem = G.nz % c->nranks;
+		all_z0[r] = r * base + (r < rem ? r : rem);
+		all_nzl[r] = base + (r < rem ? 1 : 0);
+	}
 	LFK_CUDA(c, cudaMalloc((void**)&c->mg_mask, ((size_t)G.ncl + 2) * sizeof(uint16_t)));
 	LFK_CUDA(c, cudaMemsetAsync(c->mg_mask, 0, ((size_t)G.ncl + 2) * sizeof(uint16_t), c->stream));
 	for (int l = 0; l < 16; ++l) {
@@ -504,10 +511,19 @@ static int mg_alloc(lfk_ctx *c) {
 		}
 		c->mg.push_back(L);
 		c->mg_z0.push_back(z0);
-		// slabs must stay aligned to the aggregates; stop coarsening when they would not (multi-GPU)
-		bool aligned = c->nranks == 1 || (z0 % 2 == 0 && nzl % 2 == 0 && nz % 2 == 0 && nzl >= 2);
+		// slabs must stay aligned to the aggregates; stop coarsening when they would not (multi-GPU).  The decision is
+		// taken over the slabs of ALL ranks (the layout is a pure function of nz, nranks and the level), so every rank
+		// builds the same number of levels and the halo exchanges inside the V-cycle pair up.
+		bool aligned = true;
+		if (c->nranks > 1) {
+			aligned = nz % 2 == 0;
+			for (int r = 0; r < c->nranks && aligned; ++r) {
+				aligned = all_z0[r] % 2 == 0 && all_nzl[r] % 2 == 0 && all_nzl[r] >= 2;
+			}
+		}
 		if (!aligned || (nx <= 2 && ny <= 2 && nzl <= 2)) { break; }
 		nx = (nx + 1) / 2; ny = (ny + 1) / 2; nzl = (nzl + 1) / 2; z0 /= 2; nz = (nz + 1) / 2;
+		for (int r = 0; r < c->nranks; ++r) { all_z0[r] /= 2; all_nzl[r] = (all_nzl[r] + 1) / 2; }
 	}
 	return 0;
 }

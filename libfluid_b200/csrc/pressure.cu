@@ -388,7 +388,10 @@ int lfks_solve(lfk_ctx *c, double dt, double *residual, uint64_t *iters, bool wa
 	// The loop runs entirely from device-resident scalars; the host only polls the `done` flag now and then.
 	// Kernels issued after convergence return immediately, so the iteration count stays exact.
 	const int max_it = c->prm.max_iterations;
-	int poll = G.nown >= (1ll << 22) ? 2 : (G.nown >= (1ll << 18) ? 8 : 16);
+	// every rank must issue the same number of iterations (the NCCL calls inside them pair up across ranks), so the
+	// polling interval is derived from the WHOLE grid, never from the rank's own slab (slabs may differ by a layer)
+	const long long per_rank = G.sxy * (long long)G.nz / c->nranks;
+	int poll = per_rank >= (1ll << 22) ? 2 : (per_rank >= (1ll << 18) ? 8 : 16);
 	int issued = 0;
 	bool done = false;
 	// first burst: one short of what the previous solve of this context needed (consecutive steps need about the same

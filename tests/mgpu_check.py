@@ -20,6 +20,8 @@ def main():
     from libfluid_b200 import capi, slabs
 
     rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+    import faulthandler
+    faulthandler.dump_traceback_later(int(os.environ.get("MGPU_HANG_DUMP_S", "75")), exit=True)  # a hang names its line
     local = int(os.environ.get("LOCAL_RANK", rank))
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
