@@ -1163,6 +1163,222 @@ template <bool COLLIDE> __global__ void __launch_bounds__(CT_THREADS, 2) k_corre
 	}
 }
 
+// ---- third variant: expanded-form fp32 pre-filter with per-row hit masks ------------------------------------------
+// Same tiling, culling and fp64 evaluation (reference order) as k_correct_tiled; what changes is the cost of a candidate
+// test, which is where k_correct_tiled spends its instructions (13.5 SASS instructions per candidate, ~250 candidate
+// slots per particle once warp divergence is counted):
+//   * staged entries are {x, y, z, w = |q|^2} in cell units relative to the tile centre; with n = -2 r the test
+//     |r - q|^2 < 1/2 + margin becomes  w + n.q < T,  T = 1/2 + margin - |r|^2: three FFMA and one compare;
+//   * hits are collected as BITS of a per-row mask with compile-time bit positions (one predicated OR per candidate)
+//     instead of a predicated store + index clamp + increment per candidate; a row window contributes one
+//     {mask, index of the window's first particle} record per 32 candidates to a short per-thread list;
+//   * every staged row is followed by CT3_PAD entries that can never hit, so the 4-wide groups need no tail handling
+//     (entries of the same row beyond the window may be tested: they are farther than the radius, fp64 gives them 0).
+// 7.5 instructions per candidate (cuobjdump).  The candidate's global index is row start + offset, so the index no longer needs
+// a staged word.  Rounding: as for k_correct_tiled2 (|coordinates| <= 17.1 cells, every intermediate below 620, error
+// below 4e-5 each); the margin of 2e-3 cells^2 covers their sum 10x over, so the filter never drops a true neighbour.
+#define CT3_PAD 3
+#define CT3_LIST 16
+
+template <bool COLLIDE> __global__ void __launch_bounds__(CT_THREADS, 2) k_correct_tiled3(GridDesc G, MotionParams M,
+	ParticleSoA P, double *__restrict__ nx_, double *__restrict__ ny_, double *__restrict__ nz_,
+	const uint32_t *__restrict__ begin, const uint8_t *__restrict__ typ) {
+	extern __shared__ float4 stage3[];
+	__shared__ uint32_t rowstart[CT_ROWS], rowoff[CT_ROWS + 1], cellbeg[CT_ROWS][CT_LX + 3];
+	__shared__ uint32_t ownbeg[CT_OWN], ownpre[CT_OWN + 1];
+	const double *__restrict__ px = P.f[PF_PX], *__restrict__ py = P.f[PF_PY], *__restrict__ pz = P.f[PF_PZ];
+	const int x0 = blockIdx.x * CT_LX, y0 = blockIdx.y * CT_TY, lz0 = blockIdx.z * CT_TZ + 1;
+	const int tid = threadIdx.x;
+
+	// ---- table of the staged rows (as in k_correct_tiled) ----
+	for (int e = tid; e < CT_ROWS * (CT_LX + 3); e += CT_THREADS) {
+		int r = e / (CT_LX + 3), k = e % (CT_LX + 3);
+		int y = y0 - 1 + r % CT_SY, lz = lz0 - 1 + r / CT_SY;
+		uint32_t v = 0;
+		if (y >= 0 && y < G.ny && lz >= 0 && lz < G.nlz) {
+			long long row = (long long)G.nx * (y + (long long)G.ny * lz);
+			int xa = x0 - 1 < 0 ? 0 : x0 - 1;
+			int xk = x0 - 1 + k;
+			xk = xk < 0 ? 0 : (xk > G.nx ? G.nx : xk);
+			uint32_t base = begin[row + xa];
+			v = begin[row + xk] - base;
+			if (k == 0) { rowstart[r] = base; }
+		} else if (k == 0) {
+			rowstart[r] = 0;
+		}
+		cellbeg[r][k] = v;
+	}
+	__syncthreads();
+	if (tid == 0) {
+		uint32_t acc = 0;
+		for (int r = 0; r < CT_ROWS; ++r) { // every row is followed by CT3_PAD never-hit entries
+			rowoff[r] = acc;
+			acc += cellbeg[r][CT_LX + 2] + CT3_PAD;
+		}
+		rowoff[CT_ROWS] = acc;
+		uint32_t oacc = 0;
+		for (int o = 0; o < CT_OWN; ++o) { // own rows: cells x0 .. x0 + LX - 1 (clipped) of the inner rows
+			int r = (o / CT_TY + 1) * CT_SY + (o % CT_TY + 1);
+			int y = y0 + o % CT_TY, lz = lz0 + o / CT_TY;
+			uint32_t nown = 0;
+			if (y < G.ny && lz <= G.nzl) {
+				nown = cellbeg[r][CT_LX + 1] - cellbeg[r][1];
+			}
+			ownbeg[o] = rowstart[r] + cellbeg[r][1];
+			ownpre[o] = oacc;
+			oacc += nown;
+		}
+		ownpre[CT_OWN] = oacc;
+	}
+	__syncthreads();
+	const uint32_t nown_total = ownpre[CT_OWN];
+	if (nown_total == 0) { return; }
+	const uint32_t staged = rowoff[CT_ROWS];
+	const bool use_stage = staged <= CT_CAP;
+	// tile centre, fp64; staged coordinates are relative to it, in cells
+	const double ctr[3] = { G.off[0] + ((double)x0 + 0.5 * CT_LX) * G.h, G.off[1] + ((double)y0 + 0.5 * CT_TY) * G.h,
+		G.off[2] + ((double)(lz0 - 1 + G.z0) + 0.5 * CT_TZ) * G.h };
+	if (use_stage) {
+		for (int r = 0; r < CT_ROWS; ++r) {
+			const uint32_t cnt = cellbeg[r][CT_LX + 2], gs = rowstart[r], so = rowoff[r];
+			for (uint32_t j = tid; j < cnt + CT3_PAD; j += CT_THREADS) {
+				float4 e = make_float4(0.f, 0.f, 0.f, 1e30f); // padding: never within reach
+				if (j < cnt) {
+					const uint32_t q = gs + j;
+					e.x = (float)((px[q] - ctr[0]) * G.inv_h);
+					e.y = (float)((py[q] - ctr[1]) * G.inv_h);
+					e.z = (float)((pz[q] - ctr[2]) * G.inv_h);
+					e.w = __fmaf_rn(e.z, e.z, __fmaf_rn(e.y, e.y, e.x * e.x));
+				}
+				stage3[so + j] = e;
+			}
+		}
+	}
+	__syncthreads();
+
+	for (uint32_t t = tid; t < nown_total; t += CT_THREADS) {
+		int o = 0;
+#pragma unroll
+		for (int k = 1; k < CT_OWN; ++k) {
+			if (t >= ownpre[k]) { o = k; }
+		}
+		const unsigned long long i = (unsigned long long)ownbeg[o] + (t - ownpre[o]);
+		const int oy = o % CT_TY, oz = o / CT_TY;
+		double p[3] = { px[i], py[i], pz[i] };
+		double sx = 0.0, sy = 0.0, sz = 0.0;
+		// unclamped cell and in-cell fraction (compute_cell_index)
+		long long ci[3];
+		float fr[3];
+#pragma unroll
+		for (int d = 0; d < 3; ++d) {
+			double f = div_h(p[d] - G.off[d], G);
+			unsigned long long u = (unsigned long long)f;
+			ci[d] = u > 0x7fffffffull ? 0x7fffffffll : (long long)u;
+			fr[d] = (float)(f - (double)u);
+		}
+		const bool in_tile = use_stage && ci[0] >= x0 && ci[0] < x0 + CT_LX && ci[0] < G.nx && ci[1] == y0 + oy &&
+			ci[2] == lz0 + oz - 1 + G.z0;
+		if (!in_tile) {
+			spring_global(G, M, px, py, pz, begin, i, p, sx, sy, sz);
+		} else {
+			const float rx = (float)((p[0] - ctr[0]) * G.inv_h), ry = (float)((p[1] - ctr[1]) * G.inv_h),
+				rz = (float)((p[2] - ctr[2]) * G.inv_h);
+			const float nrx = -2.f * rx, nry = -2.f * ry, nrz = -2.f * rz;
+			// |r - q|^2 < 1/2 + margin  <=>  w + n.q < T
+			const float T = (0.5f + CT2_MARGIN) - __fmaf_rn(rz, rz, __fmaf_rn(ry, ry, rx * rx));
+			const int kown = (int)(ci[0] - x0) + 1; // index of the particle's own cell in cellbeg[r][]
+			// Phase 1: fp32 scan of the staged candidates; per 32 candidates of a row window one {hit mask, index of the
+			// first particle} record
+			uint2 rec[CT3_LIST];
+			int nr = 0;
+			for (int dz = -1; dz <= 1; ++dz) {
+				// distance (in cells) from the particle to the nearest point of the neighbouring layer / row
+				const float zmin = dz < 0 ? fr[2] : (dz > 0 ? 1.f - fr[2] : 0.f);
+				const float remz = 0.501f - zmin * zmin; // (re / h)^2 = 1/2, plus a margin
+				if (remz <= 0.f) { continue; }
+				for (int dy = -1; dy <= 1; ++dy) {
+					const float ymin = dy < 0 ? fr[1] : (dy > 0 ? 1.f - fr[1] : 0.f);
+					const float rem = remz - ymin * ymin;
+					if (rem <= 0.f) { continue; }
+					const float xr = sqrtf(rem); // reach along x within this row: < 0.708 cells
+					const int klo = kown + (fr[0] - xr < 0.f ? -1 : 0);
+					const int khi = kown + (fr[0] + xr >= 1.f ? 2 : 1);
+					const int r = (oz + 1 + dz) * CT_SY + (oy + 1 + dy);
+					const uint32_t w0 = cellbeg[r][klo];
+					uint32_t s = rowoff[r] + w0;
+					const uint32_t s1 = rowoff[r] + cellbeg[r][khi];
+					uint32_t jb = rowstart[r] + w0;
+					for (; s < s1; s += 32u, jb += 32u) {
+						const float4 *__restrict__ q = stage3 + s;
+						const uint32_t left = s1 - s; // candidates left in the window; groups of 4, at most 8 per mask
+						uint32_t mask = 0;
+#define CT3_TEST(e, bit) do { const float4 q_ = q[e]; \
+	const float t_ = __fmaf_rn(nrz, q_.z, __fmaf_rn(nry, q_.y, __fmaf_rn(nrx, q_.x, q_.w))); \
+	if (t_ < T) { mask |= (bit); } } while (0)
+#pragma unroll
+						for (int g = 0; g < 8; ++g) {
+							if ((uint32_t)(4 * g) < left) {
+								CT3_TEST(4 * g + 0, 1u << (4 * g + 0));
+								CT3_TEST(4 * g + 1, 1u << (4 * g + 1));
+								CT3_TEST(4 * g + 2, 1u << (4 * g + 2));
+								CT3_TEST(4 * g + 3, 1u << (4 * g + 3));
+							}
+						}
+#undef CT3_TEST
+						if (mask) {
+							rec[nr < CT3_LIST ? nr : CT3_LIST - 1] = make_uint2(mask, jb);
+							++nr;
+						}
+					}
+				}
+			}
+			if (nr > CT3_LIST) { // more records than the list holds (very crowded rows): plain fp64 loop instead
+				spring_global(G, M, px, py, pz, begin, i, p, sx, sy, sz);
+			} else if (nr > 0) {
+				// Phase 2: the recorded candidates in staging order (= the reference's order: rows by z then y, cells by x,
+				// particles in sorted order), evaluated in fp64 from the original positions; the next candidate's position
+				// is fetched one iteration ahead of its use
+				int k = 1;
+				uint32_t m = rec[0].x, jb = rec[0].y;
+				uint32_t j = jb + (uint32_t)(__ffs((int)m) - 1);
+				m &= m - 1u;
+				double ov[3] = { px[j], py[j], pz[j] };
+				for (;;) {
+					if (m == 0u && k < nr) {
+						m = rec[k].x;
+						jb = rec[k].y;
+						++k;
+					}
+					const bool more = m != 0u;
+					uint32_t jn = (uint32_t)i;
+					if (more) {
+						jn = jb + (uint32_t)(__ffs((int)m) - 1);
+						m &= m - 1u;
+					}
+					const double on[3] = { px[jn], py[jn], pz[jn] };
+					if (j != (uint32_t)i) { pair_exact(M, p, ov, sx, sy, sz); }
+					if (!more) { break; }
+					j = jn;
+					ov[0] = on[0];
+					ov[1] = on[1];
+					ov[2] = on[2];
+				}
+			}
+		}
+		double np3[3] = { p[0] + sx * M.corr_factor, p[1] + sy * M.corr_factor, p[2] + sz * M.corr_factor };
+#pragma unroll
+		for (int d = 0; d < 3; ++d) {
+			np3[d] = dclamp_std(np3[d], M.gmin[d], M.gmax[d]);
+		}
+		if (COLLIDE) {
+			collide_one(G, M, typ, p, np3);
+		}
+		nx_[i] = np3[0];
+		ny_[i] = np3[1];
+		nz_[i] = np3[2];
+	}
+}
+
 static int correct_impl(lfk_ctx *c, double dt, bool fuse_collide) {
 	PhaseTimer T(c, LFK_PHASE_CORRECT_COLLIDE);
 	LFK_REQUIRE(c, c->table_valid, LFK_E_STATE, "lfk_correct needs the cell table of lfk_hash");
@@ -1178,11 +1394,21 @@ static int correct_impl(lfk_ctx *c, double dt, bool fuse_collide) {
 		LFK_CUDA(c, cudaFuncSetAttribute(k_correct_tiled<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
 		LFK_CUDA(c, cudaFuncSetAttribute(k_correct_tiled2<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
 		LFK_CUDA(c, cudaFuncSetAttribute(k_correct_tiled2<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+		LFK_CUDA(c, cudaFuncSetAttribute(k_correct_tiled3<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+		LFK_CUDA(c, cudaFuncSetAttribute(k_correct_tiled3<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
 		attr_set = true;
 	}
-	const bool packed = c->tune.correct == 1; // A/B: packed-fp32 pre-filter (42.6 ms at 256^3 against 30.6 for the scalar one)
+	const bool packed = c->tune.correct == 1; // A/B: packed-fp32 pre-filter (42.6 ms at 256^3; 0 = scalar pre-filter, 30.2 ms)
 	if (!fuse_collide) { LFK_TRY(materialise_old(c)); }
-	if (packed) {
+	if (c->tune.correct == 2) { // production: expanded-form pre-filter with per-row hit masks (27.7 ms at 256^3, r1d sweep)
+		if (fuse_collide) {
+			LFK_LAUNCH(c, k_correct_tiled3<true>, grid, CT_THREADS, smem, G, M, c->P, c->Palt.f[PF_PX], c->Palt.f[PF_PY],
+				c->Palt.f[PF_PZ], c->begin, c->typ);
+		} else {
+			LFK_LAUNCH(c, k_correct_tiled3<false>, grid, CT_THREADS, smem, G, M, c->P, c->Palt.f[PF_PX], c->Palt.f[PF_PY],
+				c->Palt.f[PF_PZ], c->begin, c->typ);
+		}
+	} else if (packed) {
 		if (fuse_collide) {
 			LFK_LAUNCH(c, k_correct_tiled2<true>, grid, CT_THREADS, smem, G, M, c->P, c->Palt.f[PF_PX], c->Palt.f[PF_PY],
 				c->Palt.f[PF_PZ], c->begin, c->typ);

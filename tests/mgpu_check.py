@@ -65,11 +65,19 @@ def main():
                 if zc.min() < z0 - 1 or zc.max() > z1:
                     failures.append("%s: own particle outside slab +- 1 (z cells %d..%d)" % (tag, zc.min(), zc.max()))
                     continue
-                d, idx = cKDTree(b["position"]).query(a["position"])
+                d2, idx2 = cKDTree(b["position"]).query(a["position"], k=2)
+                d, idx = d2[:, 0], idx2[:, 0]
                 # (particles clamped into the same wall corner coincide, so the match need not be injective everywhere)
                 if np.unique(idx).size < 0.995 * idx.size or d.max() > 1e-6:
                     failures.append("%s: positions differ (max %.3e, unique %d / %d)" % (tag, d.max(), np.unique(idx).size, idx.size))
                     continue
+                # coincident particles cannot be told apart by position, and under FLIP they keep distinct velocities:
+                # the per-particle payload comparison is restricted to the unambiguous matches (all but a handful)
+                clear = d2[:, 1] > 1e-9
+                if clear.sum() < 0.99 * clear.size:
+                    failures.append("%s: %d of %d matches are ambiguous" % (tag, int((~clear).sum()), clear.size))
+                    continue
+                a, idx, zc = a[clear], idx[clear], zc[clear]
                 dvv = np.abs(a["velocity"] - b["velocity"][idx]).max(axis=1)
                 dv = dvv.max()
                 if dv > 1e-4 * max(1.0, np.abs(b["velocity"]).max()):

@@ -242,23 +242,35 @@ def test_p2g_kernel_variants_agree(method):
 
 
 def test_position_correction_variants_agree():
-    """scalar fp32 pre-filter (production) against the packed-fp32 variant: both only select candidates for the same
-    fp64 evaluation in the same order, so the corrected positions are bit-identical"""
+    """scalar fp32 pre-filter (production) against the packed-fp32 and the hit-mask variants: all of them only select
+    candidates for the same fp64 evaluation in the same order, so the corrected positions are bit-identical"""
     ctx = _device_scene()
     for _ in range(4):
         ctx.time_step()
     ctx.hash()
     parts = ctx.download_particles().copy()
     outs = []
-    for v in (0, 1):
+    for v in (0, 1, 2):
         ctx.set_tuning("correct", v)
         ctx.upload_particles(parts)
         ctx.hash()
         ctx.correct(0.004)
         outs.append(ctx.download_particles().copy())
-    assert np.array_equal(outs[0]["position"].view("u8"), outs[1]["position"].view("u8"))
+    for k in (1, 2):
+        assert np.array_equal(outs[0]["position"].view("u8"), outs[k]["position"].view("u8")), k
     moved = np.abs(outs[0]["position"] - parts[np.argsort(parts["raw_cell_index"], kind="stable")]["position"]).max()
     assert moved > 1e-6
+    # the same inside the fused step (correction + second collision pass in one kernel)
+    res = []
+    for v in (0, 2):
+        ctx.set_tuning("correct", v)
+        ctx.set_tuning("warm_start", 0)
+        ctx.upload_particles(parts)
+        for _ in range(2):
+            ctx.time_step(0.002)
+        res.append(ctx.download_particles().copy())
+    for f in ("position", "velocity"):
+        assert np.array_equal(res[0][f].view("u8"), res[1][f].view("u8")), f
     ctx.close()
 
 
