@@ -773,6 +773,8 @@ extern "C" int lfk_set_tuning(lfk_ctx *c, const char *key, int value) {
 	const std::string k(key);
 	if (k == "p2g") { c->tune.p2g = value; }
 	else if (k == "correct") { c->tune.correct = value; }
+	else if (k == "g2p") { c->tune.g2p = value; }
+	else if (k == "advect") { c->tune.advect = value; }
 	else if (k == "mg_tail") { c->tune.mg_tail = value; }
 	else if (k == "spmv") { c->tune.spmv = value; }
 	else if (k == "warm_start") { c->tune.warm_start = value; }

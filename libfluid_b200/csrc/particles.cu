@@ -616,6 +616,39 @@ __global__ void k_advect_collide(GridDesc G, MotionParams M, ParticleSoA P, cons
 	P.f[PF_PZ][i] = to[2];
 }
 
+// A/B variant: two particles per thread, all twelve loads issued before the first (division-heavy) collision march --
+// twice the bytes in flight per warp for a kernel that is limited by memory latency, not by bandwidth (52 % of the
+// measured HBM peak at ideal DRAM traffic, ncu r1d).  Same arithmetic per particle, bit-identical results.
+__global__ void __launch_bounds__(128) k_advect_collide2(GridDesc G, MotionParams M, ParticleSoA P,
+	const uint8_t *__restrict__ typ, unsigned long long n) {
+	const unsigned long long i0 = (unsigned long long)blockIdx.x * 256 + threadIdx.x, i1 = i0 + 128;
+	const bool has0 = i0 < n, has1 = i1 < n;
+	double from0[3], v0[3], from1[3], v1[3];
+#pragma unroll
+	for (int d = 0; d < 3; ++d) {
+		from0[d] = has0 ? P.f[PF_PX + d][i0] : 0.0;
+		v0[d] = has0 ? P.f[PF_VX + d][i0] : 0.0;
+		from1[d] = has1 ? P.f[PF_PX + d][i1] : 0.0;
+		v1[d] = has1 ? P.f[PF_VX + d][i1] : 0.0;
+	}
+	if (has0) {
+		double to[3] = { from0[0], from0[1], from0[2] };
+		advect_one(M, to, v0);
+		collide_one(G, M, typ, from0, to);
+		P.f[PF_PX][i0] = to[0];
+		P.f[PF_PY][i0] = to[1];
+		P.f[PF_PZ][i0] = to[2];
+	}
+	if (has1) {
+		double to[3] = { from1[0], from1[1], from1[2] };
+		advect_one(M, to, v1);
+		collide_one(G, M, typ, from1, to);
+		P.f[PF_PX][i1] = to[0];
+		P.f[PF_PY][i1] = to[1];
+		P.f[PF_PZ][i1] = to[2];
+	}
+}
+
 static int materialise_old(lfk_ctx *c) {
 	if (!c->old_valid && c->np > 0) {
 		for (int d = 0; d < 3; ++d) {
@@ -655,7 +688,10 @@ int lfkp_advect_collide(lfk_ctx *c, double dt) {
 		return lfkp_collide(c);
 	}
 	LFK_TRY(lfkp_materialise_vc(c));
-	if (c->np > 0) {
+	if (c->np > 0 && c->tune.advect == 1) {
+		LFK_LAUNCH(c, k_advect_collide2, lfk_blocks((long long)c->np, 256), 128, 0, c->g, motion_params(c, dt),
+			lfk_own_view(c), c->typ, (unsigned long long)c->np);
+	} else if (c->np > 0) {
 		LFK_LAUNCH(c, k_advect_collide, lfk_blocks((long long)c->np, 128), 128, 0, c->g, motion_params(c, dt),
 			lfk_own_view(c), c->typ, (unsigned long long)c->np);
 	}
@@ -1180,7 +1216,9 @@ template <bool COLLIDE> __global__ void __launch_bounds__(CT_THREADS, 2) k_corre
 #define CT3_PAD 3
 #define CT3_LIST 16
 
-template <bool COLLIDE> __global__ void __launch_bounds__(CT_THREADS, 2) k_correct_tiled3(GridDesc G, MotionParams M,
+// PREF: the next {mask, index} record is read from the per-thread list one refill ahead of its use (the refill's
+// local-memory load sat on the critical path of every phase-2 iteration: 9.7 % of the kernel's stall samples, ncu r1d).
+template <bool COLLIDE, bool PREF> __global__ void __launch_bounds__(CT_THREADS, 2) k_correct_tiled3(GridDesc G, MotionParams M,
 	ParticleSoA P, double *__restrict__ nx_, double *__restrict__ ny_, double *__restrict__ nz_,
 	const uint32_t *__restrict__ begin, const uint8_t *__restrict__ typ) {
 	extern __shared__ float4 stage3[];
@@ -1340,14 +1378,23 @@ template <bool COLLIDE> __global__ void __launch_bounds__(CT_THREADS, 2) k_corre
 				// is fetched one iteration ahead of its use
 				int k = 1;
 				uint32_t m = rec[0].x, jb = rec[0].y;
+				uint2 nxt = make_uint2(0u, 0u);
+				if (PREF && nr > 1) { nxt = rec[1]; }
 				uint32_t j = jb + (uint32_t)(__ffs((int)m) - 1);
 				m &= m - 1u;
 				double ov[3] = { px[j], py[j], pz[j] };
 				for (;;) {
 					if (m == 0u && k < nr) {
-						m = rec[k].x;
-						jb = rec[k].y;
-						++k;
+						if (PREF) {
+							m = nxt.x;
+							jb = nxt.y;
+							++k;
+							if (k < nr) { nxt = rec[k]; }
+						} else {
+							m = rec[k].x;
+							jb = rec[k].y;
+							++k;
+						}
 					}
 					const bool more = m != 0u;
 					uint32_t jn = (uint32_t)i;
@@ -1394,18 +1441,28 @@ static int correct_impl(lfk_ctx *c, double dt, bool fuse_collide) {
 		LFK_CUDA(c, cudaFuncSetAttribute(k_correct_tiled<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
 		LFK_CUDA(c, cudaFuncSetAttribute(k_correct_tiled2<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
 		LFK_CUDA(c, cudaFuncSetAttribute(k_correct_tiled2<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-		LFK_CUDA(c, cudaFuncSetAttribute(k_correct_tiled3<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-		LFK_CUDA(c, cudaFuncSetAttribute(k_correct_tiled3<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+		LFK_CUDA(c, cudaFuncSetAttribute((k_correct_tiled3<true, false>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+		LFK_CUDA(c, cudaFuncSetAttribute((k_correct_tiled3<false, false>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+		LFK_CUDA(c, cudaFuncSetAttribute((k_correct_tiled3<true, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+		LFK_CUDA(c, cudaFuncSetAttribute((k_correct_tiled3<false, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
 		attr_set = true;
 	}
 	const bool packed = c->tune.correct == 1; // A/B: packed-fp32 pre-filter (42.6 ms at 256^3; 0 = scalar pre-filter, 30.2 ms)
 	if (!fuse_collide) { LFK_TRY(materialise_old(c)); }
 	if (c->tune.correct == 2) { // production: expanded-form pre-filter with per-row hit masks (27.7 ms at 256^3, r1d sweep)
 		if (fuse_collide) {
-			LFK_LAUNCH(c, k_correct_tiled3<true>, grid, CT_THREADS, smem, G, M, c->P, c->Palt.f[PF_PX], c->Palt.f[PF_PY],
+			LFK_LAUNCH(c, (k_correct_tiled3<true, false>), grid, CT_THREADS, smem, G, M, c->P, c->Palt.f[PF_PX], c->Palt.f[PF_PY],
 				c->Palt.f[PF_PZ], c->begin, c->typ);
 		} else {
-			LFK_LAUNCH(c, k_correct_tiled3<false>, grid, CT_THREADS, smem, G, M, c->P, c->Palt.f[PF_PX], c->Palt.f[PF_PY],
+			LFK_LAUNCH(c, (k_correct_tiled3<false, false>), grid, CT_THREADS, smem, G, M, c->P, c->Palt.f[PF_PX], c->Palt.f[PF_PY],
+				c->Palt.f[PF_PZ], c->begin, c->typ);
+		}
+	} else if (c->tune.correct == 3) { // A/B: as 2, records read one refill ahead
+		if (fuse_collide) {
+			LFK_LAUNCH(c, (k_correct_tiled3<true, true>), grid, CT_THREADS, smem, G, M, c->P, c->Palt.f[PF_PX], c->Palt.f[PF_PY],
+				c->Palt.f[PF_PZ], c->begin, c->typ);
+		} else {
+			LFK_LAUNCH(c, (k_correct_tiled3<false, true>), grid, CT_THREADS, smem, G, M, c->P, c->Palt.f[PF_PX], c->Palt.f[PF_PY],
 				c->Palt.f[PF_PZ], c->begin, c->typ);
 		}
 	} else if (packed) {

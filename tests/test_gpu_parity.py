@@ -250,27 +250,54 @@ def test_position_correction_variants_agree():
     ctx.hash()
     parts = ctx.download_particles().copy()
     outs = []
-    for v in (0, 1, 2):
+    for v in (0, 1, 2, 3):
         ctx.set_tuning("correct", v)
         ctx.upload_particles(parts)
         ctx.hash()
         ctx.correct(0.004)
         outs.append(ctx.download_particles().copy())
-    for k in (1, 2):
+    for k in (1, 2, 3):
         assert np.array_equal(outs[0]["position"].view("u8"), outs[k]["position"].view("u8")), k
     moved = np.abs(outs[0]["position"] - parts[np.argsort(parts["raw_cell_index"], kind="stable")]["position"]).max()
     assert moved > 1e-6
     # the same inside the fused step (correction + second collision pass in one kernel)
     res = []
-    for v in (0, 2):
+    for v in (0, 2, 3):
         ctx.set_tuning("correct", v)
         ctx.set_tuning("warm_start", 0)
         ctx.upload_particles(parts)
         for _ in range(2):
             ctx.time_step(0.002)
         res.append(ctx.download_particles().copy())
-    for f in ("position", "velocity"):
-        assert np.array_equal(res[0][f].view("u8"), res[1][f].view("u8")), f
+    for k in (1, 2):
+        for f in ("position", "velocity"):
+            assert np.array_equal(res[0][f].view("u8"), res[k][f].view("u8")), (k, f)
+    ctx.close()
+
+
+@pytest.mark.parametrize("method", [capi.APIC, capi.FLIP, capi.PIC])
+def test_g2p_and_advection_variants_agree(method):
+    """latency-hiding variants (all face samples requested before the first store; two particles per thread in the
+    fused advect + collide kernel) do the same arithmetic per particle: bit-identical particle state after fused
+    steps from the same state, for every transfer method"""
+    ctx = _device_scene(method=method, blending_factor=0.95)
+    for _ in range(3):
+        ctx.time_step()
+    parts, cells = ctx.download_particles().copy(), ctx.download_cells().copy()
+    res = []
+    for g2p, adv in ((0, 0), (1, 0), (0, 1), (1, 1)):
+        ctx.set_tuning("g2p", g2p)
+        ctx.set_tuning("advect", adv)
+        ctx.set_tuning("warm_start", 0)
+        ctx.upload_cells(cells)
+        ctx.upload_particles(parts)
+        for _ in range(3):
+            ctx.time_step(0.002)
+        res.append(ctx.download_particles().copy())
+    assert np.abs(res[0]["velocity"]).max() > 1.0
+    for k in (1, 2, 3):
+        for f in ("position", "velocity", "cx", "cy", "cz"):
+            assert np.array_equal(res[0][f].view("u8"), res[k][f].view("u8")), (k, f)
     ctx.close()
 
 

@@ -16,11 +16,15 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
-NEW = {"p2g": 0, "correct": 2, "mg_tail": 0, "warm_start": 1, "red_blocks": 0}  # the library defaults
-OLD = {"p2g": 1, "correct": 0, "mg_tail": 1, "warm_start": 0, "red_blocks": 16384}  # round r1b
+NEW = {"p2g": 0, "correct": 2, "g2p": 0, "advect": 0, "mg_tail": 0, "warm_start": 1, "red_blocks": 0}  # the library defaults
+OLD = {"p2g": 1, "correct": 0, "g2p": 0, "advect": 0, "mg_tail": 1, "warm_start": 0, "red_blocks": 16384}  # round r1b
 CONFIGS = [
     ("defaults", dict(NEW)),
     ("defaults+correct_scalar", dict(NEW, correct=0)),
+    ("defaults+correct_prefetch", dict(NEW, correct=3)),
+    ("defaults+g2p_batch", dict(NEW, g2p=1)),
+    ("defaults+advect_pair", dict(NEW, advect=1)),
+    ("defaults+all_new", dict(NEW, correct=3, g2p=1, advect=1)),
     ("defaults+p2g_brick", dict(NEW, p2g=1)),
     ("defaults+red_blocks_592", dict(NEW, red_blocks=592)),
     ("defaults+red_blocks_2368", dict(NEW, red_blocks=2368)),
