@@ -82,6 +82,23 @@ def measured_peak():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+TRAFFIC_KERNEL = {"p2g": "k_p2g_march<2>", "g2p": "k_g2p<2>", "correct_collide": "k_correct_tiled3<1>",
+                  "advect_collide": "k_advect_collide"}
+
+
+def captured_traffic(grid):
+    """DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum) of the single-kernel phases, from the
+    committed ncu capture of this same command at 256^3 (profiles/*_traffic_256.json, tools/ncu_traffic_table.py);
+    None for other grids or when no capture is committed."""
+    import glob
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "*_traffic_%d.json" % grid)))
+    if not files:
+        return {}, None
+    tab = json.load(open(files[-1]))["kernels"]
+    out = {ph: tab[k]["dram_bytes_per_launch"] for ph, k in TRAFFIC_KERNEL.items() if k in tab}
+    return out, os.path.relpath(files[-1], ROOT)
+
+
 # ------------------------------------------------------------------------------------------------ reference arm
 def run_reference(args, n=None, steps=None, warmup=None, quiet=False):
     """The reference's own CPU implementation (oracle/_ref = unmodified libfluid sources) on the host cores, on a
@@ -217,12 +234,18 @@ def run_ours(args):
     single = {k: phase[k] for k in alg if k in phase}
     dom = max(single, key=single.get)
     ach = alg[dom] / (single[dom] * 1e-3) / 1e9
+    traffic, traffic_src = captured_traffic(n)
     roofline = {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                "traffic": None, "peak_source": peak_src, "ms": single[dom],
-                "all": {k: {"ms": single[k], "GB/s": alg[k] / (single[k] * 1e-3) / 1e9} for k in single}}
+                "traffic": traffic.get(dom), "traffic_source": traffic_src, "algorithmic_bytes": alg[dom],
+                "peak_source": peak_src, "ms": single[dom],
+                "all": {k: {"ms": single[k], "GB/s": alg[k] / (single[k] * 1e-3) / 1e9,
+                            "frac": alg[k] / (single[k] * 1e-3) / 1e9 / peak, "algorithmic_bytes": alg[k],
+                            "traffic": traffic.get(k)} for k in single}}
     if "pcg" in phase and prof_iters:
         it_ms = phase["pcg"] * prof_steps / prof_iters
         roofline["all"]["pcg_iteration"] = {"ms": it_ms, "GB/s": 105 * nf / (it_ms * 1e-3) / 1e9,
+                                           "frac": 105 * nf / (it_ms * 1e-3) / 1e9 / peak,
+                                           "algorithmic_bytes": 105 * nf,
                                            "iters_per_step": prof_iters / prof_steps, "iters_per_s": 1e3 / it_ms}
 
     # ---- end to end through the C ABI with HOST buffers: AoS particles + cells up, step, AoS particles + cells down
