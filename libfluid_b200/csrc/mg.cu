@@ -32,6 +32,7 @@
 #define MG_PRE 2
 #define MG_POST 2
 #define MG_COARSE_SWEEPS 8
+#define MG_COARSE_SWEEPS_MULTI 4 // multi-GPU coarsest level (host-driven sweeps, one NCCL exchange per half-sweep)
 #define MG_COARSE_MAX_CELLS 4096 // a level this small is smoothed to convergence by one block
 
 // level-0 coupling mask: bits 0-2 diagonal (non-solid neighbour count), bit 3 "is an unknown", bits 4-9 "the
@@ -566,15 +567,20 @@ int lfkm_setup(lfk_ctx *c, double a_scale) {
 	return 0;
 }
 
-// one half-sweep of colour `colour` on level l; `prolong`: the neighbours carry the pending correction of level l + 1
-static int half_sweep(lfk_ctx *c, size_t l, int colour, bool prolong) {
+// one half-sweep of colour `colour` on level l; `prolong`: the neighbours carry the pending correction of level l + 1.
+// Multi-GPU: the z ghost layers of x are refreshed first unless the caller knows they are current (`x_current`):
+// every exchange is an NCCL launch of ~15 us against ~8 us of arithmetic on the coarse levels (profiles/r1d: 2.4 ms per
+// PCG iteration on 2 GPUs against 1.03 ms on one), so the ones that cannot change anything are skipped:
+//   * first half-sweep after a restriction: x == 0 on every rank, the ghost layers are zeroed locally instead;
+//   * first post-smoothing half-sweep: x of this level has not changed since the exchange before the restriction.
+static int half_sweep(lfk_ctx *c, size_t l, int colour, bool prolong, bool x_current = false) {
 	const GridDesc &G = c->g;
 	MgLevel &L = c->mg[l];
 	LevelDev Ld = level_dev(L, c->mg_z0[l]);
 	LevelDev Cd = prolong ? level_dev(c->mg[l + 1], c->mg_z0[l + 1]) : Ld;
 	unsigned nb = row_blocks(L.ny, L.nzl, 256, 1u << 20);
 	if (c->nranks > 1) {
-		LFK_TRY(lfkx_halo_f32(c, L.x, L.nx, L.ny, L.nzl));
+		if (!x_current) { LFK_TRY(lfkx_halo_f32(c, L.x, L.nx, L.ny, L.nzl)); }
 		if (prolong) { LFK_TRY(lfkx_halo_f32(c, c->mg[l + 1].x, Cd.nx, Cd.ny, Cd.nzl)); }
 	}
 	if (l == 0) {
@@ -620,19 +626,26 @@ static int vcycle(lfk_ctx *c, size_t l) {
 		}
 		return 0;
 	}
+	// x of a level > 0 is zero when its cycle starts (the restriction zeroes the owned cells, and -- multi-GPU -- the
+	// ghost layers, see below), so its first half-sweep needs no exchange
+	const bool zero_start = l > 0;
 	if (l == last) { // coarsest level reached outside the tail (multi-GPU alignment limit, or a tiny fine grid)
-		for (int s = 0; s < MG_COARSE_SWEEPS; ++s) {
-			if (!(l == 0 && s == 0)) { LFK_TRY(half_sweep(c, l, 0, false)); }
+		// multi-GPU, below level 0: a coarsest grid of a few cells per rank; tools/mg_prototype.py counts the same PCG
+		// iterations with 4 symmetric sweeps as with 8 on slab hierarchies of 1 .. 8 ranks, and every half-sweep is an
+		// exchange
+		const int sweeps = (c->nranks > 1 && l > 0) ? MG_COARSE_SWEEPS_MULTI : MG_COARSE_SWEEPS;
+		for (int s = 0; s < sweeps; ++s) {
+			if (!(l == 0 && s == 0)) { LFK_TRY(half_sweep(c, l, 0, false, zero_start && s == 0)); }
 			LFK_TRY(half_sweep(c, l, 1, false));
 		}
-		for (int s = 0; s < MG_COARSE_SWEEPS; ++s) {
+		for (int s = 0; s < sweeps; ++s) {
 			LFK_TRY(half_sweep(c, l, 1, false));
-			if (!(l == 0 && s == MG_COARSE_SWEEPS - 1)) { LFK_TRY(half_sweep(c, l, 0, false)); }
+			if (!(l == 0 && s == sweeps - 1)) { LFK_TRY(half_sweep(c, l, 0, false)); }
 		}
 		return 0;
 	}
 	for (int s = 0; s < MG_PRE; ++s) { // red, black
-		if (!(l == 0 && s == 0)) { LFK_TRY(half_sweep(c, l, 0, false)); }
+		if (!(l == 0 && s == 0)) { LFK_TRY(half_sweep(c, l, 0, false, zero_start && s == 0)); }
 		LFK_TRY(half_sweep(c, l, 1, false));
 	}
 	MgLevel &C = c->mg[l + 1];
@@ -644,9 +657,14 @@ static int vcycle(lfk_ctx *c, size_t l) {
 	} else {
 		LFK_LAUNCH(c, k_mg_restrict, rb, 128, 0, Ld, Cd, c->d_scal);
 	}
+	if (c->nranks > 1) { // the coarse x starts from zero in the ghost layers too (what an exchange would deliver)
+		LFK_CUDA(c, cudaMemsetAsync(C.x, 0, (size_t)C.sxy * sizeof(float), c->stream));
+		LFK_CUDA(c, cudaMemsetAsync(C.x + (size_t)C.sxy * (C.nzl + 1), 0, (size_t)C.sxy * sizeof(float), c->stream));
+	}
 	LFK_TRY(vcycle(c, l + 1));
 	for (int s = 0; s < MG_POST; ++s) { // black (the first one applies the prolongation on the fly), red
-		LFK_TRY(half_sweep(c, l, 1, s == 0));
+		// s == 0: x of this level is as the exchange before the restriction left it
+		LFK_TRY(half_sweep(c, l, 1, s == 0, s == 0));
 		if (!(l == 0 && s == MG_POST - 1)) { LFK_TRY(half_sweep(c, l, 0, false)); }
 	}
 	return 0;
