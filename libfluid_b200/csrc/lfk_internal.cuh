@@ -60,6 +60,8 @@ struct MgLevel {
 	float *x, *b, *r;        // solution / rhs / residual scratch (fp32)
 };
 
+#define LFK_MAX_DEVICES 64 // per-device one-time set-up flags (cudaFuncSetAttribute is a per-device setting)
+
 // A/B switches and tuning knobs (lfk_set_tuning; the defaults are the production path)
 enum { LFK_TUNE_P2G_MARCH = 0, LFK_TUNE_P2G_BRICK = 1, LFK_TUNE_P2G_GATHER = 2 };
 struct lfk_tuning {

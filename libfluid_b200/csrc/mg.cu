@@ -615,10 +615,10 @@ static int vcycle(lfk_ctx *c, size_t l) {
 		size_t smem = 0;
 		for (int k = 0; k < T.n; ++k) { smem += 6 * ((size_t)(T.L[k].sxy * (T.L[k].nzl + 2)) + 2) * sizeof(float); }
 		if (c->tune.mg_tail == 0 && smem <= 200 * 1024) {
-			static bool attr_set = false;
-			if (!attr_set) {
+			static bool attr_set[LFK_MAX_DEVICES] = {}; // function attributes are per device
+			if (!attr_set[c->device % LFK_MAX_DEVICES]) {
 				LFK_CUDA(c, cudaFuncSetAttribute(k_mg_tail_smem, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-				attr_set = true;
+				attr_set[c->device % LFK_MAX_DEVICES] = true;
 			}
 			LFK_LAUNCH(c, k_mg_tail_smem, 1, 1024, smem, T, c->d_scal);
 		} else {

@@ -218,12 +218,12 @@ int lfkg_p2g_brick(lfk_ctx *c, double gravity_dt, bool add_gravity) {
 		(unsigned)((G.nzl + PB_BZ - 1) / PB_BZ));
 	const uint32_t *permv = c->v_deferred ? c->perm : nullptr, *permc = c->c_deferred ? c->perm : nullptr;
 	const size_t smem = (size_t)(PB_ACC_COMP + PB_WARPS * PB_FIELDS * PB_FSTRIDE) * sizeof(double);
-	static bool attr_set = false;
-	if (!attr_set) {
+	static bool attr_set[LFK_MAX_DEVICES] = {}; // function attributes are per device
+	if (!attr_set[c->device % LFK_MAX_DEVICES]) {
 		LFK_CUDA(c, cudaFuncSetAttribute(k_p2g_brick<LFK_METHOD_PIC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
 		LFK_CUDA(c, cudaFuncSetAttribute(k_p2g_brick<LFK_METHOD_FLIP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
 		LFK_CUDA(c, cudaFuncSetAttribute(k_p2g_brick<LFK_METHOD_APIC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-		attr_set = true;
+		attr_set[c->device % LFK_MAX_DEVICES] = true;
 	}
 	switch (c->prm.method) {
 	case LFK_METHOD_PIC:

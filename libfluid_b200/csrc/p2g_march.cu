@@ -354,12 +354,12 @@ int lfkg_p2g_march(lfk_ctx *c, double gravity_dt, bool add_gravity) {
 	nzc = (G.nzl + chunk - 1) / chunk;
 	dim3 grid(nbx, nby, (unsigned)nzc);
 	const size_t smem = (size_t)(PM_WARPS * 2 * PM_STAGE + 2 * PM_WARPS * PM_SLOT + PM_MAX_CHUNK + 4) * sizeof(double);
-	static bool attr_set = false;
-	if (!attr_set) {
+	static bool attr_set[LFK_MAX_DEVICES] = {}; // function attributes are per device
+	if (!attr_set[c->device % LFK_MAX_DEVICES]) {
 		LFK_CUDA(c, cudaFuncSetAttribute(k_p2g_march<LFK_METHOD_PIC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
 		LFK_CUDA(c, cudaFuncSetAttribute(k_p2g_march<LFK_METHOD_FLIP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
 		LFK_CUDA(c, cudaFuncSetAttribute(k_p2g_march<LFK_METHOD_APIC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-		attr_set = true;
+		attr_set[c->device % LFK_MAX_DEVICES] = true;
 	}
 	switch (c->prm.method) {
 	case LFK_METHOD_PIC:

@@ -1435,8 +1435,8 @@ static int correct_impl(lfk_ctx *c, double dt, bool fuse_collide) {
 	dim3 grid((unsigned)((G.nx + CT_LX - 1) / CT_LX), (unsigned)((G.ny + CT_TY - 1) / CT_TY),
 		(unsigned)((G.nzl + CT_TZ - 1) / CT_TZ));
 	const size_t smem = (size_t)CT_CAP * sizeof(float4);
-	static bool attr_set = false;
-	if (!attr_set) {
+	static bool attr_set[LFK_MAX_DEVICES] = {}; // function attributes are per device
+	if (!attr_set[c->device % LFK_MAX_DEVICES]) {
 		LFK_CUDA(c, cudaFuncSetAttribute(k_correct_tiled<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
 		LFK_CUDA(c, cudaFuncSetAttribute(k_correct_tiled<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
 		LFK_CUDA(c, cudaFuncSetAttribute(k_correct_tiled2<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -1445,7 +1445,7 @@ static int correct_impl(lfk_ctx *c, double dt, bool fuse_collide) {
 		LFK_CUDA(c, cudaFuncSetAttribute((k_correct_tiled3<false, false>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
 		LFK_CUDA(c, cudaFuncSetAttribute((k_correct_tiled3<true, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
 		LFK_CUDA(c, cudaFuncSetAttribute((k_correct_tiled3<false, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-		attr_set = true;
+		attr_set[c->device % LFK_MAX_DEVICES] = true;
 	}
 	const bool packed = c->tune.correct == 1; // A/B: packed-fp32 pre-filter (42.6 ms at 256^3; 0 = scalar pre-filter, 30.2 ms)
 	if (!fuse_collide) { LFK_TRY(materialise_old(c)); }
