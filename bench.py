@@ -238,6 +238,11 @@ def run_ours(args):
     roofline = {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
                 "traffic": traffic.get(dom), "traffic_source": traffic_src, "algorithmic_bytes": alg[dom],
                 "peak_source": peak_src, "ms": single[dom],
+                "note": ("position correction is the longest kernel but is not memory bound: its DRAM traffic equals its "
+                         "algorithmic bytes and ncu shows it limited by instruction issue (61 % of issue slots busy, "
+                         "147 warp-instructions per particle) and the shared-memory pipe "
+                         "(profiles/r1d_particles128_ncu_summary.txt); the HBM-bound transfer kernels are under `all`"
+                         if dom == "correct_collide" else None),
                 "all": {k: {"ms": single[k], "GB/s": alg[k] / (single[k] * 1e-3) / 1e9,
                             "frac": alg[k] / (single[k] * 1e-3) / 1e9 / peak, "algorithmic_bytes": alg[k],
                             "traffic": traffic.get(k)} for k in single}}
