@@ -139,7 +139,15 @@ int lfkg_p2g(lfk_ctx *c, double gravity_dt, bool add_gravity) {
 	PhaseTimer T(c, LFK_PHASE_P2G);
 	LFK_REQUIRE(c, c->table_valid, LFK_E_STATE, "lfk_p2g needs the cell table of lfk_hash");
 	const GridDesc &G = c->g;
-	const bool use_gather = c->tune.p2g == LFK_TUNE_P2G_GATHER; // A/B switch: the simple gather kernel below
+	// The simple gather kernel below is the A/B reference -- and the production path for one corner of the
+	// reference's behaviour: APIC evaluates its hat weights on the raw distance, not distance / h
+	// (src/simulation.cpp:367-369), so for h < 1 a particle still weighs on the +face of the cell BEHIND its
+	// neighbour along the staggered axis (|d| up to 2 h < 1 where h < 0.5, up to 1 otherwise), which the reference's
+	// 27-cell gather visits.  The scatter kernels give every cell 2 faces along the staggered axis (all that can be
+	// reached when the weight's support is one cell), so that case goes to the gather kernel, which walks exactly the
+	// reference's 27 cells.  h >= 1 (every shipped configuration has h == 1) is unaffected.
+	const bool wide_apic = c->prm.method == LFK_METHOD_APIC && G.h < 1.0;
+	const bool use_gather = c->tune.p2g == LFK_TUNE_P2G_GATHER || wide_apic;
 	if (!use_gather) {
 		if (c->tune.p2g == LFK_TUNE_P2G_BRICK) {
 			LFK_TRY(lfkg_p2g_brick(c, gravity_dt, add_gravity));
@@ -177,6 +185,10 @@ int lfkg_p2g(lfk_ctx *c, double gravity_dt, bool add_gravity) {
 		LFK_LAUNCH(c, k_p2g_gather<LFK_METHOD_APIC>, nb, 128, 0, G, Q, c->P, c->begin, c->ctr[0], c->ctr[1], c->ctr[2],
 			c->vel[0], c->vel[1], c->vel[2], c->vel_old[0], c->vel_old[1], c->vel_old[2], c->typ);
 		break;
+	}
+	if (c->nranks > 1 && c->prm.method == LFK_METHOD_FLIP) { // as above
+		for (int d = 0; d < 3; ++d) { LFK_TRY(lfkx_halo_f64(c, c->vel_old[d])); }
+		LFK_TRY(lfkx_layer_below(c, c->vel_old[2], c->wlow[1]));
 	}
 	c->system_valid = false;
 	c->pressure_valid = false;

@@ -39,6 +39,42 @@ def make_scene(name, n=16):
 SCENES = ("cube_drop", "dam_break", "flip_obstacle", "pic_sphere")
 
 
+def make_random_scene(seed):
+    """A randomised small scene: non-cubic grid, cell size that need not be a power of two (true divisions; APIC's
+    weights without /h and face positions built by repeated addition), offset grid, any
+    of the three methods, random solid blocks, one or two moving blocks / spheres of water.  Returns (RefSim, rng);
+    None when the draw seeded no particle."""
+    rng = np.random.default_rng(1000 + seed)
+    size = tuple(int(v) for v in rng.integers(6, 15, size=3))  # (nx, ny, nz)
+    h = float(rng.choice([0.25, 0.5, 1.0, 1.7, 2.0, 0.3]))
+    offset = tuple(float(v) for v in rng.uniform(-3.0, 3.0, size=3))
+    method = int(rng.choice([RB.APIC, RB.FLIP, RB.PIC]))
+    blend = float(rng.choice([1.0, 0.95, 0.5]))
+    ref = RB.RefSim(size, h=h, offset=offset, gravity=(0.0, -981.0 * h, 0.0), method=method, blend=blend)
+    nx, ny, nz = size
+    solid = np.zeros((nz, ny, nx), dtype=bool)
+    for _ in range(int(rng.integers(0, 3))):
+        lo = [int(rng.integers(0, d - 1)) for d in (nz, ny, nx)]
+        ext = [int(rng.integers(1, 4)) for _ in range(3)]
+        solid[lo[0]:lo[0] + ext[0], lo[1]:lo[1] + ext[1], lo[2]:lo[2] + ext[2]] = True
+    if solid.any() and not solid.all():
+        ref.set_solid(solid)
+    ext = np.array(size, dtype=np.float64) * h
+    off = np.array(offset)
+    for _ in range(int(rng.integers(1, 3))):
+        a = off + rng.uniform(0.0, 0.5, size=3) * ext
+        b = rng.uniform(0.2, 0.5, size=3) * ext
+        vel = tuple(float(v) for v in rng.uniform(-40.0, 40.0, size=3) * h)
+        if rng.random() < 0.3:
+            ref.seed_sphere(tuple(a + 0.5 * b), float(0.4 * b.min()), vel=vel)
+        else:
+            ref.seed_box(tuple(a), tuple(b), vel=vel)
+    if ref.num_particles() == 0:
+        return None, rng
+    ref.reset_space_hash()
+    return ref, rng
+
+
 def oracle_for(ref):
     """A C-restatement Oracle configured like the given RefSim."""
     return OB.Oracle(ref.size, h=ref.h, offset=ref.offset, gravity=ref.gravity, method=ref.method,

@@ -98,3 +98,19 @@ def test_empty_and_degenerate_inputs():
     # positions outside the grid clamp into it (src/simulation.cpp:255-257)
     pos = np.array([[-3.0, 2.0, 1.0], [100.0, 100.0, 100.0], [3.999999, 4.999999, 2.999999]])
     assert list(orc.cell_keys(pos)) == [0 + 4 * (2 + 5 * 1), 59, 59]
+
+
+@pytest.mark.skipif(not RB.available(), reason="oracle/_ref not built (needs /root/reference)")
+@pytest.mark.parametrize("seed", range(10))
+def test_oracle_pinned_to_reference_randomised(seed):
+    """Randomised pinning (PL.make_random_scene: non-cubic grids, cell sizes that are not powers of two, offset
+    grids, all three methods, solid blocks, moving water) -- every stage of every step bit for bit against the
+    compiled reference."""
+    ref, rng = PL.make_random_scene(seed)
+    if ref is None:
+        pytest.skip("empty scene")
+    orc = PL.oracle_for(ref)
+    for step in range(6):
+        dt = min(ref.cfl_number * ref.cfl(), 0.033) if step % 2 else float(rng.choice([0.002, 0.006]))
+        rec = PL.record_step(ref, dt)
+        assert PL.check_oracle_against_record(orc, rec) == [], "seed %d step %d" % (seed, step)

@@ -54,3 +54,25 @@ def test_full_size_step_properties_256():
     b2, _ = ctx.download_rhs(dt)  # rhs of the projected field == -div/h
     assert np.abs(b2).max() < 5e-6
     ctx.close()
+
+
+@pytest.mark.parametrize("seed", [0, 3, 4, 5])
+def test_stages_match_reference_randomised(seed):
+    """Every stage of the CUDA path against the compiled reference on randomised small scenes
+    (pinlib.make_random_scene): non-cubic and offset grids, cell sizes 1.7 and 0.3 (not powers of two: the true-division
+    paths), 0.5 and 0.25, APIC / FLIP / PIC, solid blocks, water thrown at walls.  Same checks and tolerances as
+    test_stages_match_reference_live."""
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    import devlib as DL
+    import pinlib as PL
+    if not PL.RB.available():
+        pytest.skip("oracle/_ref did not travel to this box")
+    ref, rng = PL.make_random_scene(seed)
+    assert ref is not None
+    orc = PL.oracle_for(ref)
+    ctx = DL.context_for(ref, max_iterations=2000)
+    for step in range(6):
+        dt = min(ref.cfl_number * ref.cfl(), 0.033) if step % 2 else float(rng.choice([0.002, 0.006]))
+        rec = PL.record_step(ref, dt)
+        assert DL.check_device_against_record(ctx, rec, orc) == {}, "seed %d step %d" % (seed, step)
+    ctx.close()
