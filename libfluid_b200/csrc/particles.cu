@@ -1218,7 +1218,13 @@ template <bool COLLIDE> __global__ void __launch_bounds__(CT_THREADS, 2) k_corre
 
 // PREF: the next {mask, index} record is read from the per-thread list one refill ahead of its use (the refill's
 // local-memory load sat on the critical path of every phase-2 iteration: 9.7 % of the kernel's stall samples, ncu r1d).
-template <bool COLLIDE, bool PREF> __global__ void __launch_bounds__(CT_THREADS, 2) k_correct_tiled3(GridDesc G, MotionParams M,
+// CLS (experimental, lfk_set_tuning("correct", 4); not measured yet): the tile's own particles are handed to the
+// threads grouped by the part of their cell they sit in along y and z (lower / middle / upper third, 9 classes).  Which
+// of the 9 neighbour rows a particle has to scan depends on exactly that, so a warp of one class skips the rows its
+// class cannot reach, where a warp of 32 consecutive particles executes all 9 (a lane needs 5.4 on average; SIMT model
+// in DESIGN.md section 7).  A particle's result does not depend on the thread that computes it, so the output is
+// unchanged bit for bit.
+template <bool COLLIDE, bool PREF, bool CLS> __global__ void __launch_bounds__(CT_THREADS, 2) k_correct_tiled3(GridDesc G, MotionParams M,
 	ParticleSoA P, double *__restrict__ nx_, double *__restrict__ ny_, double *__restrict__ nz_,
 	const uint32_t *__restrict__ begin, const uint8_t *__restrict__ typ) {
 	extern __shared__ float4 stage3[];
@@ -1293,8 +1299,42 @@ template <bool COLLIDE, bool PREF> __global__ void __launch_bounds__(CT_THREADS,
 		}
 	}
 	__syncthreads();
+	uint32_t *ownlist = reinterpret_cast<uint32_t *>(stage3 + CT_CAP); // [CT_CAP] own-particle indices by class (CLS)
+	__shared__ uint32_t ccount[9], ccursor[9];
+	const bool by_class = CLS && use_stage;
+	if (by_class) {
+		if (tid < 9) { ccount[tid] = 0; }
+		__syncthreads();
+		// class of own particle t from its staged coordinates (cell units about the tile centre, which lies on a cell
+		// boundary in y and z, so the fractional parts are the in-cell fractions)
+		auto own_class = [&](uint32_t t) {
+			int o = 0;
+#pragma unroll
+			for (int k = 1; k < CT_OWN; ++k) {
+				if (t >= ownpre[k]) { o = k; }
+			}
+			const int r = (o / CT_TY + 1) * CT_SY + (o % CT_TY + 1);
+			const float4 e = stage3[rowoff[r] + cellbeg[r][1] + (t - ownpre[o])];
+			const float fy = e.y - floorf(e.y), fz = e.z - floorf(e.z);
+			const int cy = fy <= 0.2922f ? 0 : (fy >= 0.7078f ? 2 : 1), cz = fz <= 0.2922f ? 0 : (fz >= 0.7078f ? 2 : 1);
+			return cz * 3 + cy;
+		};
+		for (uint32_t t = tid; t < nown_total; t += CT_THREADS) { atomicAdd(&ccount[own_class(t)], 1u); }
+		__syncthreads();
+		if (tid == 0) {
+			uint32_t acc = 0;
+			for (int k = 0; k < 9; ++k) {
+				ccursor[k] = acc;
+				acc += ccount[k];
+			}
+		}
+		__syncthreads();
+		for (uint32_t t = tid; t < nown_total; t += CT_THREADS) { ownlist[atomicAdd(&ccursor[own_class(t)], 1u)] = t; }
+		__syncthreads();
+	}
 
-	for (uint32_t t = tid; t < nown_total; t += CT_THREADS) {
+	for (uint32_t tq = tid; tq < nown_total; tq += CT_THREADS) {
+		const uint32_t t = by_class ? ownlist[tq] : tq;
 		int o = 0;
 #pragma unroll
 		for (int k = 1; k < CT_OWN; ++k) {
@@ -1435,34 +1475,45 @@ static int correct_impl(lfk_ctx *c, double dt, bool fuse_collide) {
 	dim3 grid((unsigned)((G.nx + CT_LX - 1) / CT_LX), (unsigned)((G.ny + CT_TY - 1) / CT_TY),
 		(unsigned)((G.nzl + CT_TZ - 1) / CT_TZ));
 	const size_t smem = (size_t)CT_CAP * sizeof(float4);
+	const size_t smem_cls = smem + (size_t)CT_CAP * sizeof(uint32_t); // + the class-sorted own-particle list
 	static bool attr_set[LFK_MAX_DEVICES] = {}; // function attributes are per device
 	if (!attr_set[c->device % LFK_MAX_DEVICES]) {
 		LFK_CUDA(c, cudaFuncSetAttribute(k_correct_tiled<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
 		LFK_CUDA(c, cudaFuncSetAttribute(k_correct_tiled<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
 		LFK_CUDA(c, cudaFuncSetAttribute(k_correct_tiled2<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
 		LFK_CUDA(c, cudaFuncSetAttribute(k_correct_tiled2<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-		LFK_CUDA(c, cudaFuncSetAttribute((k_correct_tiled3<true, false>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-		LFK_CUDA(c, cudaFuncSetAttribute((k_correct_tiled3<false, false>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-		LFK_CUDA(c, cudaFuncSetAttribute((k_correct_tiled3<true, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-		LFK_CUDA(c, cudaFuncSetAttribute((k_correct_tiled3<false, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+		LFK_CUDA(c, cudaFuncSetAttribute((k_correct_tiled3<true, false, false>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+		LFK_CUDA(c, cudaFuncSetAttribute((k_correct_tiled3<false, false, false>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+		LFK_CUDA(c, cudaFuncSetAttribute((k_correct_tiled3<true, true, false>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+		LFK_CUDA(c, cudaFuncSetAttribute((k_correct_tiled3<false, true, false>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+		LFK_CUDA(c, cudaFuncSetAttribute((k_correct_tiled3<true, false, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cls));
+		LFK_CUDA(c, cudaFuncSetAttribute((k_correct_tiled3<false, false, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cls));
 		attr_set[c->device % LFK_MAX_DEVICES] = true;
 	}
 	const bool packed = c->tune.correct == 1; // A/B: packed-fp32 pre-filter (42.6 ms at 256^3; 0 = scalar pre-filter, 30.2 ms)
 	if (!fuse_collide) { LFK_TRY(materialise_old(c)); }
 	if (c->tune.correct == 2) { // production: expanded-form pre-filter with per-row hit masks (27.7 ms at 256^3, r1d sweep)
 		if (fuse_collide) {
-			LFK_LAUNCH(c, (k_correct_tiled3<true, false>), grid, CT_THREADS, smem, G, M, c->P, c->Palt.f[PF_PX], c->Palt.f[PF_PY],
+			LFK_LAUNCH(c, (k_correct_tiled3<true, false, false>), grid, CT_THREADS, smem, G, M, c->P, c->Palt.f[PF_PX], c->Palt.f[PF_PY],
 				c->Palt.f[PF_PZ], c->begin, c->typ);
 		} else {
-			LFK_LAUNCH(c, (k_correct_tiled3<false, false>), grid, CT_THREADS, smem, G, M, c->P, c->Palt.f[PF_PX], c->Palt.f[PF_PY],
+			LFK_LAUNCH(c, (k_correct_tiled3<false, false, false>), grid, CT_THREADS, smem, G, M, c->P, c->Palt.f[PF_PX], c->Palt.f[PF_PY],
 				c->Palt.f[PF_PZ], c->begin, c->typ);
+		}
+	} else if (c->tune.correct == 4) { // experimental: as 2, own particles grouped by (y, z) reach class
+		if (fuse_collide) {
+			LFK_LAUNCH(c, (k_correct_tiled3<true, false, true>), grid, CT_THREADS, smem_cls, G, M, c->P, c->Palt.f[PF_PX],
+				c->Palt.f[PF_PY], c->Palt.f[PF_PZ], c->begin, c->typ);
+		} else {
+			LFK_LAUNCH(c, (k_correct_tiled3<false, false, true>), grid, CT_THREADS, smem_cls, G, M, c->P, c->Palt.f[PF_PX],
+				c->Palt.f[PF_PY], c->Palt.f[PF_PZ], c->begin, c->typ);
 		}
 	} else if (c->tune.correct == 3) { // A/B: as 2, records read one refill ahead
 		if (fuse_collide) {
-			LFK_LAUNCH(c, (k_correct_tiled3<true, true>), grid, CT_THREADS, smem, G, M, c->P, c->Palt.f[PF_PX], c->Palt.f[PF_PY],
+			LFK_LAUNCH(c, (k_correct_tiled3<true, true, false>), grid, CT_THREADS, smem, G, M, c->P, c->Palt.f[PF_PX], c->Palt.f[PF_PY],
 				c->Palt.f[PF_PZ], c->begin, c->typ);
 		} else {
-			LFK_LAUNCH(c, (k_correct_tiled3<false, true>), grid, CT_THREADS, smem, G, M, c->P, c->Palt.f[PF_PX], c->Palt.f[PF_PY],
+			LFK_LAUNCH(c, (k_correct_tiled3<false, true, false>), grid, CT_THREADS, smem, G, M, c->P, c->Palt.f[PF_PX], c->Palt.f[PF_PY],
 				c->Palt.f[PF_PZ], c->begin, c->typ);
 		}
 	} else if (packed) {
