@@ -22,6 +22,7 @@ CONFIGS = [
     ("defaults", dict(NEW)),
     ("defaults+correct_scalar", dict(NEW, correct=0)),
     ("defaults+correct_prefetch", dict(NEW, correct=3)),
+    ("defaults+correct_classes", dict(NEW, correct=4)),  # experimental: check bit-identity first (tests: add 4 to the variants list)
     ("defaults+g2p_batch", dict(NEW, g2p=1)),
     ("defaults+advect_pair", dict(NEW, advect=1)),
     ("defaults+all_new", dict(NEW, correct=3, g2p=1, advect=1)),
