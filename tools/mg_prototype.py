@@ -1,7 +1,8 @@
 """CPU prototype used to choose the multigrid preconditioner that replaces the reference's sequential MIC(0).
 Builds the reference's pressure matrix (diag = #non-solid neighbours, -1 to fluid neighbours) on a synthetic
 free-surface scene with an obstacle and counts PCG iterations for several V-cycle variants.
-Usage: python tools/mg_prototype.py [n]"""
+Usage: python tools/mg_prototype.py [n] [scenes]            V-cycle variants
+       python tools/mg_prototype.py [n] [scenes] --experiments   storage precision / per-level sweeps"""
 import sys
 import time
 
@@ -144,7 +145,67 @@ def pcg(A, b, M, tol_abs, maxit=2000):
     return x, maxit
 
 
+# ---- experiments behind DESIGN.md section 7 (python tools/mg_prototype.py 64 wave,full --experiments) -------------
+def _quant(dtype):
+    return lambda v: v.astype(dtype).astype(np.float64)
+
+
+def _rbgs_q(L, x, b, order, sweeps, q):
+    for _ in range(sweeps):
+        for col in order:
+            msk = L.color == col
+            r = b - L.A @ x
+            x[msk] += r[msk] / L.D[msk]
+            x = q(x)
+    return x
+
+
+def vcycle_storage(levels, l, b, q0, pp=((2, 2),), coarse_sweeps=8, omega=1.8):
+    """V-cycle whose level-0 vectors are stored through q0 (fp16 / fp32 rounding after every half-sweep), the other
+    levels in fp32; pp[l] = (pre, post) sweeps of level l (last entry repeats)."""
+    L = levels[l]
+    q = q0 if l == 0 else _quant(np.float32)
+    x = np.zeros_like(b)
+    if l == len(levels) - 1:
+        return rbgs(L, x, b, (False, True, True, False), coarse_sweeps)
+    pre, post = pp[min(l, len(pp) - 1)]
+    x = _rbgs_q(L, x, b, (False, True), pre, q)
+    ec = vcycle_storage(levels, l + 1, L.P.T @ (b - L.A @ x), q0, pp, coarse_sweeps, omega)
+    x = q(x + omega * (L.P @ ec))
+    return _rbgs_q(L, x, b, (True, False), post, q)
+
+
+def precond_scaled(levels, r, q0, **kw):
+    """the level-0 right-hand side is r / max|r| so that it fits a 16-bit float at every stage of the solve"""
+    s = np.abs(r).max()
+    return r if s == 0 else vcycle_storage(levels, 0, q0(r / s), q0, **kw) * s
+
+
+def experiments(n, kinds):
+    for kind in kinds:
+        A, coords = build_matrix(scene(n, kind))
+        b = np.random.default_rng(1).uniform(-30, 30, A.shape[0])
+        levels = setup(A, coords)
+        print("== %s n=%d unknowns=%d" % (kind, n, A.shape[0]))
+        for name, q in (("level-0 vectors fp64", lambda v: v), ("level-0 vectors fp32 (production)", _quant(np.float32)),
+                        ("level-0 vectors fp16, rhs scaled by max|r|", _quant(np.float16))):
+            _, it = pcg(A, b, lambda r: precond_scaled(levels, r, q), 1e-6)
+            print("   %-50s iters %3d" % (name, it))
+        for name, pp in (("V(2,2) on every level (production)", ((2, 2),)), ("level 0 (1,1), coarser (2,2)", ((1, 1), (2, 2))),
+                         ("level 0 (2,2), coarser (3,3)", ((2, 2), (3, 3))), ("level 0 (2,2), coarser (4,4)", ((2, 2), (4, 4)))):
+            _, it = pcg(A, b, lambda r: precond_scaled(levels, r, _quant(np.float32), pp=pp), 1e-6)
+            print("   %-50s iters %3d" % (name, it))
+        for cs in (8, 4, 2):
+            _, it = pcg(A, b, lambda r: precond_scaled(levels, r, _quant(np.float32), coarse_sweeps=cs), 1e-6)
+            print("   %-50s iters %3d" % ("coarsest level: %d symmetric sweeps" % cs, it))
+
+
 if __name__ == "__main__":
+    if "--experiments" in sys.argv:
+        sys.argv.remove("--experiments")
+        experiments(int(sys.argv[1]) if len(sys.argv) > 1 else 48,
+                    sys.argv[2].split(",") if len(sys.argv) > 2 else ["wave", "full"])
+        sys.exit(0)
     n = int(sys.argv[1]) if len(sys.argv) > 1 else 48
     kinds = sys.argv[2].split(",") if len(sys.argv) > 2 else ["wave", "dam", "full", "splash"]
     for kind in kinds:
