@@ -774,6 +774,7 @@ extern "C" int lfk_set_tuning(lfk_ctx *c, const char *key, int value) {
 	if (k == "p2g") { c->tune.p2g = value; }
 	else if (k == "correct") { c->tune.correct = value; }
 	else if (k == "g2p") { c->tune.g2p = value; }
+	else if (k == "mg_half") { c->tune.mg_half = value; }
 	else if (k == "advect") { c->tune.advect = value; }
 	else if (k == "mg_tail") { c->tune.mg_tail = value; }
 	else if (k == "spmv") { c->tune.spmv = value; }

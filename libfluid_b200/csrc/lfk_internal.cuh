@@ -69,6 +69,7 @@ struct lfk_tuning {
 	int correct = 2;  // position correction: 2 hit-mask pre-filter (production), 0 scalar fp32 pre-filter (A/B), 1 packed-fp32 (A/B)
 	int g2p = 0;      // 0: component by component (production), 1: all 24 face samples requested before the first store (A/B)
 	int advect = 0;   // 0: one particle per thread (production), 1: two particles per thread, loads issued together (A/B)
+	int mg_half = 0;  // 1: fp16 storage of the multigrid level-0 vectors (experimental, single GPU; never run on a GPU yet)
 	int mg_tail = 0;  // 0: shared-memory coarse tail, 1: the global-memory one (A/B)
 	int spmv = 0;     // 0: production SpMV + dot, 1: the previous one (A/B)
 	int warm_start = 1; // fused step: start PCG from the previous step's pressure (0: from p = 0 like the reference)
@@ -122,6 +123,9 @@ struct lfk_ctx {
 	bool ordinal_valid = false;
 	std::vector<MgLevel> mg;
 	uint16_t *mg_mask = nullptr;   // level-0 coupling mask (mg.cu)
+	void *mg_half_b = nullptr, *mg_half_x = nullptr; // experimental fp16 copies of the level-0 rhs / solution (mg.cu)
+	float *mg_half_scale = nullptr;                  // the factor the fp16 right-hand side was divided by
+	bool mg_half_on = false;
 	std::vector<int> mg_z0;        // global z of the first owned layer, per level (red-black parity)
 	bool mg_valid = false;
 

@@ -27,6 +27,24 @@
 #include "lfk_internal.cuh"
 
 #include <algorithm>
+#include <cuda_fp16.h>
+
+// ---- storage of the level-0 vectors ---------------------------------------------------------------------------
+// Production: fp32.  Experimental (lfk_set_tuning("mg_half", 1), single GPU, never run on a GPU yet): fp16.  The
+// V-cycle is linear, so the right-hand side is first divided by S = max |b0| (its entries then lie in [-1, 1]) and the
+// result is multiplied by S again; x is stored divided by L0_XS on top of that (the solution of a Poisson problem
+// exceeds its right-hand side by up to the condition number, ~1e5 at 1024^3: 1e5 / 64 stays below the fp16 maximum,
+// and the smallest values that matter, ~1/6 / 64, stay normal).  Arithmetic is fp32 either way.
+// tools/mg_prototype.py --experiments: the PCG iteration count does not change (12 / 13 / 12 against 12 / 12 / 12).
+#define L0_XS 64.f
+__device__ __forceinline__ float l0_ld_b(const float *__restrict__ p, long long i) { return p[i]; }
+__device__ __forceinline__ float l0_ld_x(const float *__restrict__ p, long long i) { return p[i]; }
+__device__ __forceinline__ void l0_st_x(float *__restrict__ p, long long i, float v) { p[i] = v; }
+__device__ __forceinline__ float l0_ld_b(const __half *__restrict__ p, long long i) { return __half2float(p[i]); }
+__device__ __forceinline__ float l0_ld_x(const __half *__restrict__ p, long long i) { return __half2float(p[i]) * L0_XS; }
+__device__ __forceinline__ void l0_st_x(__half *__restrict__ p, long long i, float v) {
+	p[i] = __float2half_rn(v * (1.f / L0_XS));
+}
 
 #define MG_OMEGA 1.8f
 #define MG_PRE 2
@@ -119,18 +137,19 @@ struct L0Raw {
 	float e, ex, ey, ez; // coarse corrections (PROLONG only)
 	unsigned m;
 };
-template <bool PROLONG> __device__ __forceinline__ L0Raw l0_load(const GridDesc &G, const uint16_t *__restrict__ mask,
-	const float *__restrict__ b, const float *__restrict__ X, const LevelDev &C, int x, int y, int lz, long long c) {
+template <bool PROLONG, typename T> __device__ __forceinline__ L0Raw l0_load(const GridDesc &G,
+	const uint16_t *__restrict__ mask, const T *__restrict__ b, const T *__restrict__ X, const LevelDev &C, int x, int y,
+	int lz, long long c) {
 	L0Raw r;
 	r.m = mask[c];
-	r.b = b[c];
-	r.xc = X[c];
-	r.xm = X[c - 1];
-	r.xp = X[c + 1];
-	r.ym = X[c - G.nx];
-	r.yp = X[c + G.nx];
-	r.zm = X[c - G.sxy];
-	r.zp = X[c + G.sxy];
+	r.b = l0_ld_b(b, c);
+	r.xc = l0_ld_x(X, c);
+	r.xm = l0_ld_x(X, c - 1);
+	r.xp = l0_ld_x(X, c + 1);
+	r.ym = l0_ld_x(X, c - G.nx);
+	r.yp = l0_ld_x(X, c + G.nx);
+	r.zm = l0_ld_x(X, c - G.sxy);
+	r.zp = l0_ld_x(X, c + G.sxy);
 	if (PROLONG) {
 		const int X_ = x >> 1, Y_ = y >> 1, LZ = ((lz - 1) >> 1) + 1;
 		const long long cc = X_ + (long long)C.nx * (Y_ + (long long)C.ny * LZ);
@@ -167,32 +186,34 @@ __device__ __forceinline__ float l0_prolong_sum(const L0Raw &r, int x, int y, in
 }
 
 // one colour of red-black Gauss-Seidel on level 0.  PROLONG: the neighbours carry a pending coarse correction.
-template <bool PROLONG> __global__ void __launch_bounds__(256) k_mg_rbgs_l0(GridDesc G,
-	const uint16_t *__restrict__ mask, const float *__restrict__ b, float *__restrict__ X, int colour, LevelDev C,
+template <bool PROLONG, typename T> __global__ void __launch_bounds__(256) k_mg_rbgs_l0(GridDesc G,
+	const uint16_t *__restrict__ mask, const T *__restrict__ b, T *__restrict__ X, int colour, LevelDev C,
 	const PcgScalars *scal) {
 	if (scal->done) { return; }
 	rows_pipelined<4, L0Raw>(G.nx, G.ny, G.nzl, G.z0, colour,
-		[&](int x, int y, int lz, long long c) { return l0_load<PROLONG>(G, mask, b, X, C, x, y, lz, c); },
+		[&](int x, int y, int lz, long long c) { return l0_load<PROLONG, T>(G, mask, b, X, C, x, y, lz, c); },
 		[&](int x, int y, int lz, long long c, const L0Raw &r) {
 			float s = r.b + l0_offdiag_sum(r);
 			if (PROLONG) { s += l0_prolong_sum(r, x, y, lz); }
-			if ((r.m & MF_L) && MF_N(r.m) > 0) { X[c] = __fdividef(s, (float)MF_N(r.m)); }
+			if ((r.m & MF_L) && MF_N(r.m) > 0) { l0_st_x(X, c, __fdividef(s, (float)MF_N(r.m))); }
 		});
 }
 
 // last half-sweep of the cycle (colour `colour`) fused with z = x0 / a_scale (fp64), sigma_new = z.r and its finaliser
-__global__ void __launch_bounds__(RED_THREADS) k_mg_final_l0(GridDesc G, const uint16_t *__restrict__ mask,
-	const float *__restrict__ b, const float *__restrict__ X, int colour, const double *__restrict__ r,
-	double *__restrict__ z, double inv_a_scale, PcgScalars *scal, double *partials, unsigned *ticket, int finalize,
-	int first) {
+// `rescale`: NULL, or (fp16 storage) the factor S the right-hand side was divided by
+template <typename T> __global__ void __launch_bounds__(RED_THREADS) k_mg_final_l0(GridDesc G,
+	const uint16_t *__restrict__ mask, const T *__restrict__ b, const T *__restrict__ X, int colour,
+	const double *__restrict__ r, double *__restrict__ z, double inv_a_scale, PcgScalars *scal, double *partials,
+	unsigned *ticket, int finalize, int first, const float *__restrict__ rescale) {
 	if (scal->done) { return; }
+	if (sizeof(T) == 2) { inv_a_scale *= (double)*rescale; } // compile-time: the fp32 instantiation never reads it
 	double acc = 0.0;
 	struct FinRaw { L0Raw l; double r; };
 	LevelDev none{};
 	rows_pipelined<4, FinRaw>(G.nx, G.ny, G.nzl, 0, -1,
 		[&](int x, int y, int lz, long long c) {
 			FinRaw v;
-			v.l = l0_load<false>(G, mask, b, X, none, x, y, lz, c);
+			v.l = l0_load<false, T>(G, mask, b, X, none, x, y, lz, c);
 			v.r = r[c];
 			return v;
 		},
@@ -216,8 +237,9 @@ __global__ void __launch_bounds__(RED_THREADS) k_mg_final_l0(GridDesc G, const u
 }
 
 // coarse b = P^T (b - A x) of level 0, coarse x = 0.  One thread per coarse cell.
-__global__ void __launch_bounds__(128) k_mg_restrict_l0(GridDesc G, const uint16_t *__restrict__ mask,
-	const float *__restrict__ b, const float *__restrict__ X, LevelDev C, const PcgScalars *scal) {
+template <typename T> __global__ void __launch_bounds__(128) k_mg_restrict_l0(GridDesc G,
+	const uint16_t *__restrict__ mask, const T *__restrict__ b, const T *__restrict__ X, LevelDev C,
+	const PcgScalars *scal) {
 	if (scal->done) { return; }
 	// the pre-smoothing ended with a black half-sweep: black residuals are zero (to rounding), so only the 4 red
 	// cells of each aggregate are visited; (dy, dz) in {0,1}^2, dx fixed by the colour
@@ -234,7 +256,7 @@ __global__ void __launch_bounds__(128) k_mg_restrict_l0(GridDesc G, const uint16
 				x = x < G.nx ? x : G.nx - 1;
 				y = y < G.ny ? y : G.ny - 1;
 				lz = lz <= G.nzl ? lz : G.nzl;
-				v.q[k] = l0_load<false>(G, mask, b, X, none, x, y, lz, x + (long long)G.nx * (y + (long long)G.ny * lz));
+				v.q[k] = l0_load<false, T>(G, mask, b, X, none, x, y, lz, x + (long long)G.nx * (y + (long long)G.ny * lz));
 			}
 			return v;
 		},
@@ -537,6 +559,9 @@ int lfkm_free(lfk_ctx *c) {
 		}
 	}
 	if (c->mg_mask) { cudaFree(c->mg_mask); c->mg_mask = nullptr; }
+	if (c->mg_half_b) { cudaFree(c->mg_half_b); c->mg_half_b = nullptr; }
+	if (c->mg_half_x) { cudaFree(c->mg_half_x); c->mg_half_x = nullptr; }
+	if (c->mg_half_scale) { cudaFree(c->mg_half_scale); c->mg_half_scale = nullptr; }
 	c->mg.clear();
 	c->mg_z0.clear();
 	return 0;
@@ -567,6 +592,31 @@ int lfkm_setup(lfk_ctx *c, double a_scale) {
 	return 0;
 }
 
+// ---- fp16 storage of the level-0 vectors (experimental, see the top of the file) -------------------------------
+// S = max |b0| over the owned cells, as the bit pattern of a non-negative float (orders like an unsigned integer)
+__global__ void __launch_bounds__(256) k_l0_absmax(GridDesc G, const float *__restrict__ b0, unsigned *__restrict__ out,
+	const PcgScalars *scal) {
+	if (scal->done) { return; }
+	float m = 0.f;
+	for_own_cells(G, [&](int, int, int, long long c) { m = fmaxf(m, fabsf(b0[c])); });
+#pragma unroll
+	for (int o = 16; o > 0; o >>= 1) { m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o)); }
+	if ((threadIdx.x & 31) == 0 && m > 0.f) { atomicMax(out, __float_as_uint(m)); }
+}
+// hb = b0 / S, hx = x0 / S (x0: the pre-applied first red half-sweep), both rounded to fp16
+__global__ void __launch_bounds__(256) k_l0_to_half(GridDesc G, const float *__restrict__ b0,
+	const float *__restrict__ x0, __half *__restrict__ hb, __half *__restrict__ hx, float *__restrict__ scale,
+	const PcgScalars *scal) {
+	if (scal->done) { return; }
+	// *scale holds the bit pattern of max |b0| (k_l0_absmax); an all-zero right-hand side keeps S = 1
+	const float m = *scale;
+	const float S = m > 0.f ? m : 1.f, inv = 1.f / S;
+	for_own_cells(G, [&](int, int, int, long long c) {
+		hb[c] = __float2half_rn(b0[c] * inv);
+		l0_st_x(hx, c, x0[c] * inv);
+	});
+}
+
 // one half-sweep of colour `colour` on level l; `prolong`: the neighbours carry the pending correction of level l + 1.
 // Multi-GPU: the z ghost layers of x are refreshed first unless the caller knows they are current (`x_current`):
 // every exchange is an NCCL launch of ~15 us against ~8 us of arithmetic on the coarse levels (profiles/r1d: 2.4 ms per
@@ -583,11 +633,18 @@ static int half_sweep(lfk_ctx *c, size_t l, int colour, bool prolong, bool x_cur
 		if (!x_current) { LFK_TRY(lfkx_halo_f32(c, L.x, L.nx, L.ny, L.nzl)); }
 		if (prolong) { LFK_TRY(lfkx_halo_f32(c, c->mg[l + 1].x, Cd.nx, Cd.ny, Cd.nzl)); }
 	}
-	if (l == 0) {
+	if (l == 0 && c->mg_half_on) {
+		__half *hb = (__half*)c->mg_half_b, *hx = (__half*)c->mg_half_x;
 		if (prolong) {
-			LFK_LAUNCH(c, k_mg_rbgs_l0<true>, nb, 256, 0, G, c->mg_mask, L.b, L.x, colour, Cd, c->d_scal);
+			LFK_LAUNCH(c, (k_mg_rbgs_l0<true, __half>), nb, 256, 0, G, c->mg_mask, hb, hx, colour, Cd, c->d_scal);
 		} else {
-			LFK_LAUNCH(c, k_mg_rbgs_l0<false>, nb, 256, 0, G, c->mg_mask, L.b, L.x, colour, Cd, c->d_scal);
+			LFK_LAUNCH(c, (k_mg_rbgs_l0<false, __half>), nb, 256, 0, G, c->mg_mask, hb, hx, colour, Cd, c->d_scal);
+		}
+	} else if (l == 0) {
+		if (prolong) {
+			LFK_LAUNCH(c, (k_mg_rbgs_l0<true, float>), nb, 256, 0, G, c->mg_mask, L.b, L.x, colour, Cd, c->d_scal);
+		} else {
+			LFK_LAUNCH(c, (k_mg_rbgs_l0<false, float>), nb, 256, 0, G, c->mg_mask, L.b, L.x, colour, Cd, c->d_scal);
 		}
 	} else {
 		if (prolong) {
@@ -652,8 +709,11 @@ static int vcycle(lfk_ctx *c, size_t l) {
 	LevelDev Cd = level_dev(C, c->mg_z0[l + 1]);
 	if (c->nranks > 1) { LFK_TRY(lfkx_halo_f32(c, L.x, L.nx, L.ny, L.nzl)); }
 	unsigned rb = row_blocks(Cd.ny, Cd.nzl, 128, 1u << 20);
-	if (l == 0) {
-		LFK_LAUNCH(c, k_mg_restrict_l0, rb, 128, 0, G, c->mg_mask, L.b, L.x, Cd, c->d_scal);
+	if (l == 0 && c->mg_half_on) {
+		LFK_LAUNCH(c, k_mg_restrict_l0<__half>, rb, 128, 0, G, c->mg_mask, (const __half*)c->mg_half_b,
+			(const __half*)c->mg_half_x, Cd, c->d_scal);
+	} else if (l == 0) {
+		LFK_LAUNCH(c, k_mg_restrict_l0<float>, rb, 128, 0, G, c->mg_mask, L.b, L.x, Cd, c->d_scal);
 	} else {
 		LFK_LAUNCH(c, k_mg_restrict, rb, 128, 0, Ld, Cd, c->d_scal);
 	}
@@ -682,9 +742,31 @@ int lfkm_level0(lfk_ctx *c, float **b0, float **x0) {
 int lfkm_apply_preloaded(lfk_ctx *c, double a_scale, unsigned nb, int fin, int first) {
 	const GridDesc &G = c->g;
 	MgLevel &L0 = c->mg[0];
+	// experimental fp16 storage of the level-0 vectors: single GPU, and only when level 0 is not the only level
+	c->mg_half_on = c->tune.mg_half == 1 && c->nranks == 1 && c->mg.size() > 1;
+	if (c->mg_half_on) {
+		if (!c->mg_half_b) {
+			const size_t n = (size_t)L0.ncl + 2;
+			LFK_CUDA(c, cudaMalloc((void**)&c->mg_half_b, n * sizeof(__half)));
+			LFK_CUDA(c, cudaMalloc((void**)&c->mg_half_x, n * sizeof(__half)));
+			LFK_CUDA(c, cudaMalloc((void**)&c->mg_half_scale, sizeof(float)));
+			LFK_CUDA(c, cudaMemsetAsync(c->mg_half_b, 0, n * sizeof(__half), c->stream)); // ghost layers stay zero
+			LFK_CUDA(c, cudaMemsetAsync(c->mg_half_x, 0, n * sizeof(__half), c->stream));
+		}
+		LFK_CUDA(c, cudaMemsetAsync(c->mg_half_scale, 0, sizeof(float), c->stream));
+		LFK_LAUNCH(c, k_l0_absmax, lfk_row_blocks(G, 256, 1184), 256, 0, G, L0.b, (unsigned*)c->mg_half_scale, c->d_scal);
+		LFK_LAUNCH(c, k_l0_to_half, lfk_row_blocks(G, 256, 1u << 20), 256, 0, G, L0.b, L0.x, (__half*)c->mg_half_b,
+			(__half*)c->mg_half_x, c->mg_half_scale, c->d_scal);
+	}
 	LFK_TRY(vcycle(c, 0));
 	if (c->nranks > 1) { LFK_TRY(lfkx_halo_f32(c, L0.x, L0.nx, L0.ny, L0.nzl)); }
-	LFK_LAUNCH(c, k_mg_final_l0, nb, RED_THREADS, 0, G, c->mg_mask, L0.b, L0.x, 0, c->r, c->z, 1.0 / a_scale,
-		c->d_scal, c->partials, c->ticket, fin, first);
+	if (c->mg_half_on) {
+		LFK_LAUNCH(c, k_mg_final_l0<__half>, nb, RED_THREADS, 0, G, c->mg_mask, (const __half*)c->mg_half_b,
+			(const __half*)c->mg_half_x, 0, c->r, c->z, 1.0 / a_scale, c->d_scal, c->partials, c->ticket, fin, first,
+			(const float*)c->mg_half_scale);
+	} else {
+		LFK_LAUNCH(c, k_mg_final_l0<float>, nb, RED_THREADS, 0, G, c->mg_mask, L0.b, L0.x, 0, c->r, c->z, 1.0 / a_scale,
+			c->d_scal, c->partials, c->ticket, fin, first, (const float*)nullptr);
+	}
 	return 0;
 }

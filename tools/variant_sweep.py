@@ -16,12 +16,13 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
-NEW = {"p2g": 0, "correct": 2, "g2p": 0, "advect": 0, "mg_tail": 0, "warm_start": 1, "red_blocks": 0}  # the library defaults
-OLD = {"p2g": 1, "correct": 0, "g2p": 0, "advect": 0, "mg_tail": 1, "warm_start": 0, "red_blocks": 16384}  # round r1b
+NEW = {"p2g": 0, "correct": 2, "g2p": 0, "advect": 0, "mg_half": 0, "mg_tail": 0, "warm_start": 1, "red_blocks": 0}  # the library defaults
+OLD = {"p2g": 1, "correct": 0, "g2p": 0, "advect": 0, "mg_half": 0, "mg_tail": 1, "warm_start": 0, "red_blocks": 16384}  # round r1b
 CONFIGS = [
     ("defaults", dict(NEW)),
     ("defaults+correct_scalar", dict(NEW, correct=0)),
     ("defaults+correct_prefetch", dict(NEW, correct=3)),
+    ("defaults+mg_half", dict(NEW, mg_half=1)),  # experimental fp16 level-0 multigrid vectors: check residual / iterations
     ("defaults+correct_classes", dict(NEW, correct=4)),  # experimental: check bit-identity first (tests: add 4 to the variants list)
     ("defaults+g2p_batch", dict(NEW, g2p=1)),
     ("defaults+advect_pair", dict(NEW, advect=1)),
