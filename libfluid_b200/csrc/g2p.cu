@@ -112,7 +112,24 @@ template <bool GRAD> __device__ __forceinline__ void trilinear(const double *s, 
 // fetches behind the stores of the previous component: four dependent memory round trips per particle (position, u, v,
 // w samples) instead of two -- the kernel is latency bound (ncu r1d: 57 % of the stall samples are long-scoreboard
 // waits on the first use of each fetch).  Same arithmetic, bit-identical results.
-template <int METHOD, bool BATCH> __global__ void __launch_bounds__(128) k_g2p(GridDesc G, G2PArgs A,
+// the 8 samples of component K for a particle whose 3 x 3 x 3 cell neighbourhood lies inside the grid (and inside the
+// slab's layers): one base index plus constant offsets instead of 24 clamped index computations.  Same addresses, same
+// values as face_samples_comp when nothing is clamped.
+template <int K> __device__ __forceinline__ void face_samples_interior(const GridDesc &G, const double *__restrict__ comp,
+	long long base, const int *dsel, double *s) {
+#pragma unroll
+	for (int k = 0; k < 8; ++k) {
+		const int bx = k & 1, by = (k >> 1) & 1, bz = (k >> 2) & 1;
+		const int dx = K == 0 ? bx : dsel[0] + bx;
+		const int dy = K == 1 ? by : dsel[1] + by;
+		const int dz = K == 2 ? bz : dsel[2] + bz;
+		s[k] = __ldg(comp + (base + dx + (long long)G.nx * dy + G.sxy * dz));
+	}
+}
+
+// FAST (experimental, lfk_set_tuning("g2p", 2); implies BATCH; not measured yet): interior particles take
+// face_samples_interior -- index arithmetic is 37 % of this kernel's instructions (ncu r1d: IMAD + IADD3 + ISETP).
+template <int METHOD, bool BATCH, bool FAST = false> __global__ void __launch_bounds__(128) k_g2p(GridDesc G, G2PArgs A,
 	unsigned long long n) {
 	unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
 	if (i >= n) { return; }
@@ -139,18 +156,35 @@ template <int METHOD, bool BATCH> __global__ void __launch_bounds__(128) k_g2p(G
 	double s[8], vn[3], g[3];
 	if (BATCH) {
 		double s1[8], s2[8];
-		face_samples_comp<0>(G, F, A.u, nullptr, dsel, s);
-		face_samples_comp<1>(G, F, A.v, nullptr, dsel, s1);
-		face_samples_comp<2>(G, F, A.w, A.w_below, dsel, s2);
+		// cells gi - 1 .. gi + 1 per axis, none clamped (face_fetch_setup), and their layers held by this rank
+		const long long lzlo = gi[2] - 1 - G.z0 + 1;
+		const bool interior = FAST && gi[0] >= 1 && gi[0] + 2 < G.nx && gi[1] >= 1 && gi[1] + 2 < G.ny && gi[2] >= 1 &&
+			gi[2] + 2 < G.nz && lzlo >= 0 && lzlo + 2 <= G.nlz - 1;
+		const long long base = (gi[0] - 1) + (long long)G.nx * ((gi[1] - 1) + (long long)G.ny * lzlo);
+		if (interior) {
+			face_samples_interior<0>(G, A.u, base, dsel, s);
+			face_samples_interior<1>(G, A.v, base, dsel, s1);
+			face_samples_interior<2>(G, A.w, base, dsel, s2);
+		} else {
+			face_samples_comp<0>(G, F, A.u, nullptr, dsel, s);
+			face_samples_comp<1>(G, F, A.v, nullptr, dsel, s1);
+			face_samples_comp<2>(G, F, A.w, A.w_below, dsel, s2);
+		}
 		double g1[3], g2[3];
 		trilinear<APIC>(s, t[0], tmid[1], tmid[2], vn[0], g);
 		trilinear<APIC>(s1, tmid[0], t[1], tmid[2], vn[1], g1);
 		trilinear<APIC>(s2, tmid[0], tmid[1], t[2], vn[2], g2);
 		if (METHOD == LFK_METHOD_FLIP) { // v = v_new + (v_p - v_old) * blend (:463-505)
 			double vold[3], dummy[3];
-			face_samples_comp<0>(G, F, A.uo, nullptr, dsel, s);
-			face_samples_comp<1>(G, F, A.vo, nullptr, dsel, s1);
-			face_samples_comp<2>(G, F, A.wo, A.wo_below, dsel, s2);
+			if (interior) {
+				face_samples_interior<0>(G, A.uo, base, dsel, s);
+				face_samples_interior<1>(G, A.vo, base, dsel, s1);
+				face_samples_interior<2>(G, A.wo, base, dsel, s2);
+			} else {
+				face_samples_comp<0>(G, F, A.uo, nullptr, dsel, s);
+				face_samples_comp<1>(G, F, A.vo, nullptr, dsel, s1);
+				face_samples_comp<2>(G, F, A.wo, A.wo_below, dsel, s2);
+			}
 			const unsigned long long src = A.perm ? (unsigned long long)A.perm[i] : i;
 			const double vp[3] = { A.vs[0][src], A.vs[1][src], A.vs[2][src] };
 			trilinear<false>(s, t[0], tmid[1], tmid[2], vold[0], dummy);
@@ -248,6 +282,19 @@ int lfkp_g2p(lfk_ctx *c) {
 		unsigned nb = lfk_blocks((long long)c->np, 128);
 		unsigned long long n = c->np;
 		const bool batch = c->tune.g2p == 1; // A/B: all face samples in flight before the first store
+		if (c->tune.g2p == 2) { // experimental: batch + constant-offset indexing for interior particles
+			switch (method) {
+			case LFK_METHOD_PIC:
+				LFK_LAUNCH(c, (k_g2p<LFK_METHOD_PIC, true, true>), nb, 128, 0, c->g, A, n);
+				break;
+			case LFK_METHOD_FLIP:
+				LFK_LAUNCH(c, (k_g2p<LFK_METHOD_FLIP, true, true>), nb, 128, 0, c->g, A, n);
+				break;
+			default:
+				LFK_LAUNCH(c, (k_g2p<LFK_METHOD_APIC, true, true>), nb, 128, 0, c->g, A, n);
+				break;
+			}
+		} else
 		switch (method) {
 		case LFK_METHOD_PIC:
 			if (batch) { LFK_LAUNCH(c, (k_g2p<LFK_METHOD_PIC, true>), nb, 128, 0, c->g, A, n); }

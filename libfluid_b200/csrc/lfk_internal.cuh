@@ -67,7 +67,8 @@ enum { LFK_TUNE_P2G_MARCH = 0, LFK_TUNE_P2G_BRICK = 1, LFK_TUNE_P2G_GATHER = 2 }
 struct lfk_tuning {
 	int p2g = LFK_TUNE_P2G_MARCH;
 	int correct = 2;  // position correction: 2 hit-mask pre-filter (production), 0 scalar fp32 pre-filter (A/B), 1 packed-fp32 (A/B)
-	int g2p = 0;      // 0: component by component (production), 1: all 24 face samples requested before the first store (A/B)
+	int g2p = 0;      // 0: component by component (production), 1: all 24 face samples requested before the first store (A/B),
+	                  // 2: 1 + constant-offset sample indexing for interior particles (experimental, never run on a GPU yet)
 	int advect = 0;   // 0: one particle per thread (production), 1: two particles per thread, loads issued together (A/B)
 	int mg_half = 0;  // 1: fp16 storage of the multigrid level-0 vectors (experimental, single GPU; never run on a GPU yet)
 	int mg_tail = 0;  // 0: shared-memory coarse tail, 1: the global-memory one (A/B)
