@@ -14,6 +14,10 @@ from pinlib import OB, RB
 
 pytestmark = pytest.mark.gpu
 
+# LFK_TEST_EXPERIMENTAL=1 also runs the kernel variants that are written but have never been on a GPU (DESIGN.md
+# section 7): position correction 4 (class-grouped), G2P 2 (interior indexing), multigrid fp16 level-0 storage
+EXPERIMENTAL = os.environ.get("LFK_TEST_EXPERIMENTAL") == "1"
+
 
 def load_golden(scene):
     z = np.load(os.path.join(PL.GOLDEN_DIR, scene + ".npz"))
@@ -250,28 +254,30 @@ def test_position_correction_variants_agree():
     ctx.hash()
     parts = ctx.download_particles().copy()
     outs = []
-    for v in (0, 1, 2, 3):
+    variants = (0, 1, 2, 3) + ((4,) if EXPERIMENTAL else ())
+    for v in variants:
         ctx.set_tuning("correct", v)
         ctx.upload_particles(parts)
         ctx.hash()
         ctx.correct(0.004)
         outs.append(ctx.download_particles().copy())
-    for k in (1, 2, 3):
-        assert np.array_equal(outs[0]["position"].view("u8"), outs[k]["position"].view("u8")), k
+    for k in range(1, len(variants)):
+        assert np.array_equal(outs[0]["position"].view("u8"), outs[k]["position"].view("u8")), variants[k]
     moved = np.abs(outs[0]["position"] - parts[np.argsort(parts["raw_cell_index"], kind="stable")]["position"]).max()
     assert moved > 1e-6
     # the same inside the fused step (correction + second collision pass in one kernel)
     res = []
-    for v in (0, 2, 3):
+    fused = (0, 2, 3) + ((4,) if EXPERIMENTAL else ())
+    for v in fused:
         ctx.set_tuning("correct", v)
         ctx.set_tuning("warm_start", 0)
         ctx.upload_particles(parts)
         for _ in range(2):
             ctx.time_step(0.002)
         res.append(ctx.download_particles().copy())
-    for k in (1, 2):
+    for k in range(1, len(fused)):
         for f in ("position", "velocity"):
-            assert np.array_equal(res[0][f].view("u8"), res[k][f].view("u8")), (k, f)
+            assert np.array_equal(res[0][f].view("u8"), res[k][f].view("u8")), (fused[k], f)
     ctx.close()
 
 
@@ -285,7 +291,8 @@ def test_g2p_and_advection_variants_agree(method):
         ctx.time_step()
     parts, cells = ctx.download_particles().copy(), ctx.download_cells().copy()
     res = []
-    for g2p, adv in ((0, 0), (1, 0), (0, 1), (1, 1)):
+    combos = ((0, 0), (1, 0), (0, 1), (1, 1)) + (((2, 0),) if EXPERIMENTAL else ())
+    for g2p, adv in combos:
         ctx.set_tuning("g2p", g2p)
         ctx.set_tuning("advect", adv)
         ctx.set_tuning("warm_start", 0)
@@ -295,10 +302,29 @@ def test_g2p_and_advection_variants_agree(method):
             ctx.time_step(0.002)
         res.append(ctx.download_particles().copy())
     assert np.abs(res[0]["velocity"]).max() > 1.0
-    for k in (1, 2, 3):
+    for k in range(1, len(combos)):
         for f in ("position", "velocity", "cx", "cy", "cz"):
-            assert np.array_equal(res[0][f].view("u8"), res[k][f].view("u8")), (k, f)
+            assert np.array_equal(res[0][f].view("u8"), res[k][f].view("u8")), (combos[k], f)
     ctx.close()
+
+
+@pytest.mark.skipif(not EXPERIMENTAL, reason="fp16 level-0 multigrid storage has not been on a GPU yet (LFK_TEST_EXPERIMENTAL=1)")
+def test_mg_half_storage_reaches_the_same_tolerance():
+    """fp16 storage of the multigrid level-0 vectors only changes the preconditioner's rounding: same tolerance, about
+    the same iteration count, pressure equal to solver accuracy"""
+    n = 96
+    out = []
+    for half in (0, 1):
+        ctx = capi.Context((n, n, n), cell_size=1.0, max_iterations=2000)
+        ctx.set_tuning("mg_half", half)
+        ctx.synthetic_projection_device(seed=5)
+        res, iters = ctx.pressure_solve(1.0 / 60.0)
+        assert res < 1e-6 and 0 < iters < 100
+        out.append((ctx.download_pressure().copy(), iters))
+        ctx.close()
+    (pa, ia), (pb, ib) = out
+    assert ib <= ia + 3, (ia, ib)
+    assert PL.rel_l2(pa, pb) < 1e-5
 
 
 def test_warm_started_solve_reaches_the_same_tolerance():
