@@ -174,7 +174,8 @@ int lfk_set_timing(lfk_ctx *ctx, int enabled);
  * 0 scalar pre-filter, 1 packed-fp32 pre-filter, 3 hit-mask with record prefetch, 4 hit-mask with own particles grouped
  * by reach class (experimental, unmeasured); "g2p" 0 / 1 (all face samples
  * requested before the first store) / 2 (1 + constant-offset indexing for interior particles; experimental, unmeasured); "advect" 0 / 1 (two particles per thread); "mg_half" 0 / 1 (fp16 storage of the multigrid
- * level-0 vectors; experimental, unmeasured); "mg_tail" 0 / 1; "spmv" 0 / 1;
+ * level-0 vectors; experimental, unmeasured); "mg_agg" 0 / 1 (multi-GPU: coarse multigrid levels
+ * agglomerated onto every rank; experimental, unmeasured; must be set on every rank alike); "mg_tail" 0 / 1; "spmv" 0 / 1;
  * "warm_start" 1 / 0; "red_blocks" n.  The environment variable LFK_TUNE="key=value,..." applies the same switches
  * to every context of the process.  Unknown key: LFK_E_INVALID. */
 int lfk_set_tuning(lfk_ctx *ctx, const char *key, int value);

@@ -132,6 +132,11 @@ int lfkx_allreduce_sum(lfk_ctx *c, double *d_vals, int n) {
 	LFK_NCCL(c, g_nccl.AllReduce(d_vals, d_vals, (size_t)n, ncclDouble, ncclSum, (ncclComm_t)c->comm, c->stream));
 	return 0;
 }
+int lfkx_allreduce_sum_f32(lfk_ctx *c, float *d_vals, int n) {
+	if (c->nranks == 1) { return 0; }
+	LFK_NCCL(c, g_nccl.AllReduce(d_vals, d_vals, (size_t)n, ncclFloat, ncclSum, (ncclComm_t)c->comm, c->stream));
+	return 0;
+}
 int lfkx_allreduce_max(lfk_ctx *c, double *d_vals, int n) {
 	if (c->nranks == 1) { return 0; }
 	LFK_NCCL(c, g_nccl.AllReduce(d_vals, d_vals, (size_t)n, ncclDouble, ncclMax, (ncclComm_t)c->comm, c->stream));

@@ -775,6 +775,7 @@ extern "C" int lfk_set_tuning(lfk_ctx *c, const char *key, int value) {
 	else if (k == "correct") { c->tune.correct = value; }
 	else if (k == "g2p") { c->tune.g2p = value; }
 	else if (k == "mg_half") { c->tune.mg_half = value; }
+	else if (k == "mg_agg") { c->tune.mg_agg = value; }
 	else if (k == "advect") { c->tune.advect = value; }
 	else if (k == "mg_tail") { c->tune.mg_tail = value; }
 	else if (k == "spmv") { c->tune.spmv = value; }

@@ -71,6 +71,7 @@ struct lfk_tuning {
 	                  // 2: 1 + constant-offset sample indexing for interior particles (experimental, never run on a GPU yet)
 	int advect = 0;   // 0: one particle per thread (production), 1: two particles per thread, loads issued together (A/B)
 	int mg_half = 0;  // 1: fp16 storage of the multigrid level-0 vectors (experimental, single GPU; never run on a GPU yet)
+	int mg_agg = 0;   // 1: multi-GPU coarse levels agglomerated onto every rank (experimental; never run on a GPU yet)
 	int mg_tail = 0;  // 0: shared-memory coarse tail, 1: the global-memory one (A/B)
 	int spmv = 0;     // 0: production SpMV + dot, 1: the previous one (A/B)
 	int warm_start = 1; // fused step: start PCG from the previous step's pressure (0: from p = 0 like the reference)
@@ -127,6 +128,8 @@ struct lfk_ctx {
 	void *mg_half_b = nullptr, *mg_half_x = nullptr; // experimental fp16 copies of the level-0 rhs / solution (mg.cu)
 	float *mg_half_scale = nullptr;                  // the factor the fp16 right-hand side was divided by
 	bool mg_half_on = false;
+	std::vector<MgLevel> mg_agg;   // multi-GPU: agglomerated global coarse levels (experimental, mg.cu)
+	int mg_agg_level = -1;         // distributed level they replace; -1 undecided, -2 none
 	std::vector<int> mg_z0;        // global z of the first owned layer, per level (red-black parity)
 	bool mg_valid = false;
 
@@ -244,6 +247,7 @@ int lfkx_layer_below(lfk_ctx *c, const double *field, double *dst); // dst <- th
 int lfkx_exchange_particles(lfk_ctx *c, uint64_t *n_in);
 int lfkx_allreduce_sum(lfk_ctx *c, double *d_vals, int n);
 int lfkx_allreduce_max(lfk_ctx *c, double *d_vals, int n);
+int lfkx_allreduce_sum_f32(lfk_ctx *c, float *d_vals, int n);
 
 // device helpers ------------------------------------------------------------------------------------------
 #ifdef __CUDACC__

@@ -562,8 +562,105 @@ int lfkm_free(lfk_ctx *c) {
 	if (c->mg_half_b) { cudaFree(c->mg_half_b); c->mg_half_b = nullptr; }
 	if (c->mg_half_x) { cudaFree(c->mg_half_x); c->mg_half_x = nullptr; }
 	if (c->mg_half_scale) { cudaFree(c->mg_half_scale); c->mg_half_scale = nullptr; }
+	for (MgLevel &L : c->mg_agg) {
+		float *arrs[] = { L.x, L.b, L.diag, L.cx, L.cy, L.cz };
+		for (float *p : arrs) {
+			if (p) { cudaFree(p); }
+		}
+	}
+	c->mg_agg.clear();
+	c->mg_agg_level = -1;
 	c->mg.clear();
 	c->mg_z0.clear();
+	return 0;
+}
+
+// ---- multi-GPU: agglomerated coarse levels (experimental, lfk_set_tuning("mg_agg", 1); never run on a GPU yet) ---
+// Below a few thousand cells in the WHOLE grid a distributed level is pure latency: every half-sweep is an NCCL
+// exchange (~13 us) for microseconds of arithmetic, and the hierarchy has to stop where the slabs stop being aligned
+// to the 2x2x2 aggregates.  With the switch on, the first level whose global size fits the single-block tail kernel
+// is assembled on EVERY rank (operators once per solve, right-hand side once per cycle: each rank writes its own
+// layers into a zeroed global array and one all-reduce adds them up -- exact, every element has one non-zero
+// contributor), the hierarchy continues below it on the global grid down to a handful of cells, the whole tail runs
+// redundantly on every rank in one launch (k_mg_tail*), and the rank copies its own layers plus the two ghost layers
+// of the result back.  Per cycle: one all-reduce instead of ~8 exchanges per distributed level below that point and
+// 16 on the coarsest one.
+static int mg_agg_alloc(lfk_ctx *c) {
+	if (!c->mg_agg.empty() || c->mg_agg_level == -2) { return 0; }
+	c->mg_agg_level = -2; // decided: none (unless found below)
+	const GridDesc &G = c->g;
+	int la = -1;
+	for (size_t l = 1; l < c->mg.size(); ++l) { // aligned coarsening: the global depth of level l is nz >> l
+		const long long gnz = G.nz >> l;
+		if ((long long)c->mg[l].nx * c->mg[l].ny * gnz <= MG_COARSE_MAX_CELLS) { la = (int)l; break; }
+	}
+	if (la < 0) { return 0; }
+	int nx = c->mg[la].nx, ny = c->mg[la].ny, nz = G.nz >> la;
+	for (int k = 0; k < MG_TAIL_MAX_LEVELS; ++k) {
+		MgLevel L{};
+		L.nx = nx; L.ny = ny; L.nzl = nz; L.nlz = nz + 2;
+		L.sxy = (long long)nx * ny;
+		L.ncl = L.sxy * L.nlz;
+		const size_t n = (size_t)L.ncl + 2;
+		float **arrs[] = { &L.x, &L.b, &L.diag, &L.cx, &L.cy, &L.cz };
+		for (float **a : arrs) {
+			LFK_CUDA(c, cudaMalloc((void**)a, n * sizeof(float)));
+			LFK_CUDA(c, cudaMemsetAsync(*a, 0, n * sizeof(float), c->stream));
+		}
+		c->mg_agg.push_back(L);
+		if (nx <= 2 && ny <= 2 && nz <= 2) { break; }
+		nx = (nx + 1) / 2; ny = (ny + 1) / 2; nz = (nz + 1) / 2;
+	}
+	c->mg_agg_level = la;
+	return 0;
+}
+
+// own layers of a distributed level-`la` array -> their place in the zeroed global array, then the sum over the ranks
+static int mg_agg_gather(lfk_ctx *c, const MgLevel &D, int z0, const float *src, const MgLevel &Gl, float *dst) {
+	const size_t n = (size_t)Gl.ncl + 2;
+	LFK_CUDA(c, cudaMemsetAsync(dst, 0, n * sizeof(float), c->stream));
+	LFK_CUDA(c, cudaMemcpyAsync(dst + (size_t)Gl.sxy * (1 + z0), src + (size_t)D.sxy, (size_t)D.sxy * D.nzl * sizeof(float),
+		cudaMemcpyDeviceToDevice, c->stream));
+	return lfkx_allreduce_sum_f32(c, dst, (int)n);
+}
+
+static int mg_agg_setup(lfk_ctx *c) { // after the distributed operators of this solve exist
+	LFK_TRY(mg_agg_alloc(c));
+	if (c->mg_agg_level < 0) { return 0; }
+	const int la = c->mg_agg_level;
+	const MgLevel &D = c->mg[la];
+	MgLevel &Gl = c->mg_agg[0];
+	const int z0 = c->mg_z0[la];
+	LFK_TRY(mg_agg_gather(c, D, z0, D.diag, Gl, Gl.diag));
+	LFK_TRY(mg_agg_gather(c, D, z0, D.cx, Gl, Gl.cx));
+	LFK_TRY(mg_agg_gather(c, D, z0, D.cy, Gl, Gl.cy));
+	LFK_TRY(mg_agg_gather(c, D, z0, D.cz, Gl, Gl.cz));
+	for (size_t k = 1; k < c->mg_agg.size(); ++k) {
+		MgLevel &C = c->mg_agg[k];
+		LevelDev Cd = level_dev(C, 0);
+		LevelOut O{ C.diag, C.cx, C.cy, C.cz };
+		LFK_LAUNCH(c, k_mg_build, row_blocks(Cd.ny, Cd.nzl, 128, 1u << 20), 128, 0, level_dev(c->mg_agg[k - 1], 0), Cd, O);
+	}
+	return 0;
+}
+
+static int launch_tail(lfk_ctx *c, const TailLevels &T);
+
+// the cycle of distributed level `la` and everything below it, on the agglomerated grid
+static int mg_agg_cycle(lfk_ctx *c) {
+	const int la = c->mg_agg_level;
+	MgLevel &D = c->mg[la];
+	MgLevel &Gl = c->mg_agg[0];
+	const int z0 = c->mg_z0[la];
+	LFK_TRY(mg_agg_gather(c, D, z0, D.b, Gl, Gl.b));
+	LFK_CUDA(c, cudaMemsetAsync(Gl.x, 0, ((size_t)Gl.ncl + 2) * sizeof(float), c->stream));
+	TailLevels T;
+	T.n = 0;
+	for (const MgLevel &L : c->mg_agg) { T.L[T.n++] = level_dev(L, 0); }
+	LFK_TRY(launch_tail(c, T));
+	// my layers and the ghost layer either side: global layer index of local layer 0 is z0 - 1 + 1 = z0
+	LFK_CUDA(c, cudaMemcpyAsync(D.x, Gl.x + (size_t)Gl.sxy * z0, (size_t)D.sxy * (D.nzl + 2) * sizeof(float),
+		cudaMemcpyDeviceToDevice, c->stream));
 	return 0;
 }
 
@@ -588,6 +685,7 @@ int lfkm_setup(lfk_ctx *c, double a_scale) {
 			LFK_TRY(lfkx_halo_f32(c, C.diag, C.nx, C.ny, C.nzl));
 		}
 	}
+	if (c->nranks > 1 && c->tune.mg_agg == 1) { LFK_TRY(mg_agg_setup(c)); }
 	c->mg_valid = true;
 	return 0;
 }
@@ -658,6 +756,23 @@ static int half_sweep(lfk_ctx *c, size_t l, int colour, bool prolong, bool x_cur
 
 // V-cycle on levels >= l.  At level 0 the first red half-sweep was pre-applied by the kernel that produced b0 / x0,
 // and the very last (red) half-sweep is left to k_mg_final_l0.
+// every level of T in one block, one launch (shared-memory copy of the levels when they fit)
+static int launch_tail(lfk_ctx *c, const TailLevels &T) {
+	size_t smem = 0;
+	for (int k = 0; k < T.n; ++k) { smem += 6 * ((size_t)(T.L[k].sxy * (T.L[k].nzl + 2)) + 2) * sizeof(float); }
+	if (c->tune.mg_tail == 0 && smem <= 200 * 1024) {
+		static bool attr_set[LFK_MAX_DEVICES] = {}; // function attributes are per device
+		if (!attr_set[c->device % LFK_MAX_DEVICES]) {
+			LFK_CUDA(c, cudaFuncSetAttribute(k_mg_tail_smem, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+			attr_set[c->device % LFK_MAX_DEVICES] = true;
+		}
+		LFK_LAUNCH(c, k_mg_tail_smem, 1, 1024, smem, T, c->d_scal);
+	} else {
+		LFK_LAUNCH(c, k_mg_tail, 1, 1024, 0, T, c->d_scal);
+	}
+	return 0;
+}
+
 static int vcycle(lfk_ctx *c, size_t l) {
 	const GridDesc &G = c->g;
 	size_t last = c->mg.size() - 1;
@@ -669,19 +784,10 @@ static int vcycle(lfk_ctx *c, size_t l) {
 		for (size_t k = l; k <= last; ++k) {
 			T.L[T.n++] = level_dev(c->mg[k], c->mg_z0[k]);
 		}
-		size_t smem = 0;
-		for (int k = 0; k < T.n; ++k) { smem += 6 * ((size_t)(T.L[k].sxy * (T.L[k].nzl + 2)) + 2) * sizeof(float); }
-		if (c->tune.mg_tail == 0 && smem <= 200 * 1024) {
-			static bool attr_set[LFK_MAX_DEVICES] = {}; // function attributes are per device
-			if (!attr_set[c->device % LFK_MAX_DEVICES]) {
-				LFK_CUDA(c, cudaFuncSetAttribute(k_mg_tail_smem, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-				attr_set[c->device % LFK_MAX_DEVICES] = true;
-			}
-			LFK_LAUNCH(c, k_mg_tail_smem, 1, 1024, smem, T, c->d_scal);
-		} else {
-			LFK_LAUNCH(c, k_mg_tail, 1, 1024, 0, T, c->d_scal);
-		}
-		return 0;
+		return launch_tail(c, T);
+	}
+	if (c->nranks > 1 && c->tune.mg_agg == 1 && c->mg_agg_level > 0 && (int)l == c->mg_agg_level) {
+		return mg_agg_cycle(c);
 	}
 	// x of a level > 0 is zero when its cycle starts (the restriction zeroes the owned cells, and -- multi-GPU -- the
 	// ghost layers, see below), so its first half-sweep needs no exchange
