@@ -29,7 +29,10 @@ def main():
     for method in (capi.APIC, capi.FLIP):
         box = [capi.nccl_unique_id() if rank == 0 else None]  # one NCCL id per communicator
         dist.broadcast_object_list(box, src=0)
-        n = (24, 20, 8 * world + 3)
+        # default: slabs of unequal thickness and an odd depth (no slab-aligned coarsening: level 0 is the only
+        # distributed multigrid level); MGPU_ALIGNED=1: even slabs, so the distributed hierarchy -- and, with
+        # LFK_TUNE=mg_agg=1, the agglomerated coarse levels -- are exercised
+        n = (24, 20, 16 * world) if os.environ.get("MGPU_ALIGNED") == "1" else (24, 20, 8 * world + 3)
         kw = dict(cell_size=1.0, gravity=(0.0, -981.0, 0.0), method=method, blending_factor=0.95, max_iterations=2000)
         multi = capi.Context(n, device=local, nranks=world, rank=rank, nccl_id=box[0], **kw)
         whole = capi.Context(n, device=local, **kw)
