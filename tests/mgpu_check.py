@@ -26,13 +26,17 @@ def main():
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     failures = []
-    for method in (capi.APIC, capi.FLIP):
+    # two layouts: slabs of unequal thickness and an odd depth (no slab-aligned coarsening: level 0 is the only
+    # distributed multigrid level), and even slabs, where the distributed hierarchy -- and, with LFK_TUNE=mg_agg=1, the
+    # agglomerated coarse levels -- are exercised.  MGPU_ALIGNED=0 / 1 restricts the run to one of them.
+    only = os.environ.get("MGPU_ALIGNED")
+    layouts = [(capi.APIC, False), (capi.FLIP, False), (capi.APIC, True)]
+    if only in ("0", "1"):
+        layouts = [(capi.APIC, only == "1"), (capi.FLIP, only == "1")]
+    for method, aligned in layouts:
         box = [capi.nccl_unique_id() if rank == 0 else None]  # one NCCL id per communicator
         dist.broadcast_object_list(box, src=0)
-        # default: slabs of unequal thickness and an odd depth (no slab-aligned coarsening: level 0 is the only
-        # distributed multigrid level); MGPU_ALIGNED=1: even slabs, so the distributed hierarchy -- and, with
-        # LFK_TUNE=mg_agg=1, the agglomerated coarse levels -- are exercised
-        n = (24, 20, 16 * world) if os.environ.get("MGPU_ALIGNED") == "1" else (24, 20, 8 * world + 3)
+        n = (24, 20, 16 * world) if aligned else (24, 20, 8 * world + 3)
         kw = dict(cell_size=1.0, gravity=(0.0, -981.0, 0.0), method=method, blending_factor=0.95, max_iterations=2000)
         multi = capi.Context(n, device=local, nranks=world, rank=rank, nccl_id=box[0], **kw)
         whole = capi.Context(n, device=local, **kw)
@@ -57,7 +61,7 @@ def main():
             # ownership is settled by the sort (after advection); the position correction may then nudge a boundary
             # particle one cell across, so a rank's particles are matched against the WHOLE scene, and the ranks'
             # sets must partition it
-            tag = "method %d step %d rank %d" % (method, step, rank)
+            tag = "method %d%s step %d rank %d" % (method, " aligned" if aligned else "", step, rank)
             cnt = torch.tensor([a.shape[0]], dtype=torch.int64, device="cuda")
             dist.all_reduce(cnt)
             if int(cnt.item()) != b.shape[0]:
@@ -105,7 +109,8 @@ def main():
                 failures.append("%s: face velocities differ (max %.3e; %d cells, z %d..%d; slab %d..%d)"
                                 % (tag, dvel.max(), badc.size, zz.min(), zz.max(), z0, z1))
         if rank == 0:
-            print("method %d: %d steps compared, %d particles exchanged by rank 0" % (method, step + 1, moved), flush=True)
+            print("method %d%s: %d steps compared, %d particles exchanged by rank 0"
+                  % (method, " (aligned slabs)" if aligned else "", step + 1, moved), flush=True)
         ex = torch.tensor([moved], dtype=torch.int64, device="cuda")
         dist.all_reduce(ex)
         if int(ex.item()) == 0:
