@@ -55,15 +55,23 @@ def main():
             lines.append(cur)
     if len(lines) != len(body):
         print("warning: %d instructions in the disassembly, %d in the export" % (len(lines), len(body)))
+    stall_cols = {}
+    for i, h in enumerate(H):
+        if h.startswith("stall_") and "Not Issued" not in h and h not in stall_cols:
+            stall_cols[h] = i
     agg = collections.defaultdict(lambda: [0, 0])
+    why = collections.defaultdict(lambda: collections.Counter())
     for k, r in enumerate(body[:len(lines)]):
         a = agg[lines[k]]
         a[0] += num(r[si])
         a[1] += num(r[ii])
+        for h, i in stall_cols.items():
+            if i < len(r):
+                why[lines[k]][h[6:]] += num(r[i])
     ts = sum(a[0] for a in agg.values()) or 1
     ti = sum(a[1] for a in agg.values()) or 1
     cache = {}
-    print("%-28s %8s %8s" % ("source line", "samples", "instrs"))
+    print("%-28s %8s %8s  %-34s" % ("source line", "samples", "instrs", "top stall reasons of the line"))
     for (f, n), (s_, i_) in sorted(agg.items(), key=lambda kv: -kv[1][1])[:top]:
         text = ""
         for root in ("libfluid_b200/csrc", "."):
@@ -74,7 +82,10 @@ def main():
                 if 0 < n <= len(cache[path]):
                     text = cache[path][n - 1].strip()[:70]
                 break
-        print("%-20s:%-5d %7.2f%% %7.2f%%  %s" % (f, n, 100.0 * s_ / ts, 100.0 * i_ / ti, text))
+        w = why[(f, n)]
+        tot = sum(w.values()) or 1
+        reasons = " ".join("%s:%d%%" % (k, round(100.0 * v / tot)) for k, v in w.most_common(2))
+        print("%-20s:%-5d %7.2f%% %7.2f%%  %-34s %s" % (f, n, 100.0 * s_ / ts, 100.0 * i_ / ti, reasons, text[:60]))
     byfile = collections.defaultdict(lambda: [0, 0])
     for (f, n), (s_, i_) in agg.items():
         byfile[f][0] += s_
