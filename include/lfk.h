@@ -172,7 +172,7 @@ int lfk_set_timing(lfk_ctx *ctx, int enabled);
 /* A/B switches between kernel variants that compute the same result (profiling aid; every default is the production
  * path).  Keys: "p2g" 0 z-marching kernel, 1 brick kernel, 2 plain gather; "correct" 2 hit-mask pre-filter (default),
  * 0 scalar pre-filter, 1 packed-fp32 pre-filter, 3 hit-mask with record prefetch, 4 hit-mask with own particles grouped
- * by reach class (experimental, unmeasured); "g2p" 0 / 1 (all face samples
+ * by reach class, 5 hit-mask with 8-wide groups (4, 5: experimental, unmeasured); "g2p" 0 / 1 (all face samples
  * requested before the first store) / 2 (1 + constant-offset indexing for interior particles; experimental, unmeasured); "advect" 0 / 1 (two particles per thread); "mg_half" 0 / 1 (fp16 storage of the multigrid
  * level-0 vectors; experimental, unmeasured); "mg_agg" 0 / 1 (multi-GPU: coarse multigrid levels
  * agglomerated onto every rank; experimental, unmeasured; must be set on every rank alike); "mg_tail" 0 / 1; "spmv" 0 / 1;

@@ -1224,7 +1224,11 @@ template <bool COLLIDE> __global__ void __launch_bounds__(CT_THREADS, 2) k_corre
 // class cannot reach, where a warp of 32 consecutive particles executes all 9 (a lane needs 5.4 on average; SIMT model
 // in DESIGN.md section 7).  A particle's result does not depend on the thread that computes it, so the output is
 // unchanged bit for bit.
-template <bool COLLIDE, bool PREF, bool CLS> __global__ void __launch_bounds__(CT_THREADS, 2) k_correct_tiled3(GridDesc G, MotionParams M,
+// GW (experimental, lfk_set_tuning("correct", 5): GW = 8; not measured yet): candidates per guarded group of the scan.
+// The first test of a group waits for the group's shared-memory loads (13.5 % of the kernel's stall samples, short
+// scoreboard); 8 instead of 4 candidates per group halve the number of such waits per candidate, at the price of up to
+// 4 more wasted slots per row window and 16 more live registers.  Rows are padded by GW - 1 never-hit entries.
+template <bool COLLIDE, bool PREF, bool CLS, int GW = 4> __global__ void __launch_bounds__(CT_THREADS, 2) k_correct_tiled3(GridDesc G, MotionParams M,
 	ParticleSoA P, double *__restrict__ nx_, double *__restrict__ ny_, double *__restrict__ nz_,
 	const uint32_t *__restrict__ begin, const uint8_t *__restrict__ typ) {
 	extern __shared__ float4 stage3[];
@@ -1255,9 +1259,9 @@ template <bool COLLIDE, bool PREF, bool CLS> __global__ void __launch_bounds__(C
 	__syncthreads();
 	if (tid == 0) {
 		uint32_t acc = 0;
-		for (int r = 0; r < CT_ROWS; ++r) { // every row is followed by CT3_PAD never-hit entries
+		for (int r = 0; r < CT_ROWS; ++r) { // every row is followed by GW - 1 never-hit entries
 			rowoff[r] = acc;
-			acc += cellbeg[r][CT_LX + 2] + CT3_PAD;
+			acc += cellbeg[r][CT_LX + 2] + (GW - 1);
 		}
 		rowoff[CT_ROWS] = acc;
 		uint32_t oacc = 0;
@@ -1285,7 +1289,7 @@ template <bool COLLIDE, bool PREF, bool CLS> __global__ void __launch_bounds__(C
 	if (use_stage) {
 		for (int r = 0; r < CT_ROWS; ++r) {
 			const uint32_t cnt = cellbeg[r][CT_LX + 2], gs = rowstart[r], so = rowoff[r];
-			for (uint32_t j = tid; j < cnt + CT3_PAD; j += CT_THREADS) {
+			for (uint32_t j = tid; j < cnt + (GW - 1); j += CT_THREADS) {
 				float4 e = make_float4(0.f, 0.f, 0.f, 1e30f); // padding: never within reach
 				if (j < cnt) {
 					const uint32_t q = gs + j;
@@ -1394,12 +1398,18 @@ template <bool COLLIDE, bool PREF, bool CLS> __global__ void __launch_bounds__(C
 	const float t_ = __fmaf_rn(nrz, q_.z, __fmaf_rn(nry, q_.y, __fmaf_rn(nrx, q_.x, q_.w))); \
 	if (t_ < T) { mask |= (bit); } } while (0)
 #pragma unroll
-						for (int g = 0; g < 8; ++g) {
-							if ((uint32_t)(4 * g) < left) {
-								CT3_TEST(4 * g + 0, 1u << (4 * g + 0));
-								CT3_TEST(4 * g + 1, 1u << (4 * g + 1));
-								CT3_TEST(4 * g + 2, 1u << (4 * g + 2));
-								CT3_TEST(4 * g + 3, 1u << (4 * g + 3));
+						for (int g = 0; g < 32 / GW; ++g) {
+							if ((uint32_t)(GW * g) < left) {
+								CT3_TEST(GW * g + 0, 1u << (GW * g + 0));
+								CT3_TEST(GW * g + 1, 1u << (GW * g + 1));
+								CT3_TEST(GW * g + 2, 1u << (GW * g + 2));
+								CT3_TEST(GW * g + 3, 1u << (GW * g + 3));
+								if (GW == 8) {
+									CT3_TEST(GW * g + 4, 1u << (GW * g + 4));
+									CT3_TEST(GW * g + 5, 1u << (GW * g + 5));
+									CT3_TEST(GW * g + 6, 1u << (GW * g + 6));
+									CT3_TEST(GW * g + 7, 1u << (GW * g + 7));
+								}
 							}
 						}
 #undef CT3_TEST
@@ -1486,6 +1496,8 @@ static int correct_impl(lfk_ctx *c, double dt, bool fuse_collide) {
 		LFK_CUDA(c, cudaFuncSetAttribute((k_correct_tiled3<false, false, false>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
 		LFK_CUDA(c, cudaFuncSetAttribute((k_correct_tiled3<true, true, false>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
 		LFK_CUDA(c, cudaFuncSetAttribute((k_correct_tiled3<false, true, false>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+		LFK_CUDA(c, cudaFuncSetAttribute((k_correct_tiled3<true, false, false, 8>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+		LFK_CUDA(c, cudaFuncSetAttribute((k_correct_tiled3<false, false, false, 8>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
 		LFK_CUDA(c, cudaFuncSetAttribute((k_correct_tiled3<true, false, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cls));
 		LFK_CUDA(c, cudaFuncSetAttribute((k_correct_tiled3<false, false, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cls));
 		attr_set[c->device % LFK_MAX_DEVICES] = true;
@@ -1499,6 +1511,14 @@ static int correct_impl(lfk_ctx *c, double dt, bool fuse_collide) {
 		} else {
 			LFK_LAUNCH(c, (k_correct_tiled3<false, false, false>), grid, CT_THREADS, smem, G, M, c->P, c->Palt.f[PF_PX], c->Palt.f[PF_PY],
 				c->Palt.f[PF_PZ], c->begin, c->typ);
+		}
+	} else if (c->tune.correct == 5) { // experimental: as 2, 8 candidates per guarded group
+		if (fuse_collide) {
+			LFK_LAUNCH(c, (k_correct_tiled3<true, false, false, 8>), grid, CT_THREADS, smem, G, M, c->P, c->Palt.f[PF_PX],
+				c->Palt.f[PF_PY], c->Palt.f[PF_PZ], c->begin, c->typ);
+		} else {
+			LFK_LAUNCH(c, (k_correct_tiled3<false, false, false, 8>), grid, CT_THREADS, smem, G, M, c->P, c->Palt.f[PF_PX],
+				c->Palt.f[PF_PY], c->Palt.f[PF_PZ], c->begin, c->typ);
 		}
 	} else if (c->tune.correct == 4) { // experimental: as 2, own particles grouped by (y, z) reach class
 		if (fuse_collide) {

@@ -15,7 +15,7 @@ from pinlib import OB, RB
 pytestmark = pytest.mark.gpu
 
 # LFK_TEST_EXPERIMENTAL=1 also runs the kernel variants that are written but have never been on a GPU (DESIGN.md
-# section 7): position correction 4 (class-grouped), G2P 2 (interior indexing), multigrid fp16 level-0 storage
+# section 7): position correction 4 (class-grouped) and 5 (8-wide groups), G2P 2 (interior indexing), multigrid fp16 level-0 storage
 EXPERIMENTAL = os.environ.get("LFK_TEST_EXPERIMENTAL") == "1"
 
 
@@ -254,7 +254,7 @@ def test_position_correction_variants_agree():
     ctx.hash()
     parts = ctx.download_particles().copy()
     outs = []
-    variants = (0, 1, 2, 3) + ((4,) if EXPERIMENTAL else ())
+    variants = (0, 1, 2, 3) + ((4, 5) if EXPERIMENTAL else ())
     for v in variants:
         ctx.set_tuning("correct", v)
         ctx.upload_particles(parts)
@@ -267,7 +267,7 @@ def test_position_correction_variants_agree():
     assert moved > 1e-6
     # the same inside the fused step (correction + second collision pass in one kernel)
     res = []
-    fused = (0, 2, 3) + ((4,) if EXPERIMENTAL else ())
+    fused = (0, 2, 3) + ((4, 5) if EXPERIMENTAL else ())
     for v in fused:
         ctx.set_tuning("correct", v)
         ctx.set_tuning("warm_start", 0)

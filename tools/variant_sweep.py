@@ -23,7 +23,8 @@ CONFIGS = [
     ("defaults+correct_scalar", dict(NEW, correct=0)),
     ("defaults+correct_prefetch", dict(NEW, correct=3)),
     ("defaults+mg_half", dict(NEW, mg_half=1)),  # experimental fp16 level-0 multigrid vectors: check residual / iterations
-    ("defaults+correct_classes", dict(NEW, correct=4)),  # experimental: check bit-identity first (tests: add 4 to the variants list)
+    ("defaults+correct_classes", dict(NEW, correct=4)),
+    ("defaults+correct_wide", dict(NEW, correct=5)),  # experimental: 8 candidates per guarded group  # experimental: check bit-identity first (tests: add 4 to the variants list)
     ("defaults+g2p_batch", dict(NEW, g2p=1)),
     ("defaults+g2p_interior", dict(NEW, g2p=2)),  # experimental: add (2, 0) to test_g2p_and_advection_variants_agree first
     ("defaults+advect_pair", dict(NEW, advect=1)),
