@@ -7,7 +7,8 @@
 A "step" is one simulation::time_step() (CFL-limited dt, src/simulation.cpp:127-129) over the resident scene:
 advect + collide, cell sort, P2G (+gravity), pressure solve, pressure update, position correction + collide,
 extrapolation, G2P.  N = 1: 256^3 grid, APIC, 8 particles per cell, ~130 M particles (BASELINE configs[2], the
-configuration the metric is quoted on).  N > 1: the same slab per GPU (weak scaling), z-slab decomposition.
+configuration the metric is quoted on).  N > 1: weak scaling with 256^3 cells per GPU, z-slab decomposition:
+512x256x256 on 2 GPUs, 512x512x256 on 4, 512^3 on 8 (BASELINE configs[3]).
 One JSON line on stdout (rank 0).
 """
 import argparse
@@ -27,10 +28,10 @@ UNIT = "particle-substeps/s"
 GRAVITY = (0.0, -981.0, 0.0)
 
 
-def scene_boxes(n, nz):
-    """tidal step: water fills the box up to y = n - 2 on the left half and n - 14 (scaled) on the right half"""
-    hi, lo = n - max(2, n // 128), n - max(3, (14 * n) // 256)
-    return [((0.0, 0.0, 0.0), (n / 2.0, float(hi), float(nz))), ((n / 2.0, 0.0, 0.0), (n / 2.0, float(lo), float(nz)))]
+def scene_boxes(nx, ny, nz):
+    """tidal step: water fills the box up to y = ny - 2 on the left half and ny - 14 (scaled) on the right half"""
+    hi, lo = ny - max(2, ny // 128), ny - max(3, (14 * ny) // 256)
+    return [((0.0, 0.0, 0.0), (nx / 2.0, float(hi), float(nz))), ((nx / 2.0, 0.0, 0.0), (nx / 2.0, float(lo), float(nz)))]
 
 
 class ClockSampler(threading.Thread):
@@ -108,13 +109,14 @@ def run_reference(args, n=None, steps=None, warmup=None, quiet=False):
     n = n or args.ref_grid
     steps = steps if steps is not None else args.steps
     warmup = warmup if warmup is not None else args.warmup
-    cores = os.cpu_count() or 1
-    os.environ.setdefault("OMP_NUM_THREADS", str(cores))
+    cores = int(os.environ.get("LFK_REF_THREADS", "0")) or os.cpu_count() or 1
+    # (torchrun exports OMP_NUM_THREADS=1 to its workers: the reference's OpenMP phases would silently run on one core)
+    os.environ["OMP_NUM_THREADS"] = str(cores)
     if not RB.available():
         raise SystemExit("oracle/_ref/libfluid_ref.so is missing (built by __graft_entry__.build() where "
                          "/root/reference exists)")
     sim = RB.RefSim((n, n, n), gravity=GRAVITY, method=RB.APIC)
-    for start, size in scene_boxes(n, n):
+    for start, size in scene_boxes(n, n, n):
         sim.seed_box(start, size)
     sim.reset_space_hash()
     npart = sim.num_particles()
@@ -141,7 +143,31 @@ def run_reference(args, n=None, steps=None, warmup=None, quiet=False):
 
 
 # ------------------------------------------------------------------------------------------------------ our arm
+def workload_dims(n, world):
+    """Weak scaling towards BASELINE configs[3]: one axis doubles per doubling of the GPU count, so that 8 GPUs run
+    512^3 (64-cell z-slabs) and every GPU always owns n^3 cells: 1: n^3, 2: 2n x n x n, 4: 2n x 2n x n, 8: (2n)^3.
+    Other rank counts: n x n x (n * world).  z is the slab axis."""
+    if world in (1, 2, 4, 8):
+        return n * (2 if world >= 2 else 1), n * (2 if world >= 4 else 1), n * (2 if world >= 8 else 1)
+    return n, n, n * world
+
+
 def run_ours(args):
+    import faulthandler
+    import traceback
+    # a hang (a rank waiting in a collective for a peer that died) must end the run, not sit until the driver's limit
+    faulthandler.dump_traceback_later(int(os.environ.get("BENCH_WATCHDOG_S", "780")), exit=True)
+    try:
+        _run_ours(args)
+    except BaseException as ex:  # one rank failing alone would leave its peers inside NCCL: die hard, torchrun reaps them
+        if isinstance(ex, SystemExit) and ex.code in (0, None):
+            raise
+        sys.stderr.write("[rank %s] bench.py failed:\n%s\n" % (os.environ.get("RANK", "0"), traceback.format_exc()))
+        sys.stderr.flush()
+        os._exit(1)
+
+
+def _run_ours(args):
     import torch
     from libfluid_b200 import capi
 
@@ -161,16 +187,17 @@ def run_ours(args):
         nccl_id = box[0]
 
     n = args.grid
-    nz = n * world  # weak scaling: one n^3 slab per GPU
+    nx, ny, nz = workload_dims(n, world)
     # a real (non-default) torch stream: lfk launches on it and torch.cuda.Event times on it
     tstream = torch.cuda.Stream(device=local_rank)
     torch.cuda.set_stream(tstream)
     stream = tstream.cuda_stream
     assert stream != 0
-    ctx = capi.Context((n, n, nz), device=local_rank, stream=stream, nranks=world, rank=rank, nccl_id=nccl_id,
+    ctx = capi.Context((nx, ny, nz), device=local_rank, stream=stream, nranks=world, rank=rank, nccl_id=nccl_id,
                        cell_size=1.0, gravity=GRAVITY, method=capi.APIC, max_iterations=args.max_iterations,
                        preconditioner=capi.PRECOND_MULTIGRID)
-    for k, (start, size) in enumerate(scene_boxes(n, nz)):
+    z0, z1 = ctx.slab()
+    for k, (start, size) in enumerate(scene_boxes(nx, ny, nz)):
         ctx.seed_box_device(start, size, density=2, seed=20261017, append=k > 0)
     np_local = ctx.num_particles()
 
@@ -192,6 +219,13 @@ def run_ours(args):
         t = torch.tensor([float(v)], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
+
+    def agree(ok, what):
+        """every rank learns whether ANY rank failed a local check before the next collective is entered"""
+        if allmax(0.0 if ok else 1.0) != 0.0:
+            if not ok:
+                sys.stderr.write("[rank %d] %s\n" % (rank, what))
+            raise SystemExit(3)
 
     np_total = int(allsum(np_local))
     for _ in range(args.warmup):
@@ -225,24 +259,26 @@ def run_ours(args):
     st = ctx.stats()
     ctx.set_timing(False)
     phase = {k: v / prof_steps for k, v in st["phase_ms"].items() if v > 0}
+    # PCG iterations of one step started from p = 0 like the reference (the fused step warm-starts from the last p)
+    ctx.set_tuning("warm_start", 0)
+    ctx.time_step()
+    cold_iters = ctx.stats()["pcg_iterations"]
+    ctx.set_tuning("warm_start", 1)
+    ctx.time_step()
+    np_now = ctx.num_particles()
     nf = ctx.num_fluid_cells()
-    ncl = n * n * n
+    ncl = nx * ny * (z1 - z0)
     peak, peak_src = measured_peak()
     # algorithmic bytes per launch (DESIGN.md "Kernels"): single-kernel phases only
-    alg = {"p2g": 120 * np_local + 26 * ncl, "g2p": 120 * np_local + 24 * ncl,
-           "correct_collide": 48 * np_local + ncl, "advect_collide": 72 * np_local + ncl}
+    alg = {"p2g": 120 * np_now + 26 * ncl, "g2p": 120 * np_now + 24 * ncl,
+           "correct_collide": 48 * np_now + ncl, "advect_collide": 72 * np_now + ncl}
     single = {k: phase[k] for k in alg if k in phase}
     dom = max(single, key=single.get)
     ach = alg[dom] / (single[dom] * 1e-3) / 1e9
-    traffic, traffic_src = captured_traffic(n)
+    traffic, traffic_src = captured_traffic(n) if world == 1 else ({}, None)
     roofline = {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
                 "traffic": traffic.get(dom), "traffic_source": traffic_src, "algorithmic_bytes": alg[dom],
                 "peak_source": peak_src, "ms": single[dom],
-                "note": ("position correction is the longest kernel but is not memory bound: its DRAM traffic equals its "
-                         "algorithmic bytes and ncu shows it limited by instruction issue (61 % of issue slots busy, "
-                         "147 warp-instructions per particle) and the shared-memory pipe "
-                         "(profiles/r1d_particles128_ncu_summary.txt); the HBM-bound transfer kernels are under `all`"
-                         if dom == "correct_collide" else None),
                 "all": {k: {"ms": single[k], "GB/s": alg[k] / (single[k] * 1e-3) / 1e9,
                             "frac": alg[k] / (single[k] * 1e-3) / 1e9 / peak, "algorithmic_bytes": alg[k],
                             "traffic": traffic.get(k)} for k in single}}
@@ -253,40 +289,58 @@ def run_ours(args):
                                            "algorithmic_bytes": 105 * nf,
                                            "iters_per_step": prof_iters / prof_steps, "iters_per_s": 1e3 / it_ms}
 
-    # ---- end to end through the C ABI with HOST buffers: AoS particles + cells up, step, AoS particles + cells down
+    # ---- end to end through the C ABI with HOST buffers: AoS particles + cells up, step, AoS particles + cells down.
+    # The particle count of a rank changes from step to step (migration across the slab boundaries), so the count is
+    # read every step and the pinned buffer carries headroom; the ranks agree on every local check before the step's
+    # collectives are entered.
     e2e = None
     if not args.no_e2e:
-        import numpy as np
-        nbytes = np_local * 152
-        host_p = torch.empty(max(nbytes, 8), dtype=torch.uint8, pin_memory=True)
-        host_c = torch.empty(n * n * nz * 32, dtype=torch.uint8, pin_memory=True)
-        cells_np = host_c.numpy().view(capi.CELL_DTYPE)
-        ctx.download_particles((host_p.data_ptr(), np_local))
-        ctx.download_cells(cells_np)
+        cap = int(np_now * 1.03) + (1 << 16)
+        zlo, zhi = max(z0 - 1, 0), min(z1 + 1, nz)
+        ok = True
+        try:
+            host_p = torch.empty(cap * 152, dtype=torch.uint8, pin_memory=True)
+            host_c = torch.empty(nx * ny * (zhi - zlo) * 32, dtype=torch.uint8, pin_memory=True)
+        except RuntimeError as ex:
+            ok, why = False, "pinned host allocation failed: %s" % ex
+        agree(ok, why if not ok else "")
+        own_off = (z0 - zlo) * nx * ny * 32  # the owned layers inside the slab buffer
+        cnt = ctx.download_particles((host_p.data_ptr(), cap))
+        ctx.download_cells_slab(host_c.data_ptr() + own_off)
         barrier()
+        up_bytes = down_bytes = 0
         t0 = time.perf_counter()
         for _ in range(args.e2e_steps):
-            ctx.upload_cells(cells_np)
-            ctx.upload_particles((host_p.data_ptr(), np_local))
+            ctx.upload_cells_slab(host_c.data_ptr())
+            ctx.upload_particles((host_p.data_ptr(), cnt))
+            up_bytes += cnt * 152 + host_c.numel()
             ctx.time_step()
-            ctx.download_particles((host_p.data_ptr(), np_local))
-            ctx.download_cells(cells_np)
+            now = ctx.num_particles()
+            agree(now <= cap, "e2e: %d particles exceed the pinned buffer (%d)" % (now, cap))
+            cnt = ctx.download_particles((host_p.data_ptr(), cap))
+            ctx.download_cells_slab(host_c.data_ptr() + own_off)
+            down_bytes += cnt * 152 + ncl * 32
         barrier()
         dt_e2e = allmax(time.perf_counter() - t0)
-        own_cells = n * n * n
         e2e = {"value": np_total * args.e2e_steps / dt_e2e, "unit": UNIT,
-               "h2d_bytes_per_step": int(nbytes + min(n * n * nz, own_cells + 2 * n * n) * 32),
-               "d2h_bytes_per_step": int(nbytes + own_cells * 32), "steps": args.e2e_steps,
-               "what": "lfk_upload_cells + lfk_upload_particles (pinned AoS, reference layouts) + lfk_time_step_cfl"
-                       " + lfk_download_particles + lfk_download_cells, per step, wall clock"}
+               "h2d_bytes_per_step": int(up_bytes // args.e2e_steps),
+               "d2h_bytes_per_step": int(down_bytes // args.e2e_steps), "steps": args.e2e_steps,
+               "bytes_are": "this rank's; every rank moves about as much",
+               "what": "lfk_upload_cells_slab + lfk_upload_particles (pinned AoS, reference layouts) + lfk_time_step_cfl"
+                       " + lfk_download_particles + lfk_download_cells_slab, per step, wall clock, max over ranks",
+               "pcie_floor_s_per_step": (up_bytes + down_bytes) / args.e2e_steps / 55e9}
         del host_p, host_c
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "%dx%dx%d MAC grid (one %d^3 z-slab per GPU), APIC, tidal-step scene, 8 ppc, "
-                                   "%d particles, full simulation::time_step() with CFL dt" % (n, n, nz, n, np_total),
+            "config": {"workload": "%dx%dx%d MAC grid (%s; %d^3 cells per GPU, z-slabs of %d layers), APIC, "
+                                   "tidal-step scene, 8 ppc, %d particles, full simulation::time_step() with CFL dt"
+                                   % (nx, ny, nz, "BASELINE configs[2]" if world == 1 else
+                                      ("BASELINE configs[3]" if (nx, ny, nz) == (512, 512, 512) else
+                                       "weak-scaling step towards configs[3]"), n, z1 - z0, np_total),
                        "particles": np_total, "fluid_cells_rank0": nf, "pcg_iters_per_step": iters / args.steps,
+                       "pcg_iters_cold_start": cold_iters,
                        "l2_policy": "inputs (>= 16 GB of particle state per step) are far larger than the 126 MB L2",
                        "preconditioner": "aggregation multigrid V(2,2), fp32", "tolerance": 1e-6},
             "phase_ms": phase, "roofline": roofline, "clocks": clocks, "gpu_launches": int(launches), "e2e": e2e}
@@ -295,9 +349,12 @@ def run_ours(args):
         if world == 1 and not args.no_cpu_baseline:
             try:
                 line["cpu_baseline"] = run_reference(args, n=args.ref_grid, steps=2, warmup=1, quiet=True)
+                if args.ref_grid_large > args.ref_grid:  # the size trend of the CPU path (one step is ~40 s)
+                    line["cpu_baseline"]["larger_sample"] = run_reference(args, n=args.ref_grid_large, steps=1, warmup=1,
+                                                                          quiet=True)
             except SystemExit as ex:
                 line["cpu_baseline"] = {"unavailable": str(ex)}
-        print(json.dumps(line))
+        print(json.dumps(line), flush=True)
     if dist is not None:
         dist.destroy_process_group()
 
@@ -310,6 +367,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--grid", type=int, default=256)
     ap.add_argument("--ref-grid", type=int, default=64, help="grid of the bounded CPU sample")
+    ap.add_argument("--ref-grid-large", type=int, default=128, help="second, larger CPU sample (0: skip)")
     ap.add_argument("--max-iterations", type=int, default=1000)
     ap.add_argument("--e2e-steps", type=int, default=2)
     ap.add_argument("--no-e2e", action="store_true")

@@ -110,6 +110,11 @@ int lfk_download_positions(lfk_ctx *ctx, double *xyz, uint64_t capacity, uint64_
 int lfk_upload_cells(lfk_ctx *ctx, const void *aos32);
 /* writes the cells this rank owns into the whole-grid array (other entries untouched) */
 int lfk_download_cells(lfk_ctx *ctx, void *aos32);
+/* Multi-GPU hosts that mirror only their own slab: the same two transfers on slab-sized buffers.  Upload: the buffer
+ * holds the layers [max(z_begin - 1, 0), min(z_end + 1, nz)) (the slab plus its in-domain ghost layers); download: the
+ * owned layers [z_begin, z_end) (lfk_slab). */
+int lfk_upload_cells_slab(lfk_ctx *ctx, const void *aos32_slab);
+int lfk_download_cells_slab(lfk_ctx *ctx, void *aos32_own);
 /* simulation::_old_grid (simulation.h:201-202), FLIP only */
 int lfk_upload_old_cells(lfk_ctx *ctx, const void *aos32);
 int lfk_download_old_cells(lfk_ctx *ctx, void *aos32);

@@ -51,7 +51,7 @@ SYMBOLS = (
     "lfk_abi_version", "lfk_nccl_unique_id", "lfk_create", "lfk_destroy", "lfk_last_error", "lfk_set_params",
     "lfk_get_params", "lfk_sync", "lfk_slab", "lfk_upload_particles", "lfk_num_particles",
     "lfk_download_particles", "lfk_download_positions", "lfk_upload_cells", "lfk_download_cells",
-    "lfk_upload_old_cells", "lfk_download_old_cells", "lfk_download_table", "lfk_num_fluid_cells",
+    "lfk_upload_cells_slab", "lfk_download_cells_slab", "lfk_upload_old_cells", "lfk_download_old_cells", "lfk_download_table", "lfk_num_fluid_cells",
     "lfk_download_fluid_cells", "lfk_hash", "lfk_advect", "lfk_collide", "lfk_p2g", "lfk_gravity",
     "lfk_pressure_solve", "lfk_download_rhs", "lfk_download_pressure", "lfk_upload_pressure", "lfk_apply_a",
     "lfk_apply_pressure", "lfk_correct", "lfk_extrapolate", "lfk_g2p", "lfk_cfl", "lfk_time_step",
@@ -84,7 +84,8 @@ def load_library():
     L.lfk_num_particles.argtypes = [vp, C.POINTER(u64)]
     L.lfk_download_particles.argtypes = [vp, vp, u64, C.POINTER(u64)]
     L.lfk_download_positions.argtypes = [vp, vp, u64, C.POINTER(u64)]
-    for n in ("lfk_upload_cells", "lfk_download_cells", "lfk_upload_old_cells", "lfk_download_old_cells"):
+    for n in ("lfk_upload_cells", "lfk_download_cells", "lfk_upload_old_cells", "lfk_download_old_cells",
+              "lfk_upload_cells_slab", "lfk_download_cells_slab"):
         getattr(L, n).argtypes = [vp, vp]
     L.lfk_download_table.argtypes = [vp, vp, vp]
     L.lfk_num_fluid_cells.argtypes = [vp, C.POINTER(u64)]
@@ -233,6 +234,14 @@ class Context:
             out = np.zeros(self.ncells, dtype=CELL_DTYPE)
         self._ck(self.L.lfk_download_cells(self.ptr, _ptr(out)))
         return out
+
+    def upload_cells_slab(self, ptr):
+        """raw host pointer to the slab's layers [max(z0 - 1, 0), min(z1 + 1, nz)) (multi-GPU hosts, pinned memory)"""
+        self._ck(self.L.lfk_upload_cells_slab(self.ptr, C.c_void_p(int(ptr))))
+
+    def download_cells_slab(self, ptr):
+        """raw host pointer to room for the owned layers [z0, z1)"""
+        self._ck(self.L.lfk_download_cells_slab(self.ptr, C.c_void_p(int(ptr))))
 
     def upload_old_cells(self, arr):
         arr = np.ascontiguousarray(arr, dtype=CELL_DTYPE)

@@ -47,6 +47,9 @@ int lfkp_reserve_particles(lfk_ctx *c, uint64_t n) {
 	if (c->first + n <= c->cap) { return 0; }
 	if (c->np > 0) { LFK_TRY(lfkp_materialise_vc(c)); } // the permutation buffer is reallocated below
 	uint64_t ncap = std::max<uint64_t>(n, c->cap + c->cap / 4);
+	// multi-GPU: every sort appends the neighbours' boundary layers (ghost copies) and immigrants behind the own
+	// particles; room for two layers per side at 8 particles per cell up front avoids a reallocation in the first step
+	if (c->nranks > 1) { ncap += (uint64_t)c->g.sxy * 32; }
 	ncap = (ncap + 1023) / 1024 * 1024;
 	ParticleSoA nP{}, nA{};
 	uint32_t *nkey = nullptr, *nkalt = nullptr, *nslot = nullptr, *nperm = nullptr;
@@ -475,26 +478,27 @@ __global__ void k_cells_to_aos(GridDesc G, unsigned long long *__restrict__ aos,
 	rec[3] = (unsigned long long)typ[i];
 }
 
-static int upload_cells_impl(lfk_ctx *c, const void *aos32, double **vel, uint8_t *typ) {
+// whole_grid: aos32 is the whole nx*ny*nz array; otherwise it starts at layer max(z0 - 1, 0) (slab + in-domain ghosts)
+static int upload_cells_impl(lfk_ctx *c, const void *aos32, double **vel, uint8_t *typ, bool whole_grid = true) {
 	const GridDesc &G = c->g;
 	PhaseTimer T(c, LFK_PHASE_TRANSFER);
 	int zfirst = std::max(G.z0 - 1, 0), zlast = std::min(G.z0 + G.nzl + 1, G.nz);
 	size_t ncopy = (size_t)(zlast - zfirst) * (size_t)G.sxy;
 	LFK_TRY(reserve_staging(c, ncopy * 32));
-	LFK_CUDA(c, cudaMemcpyAsync(c->staging, (const char*)aos32 + (size_t)zfirst * G.sxy * 32, ncopy * 32,
+	LFK_CUDA(c, cudaMemcpyAsync(c->staging, (const char*)aos32 + (whole_grid ? (size_t)zfirst * G.sxy * 32 : 0), ncopy * 32,
 		cudaMemcpyHostToDevice, c->stream));
 	LFK_LAUNCH(c, k_cells_from_aos, lfk_blocks(G.ncl, 256), 256, 0, G, (const unsigned long long*)c->staging,
 		vel[0], vel[1], vel[2], typ);
 	return 0;
 }
-static int download_cells_impl(lfk_ctx *c, void *aos32, double **vel) {
+static int download_cells_impl(lfk_ctx *c, void *aos32, double **vel, bool whole_grid = true) {
 	const GridDesc &G = c->g;
 	PhaseTimer T(c, LFK_PHASE_TRANSFER);
 	size_t nown = (size_t)G.nown;
 	LFK_TRY(reserve_staging(c, nown * 32));
 	LFK_LAUNCH(c, k_cells_to_aos, lfk_blocks(G.nown, 256), 256, 0, G, (unsigned long long*)c->staging, vel[0],
 		vel[1], vel[2], c->typ);
-	LFK_CUDA(c, cudaMemcpyAsync((char*)aos32 + (size_t)G.z0 * G.sxy * 32, c->staging, nown * 32,
+	LFK_CUDA(c, cudaMemcpyAsync((char*)aos32 + (whole_grid ? (size_t)G.z0 * G.sxy * 32 : 0), c->staging, nown * 32,
 		cudaMemcpyDeviceToHost, c->stream));
 	LFK_CUDA(c, cudaStreamSynchronize(c->stream));
 	return 0;
@@ -510,6 +514,17 @@ extern "C" int lfk_upload_cells(lfk_ctx *c, const void *aos32) {
 extern "C" int lfk_download_cells(lfk_ctx *c, void *aos32) {
 	if (!c || !aos32) { return LFK_E_INVALID; }
 	return download_cells_impl(c, aos32, c->vel);
+}
+extern "C" int lfk_upload_cells_slab(lfk_ctx *c, const void *aos32_slab) {
+	if (!c || !aos32_slab) { return LFK_E_INVALID; }
+	LFK_TRY(upload_cells_impl(c, aos32_slab, c->vel, c->typ, false));
+	c->system_valid = false;
+	c->pressure_valid = false;
+	return 0;
+}
+extern "C" int lfk_download_cells_slab(lfk_ctx *c, void *aos32_own) {
+	if (!c || !aos32_own) { return LFK_E_INVALID; }
+	return download_cells_impl(c, aos32_own, c->vel, false);
 }
 extern "C" int lfk_upload_old_cells(lfk_ctx *c, const void *aos32) {
 	if (!c || !aos32) { return LFK_E_INVALID; }

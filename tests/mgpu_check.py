@@ -47,6 +47,17 @@ def main():
             ctx.seed_box_device((2.0, 1.0, 1.0), (14.0, 9.0, n[2] * 0.45), velocity=(3.0, 0.0, 55.0), density=2, seed=7)
             ctx.seed_box_device((6.0, 3.0, n[2] * 0.55), (15.0, 12.0, n[2] * 0.4), velocity=(-2.0, 0.0, -48.0),
                                 density=2, seed=9, append=True)
+        # FLIP / PIC leave the APIC c rows untouched, so they travel with the particle through sorts and exchanges: the
+        # check tags cx[0] with a particle id there and matches particles by id.  (APIC overwrites c every step, but
+        # particles that coincide -- clamped into the same corner -- then also agree in every field, so matching by
+        # position is unambiguous for everything that is compared.)
+        by_id = method != capi.APIC
+        if by_id:
+            allp = whole.download_particles()
+            allp["cx"][:, 0] = np.arange(allp.shape[0], dtype=np.float64)
+            whole.upload_particles(allp)
+            zc0 = slabs.z_cell(allp["position"][:, 2], n[2])
+            multi.upload_particles(allp[(zc0 >= z0) & (zc0 < z1)])
         total = torch.tensor([multi.num_particles()], dtype=torch.int64, device="cuda")
         dist.all_reduce(total)
         if int(total.item()) != whole.num_particles():
@@ -72,32 +83,37 @@ def main():
                 if zc.min() < z0 - 1 or zc.max() > z1:
                     failures.append("%s: own particle outside slab +- 1 (z cells %d..%d)" % (tag, zc.min(), zc.max()))
                     continue
-                d2, idx2 = cKDTree(b["position"]).query(a["position"], k=2)
-                d, idx = d2[:, 0], idx2[:, 0]
-                # (particles clamped into the same wall corner coincide, so the match need not be injective everywhere)
-                if np.unique(idx).size < 0.995 * idx.size or d.max() > 1e-6:
-                    failures.append("%s: positions differ (max %.3e, unique %d / %d)" % (tag, d.max(), np.unique(idx).size, idx.size))
-                    continue
-                # coincident particles cannot be told apart by position, and under FLIP they keep distinct velocities:
-                # the per-particle payload comparison is restricted to the unambiguous matches (all but a handful)
-                clear = d2[:, 1] > 1e-9
-                if clear.sum() < 0.99 * clear.size:
-                    failures.append("%s: %d of %d matches are ambiguous" % (tag, int((~clear).sum()), clear.size))
-                    continue
-                a, idx, zc = a[clear], idx[clear], zc[clear]
+                vmax = max(1.0, np.abs(b["velocity"]).max())
+                if by_id:
+                    ids = np.rint(a["cx"][:, 0]).astype(np.int64)
+                    order = np.argsort(np.rint(b["cx"][:, 0]).astype(np.int64))
+                    if np.unique(ids).size != ids.size or ids.min() < 0 or ids.max() >= b.shape[0]:
+                        failures.append("%s: particle ids are not a subset of the whole scene's" % tag)
+                        continue
+                    idx = order[ids]
+                    d = np.abs(a["position"] - b["position"][idx]).max(axis=1)
+                    if d.max() > 1e-6:
+                        failures.append("%s: positions differ by id (max %.3e)" % (tag, d.max()))
+                        continue
+                else:
+                    d, idx = cKDTree(b["position"]).query(a["position"])
+                    # (particles clamped into the same wall corner coincide, so the match need not be injective there)
+                    if np.unique(idx).size < 0.995 * idx.size or d.max() > 1e-6:
+                        failures.append("%s: positions differ (max %.3e, unique %d / %d)" % (tag, d.max(), np.unique(idx).size, idx.size))
+                        continue
                 dvv = np.abs(a["velocity"] - b["velocity"][idx]).max(axis=1)
                 dv = dvv.max()
-                if dv > 1e-4 * max(1.0, np.abs(b["velocity"]).max()):
+                if dv > 1e-4 * vmax:
                     w = int(np.argmax(dvv))
-                    nbad = int((dvv > 1e-4 * max(1.0, np.abs(b["velocity"]).max())).sum())
-                    zb = zc[dvv > 1e-4 * max(1.0, np.abs(b["velocity"]).max())]
+                    zb = zc[dvv > 1e-4 * vmax]
                     failures.append("%s: velocities differ (max %.3e at pos %s, v %s vs %s; %d bad, z cells %d..%d; slab %d..%d)"
-                                    % (tag, dv, a["position"][w], a["velocity"][w], b["velocity"][idx[w]], nbad,
+                                    % (tag, dv, a["position"][w], a["velocity"][w], b["velocity"][idx[w]], zb.size,
                                        zb.min(), zb.max(), z0, z1))
-                dc = max(np.abs(a[f] - b[f][idx]).max() for f in ("cx", "cy", "cz"))
-                if dc > 1e-4 * max(1.0, np.abs(b["velocity"]).max()):
-                    failures.append("%s: APIC c rows differ (max %.3e)" % (tag, dc))
-                    continue
+                if not by_id:
+                    dc = max(np.abs(a[f] - b[f][idx]).max() for f in ("cx", "cy", "cz"))
+                    if dc > 1e-4 * vmax:
+                        failures.append("%s: APIC c rows differ (max %.3e)" % (tag, dc))
+                        continue
             ca, cb = multi.download_cells(), whole.download_cells()
             own = slice(z0 * n[0] * n[1], z1 * n[0] * n[1])
             if not np.array_equal(ca["type"][own], cb["type"][own]):
