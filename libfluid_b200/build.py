@@ -12,7 +12,7 @@ ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
 OUT_DIR = os.path.join(HERE, "_lib")
 LIB = os.path.join(OUT_DIR, "liblfk.so")
-SOURCES = ["lfk_api.cu", "particles.cu", "g2p.cu", "p2g.cu", "p2g_brick.cu", "p2g_march.cu", "pressure.cu", "mg.cu", "exchange.cu"]
+SOURCES = ["lfk_api.cu", "particles.cu", "g2p.cu", "p2g.cu", "p2g_march.cu", "pressure.cu", "mg.cu", "exchange.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 # --fmad=false: the reference's CPU build does no FMA contraction; particle motion / classification must be
@@ -20,7 +20,7 @@ ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 COMMON = ["-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC", "-I" + os.path.join(ROOT, "include"),
           "-I" + CSRC]
 # fused multiply-add only where the summation order already differs from the reference (tolerance-checked)
-FMAD_ON = {"p2g_brick.cu", "p2g_march.cu", "mg.cu", "g2p.cu"}
+FMAD_ON = {"p2g_march.cu", "mg.cu", "g2p.cu"}
 PER_FILE = {src: (["--fmad=true"] if src in FMAD_ON else ["--fmad=false"]) for src in SOURCES}
 
 

@@ -107,11 +107,6 @@ template <bool GRAD> __device__ __forceinline__ void trilinear(const double *s, 
 	}
 }
 
-// BATCH: all 24 face samples of a particle are requested before the first result is stored.  The stores may alias the
-// sample arrays as far as the compiler can tell, so in the component-by-component form it keeps the three sample
-// fetches behind the stores of the previous component: four dependent memory round trips per particle (position, u, v,
-// w samples) instead of two -- the kernel is latency bound (ncu r1d: 57 % of the stall samples are long-scoreboard
-// waits on the first use of each fetch).  Same arithmetic, bit-identical results.
 // the 8 samples of component K for a particle whose 3 x 3 x 3 cell neighbourhood lies inside the grid (and inside the
 // slab's layers): one base index plus constant offsets instead of 24 clamped index computations.  Same addresses, same
 // values as face_samples_comp when nothing is clamped.
@@ -127,10 +122,12 @@ template <int K> __device__ __forceinline__ void face_samples_interior(const Gri
 	}
 }
 
-// FAST (experimental, lfk_set_tuning("g2p", 2); implies BATCH; not measured yet): interior particles take
-// face_samples_interior -- index arithmetic is 37 % of this kernel's instructions (ncu r1d: IMAD + IADD3 + ISETP).
-template <int METHOD, bool BATCH, bool FAST = false> __global__ void __launch_bounds__(128) k_g2p(GridDesc G, G2PArgs A,
-	unsigned long long n) {
+// Thread per particle.  All 24 face samples of a particle are requested before the first result is stored (the stores
+// may alias the sample arrays as far as the compiler can tell, so a component-by-component form serialises four memory
+// round trips per particle; the kernel is latency bound), and particles whose 3 x 3 x 3 cell neighbourhood is interior
+// take face_samples_interior (index arithmetic was 37 % of the instructions, ncu r1d).  Measured at 256^3 (r2a sweep):
+// 4.09 ms against 4.59 ms component by component and 4.47 ms batched with clamped indexing.
+template <int METHOD> __global__ void __launch_bounds__(128) k_g2p(GridDesc G, G2PArgs A, unsigned long long n) {
 	unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
 	if (i >= n) { return; }
 	constexpr bool APIC = METHOD == LFK_METHOD_APIC;
@@ -154,11 +151,11 @@ template <int METHOD, bool BATCH, bool FAST = false> __global__ void __launch_bo
 	FaceFetch F;
 	face_fetch_setup(G, gi, F);
 	double s[8], vn[3], g[3];
-	if (BATCH) {
+	{
 		double s1[8], s2[8];
 		// cells gi - 1 .. gi + 1 per axis, none clamped (face_fetch_setup), and their layers held by this rank
 		const long long lzlo = gi[2] - 1 - G.z0 + 1;
-		const bool interior = FAST && gi[0] >= 1 && gi[0] + 2 < G.nx && gi[1] >= 1 && gi[1] + 2 < G.ny && gi[2] >= 1 &&
+		const bool interior = gi[0] >= 1 && gi[0] + 2 < G.nx && gi[1] >= 1 && gi[1] + 2 < G.ny && gi[2] >= 1 &&
 			gi[2] + 2 < G.nz && lzlo >= 0 && lzlo + 2 <= G.nlz - 1;
 		const long long base = (gi[0] - 1) + (long long)G.nx * ((gi[1] - 1) + (long long)G.ny * lzlo);
 		if (interior) {
@@ -206,47 +203,7 @@ template <int METHOD, bool BATCH, bool FAST = false> __global__ void __launch_bo
 		A.vd[0][i] = vn[0];
 		A.vd[1][i] = vn[1];
 		A.vd[2][i] = vn[2];
-		return;
 	}
-	// x component: weights (t.x, tmid.y, tmid.z)
-	face_samples_comp<0>(G, F, A.u, nullptr, dsel, s);
-	trilinear<APIC>(s, t[0], tmid[1], tmid[2], vn[0], g);
-	if (APIC) {
-		A.cd[0][i] = div_h(g[0], G);
-		A.cd[1][i] = div_h(g[1], G);
-		A.cd[2][i] = div_h(g[2], G);
-	}
-	face_samples_comp<1>(G, F, A.v, nullptr, dsel, s);
-	trilinear<APIC>(s, tmid[0], t[1], tmid[2], vn[1], g);
-	if (APIC) {
-		A.cd[3][i] = div_h(g[0], G);
-		A.cd[4][i] = div_h(g[1], G);
-		A.cd[5][i] = div_h(g[2], G);
-	}
-	face_samples_comp<2>(G, F, A.w, A.w_below, dsel, s);
-	trilinear<APIC>(s, tmid[0], tmid[1], t[2], vn[2], g);
-	if (APIC) {
-		A.cd[6][i] = div_h(g[0], G);
-		A.cd[7][i] = div_h(g[1], G);
-		A.cd[8][i] = div_h(g[2], G);
-	}
-	if (METHOD == LFK_METHOD_FLIP) { // v = v_new + (v_p - v_old) * blend (:463-505)
-		double vold[3], dummy[3];
-		face_samples_comp<0>(G, F, A.uo, nullptr, dsel, s);
-		trilinear<false>(s, t[0], tmid[1], tmid[2], vold[0], dummy);
-		face_samples_comp<1>(G, F, A.vo, nullptr, dsel, s);
-		trilinear<false>(s, tmid[0], t[1], tmid[2], vold[1], dummy);
-		face_samples_comp<2>(G, F, A.wo, A.wo_below, dsel, s);
-		trilinear<false>(s, tmid[0], tmid[1], t[2], vold[2], dummy);
-		const unsigned long long src = A.perm ? (unsigned long long)A.perm[i] : i;
-#pragma unroll
-		for (int d = 0; d < 3; ++d) {
-			vn[d] = vn[d] + (A.vs[d][src] - vold[d]) * A.blend;
-		}
-	}
-	A.vd[0][i] = vn[0];
-	A.vd[1][i] = vn[1];
-	A.vd[2][i] = vn[2];
 }
 
 int lfkp_g2p(lfk_ctx *c) {
@@ -281,32 +238,15 @@ int lfkp_g2p(lfk_ctx *c) {
 		A.blend = c->prm.blending_factor;
 		unsigned nb = lfk_blocks((long long)c->np, 128);
 		unsigned long long n = c->np;
-		const bool batch = c->tune.g2p == 1; // A/B: all face samples in flight before the first store
-		if (c->tune.g2p == 2) { // experimental: batch + constant-offset indexing for interior particles
-			switch (method) {
-			case LFK_METHOD_PIC:
-				LFK_LAUNCH(c, (k_g2p<LFK_METHOD_PIC, true, true>), nb, 128, 0, c->g, A, n);
-				break;
-			case LFK_METHOD_FLIP:
-				LFK_LAUNCH(c, (k_g2p<LFK_METHOD_FLIP, true, true>), nb, 128, 0, c->g, A, n);
-				break;
-			default:
-				LFK_LAUNCH(c, (k_g2p<LFK_METHOD_APIC, true, true>), nb, 128, 0, c->g, A, n);
-				break;
-			}
-		} else
 		switch (method) {
 		case LFK_METHOD_PIC:
-			if (batch) { LFK_LAUNCH(c, (k_g2p<LFK_METHOD_PIC, true>), nb, 128, 0, c->g, A, n); }
-			else { LFK_LAUNCH(c, (k_g2p<LFK_METHOD_PIC, false>), nb, 128, 0, c->g, A, n); }
+			LFK_LAUNCH(c, k_g2p<LFK_METHOD_PIC>, nb, 128, 0, c->g, A, n);
 			break;
 		case LFK_METHOD_FLIP:
-			if (batch) { LFK_LAUNCH(c, (k_g2p<LFK_METHOD_FLIP, true>), nb, 128, 0, c->g, A, n); }
-			else { LFK_LAUNCH(c, (k_g2p<LFK_METHOD_FLIP, false>), nb, 128, 0, c->g, A, n); }
+			LFK_LAUNCH(c, k_g2p<LFK_METHOD_FLIP>, nb, 128, 0, c->g, A, n);
 			break;
 		default:
-			if (batch) { LFK_LAUNCH(c, (k_g2p<LFK_METHOD_APIC, true>), nb, 128, 0, c->g, A, n); }
-			else { LFK_LAUNCH(c, (k_g2p<LFK_METHOD_APIC, false>), nb, 128, 0, c->g, A, n); }
+			LFK_LAUNCH(c, k_g2p<LFK_METHOD_APIC>, nb, 128, 0, c->g, A, n);
 			break;
 		}
 		if (indirect) {

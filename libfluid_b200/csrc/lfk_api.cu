@@ -787,13 +787,7 @@ extern "C" int lfk_set_tuning(lfk_ctx *c, const char *key, int value) {
 	if (!c || !key) { return LFK_E_INVALID; }
 	const std::string k(key);
 	if (k == "p2g") { c->tune.p2g = value; }
-	else if (k == "correct") { c->tune.correct = value; }
-	else if (k == "g2p") { c->tune.g2p = value; }
-	else if (k == "mg_half") { c->tune.mg_half = value; }
 	else if (k == "mg_agg") { c->tune.mg_agg = value; }
-	else if (k == "advect") { c->tune.advect = value; }
-	else if (k == "mg_tail") { c->tune.mg_tail = value; }
-	else if (k == "spmv") { c->tune.spmv = value; }
 	else if (k == "warm_start") { c->tune.warm_start = value; }
 	else if (k == "red_blocks") { c->tune.red_blocks = value; }
 	else { return lfk_fail(c, LFK_E_INVALID, "lfk_set_tuning: unknown key", __FILE__, __LINE__); }

@@ -63,17 +63,10 @@ struct MgLevel {
 #define LFK_MAX_DEVICES 64 // per-device one-time set-up flags (cudaFuncSetAttribute is a per-device setting)
 
 // A/B switches and tuning knobs (lfk_set_tuning; the defaults are the production path)
-enum { LFK_TUNE_P2G_MARCH = 0, LFK_TUNE_P2G_BRICK = 1, LFK_TUNE_P2G_GATHER = 2 };
+enum { LFK_TUNE_P2G_MARCH = 0, LFK_TUNE_P2G_GATHER = 2 };
 struct lfk_tuning {
-	int p2g = LFK_TUNE_P2G_MARCH;
-	int correct = 2;  // position correction: 2 hit-mask pre-filter (production), 0 scalar fp32 pre-filter (A/B), 1 packed-fp32 (A/B)
-	int g2p = 0;      // 0: component by component (production), 1: all 24 face samples requested before the first store (A/B),
-	                  // 2: 1 + constant-offset sample indexing for interior particles (experimental, never run on a GPU yet)
-	int advect = 0;   // 0: one particle per thread (production), 1: two particles per thread, loads issued together (A/B)
-	int mg_half = 0;  // 1: fp16 storage of the multigrid level-0 vectors (experimental, single GPU; never run on a GPU yet)
-	int mg_agg = 0;   // 1: multi-GPU coarse levels agglomerated onto every rank (experimental; never run on a GPU yet)
-	int mg_tail = 0;  // 0: shared-memory coarse tail, 1: the global-memory one (A/B)
-	int spmv = 0;     // 0: production SpMV + dot, 1: the previous one (A/B)
+	int p2g = LFK_TUNE_P2G_MARCH; // 2: the plain per-cell gather (the reference's loop literally; also taken for APIC with h < 1)
+	int mg_agg = 0;   // 1: multi-GPU coarse levels agglomerated onto every rank
 	int warm_start = 1; // fused step: start PCG from the previous step's pressure (0: from p = 0 like the reference)
 	int red_blocks = 0; // > 0: cap on the grid of the PCG reduction kernels (default 8 x SM count)
 };
@@ -125,9 +118,6 @@ struct lfk_ctx {
 	bool ordinal_valid = false;
 	std::vector<MgLevel> mg;
 	uint16_t *mg_mask = nullptr;   // level-0 coupling mask (mg.cu)
-	void *mg_half_b = nullptr, *mg_half_x = nullptr; // experimental fp16 copies of the level-0 rhs / solution (mg.cu)
-	float *mg_half_scale = nullptr;                  // the factor the fp16 right-hand side was divided by
-	bool mg_half_on = false;
 	std::vector<MgLevel> mg_agg;   // multi-GPU: agglomerated global coarse levels (experimental, mg.cu)
 	int mg_agg_level = -1;         // distributed level they replace; -1 undecided, -2 none
 	std::vector<int> mg_z0;        // global z of the first owned layer, per level (red-black parity)

@@ -27,24 +27,12 @@
 #include "lfk_internal.cuh"
 
 #include <algorithm>
-#include <cuda_fp16.h>
 
-// ---- storage of the level-0 vectors ---------------------------------------------------------------------------
-// Production: fp32.  Experimental (lfk_set_tuning("mg_half", 1), single GPU, never run on a GPU yet): fp16.  The
-// V-cycle is linear, so the right-hand side is first divided by S = max |b0| (its entries then lie in [-1, 1]) and the
-// result is multiplied by S again; x is stored divided by L0_XS on top of that (the solution of a Poisson problem
-// exceeds its right-hand side by up to the condition number, ~1e5 at 1024^3: 1e5 / 64 stays below the fp16 maximum,
-// and the smallest values that matter, ~1/6 / 64, stay normal).  Arithmetic is fp32 either way.
-// tools/mg_prototype.py --experiments: the PCG iteration count does not change (12 / 13 / 12 against 12 / 12 / 12).
-#define L0_XS 64.f
+// ---- storage of the level-0 vectors: fp32 (fp16 storage was measured in r2a and changed nothing: 1.039 against
+// 1.035 ms per iteration at 256^3 -- the level-0 passes are not limited by their bytes; removed) --------------------
 __device__ __forceinline__ float l0_ld_b(const float *__restrict__ p, long long i) { return p[i]; }
 __device__ __forceinline__ float l0_ld_x(const float *__restrict__ p, long long i) { return p[i]; }
 __device__ __forceinline__ void l0_st_x(float *__restrict__ p, long long i, float v) { p[i] = v; }
-__device__ __forceinline__ float l0_ld_b(const __half *__restrict__ p, long long i) { return __half2float(p[i]); }
-__device__ __forceinline__ float l0_ld_x(const __half *__restrict__ p, long long i) { return __half2float(p[i]) * L0_XS; }
-__device__ __forceinline__ void l0_st_x(__half *__restrict__ p, long long i, float v) {
-	p[i] = __float2half_rn(v * (1.f / L0_XS));
-}
 
 #define MG_OMEGA 1.8f
 #define MG_PRE 2
@@ -200,13 +188,11 @@ template <bool PROLONG, typename T> __global__ void __launch_bounds__(256) k_mg_
 }
 
 // last half-sweep of the cycle (colour `colour`) fused with z = x0 / a_scale (fp64), sigma_new = z.r and its finaliser
-// `rescale`: NULL, or (fp16 storage) the factor S the right-hand side was divided by
 template <typename T> __global__ void __launch_bounds__(RED_THREADS) k_mg_final_l0(GridDesc G,
 	const uint16_t *__restrict__ mask, const T *__restrict__ b, const T *__restrict__ X, int colour,
 	const double *__restrict__ r, double *__restrict__ z, double inv_a_scale, PcgScalars *scal, double *partials,
 	unsigned *ticket, int finalize, int first, const float *__restrict__ rescale) {
 	if (scal->done) { return; }
-	if (sizeof(T) == 2) { inv_a_scale *= (double)*rescale; } // compile-time: the fp32 instantiation never reads it
 	double acc = 0.0;
 	struct FinRaw { L0Raw l; double r; };
 	LevelDev none{};
@@ -559,9 +545,6 @@ int lfkm_free(lfk_ctx *c) {
 		}
 	}
 	if (c->mg_mask) { cudaFree(c->mg_mask); c->mg_mask = nullptr; }
-	if (c->mg_half_b) { cudaFree(c->mg_half_b); c->mg_half_b = nullptr; }
-	if (c->mg_half_x) { cudaFree(c->mg_half_x); c->mg_half_x = nullptr; }
-	if (c->mg_half_scale) { cudaFree(c->mg_half_scale); c->mg_half_scale = nullptr; }
 	for (MgLevel &L : c->mg_agg) {
 		float *arrs[] = { L.x, L.b, L.diag, L.cx, L.cy, L.cz };
 		for (float *p : arrs) {
@@ -690,31 +673,6 @@ int lfkm_setup(lfk_ctx *c, double a_scale) {
 	return 0;
 }
 
-// ---- fp16 storage of the level-0 vectors (experimental, see the top of the file) -------------------------------
-// S = max |b0| over the owned cells, as the bit pattern of a non-negative float (orders like an unsigned integer)
-__global__ void __launch_bounds__(256) k_l0_absmax(GridDesc G, const float *__restrict__ b0, unsigned *__restrict__ out,
-	const PcgScalars *scal) {
-	if (scal->done) { return; }
-	float m = 0.f;
-	for_own_cells(G, [&](int, int, int, long long c) { m = fmaxf(m, fabsf(b0[c])); });
-#pragma unroll
-	for (int o = 16; o > 0; o >>= 1) { m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o)); }
-	if ((threadIdx.x & 31) == 0 && m > 0.f) { atomicMax(out, __float_as_uint(m)); }
-}
-// hb = b0 / S, hx = x0 / S (x0: the pre-applied first red half-sweep), both rounded to fp16
-__global__ void __launch_bounds__(256) k_l0_to_half(GridDesc G, const float *__restrict__ b0,
-	const float *__restrict__ x0, __half *__restrict__ hb, __half *__restrict__ hx, float *__restrict__ scale,
-	const PcgScalars *scal) {
-	if (scal->done) { return; }
-	// *scale holds the bit pattern of max |b0| (k_l0_absmax); an all-zero right-hand side keeps S = 1
-	const float m = *scale;
-	const float S = m > 0.f ? m : 1.f, inv = 1.f / S;
-	for_own_cells(G, [&](int, int, int, long long c) {
-		hb[c] = __float2half_rn(b0[c] * inv);
-		l0_st_x(hx, c, x0[c] * inv);
-	});
-}
-
 // one half-sweep of colour `colour` on level l; `prolong`: the neighbours carry the pending correction of level l + 1.
 // Multi-GPU: the z ghost layers of x are refreshed first unless the caller knows they are current (`x_current`):
 // every exchange is an NCCL launch of ~15 us against ~8 us of arithmetic on the coarse levels (profiles/r1d: 2.4 ms per
@@ -731,14 +689,7 @@ static int half_sweep(lfk_ctx *c, size_t l, int colour, bool prolong, bool x_cur
 		if (!x_current) { LFK_TRY(lfkx_halo_f32(c, L.x, L.nx, L.ny, L.nzl)); }
 		if (prolong) { LFK_TRY(lfkx_halo_f32(c, c->mg[l + 1].x, Cd.nx, Cd.ny, Cd.nzl)); }
 	}
-	if (l == 0 && c->mg_half_on) {
-		__half *hb = (__half*)c->mg_half_b, *hx = (__half*)c->mg_half_x;
-		if (prolong) {
-			LFK_LAUNCH(c, (k_mg_rbgs_l0<true, __half>), nb, 256, 0, G, c->mg_mask, hb, hx, colour, Cd, c->d_scal);
-		} else {
-			LFK_LAUNCH(c, (k_mg_rbgs_l0<false, __half>), nb, 256, 0, G, c->mg_mask, hb, hx, colour, Cd, c->d_scal);
-		}
-	} else if (l == 0) {
+	if (l == 0) {
 		if (prolong) {
 			LFK_LAUNCH(c, (k_mg_rbgs_l0<true, float>), nb, 256, 0, G, c->mg_mask, L.b, L.x, colour, Cd, c->d_scal);
 		} else {
@@ -760,7 +711,7 @@ static int half_sweep(lfk_ctx *c, size_t l, int colour, bool prolong, bool x_cur
 static int launch_tail(lfk_ctx *c, const TailLevels &T) {
 	size_t smem = 0;
 	for (int k = 0; k < T.n; ++k) { smem += 6 * ((size_t)(T.L[k].sxy * (T.L[k].nzl + 2)) + 2) * sizeof(float); }
-	if (c->tune.mg_tail == 0 && smem <= 200 * 1024) {
+	if (smem <= 200 * 1024) {
 		static bool attr_set[LFK_MAX_DEVICES] = {}; // function attributes are per device
 		if (!attr_set[c->device % LFK_MAX_DEVICES]) {
 			LFK_CUDA(c, cudaFuncSetAttribute(k_mg_tail_smem, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
@@ -815,10 +766,7 @@ static int vcycle(lfk_ctx *c, size_t l) {
 	LevelDev Cd = level_dev(C, c->mg_z0[l + 1]);
 	if (c->nranks > 1) { LFK_TRY(lfkx_halo_f32(c, L.x, L.nx, L.ny, L.nzl)); }
 	unsigned rb = row_blocks(Cd.ny, Cd.nzl, 128, 1u << 20);
-	if (l == 0 && c->mg_half_on) {
-		LFK_LAUNCH(c, k_mg_restrict_l0<__half>, rb, 128, 0, G, c->mg_mask, (const __half*)c->mg_half_b,
-			(const __half*)c->mg_half_x, Cd, c->d_scal);
-	} else if (l == 0) {
+	if (l == 0) {
 		LFK_LAUNCH(c, k_mg_restrict_l0<float>, rb, 128, 0, G, c->mg_mask, L.b, L.x, Cd, c->d_scal);
 	} else {
 		LFK_LAUNCH(c, k_mg_restrict, rb, 128, 0, Ld, Cd, c->d_scal);
@@ -848,29 +796,9 @@ int lfkm_level0(lfk_ctx *c, float **b0, float **x0) {
 int lfkm_apply_preloaded(lfk_ctx *c, double a_scale, unsigned nb, int fin, int first) {
 	const GridDesc &G = c->g;
 	MgLevel &L0 = c->mg[0];
-	// experimental fp16 storage of the level-0 vectors: single GPU, and only when level 0 is not the only level
-	c->mg_half_on = c->tune.mg_half == 1 && c->nranks == 1 && c->mg.size() > 1;
-	if (c->mg_half_on) {
-		if (!c->mg_half_b) {
-			const size_t n = (size_t)L0.ncl + 2;
-			LFK_CUDA(c, cudaMalloc((void**)&c->mg_half_b, n * sizeof(__half)));
-			LFK_CUDA(c, cudaMalloc((void**)&c->mg_half_x, n * sizeof(__half)));
-			LFK_CUDA(c, cudaMalloc((void**)&c->mg_half_scale, sizeof(float)));
-			LFK_CUDA(c, cudaMemsetAsync(c->mg_half_b, 0, n * sizeof(__half), c->stream)); // ghost layers stay zero
-			LFK_CUDA(c, cudaMemsetAsync(c->mg_half_x, 0, n * sizeof(__half), c->stream));
-		}
-		LFK_CUDA(c, cudaMemsetAsync(c->mg_half_scale, 0, sizeof(float), c->stream));
-		LFK_LAUNCH(c, k_l0_absmax, lfk_row_blocks(G, 256, 1184), 256, 0, G, L0.b, (unsigned*)c->mg_half_scale, c->d_scal);
-		LFK_LAUNCH(c, k_l0_to_half, lfk_row_blocks(G, 256, 1u << 20), 256, 0, G, L0.b, L0.x, (__half*)c->mg_half_b,
-			(__half*)c->mg_half_x, c->mg_half_scale, c->d_scal);
-	}
 	LFK_TRY(vcycle(c, 0));
 	if (c->nranks > 1) { LFK_TRY(lfkx_halo_f32(c, L0.x, L0.nx, L0.ny, L0.nzl)); }
-	if (c->mg_half_on) {
-		LFK_LAUNCH(c, k_mg_final_l0<__half>, nb, RED_THREADS, 0, G, c->mg_mask, (const __half*)c->mg_half_b,
-			(const __half*)c->mg_half_x, 0, c->r, c->z, 1.0 / a_scale, c->d_scal, c->partials, c->ticket, fin, first,
-			(const float*)c->mg_half_scale);
-	} else {
+	{
 		LFK_LAUNCH(c, k_mg_final_l0<float>, nb, RED_THREADS, 0, G, c->mg_mask, L0.b, L0.x, 0, c->r, c->z, 1.0 / a_scale,
 			c->d_scal, c->partials, c->ticket, fin, first, (const float*)nullptr);
 	}

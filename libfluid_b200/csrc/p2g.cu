@@ -132,7 +132,6 @@ __global__ void k_gravity(GridDesc G, double g0, double g1, double g2, double *_
 	w[me] += g2;
 }
 
-int lfkg_p2g_brick(lfk_ctx *c, double gravity_dt, bool add_gravity); // p2g_brick.cu
 int lfkg_p2g_march(lfk_ctx *c, double gravity_dt, bool add_gravity); // p2g_march.cu
 
 int lfkg_p2g(lfk_ctx *c, double gravity_dt, bool add_gravity) {
@@ -149,11 +148,7 @@ int lfkg_p2g(lfk_ctx *c, double gravity_dt, bool add_gravity) {
 	const bool wide_apic = c->prm.method == LFK_METHOD_APIC && G.h < 1.0;
 	const bool use_gather = c->tune.p2g == LFK_TUNE_P2G_GATHER || wide_apic;
 	if (!use_gather) {
-		if (c->tune.p2g == LFK_TUNE_P2G_BRICK) {
-			LFK_TRY(lfkg_p2g_brick(c, gravity_dt, add_gravity));
-		} else {
-			LFK_TRY(lfkg_p2g_march(c, gravity_dt, add_gravity));
-		}
+		LFK_TRY(lfkg_p2g_march(c, gravity_dt, add_gravity));
 		if (c->nranks > 1 && c->prm.method == LFK_METHOD_FLIP) { // FLIP's G2P samples the snapshot in the ghost layers
 			for (int d = 0; d < 3; ++d) { LFK_TRY(lfkx_halo_f64(c, c->vel_old[d])); }
 			LFK_TRY(lfkx_layer_below(c, c->vel_old[2], c->wlow[1]));

@@ -616,39 +616,6 @@ __global__ void k_advect_collide(GridDesc G, MotionParams M, ParticleSoA P, cons
 	P.f[PF_PZ][i] = to[2];
 }
 
-// A/B variant: two particles per thread, all twelve loads issued before the first (division-heavy) collision march --
-// twice the bytes in flight per warp for a kernel that is limited by memory latency, not by bandwidth (52 % of the
-// measured HBM peak at ideal DRAM traffic, ncu r1d).  Same arithmetic per particle, bit-identical results.
-__global__ void __launch_bounds__(128) k_advect_collide2(GridDesc G, MotionParams M, ParticleSoA P,
-	const uint8_t *__restrict__ typ, unsigned long long n) {
-	const unsigned long long i0 = (unsigned long long)blockIdx.x * 256 + threadIdx.x, i1 = i0 + 128;
-	const bool has0 = i0 < n, has1 = i1 < n;
-	double from0[3], v0[3], from1[3], v1[3];
-#pragma unroll
-	for (int d = 0; d < 3; ++d) {
-		from0[d] = has0 ? P.f[PF_PX + d][i0] : 0.0;
-		v0[d] = has0 ? P.f[PF_VX + d][i0] : 0.0;
-		from1[d] = has1 ? P.f[PF_PX + d][i1] : 0.0;
-		v1[d] = has1 ? P.f[PF_VX + d][i1] : 0.0;
-	}
-	if (has0) {
-		double to[3] = { from0[0], from0[1], from0[2] };
-		advect_one(M, to, v0);
-		collide_one(G, M, typ, from0, to);
-		P.f[PF_PX][i0] = to[0];
-		P.f[PF_PY][i0] = to[1];
-		P.f[PF_PZ][i0] = to[2];
-	}
-	if (has1) {
-		double to[3] = { from1[0], from1[1], from1[2] };
-		advect_one(M, to, v1);
-		collide_one(G, M, typ, from1, to);
-		P.f[PF_PX][i1] = to[0];
-		P.f[PF_PY][i1] = to[1];
-		P.f[PF_PZ][i1] = to[2];
-	}
-}
-
 static int materialise_old(lfk_ctx *c) {
 	if (!c->old_valid && c->np > 0) {
 		for (int d = 0; d < 3; ++d) {
@@ -688,10 +655,7 @@ int lfkp_advect_collide(lfk_ctx *c, double dt) {
 		return lfkp_collide(c);
 	}
 	LFK_TRY(lfkp_materialise_vc(c));
-	if (c->np > 0 && c->tune.advect == 1) {
-		LFK_LAUNCH(c, k_advect_collide2, lfk_blocks((long long)c->np, 256), 128, 0, c->g, motion_params(c, dt),
-			lfk_own_view(c), c->typ, (unsigned long long)c->np);
-	} else if (c->np > 0) {
+	if (c->np > 0) {
 		LFK_LAUNCH(c, k_advect_collide, lfk_blocks((long long)c->np, 128), 128, 0, c->g, motion_params(c, dt),
 			lfk_own_view(c), c->typ, (unsigned long long)c->np);
 	}
@@ -715,13 +679,21 @@ __device__ __forceinline__ void degenerate_kick(const double *p, const double *o
 	}
 }
 
-// A block owns a tile of CT_TY x CT_TZ rows x CT_LX cells.  The positions of every particle in the tile plus its
-// one-cell halo are staged ONCE in shared memory as fp32 coordinates relative to the tile origin (16 B each, with
-// the particle's global index), so the candidate tests per particle run on fp32 data from shared memory instead of
-// fp64 data from L1/L2.  The fp32 test is only a conservative PRE-FILTER (its threshold carries a 10x margin over
-// the worst-case rounding error); candidates that pass are re-evaluated in fp64 from the original positions, in the
-// reference's order.  Per neighbouring row only the cells that the kernel radius can reach are scanned
-// (re^2 - dy_min^2 - dz_min^2 leaves an x window of 0..3 cells).
+// A block owns a tile of CT_TY x CT_TZ rows x CT_LX cells and stages every particle of the tile plus its one-cell halo
+// ONCE in shared memory as {x, y, z, |q|^2} in fp32, in cell units about the tile centre.
+// Phase 1 (fp32, conservative pre-filter): per neighbouring row only the cells the kernel radius re = h / sqrt(2) can
+// reach are scanned (re^2 - dy_min^2 - dz_min^2 leaves an x window of 1 .. 3 cells); with n = -2 r the test
+// |r - q|^2 < 1/2 + margin is  w + n.q < T,  T = 1/2 + margin - |r|^2: three FFMA and a compare; hits are bits of a per-row
+// mask with compile-time positions, one {mask, index of the window's first particle} record per 32 candidates.
+// Every staged row is followed by CT_PAD entries that can never hit, so the 4-wide groups need no tail handling.
+// Rounding: |coordinates| <= 17.1 cells, every intermediate below 620 with an error below 4e-5; the margin of 2e-3 cells^2
+// covers their sum 10x over, so the filter never drops a true neighbour.
+// Phase 2 (fp64): the recorded candidates in staging order (= the reference's order: rows by z then y, cells by x,
+// particles in sorted order), evaluated from the original positions => the result is the plain fp64 loop's, bit for bit.
+// Measured alternatives (256^3, 27.6 ms for this kernel): own particles grouped by (y, z) reach class 38.5 ms, 8-wide
+// guarded groups 28.3 ms, packed f32x2 tests 42.6 ms, scalar d^2 test 30.3 ms (r2a sweep); fp64 positions staged in
+// shared memory as well, one 1024-thread block per SM: 35.2 ms (r2b) -- two resident blocks per SM that overlap each
+// other's staging and tails are worth more than the L1 / L2 latency of phase 2.
 #define CT_LX 32
 #define CT_TY 2
 #define CT_TZ 2
@@ -731,7 +703,9 @@ __device__ __forceinline__ void degenerate_kick(const double *p, const double *o
 #define CT_OWN (CT_TY * CT_TZ)
 #define CT_CAP 5120           // staged particles per tile (80 KB); denser tiles take the global-memory path
 #define CT_THREADS 512
-#define CT_LIST 40
+#define CT_PAD 3
+#define CT_LIST 16
+#define CT_MARGIN 2e-3f
 
 // 1 / sqrt(x) for x in the normal range: hardware seed (rel. error 2^-22) + two Newton steps (~1 ulp)
 __device__ __forceinline__ double fast_rsqrt(double x) {
@@ -769,7 +743,8 @@ __device__ __forceinline__ void pair_exact(const MotionParams &M, const double *
 	}
 }
 
-// the plain fp64 neighbourhood loop (fallback for over-full tiles and for particles outside their key cell)
+// the plain fp64 neighbourhood loop (over-full tiles, particles outside their key cell, crowded rows): the reference's
+// loop literally (src/simulation.cpp:572-600)
 __device__ void spring_global(const GridDesc &G, const MotionParams &M, const double *__restrict__ px,
 	const double *__restrict__ py, const double *__restrict__ pz, const uint32_t *__restrict__ begin,
 	unsigned long long i, const double *p, double &sx, double &sy, double &sz) {
@@ -799,17 +774,17 @@ __device__ void spring_global(const GridDesc &G, const MotionParams &M, const do
 	}
 }
 
-template <bool COLLIDE> __global__ void __launch_bounds__(CT_THREADS, 2) k_correct_tiled(GridDesc G, MotionParams M,
+template <bool COLLIDE> __global__ void __launch_bounds__(CT_THREADS, 2) k_correct_tile(GridDesc G, MotionParams M,
 	ParticleSoA P, double *__restrict__ nx_, double *__restrict__ ny_, double *__restrict__ nz_,
 	const uint32_t *__restrict__ begin, const uint8_t *__restrict__ typ) {
-	extern __shared__ float4 stage[];
+	extern __shared__ float4 stage[];                            // [CT_CAP] fp32 scan entries
 	__shared__ uint32_t rowstart[CT_ROWS], rowoff[CT_ROWS + 1], cellbeg[CT_ROWS][CT_LX + 3];
 	__shared__ uint32_t ownbeg[CT_OWN], ownpre[CT_OWN + 1];
 	const double *__restrict__ px = P.f[PF_PX], *__restrict__ py = P.f[PF_PY], *__restrict__ pz = P.f[PF_PZ];
 	const int x0 = blockIdx.x * CT_LX, y0 = blockIdx.y * CT_TY, lz0 = blockIdx.z * CT_TZ + 1;
 	const int tid = threadIdx.x;
 
-	// ---- table of the staged rows ----
+	// ---- table of the staged rows: row r = (lz0 - 1 + r / CT_SY, y0 - 1 + r % CT_SY), cells x0 - 1 .. x0 + CT_LX ----
 	for (int e = tid; e < CT_ROWS * (CT_LX + 3); e += CT_THREADS) {
 		int r = e / (CT_LX + 3), k = e % (CT_LX + 3);
 		int y = y0 - 1 + r % CT_SY, lz = lz0 - 1 + r / CT_SY;
@@ -830,9 +805,9 @@ template <bool COLLIDE> __global__ void __launch_bounds__(CT_THREADS, 2) k_corre
 	__syncthreads();
 	if (tid == 0) {
 		uint32_t acc = 0;
-		for (int r = 0; r < CT_ROWS; ++r) {
+		for (int r = 0; r < CT_ROWS; ++r) { // every row is followed by CT_PAD never-hit entries
 			rowoff[r] = acc;
-			acc += cellbeg[r][CT_LX + 2];
+			acc += cellbeg[r][CT_LX + 2] + CT_PAD;
 		}
 		rowoff[CT_ROWS] = acc;
 		uint32_t oacc = 0;
@@ -854,226 +829,26 @@ template <bool COLLIDE> __global__ void __launch_bounds__(CT_THREADS, 2) k_corre
 	if (nown_total == 0) { return; }
 	const uint32_t staged = rowoff[CT_ROWS];
 	const bool use_stage = staged <= CT_CAP;
-	// tile origin (one cell below the tile in every axis), fp64; staged coordinates are relative to it
-	const double org[3] = { G.off[0] + (double)(x0 - 1) * G.h, G.off[1] + (double)(y0 - 1) * G.h,
-		G.off[2] + (double)(lz0 - 2 + G.z0) * G.h };
-	if (use_stage) {
-		for (int r = 0; r < CT_ROWS; ++r) {
-			uint32_t cnt = cellbeg[r][CT_LX + 2], gs = rowstart[r], so = rowoff[r];
-			for (uint32_t j = tid; j < cnt; j += CT_THREADS) {
-				uint32_t q = gs + j;
-				stage[so + j] = make_float4((float)(px[q] - org[0]), (float)(py[q] - org[1]), (float)(pz[q] - org[2]),
-					__uint_as_float(q));
-			}
-		}
-	}
-	__syncthreads();
-	const float thr = (float)(M.re2 + 1e-4 * G.h * G.h);
-
-	for (uint32_t t = tid; t < nown_total; t += CT_THREADS) {
-		int o = 0;
-#pragma unroll
-		for (int k = 1; k < CT_OWN; ++k) {
-			if (t >= ownpre[k]) { o = k; }
-		}
-		const unsigned long long i = (unsigned long long)ownbeg[o] + (t - ownpre[o]);
-		const int oy = o % CT_TY, oz = o / CT_TY;
-		double p[3] = { px[i], py[i], pz[i] };
-		double sx = 0.0, sy = 0.0, sz = 0.0;
-		// unclamped cell and in-cell fraction (compute_cell_index)
-		long long ci[3];
-		float fr[3];
-#pragma unroll
-		for (int d = 0; d < 3; ++d) {
-			double f = div_h(p[d] - G.off[d], G);
-			unsigned long long u = (unsigned long long)f;
-			ci[d] = u > 0x7fffffffull ? 0x7fffffffll : (long long)u;
-			fr[d] = (float)(f - (double)u);
-		}
-		const bool in_tile = use_stage && ci[0] >= x0 && ci[0] < x0 + CT_LX && ci[0] < G.nx && ci[1] == y0 + oy &&
-			ci[2] == lz0 + oz - 1 + G.z0;
-		if (!in_tile) {
-			spring_global(G, M, px, py, pz, begin, i, p, sx, sy, sz);
-		} else {
-			const float rx = (float)(p[0] - org[0]), ry = (float)(p[1] - org[1]), rz = (float)(p[2] - org[2]);
-			const int kown = (int)(ci[0] - x0) + 1; // index of the particle's own cell in cellbeg[r][]
-			// Phase 1: fp32 scan of the staged candidates, four at a time (four independent LDS.128 in flight); the
-			// survivors' particle indices go to a small per-thread list.  Phase 2 evaluates them in fp64, in order.
-			uint32_t cand[CT_LIST];
-			int nc = 0;
-			const float4 *__restrict__ sbase = stage;
-#define CT_TEST(q) do { float dx_ = rx - (q).x, dy_ = ry - (q).y, dz_ = rz - (q).z; \
-	float d2_ = __fmaf_rn(dz_, dz_, __fmaf_rn(dy_, dy_, dx_ * dx_)); \
-	if (d2_ < thr) { cand[nc < CT_LIST ? nc : CT_LIST - 1] = __float_as_uint((q).w); ++nc; } } while (0)
-			for (int dz = -1; dz <= 1; ++dz) {
-				// distance (in cells) from the particle to the nearest point of the neighbouring layer / row
-				const float zmin = dz < 0 ? fr[2] : (dz > 0 ? 1.f - fr[2] : 0.f);
-				const float remz = 0.501f - zmin * zmin; // (re / h)^2 = 1/2, plus the pre-filter's margin
-				if (remz <= 0.f) { continue; }
-				for (int dy = -1; dy <= 1; ++dy) {
-					const float ymin = dy < 0 ? fr[1] : (dy > 0 ? 1.f - fr[1] : 0.f);
-					const float rem = remz - ymin * ymin;
-					if (rem <= 0.f) { continue; }
-					const float xr = sqrtf(rem); // reach along x within this row: < 0.708 cells
-					const int klo = kown + (fr[0] - xr < 0.f ? -1 : 0);
-					const int khi = kown + (fr[0] + xr >= 1.f ? 2 : 1);
-					const int r = (oz + 1 + dz) * CT_SY + (oy + 1 + dy);
-					uint32_t s = rowoff[r] + cellbeg[r][klo];
-					const uint32_t s1 = rowoff[r] + cellbeg[r][khi];
-					for (; s + 4 <= s1; s += 4) {
-						const float4 q0 = sbase[s], q1 = sbase[s + 1], q2 = sbase[s + 2], q3 = sbase[s + 3];
-						CT_TEST(q0);
-						CT_TEST(q1);
-						CT_TEST(q2);
-						CT_TEST(q3);
-					}
-					for (; s < s1; ++s) {
-						const float4 q0 = sbase[s];
-						CT_TEST(q0);
-					}
-				}
-			}
-#undef CT_TEST
-			if (nc > CT_LIST) { // more neighbours within reach than the list holds (a clump): plain fp64 loop instead
-				spring_global(G, M, px, py, pz, begin, i, p, sx, sy, sz);
-			} else {
-				// candidate positions are fetched one iteration ahead of their use
-				uint32_t j = nc > 0 ? cand[0] : (uint32_t)i;
-				double ov[3] = { px[j], py[j], pz[j] };
-				for (int k = 0; k < nc; ++k) {
-					const uint32_t jn = k + 1 < nc ? cand[k + 1] : j;
-					const double on[3] = { px[jn], py[jn], pz[jn] };
-					if (j != i) { pair_exact(M, p, ov, sx, sy, sz); }
-					j = jn;
-					ov[0] = on[0];
-					ov[1] = on[1];
-					ov[2] = on[2];
-				}
-			}
-		}
-		double np3[3] = { p[0] + sx * M.corr_factor, p[1] + sy * M.corr_factor, p[2] + sz * M.corr_factor };
-#pragma unroll
-		for (int d = 0; d < 3; ++d) {
-			np3[d] = dclamp_std(np3[d], M.gmin[d], M.gmax[d]);
-		}
-		if (COLLIDE) {
-			collide_one(G, M, typ, p, np3);
-		}
-		nx_[i] = np3[0];
-		ny_[i] = np3[1];
-		nz_[i] = np3[2];
-	}
-}
-
-// ---- production variant of the tiled kernel: packed-fp32 pre-filter --------------------------------------------
-// Same tiling, same culling, same fp64 evaluation in the reference's order; what changes is the candidate test, which
-// is where the instructions go (~100 candidates per particle, ~12 of them within the kernel radius):
-//   * staged coordinates are in CELL units relative to the tile centre, stored as PAIRS of candidates
-//     {x0 x1 y0 y1} {z0 z1 w0 w1} with w = |q|^2, so that d^2 - T = w - 2 r.q - T (T = radius^2 + margin - |r|^2) of
-//     two candidates costs three packed FMAs and one packed add (sm_100 FFMA2 / FADD2), and its SIGN is the test;
-//   * the sign bytes of four candidates are gathered with three byte-permutes into one word; one mask test decides
-//     whether the group is recorded (the word plus the pair index), so a miss costs no predicated bookkeeping.
-// ~4.75 instructions per candidate against ~10 for the scalar d^2 test of k_correct_tiled (kept as the A/B kernel).
-// Rounding: |coordinates| <= 17.1 cells, so every intermediate is below 620 and carries an error below 4e-5; the
-// margin of 2e-3 cells^2 covers the sum of all of them 10x over, so the filter never drops a true neighbour.
-#define CT2_MARGIN 2e-3f
-#define CT2_LIST 32 // recorded groups per particle (each holds up to 4 neighbours)
-
-__device__ __forceinline__ unsigned long long f32x2_fma(unsigned long long a, unsigned long long b,
-	unsigned long long c) {
-	unsigned long long d;
-	asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
-	return d;
-}
-__device__ __forceinline__ unsigned long long f32x2_add(unsigned long long a, unsigned long long b) {
-	unsigned long long d;
-	asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
-	return d;
-}
-__device__ __forceinline__ unsigned long long f32x2_splat(float v) {
-	const unsigned long long u = (unsigned long long)__float_as_uint(v);
-	return (u << 32) | u;
-}
-
-template <bool COLLIDE> __global__ void __launch_bounds__(CT_THREADS, 2) k_correct_tiled2(GridDesc G, MotionParams M,
-	ParticleSoA P, double *__restrict__ nx_, double *__restrict__ ny_, double *__restrict__ nz_,
-	const uint32_t *__restrict__ begin, const uint8_t *__restrict__ typ) {
-	extern __shared__ ulonglong2 stage2[]; // pair g: stage2[2 g] = {x0 x1 | y0 y1}, stage2[2 g + 1] = {z0 z1 | w0 w1}
-	__shared__ uint32_t rowstart[CT_ROWS], rowoff[CT_ROWS + 1], cellbeg[CT_ROWS][CT_LX + 3];
-	__shared__ uint32_t ownbeg[CT_OWN], ownpre[CT_OWN + 1];
-	const double *__restrict__ px = P.f[PF_PX], *__restrict__ py = P.f[PF_PY], *__restrict__ pz = P.f[PF_PZ];
-	const int x0 = blockIdx.x * CT_LX, y0 = blockIdx.y * CT_TY, lz0 = blockIdx.z * CT_TZ + 1;
-	const int tid = threadIdx.x;
-
-	// ---- table of the staged rows ----
-	for (int e = tid; e < CT_ROWS * (CT_LX + 3); e += CT_THREADS) {
-		int r = e / (CT_LX + 3), k = e % (CT_LX + 3);
-		int y = y0 - 1 + r % CT_SY, lz = lz0 - 1 + r / CT_SY;
-		uint32_t v = 0;
-		if (y >= 0 && y < G.ny && lz >= 0 && lz < G.nlz) {
-			long long row = (long long)G.nx * (y + (long long)G.ny * lz);
-			int xa = x0 - 1 < 0 ? 0 : x0 - 1;
-			int xk = x0 - 1 + k;
-			xk = xk < 0 ? 0 : (xk > G.nx ? G.nx : xk);
-			uint32_t base = begin[row + xa];
-			v = begin[row + xk] - base;
-			if (k == 0) { rowstart[r] = base; }
-		} else if (k == 0) {
-			rowstart[r] = 0;
-		}
-		cellbeg[r][k] = v;
-	}
-	__syncthreads();
-	if (tid == 0) {
-		uint32_t acc = 0;
-		for (int r = 0; r < CT_ROWS; ++r) { // every row starts on a pair boundary
-			rowoff[r] = acc;
-			acc += (cellbeg[r][CT_LX + 2] + 1u) & ~1u;
-		}
-		rowoff[CT_ROWS] = acc;
-		uint32_t oacc = 0;
-		for (int o = 0; o < CT_OWN; ++o) { // own rows: cells x0 .. x0 + LX - 1 (clipped) of the inner rows
-			int r = (o / CT_TY + 1) * CT_SY + (o % CT_TY + 1);
-			int y = y0 + o % CT_TY, lz = lz0 + o / CT_TY;
-			uint32_t nown = 0;
-			if (y < G.ny && lz <= G.nzl) {
-				nown = cellbeg[r][CT_LX + 1] - cellbeg[r][1];
-			}
-			ownbeg[o] = rowstart[r] + cellbeg[r][1];
-			ownpre[o] = oacc;
-			oacc += nown;
-		}
-		ownpre[CT_OWN] = oacc;
-	}
-	__syncthreads();
-	const uint32_t nown_total = ownpre[CT_OWN];
-	if (nown_total == 0) { return; }
-	const uint32_t staged = rowoff[CT_ROWS];
-	const bool use_stage = staged <= CT_CAP;
-	// tile centre, fp64; staged coordinates are relative to it, in cells
+	// tile centre, fp64; the scan entries are relative to it, in cells
 	const double ctr[3] = { G.off[0] + ((double)x0 + 0.5 * CT_LX) * G.h, G.off[1] + ((double)y0 + 0.5 * CT_TY) * G.h,
 		G.off[2] + ((double)(lz0 - 1 + G.z0) + 0.5 * CT_TZ) * G.h };
 	if (use_stage) {
-		float *sf = reinterpret_cast<float *>(stage2); // pair g: floats 8 g + {0 1 | 2 3 | 4 5 | 6 7} = x x y y z z w w
-		for (int r = 0; r < CT_ROWS; ++r) {
-			const uint32_t cnt = cellbeg[r][CT_LX + 2], gs = rowstart[r], so = rowoff[r];
-			const uint32_t padded = (cnt + 1u) & ~1u;
-			for (uint32_t j = tid; j < padded; j += CT_THREADS) {
-				float fx = 0.f, fy = 0.f, fz = 0.f, fw = 1e30f; // padding: never within reach
-				if (j < cnt) {
-					const uint32_t q = gs + j;
-					fx = (float)((px[q] - ctr[0]) * G.inv_h);
-					fy = (float)((py[q] - ctr[1]) * G.inv_h);
-					fz = (float)((pz[q] - ctr[2]) * G.inv_h);
-					fw = __fmaf_rn(fz, fz, __fmaf_rn(fy, fy, fx * fx));
-				}
-				const uint32_t s = so + j;
-				float *dst = sf + (s >> 1) * 8 + (s & 1u);
-				dst[0] = fx;
-				dst[2] = fy;
-				dst[4] = fz;
-				dst[6] = fw;
+		for (uint32_t e = tid; e < staged; e += CT_THREADS) {
+			int r = 0; // row of staged entry e (binary search over the 16 row offsets)
+			if (e >= rowoff[8]) { r = 8; }
+			if (e >= rowoff[r + 4]) { r += 4; }
+			if (e >= rowoff[r + 2]) { r += 2; }
+			if (e >= rowoff[r + 1]) { r += 1; }
+			const uint32_t j = e - rowoff[r];
+			float4 f = make_float4(0.f, 0.f, 0.f, 1e30f); // padding: never within reach
+			if (j < cellbeg[r][CT_LX + 2]) {
+				const uint32_t q = rowstart[r] + j;
+				f.x = (float)((px[q] - ctr[0]) * G.inv_h);
+				f.y = (float)((py[q] - ctr[1]) * G.inv_h);
+				f.z = (float)((pz[q] - ctr[2]) * G.inv_h);
+				f.w = __fmaf_rn(f.z, f.z, __fmaf_rn(f.y, f.y, f.x * f.x));
 			}
+			stage[e] = f;
 		}
 	}
 	__syncthreads();
@@ -1084,8 +859,11 @@ template <bool COLLIDE> __global__ void __launch_bounds__(CT_THREADS, 2) k_corre
 		for (int k = 1; k < CT_OWN; ++k) {
 			if (t >= ownpre[k]) { o = k; }
 		}
-		const unsigned long long i = (unsigned long long)ownbeg[o] + (t - ownpre[o]);
+		const uint32_t within = t - ownpre[o];
+		const unsigned long long i = (unsigned long long)ownbeg[o] + within;
 		const int oy = o % CT_TY, oz = o / CT_TY;
+		const int rown = (oz + 1) * CT_SY + (oy + 1);
+		const uint32_t so = rowoff[rown] + cellbeg[rown][1] + within; // this particle's own staged entry
 		double p[3] = { px[i], py[i], pz[i] };
 		double sx = 0.0, sy = 0.0, sz = 0.0;
 		// unclamped cell and in-cell fraction (compute_cell_index)
@@ -1103,275 +881,14 @@ template <bool COLLIDE> __global__ void __launch_bounds__(CT_THREADS, 2) k_corre
 		if (!in_tile) {
 			spring_global(G, M, px, py, pz, begin, i, p, sx, sy, sz);
 		} else {
-			const float rx = (float)((p[0] - ctr[0]) * G.inv_h), ry = (float)((p[1] - ctr[1]) * G.inv_h),
-				rz = (float)((p[2] - ctr[2]) * G.inv_h);
-			const unsigned long long NRX = f32x2_splat(-2.f * rx), NRY = f32x2_splat(-2.f * ry),
-				NRZ = f32x2_splat(-2.f * rz);
-			// d^2 < 1/2 + margin  <=>  w - 2 r.q - T < 0,  T = 1/2 + margin - |r|^2
-			const unsigned long long NT = f32x2_splat(__fmaf_rn(rz, rz, __fmaf_rn(ry, ry, rx * rx)) - (0.5f + CT2_MARGIN));
-			const int kown = (int)(ci[0] - x0) + 1; // index of the particle's own cell in cellbeg[r][]
-			// Phase 1: packed fp32 scan of the staged candidates; groups with a hit are recorded (sign bytes + pair index)
-			uint2 rec[CT2_LIST];
-			int nr = 0;
-			for (int dz = -1; dz <= 1; ++dz) {
-				// distance (in cells) from the particle to the nearest point of the neighbouring layer / row
-				const float zmin = dz < 0 ? fr[2] : (dz > 0 ? 1.f - fr[2] : 0.f);
-				const float remz = 0.501f - zmin * zmin; // (re / h)^2 = 1/2, plus a margin
-				if (remz <= 0.f) { continue; }
-				for (int dy = -1; dy <= 1; ++dy) {
-					const float ymin = dy < 0 ? fr[1] : (dy > 0 ? 1.f - fr[1] : 0.f);
-					const float rem = remz - ymin * ymin;
-					if (rem <= 0.f) { continue; }
-					const float xr = sqrtf(rem); // reach along x within this row: < 0.708 cells
-					const int klo = kown + (fr[0] - xr < 0.f ? -1 : 0);
-					const int khi = kown + (fr[0] + xr >= 1.f ? 2 : 1);
-					const int r = (oz + 1 + dz) * CT_SY + (oy + 1 + dy);
-					// pairs [g, g1): the window rounded outwards to pair boundaries -- the extra candidates are particles
-					// of the same row outside the window (farther than the radius) or the row's padding entry
-					uint32_t g = (rowoff[r] + cellbeg[r][klo]) >> 1;
-					const uint32_t g1 = (rowoff[r] + cellbeg[r][khi] + 1u) >> 1;
-					for (; g + 2 <= g1; g += 2) {
-						const ulonglong2 a0 = stage2[2 * g], b0 = stage2[2 * g + 1], a1 = stage2[2 * g + 2], b1 = stage2[2 * g + 3];
-						unsigned long long c0 = f32x2_fma(NRX, a0.x, b0.y);
-						unsigned long long c1 = f32x2_fma(NRX, a1.x, b1.y);
-						c0 = f32x2_fma(NRY, a0.y, c0);
-						c1 = f32x2_fma(NRY, a1.y, c1);
-						c0 = f32x2_fma(NRZ, b0.x, c0);
-						c1 = f32x2_fma(NRZ, b1.x, c1);
-						c0 = f32x2_add(c0, NT);
-						c1 = f32x2_add(c1, NT);
-						const unsigned t01 = __byte_perm((unsigned)c0, (unsigned)(c0 >> 32), 0x0073);
-						const unsigned t23 = __byte_perm((unsigned)c1, (unsigned)(c1 >> 32), 0x0073);
-						const unsigned sg = __byte_perm(t01, t23, 0x5410);
-						if (sg & 0x80808080u) {
-							rec[nr < CT2_LIST ? nr : CT2_LIST - 1] = make_uint2(sg & 0x80808080u, g);
-							++nr;
-						}
-					}
-					if (g < g1) {
-						const ulonglong2 a0 = stage2[2 * g], b0 = stage2[2 * g + 1];
-						unsigned long long c0 = f32x2_fma(NRX, a0.x, b0.y);
-						c0 = f32x2_fma(NRY, a0.y, c0);
-						c0 = f32x2_fma(NRZ, b0.x, c0);
-						c0 = f32x2_add(c0, NT);
-						const unsigned sg = __byte_perm((unsigned)c0, (unsigned)(c0 >> 32), 0x0073) & 0x8080u;
-						if (sg) {
-							rec[nr < CT2_LIST ? nr : CT2_LIST - 1] = make_uint2(sg, g);
-							++nr;
-						}
-					}
-				}
-			}
-			if (nr > CT2_LIST) { // more neighbour groups than the list holds (a clump): plain fp64 loop instead
-				spring_global(G, M, px, py, pz, begin, i, p, sx, sy, sz);
-			} else {
-				// Phase 2: the recorded candidates in staging order (= the reference's order: rows by z then y, cells by
-				// x, particles in sorted order), evaluated in fp64 from the original positions
-				int row = 0;
-				for (int k = 0; k < nr; ++k) {
-					const uint2 rc = rec[k];
-					unsigned m = rc.x;
-					while (m) {
-						const int b = __ffs((int)m) - 1; // bit 8 j + 7 <-> candidate j of the group
-						m &= m - 1u;
-						const uint32_t s = 2u * rc.y + (uint32_t)(b >> 3);
-						while (s >= rowoff[row + 1]) { ++row; }
-						const uint32_t j = rowstart[row] + (s - rowoff[row]);
-						if (j != (uint32_t)i) {
-							const double ov[3] = { px[j], py[j], pz[j] };
-							pair_exact(M, p, ov, sx, sy, sz);
-						}
-					}
-				}
-			}
-		}
-		double np3[3] = { p[0] + sx * M.corr_factor, p[1] + sy * M.corr_factor, p[2] + sz * M.corr_factor };
-#pragma unroll
-		for (int d = 0; d < 3; ++d) {
-			np3[d] = dclamp_std(np3[d], M.gmin[d], M.gmax[d]);
-		}
-		if (COLLIDE) {
-			collide_one(G, M, typ, p, np3);
-		}
-		nx_[i] = np3[0];
-		ny_[i] = np3[1];
-		nz_[i] = np3[2];
-	}
-}
-
-// ---- third variant: expanded-form fp32 pre-filter with per-row hit masks ------------------------------------------
-// Same tiling, culling and fp64 evaluation (reference order) as k_correct_tiled; what changes is the cost of a candidate
-// test, which is where k_correct_tiled spends its instructions (13.5 SASS instructions per candidate, ~250 candidate
-// slots per particle once warp divergence is counted):
-//   * staged entries are {x, y, z, w = |q|^2} in cell units relative to the tile centre; with n = -2 r the test
-//     |r - q|^2 < 1/2 + margin becomes  w + n.q < T,  T = 1/2 + margin - |r|^2: three FFMA and one compare;
-//   * hits are collected as BITS of a per-row mask with compile-time bit positions (one predicated OR per candidate)
-//     instead of a predicated store + index clamp + increment per candidate; a row window contributes one
-//     {mask, index of the window's first particle} record per 32 candidates to a short per-thread list;
-//   * every staged row is followed by CT3_PAD entries that can never hit, so the 4-wide groups need no tail handling
-//     (entries of the same row beyond the window may be tested: they are farther than the radius, fp64 gives them 0).
-// 7.5 instructions per candidate (cuobjdump).  The candidate's global index is row start + offset, so the index no longer needs
-// a staged word.  Rounding: as for k_correct_tiled2 (|coordinates| <= 17.1 cells, every intermediate below 620, error
-// below 4e-5 each); the margin of 2e-3 cells^2 covers their sum 10x over, so the filter never drops a true neighbour.
-#define CT3_PAD 3
-#define CT3_LIST 16
-
-// PREF: the next {mask, index} record is read from the per-thread list one refill ahead of its use (the refill's
-// local-memory load sat on the critical path of every phase-2 iteration: 9.7 % of the kernel's stall samples, ncu r1d).
-// CLS (experimental, lfk_set_tuning("correct", 4); not measured yet): the tile's own particles are handed to the
-// threads grouped by the part of their cell they sit in along y and z (lower / middle / upper third, 9 classes).  Which
-// of the 9 neighbour rows a particle has to scan depends on exactly that, so a warp of one class skips the rows its
-// class cannot reach, where a warp of 32 consecutive particles executes all 9 (a lane needs 5.4 on average; SIMT model
-// in DESIGN.md section 7).  A particle's result does not depend on the thread that computes it, so the output is
-// unchanged bit for bit.
-// GW (experimental, lfk_set_tuning("correct", 5): GW = 8; not measured yet): candidates per guarded group of the scan.
-// The first test of a group waits for the group's shared-memory loads (13.5 % of the kernel's stall samples, short
-// scoreboard); 8 instead of 4 candidates per group halve the number of such waits per candidate, at the price of up to
-// 4 more wasted slots per row window and 16 more live registers.  Rows are padded by GW - 1 never-hit entries.
-template <bool COLLIDE, bool PREF, bool CLS, int GW = 4> __global__ void __launch_bounds__(CT_THREADS, 2) k_correct_tiled3(GridDesc G, MotionParams M,
-	ParticleSoA P, double *__restrict__ nx_, double *__restrict__ ny_, double *__restrict__ nz_,
-	const uint32_t *__restrict__ begin, const uint8_t *__restrict__ typ) {
-	extern __shared__ float4 stage3[];
-	__shared__ uint32_t rowstart[CT_ROWS], rowoff[CT_ROWS + 1], cellbeg[CT_ROWS][CT_LX + 3];
-	__shared__ uint32_t ownbeg[CT_OWN], ownpre[CT_OWN + 1];
-	const double *__restrict__ px = P.f[PF_PX], *__restrict__ py = P.f[PF_PY], *__restrict__ pz = P.f[PF_PZ];
-	const int x0 = blockIdx.x * CT_LX, y0 = blockIdx.y * CT_TY, lz0 = blockIdx.z * CT_TZ + 1;
-	const int tid = threadIdx.x;
-
-	// ---- table of the staged rows (as in k_correct_tiled) ----
-	for (int e = tid; e < CT_ROWS * (CT_LX + 3); e += CT_THREADS) {
-		int r = e / (CT_LX + 3), k = e % (CT_LX + 3);
-		int y = y0 - 1 + r % CT_SY, lz = lz0 - 1 + r / CT_SY;
-		uint32_t v = 0;
-		if (y >= 0 && y < G.ny && lz >= 0 && lz < G.nlz) {
-			long long row = (long long)G.nx * (y + (long long)G.ny * lz);
-			int xa = x0 - 1 < 0 ? 0 : x0 - 1;
-			int xk = x0 - 1 + k;
-			xk = xk < 0 ? 0 : (xk > G.nx ? G.nx : xk);
-			uint32_t base = begin[row + xa];
-			v = begin[row + xk] - base;
-			if (k == 0) { rowstart[r] = base; }
-		} else if (k == 0) {
-			rowstart[r] = 0;
-		}
-		cellbeg[r][k] = v;
-	}
-	__syncthreads();
-	if (tid == 0) {
-		uint32_t acc = 0;
-		for (int r = 0; r < CT_ROWS; ++r) { // every row is followed by GW - 1 never-hit entries
-			rowoff[r] = acc;
-			acc += cellbeg[r][CT_LX + 2] + (GW - 1);
-		}
-		rowoff[CT_ROWS] = acc;
-		uint32_t oacc = 0;
-		for (int o = 0; o < CT_OWN; ++o) { // own rows: cells x0 .. x0 + LX - 1 (clipped) of the inner rows
-			int r = (o / CT_TY + 1) * CT_SY + (o % CT_TY + 1);
-			int y = y0 + o % CT_TY, lz = lz0 + o / CT_TY;
-			uint32_t nown = 0;
-			if (y < G.ny && lz <= G.nzl) {
-				nown = cellbeg[r][CT_LX + 1] - cellbeg[r][1];
-			}
-			ownbeg[o] = rowstart[r] + cellbeg[r][1];
-			ownpre[o] = oacc;
-			oacc += nown;
-		}
-		ownpre[CT_OWN] = oacc;
-	}
-	__syncthreads();
-	const uint32_t nown_total = ownpre[CT_OWN];
-	if (nown_total == 0) { return; }
-	const uint32_t staged = rowoff[CT_ROWS];
-	const bool use_stage = staged <= CT_CAP;
-	// tile centre, fp64; staged coordinates are relative to it, in cells
-	const double ctr[3] = { G.off[0] + ((double)x0 + 0.5 * CT_LX) * G.h, G.off[1] + ((double)y0 + 0.5 * CT_TY) * G.h,
-		G.off[2] + ((double)(lz0 - 1 + G.z0) + 0.5 * CT_TZ) * G.h };
-	if (use_stage) {
-		for (int r = 0; r < CT_ROWS; ++r) {
-			const uint32_t cnt = cellbeg[r][CT_LX + 2], gs = rowstart[r], so = rowoff[r];
-			for (uint32_t j = tid; j < cnt + (GW - 1); j += CT_THREADS) {
-				float4 e = make_float4(0.f, 0.f, 0.f, 1e30f); // padding: never within reach
-				if (j < cnt) {
-					const uint32_t q = gs + j;
-					e.x = (float)((px[q] - ctr[0]) * G.inv_h);
-					e.y = (float)((py[q] - ctr[1]) * G.inv_h);
-					e.z = (float)((pz[q] - ctr[2]) * G.inv_h);
-					e.w = __fmaf_rn(e.z, e.z, __fmaf_rn(e.y, e.y, e.x * e.x));
-				}
-				stage3[so + j] = e;
-			}
-		}
-	}
-	__syncthreads();
-	uint32_t *ownlist = reinterpret_cast<uint32_t *>(stage3 + CT_CAP); // [CT_CAP] own-particle indices by class (CLS)
-	__shared__ uint32_t ccount[9], ccursor[9];
-	const bool by_class = CLS && use_stage;
-	if (by_class) {
-		if (tid < 9) { ccount[tid] = 0; }
-		__syncthreads();
-		// class of own particle t from its staged coordinates (cell units about the tile centre, which lies on a cell
-		// boundary in y and z, so the fractional parts are the in-cell fractions)
-		auto own_class = [&](uint32_t t) {
-			int o = 0;
-#pragma unroll
-			for (int k = 1; k < CT_OWN; ++k) {
-				if (t >= ownpre[k]) { o = k; }
-			}
-			const int r = (o / CT_TY + 1) * CT_SY + (o % CT_TY + 1);
-			const float4 e = stage3[rowoff[r] + cellbeg[r][1] + (t - ownpre[o])];
-			const float fy = e.y - floorf(e.y), fz = e.z - floorf(e.z);
-			const int cy = fy <= 0.2922f ? 0 : (fy >= 0.7078f ? 2 : 1), cz = fz <= 0.2922f ? 0 : (fz >= 0.7078f ? 2 : 1);
-			return cz * 3 + cy;
-		};
-		for (uint32_t t = tid; t < nown_total; t += CT_THREADS) { atomicAdd(&ccount[own_class(t)], 1u); }
-		__syncthreads();
-		if (tid == 0) {
-			uint32_t acc = 0;
-			for (int k = 0; k < 9; ++k) {
-				ccursor[k] = acc;
-				acc += ccount[k];
-			}
-		}
-		__syncthreads();
-		for (uint32_t t = tid; t < nown_total; t += CT_THREADS) { ownlist[atomicAdd(&ccursor[own_class(t)], 1u)] = t; }
-		__syncthreads();
-	}
-
-	for (uint32_t tq = tid; tq < nown_total; tq += CT_THREADS) {
-		const uint32_t t = by_class ? ownlist[tq] : tq;
-		int o = 0;
-#pragma unroll
-		for (int k = 1; k < CT_OWN; ++k) {
-			if (t >= ownpre[k]) { o = k; }
-		}
-		const unsigned long long i = (unsigned long long)ownbeg[o] + (t - ownpre[o]);
-		const int oy = o % CT_TY, oz = o / CT_TY;
-		double p[3] = { px[i], py[i], pz[i] };
-		double sx = 0.0, sy = 0.0, sz = 0.0;
-		// unclamped cell and in-cell fraction (compute_cell_index)
-		long long ci[3];
-		float fr[3];
-#pragma unroll
-		for (int d = 0; d < 3; ++d) {
-			double f = div_h(p[d] - G.off[d], G);
-			unsigned long long u = (unsigned long long)f;
-			ci[d] = u > 0x7fffffffull ? 0x7fffffffll : (long long)u;
-			fr[d] = (float)(f - (double)u);
-		}
-		const bool in_tile = use_stage && ci[0] >= x0 && ci[0] < x0 + CT_LX && ci[0] < G.nx && ci[1] == y0 + oy &&
-			ci[2] == lz0 + oz - 1 + G.z0;
-		if (!in_tile) {
-			spring_global(G, M, px, py, pz, begin, i, p, sx, sy, sz);
-		} else {
-			const float rx = (float)((p[0] - ctr[0]) * G.inv_h), ry = (float)((p[1] - ctr[1]) * G.inv_h),
-				rz = (float)((p[2] - ctr[2]) * G.inv_h);
-			const float nrx = -2.f * rx, nry = -2.f * ry, nrz = -2.f * rz;
+			const float4 self = stage[so];
+			const float nrx = -2.f * self.x, nry = -2.f * self.y, nrz = -2.f * self.z;
 			// |r - q|^2 < 1/2 + margin  <=>  w + n.q < T
-			const float T = (0.5f + CT2_MARGIN) - __fmaf_rn(rz, rz, __fmaf_rn(ry, ry, rx * rx));
+			const float T = (0.5f + CT_MARGIN) - self.w;
 			const int kown = (int)(ci[0] - x0) + 1; // index of the particle's own cell in cellbeg[r][]
-			// Phase 1: fp32 scan of the staged candidates; per 32 candidates of a row window one {hit mask, index of the
-			// first particle} record
-			uint2 rec[CT3_LIST];
+			// Phase 1: fp32 scan of the staged candidates; per 32 candidates of a row window one {hit mask, staged index
+			// of the first candidate} record
+			uint2 rec[CT_LIST];
 			int nr = 0;
 			for (int dz = -1; dz <= 1; ++dz) {
 				// distance (in cells) from the particle to the nearest point of the neighbouring layer / row
@@ -1389,72 +906,59 @@ template <bool COLLIDE, bool PREF, bool CLS, int GW = 4> __global__ void __launc
 					const uint32_t w0 = cellbeg[r][klo];
 					uint32_t s = rowoff[r] + w0;
 					const uint32_t s1 = rowoff[r] + cellbeg[r][khi];
-					uint32_t jb = rowstart[r] + w0;
-					for (; s < s1; s += 32u, jb += 32u) {
-						const float4 *__restrict__ q = stage3 + s;
+					uint32_t jb0 = rowstart[r] + w0;
+					for (; s < s1; s += 32u, jb0 += 32u) {
+						const float4 *__restrict__ q = stage + s;
 						const uint32_t left = s1 - s; // candidates left in the window; groups of 4, at most 8 per mask
 						uint32_t mask = 0;
-#define CT3_TEST(e, bit) do { const float4 q_ = q[e]; \
+#define CT_TEST(e, bit) do { const float4 q_ = q[e]; \
 	const float t_ = __fmaf_rn(nrz, q_.z, __fmaf_rn(nry, q_.y, __fmaf_rn(nrx, q_.x, q_.w))); \
 	if (t_ < T) { mask |= (bit); } } while (0)
 #pragma unroll
-						for (int g = 0; g < 32 / GW; ++g) {
-							if ((uint32_t)(GW * g) < left) {
-								CT3_TEST(GW * g + 0, 1u << (GW * g + 0));
-								CT3_TEST(GW * g + 1, 1u << (GW * g + 1));
-								CT3_TEST(GW * g + 2, 1u << (GW * g + 2));
-								CT3_TEST(GW * g + 3, 1u << (GW * g + 3));
-								if (GW == 8) {
-									CT3_TEST(GW * g + 4, 1u << (GW * g + 4));
-									CT3_TEST(GW * g + 5, 1u << (GW * g + 5));
-									CT3_TEST(GW * g + 6, 1u << (GW * g + 6));
-									CT3_TEST(GW * g + 7, 1u << (GW * g + 7));
-								}
+						for (int g = 0; g < 8; ++g) {
+							if ((uint32_t)(4 * g) < left) {
+								CT_TEST(4 * g + 0, 1u << (4 * g + 0));
+								CT_TEST(4 * g + 1, 1u << (4 * g + 1));
+								CT_TEST(4 * g + 2, 1u << (4 * g + 2));
+								CT_TEST(4 * g + 3, 1u << (4 * g + 3));
 							}
 						}
-#undef CT3_TEST
+#undef CT_TEST
 						if (mask) {
-							rec[nr < CT3_LIST ? nr : CT3_LIST - 1] = make_uint2(mask, jb);
+							rec[nr < CT_LIST ? nr : CT_LIST - 1] = make_uint2(mask, jb0);
 							++nr;
 						}
 					}
 				}
 			}
-			if (nr > CT3_LIST) { // more records than the list holds (very crowded rows): plain fp64 loop instead
+			if (nr > CT_LIST) { // more records than the list holds (very crowded rows): plain fp64 loop instead
 				spring_global(G, M, px, py, pz, begin, i, p, sx, sy, sz);
-			} else if (nr > 0) {
-				// Phase 2: the recorded candidates in staging order (= the reference's order: rows by z then y, cells by x,
-				// particles in sorted order), evaluated in fp64 from the original positions; the next candidate's position
-				// is fetched one iteration ahead of its use
-				int k = 1;
-				uint32_t m = rec[0].x, jb = rec[0].y;
-				uint2 nxt = make_uint2(0u, 0u);
-				if (PREF && nr > 1) { nxt = rec[1]; }
-				uint32_t j = jb + (uint32_t)(__ffs((int)m) - 1);
-				m &= m - 1u;
-				double ov[3] = { px[j], py[j], pz[j] };
-				for (;;) {
-					if (m == 0u && k < nr) {
-						if (PREF) {
-							m = nxt.x;
-							jb = nxt.y;
-							++k;
-							if (k < nr) { nxt = rec[k]; }
-						} else {
-							m = rec[k].x;
-							jb = rec[k].y;
-							++k;
-						}
+			} else {
+				// Phase 2: the recorded candidates in staging order, fp64, from the original positions; the next
+				// candidate's position is fetched one iteration ahead of its use
+				int k = 0;
+				uint32_t m = 0, jb = 0;
+				auto next_hit = [&](uint32_t &j) -> bool { // advances to the next recorded candidate
+					while (m == 0u) {
+						if (k >= nr) { return false; }
+						m = rec[k].x;
+						jb = rec[k].y;
+						++k;
 					}
-					const bool more = m != 0u;
+					j = jb + (uint32_t)(__ffs((int)m) - 1);
+					m &= m - 1u;
+					return true;
+				};
+				uint32_t j = 0;
+				bool have = next_hit(j);
+				double ov[3] = { 0.0, 0.0, 0.0 };
+				if (have) { ov[0] = px[j]; ov[1] = py[j]; ov[2] = pz[j]; }
+				while (have) {
 					uint32_t jn = (uint32_t)i;
-					if (more) {
-						jn = jb + (uint32_t)(__ffs((int)m) - 1);
-						m &= m - 1u;
-					}
+					const bool more = next_hit(jn);
 					const double on[3] = { px[jn], py[jn], pz[jn] };
 					if (j != (uint32_t)i) { pair_exact(M, p, ov, sx, sy, sz); }
-					if (!more) { break; }
+					have = more;
 					j = jn;
 					ov[0] = on[0];
 					ov[1] = on[1];
@@ -1485,70 +989,18 @@ static int correct_impl(lfk_ctx *c, double dt, bool fuse_collide) {
 	dim3 grid((unsigned)((G.nx + CT_LX - 1) / CT_LX), (unsigned)((G.ny + CT_TY - 1) / CT_TY),
 		(unsigned)((G.nzl + CT_TZ - 1) / CT_TZ));
 	const size_t smem = (size_t)CT_CAP * sizeof(float4);
-	const size_t smem_cls = smem + (size_t)CT_CAP * sizeof(uint32_t); // + the class-sorted own-particle list
 	static bool attr_set[LFK_MAX_DEVICES] = {}; // function attributes are per device
 	if (!attr_set[c->device % LFK_MAX_DEVICES]) {
-		LFK_CUDA(c, cudaFuncSetAttribute(k_correct_tiled<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-		LFK_CUDA(c, cudaFuncSetAttribute(k_correct_tiled<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-		LFK_CUDA(c, cudaFuncSetAttribute(k_correct_tiled2<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-		LFK_CUDA(c, cudaFuncSetAttribute(k_correct_tiled2<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-		LFK_CUDA(c, cudaFuncSetAttribute((k_correct_tiled3<true, false, false>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-		LFK_CUDA(c, cudaFuncSetAttribute((k_correct_tiled3<false, false, false>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-		LFK_CUDA(c, cudaFuncSetAttribute((k_correct_tiled3<true, true, false>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-		LFK_CUDA(c, cudaFuncSetAttribute((k_correct_tiled3<false, true, false>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-		LFK_CUDA(c, cudaFuncSetAttribute((k_correct_tiled3<true, false, false, 8>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-		LFK_CUDA(c, cudaFuncSetAttribute((k_correct_tiled3<false, false, false, 8>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-		LFK_CUDA(c, cudaFuncSetAttribute((k_correct_tiled3<true, false, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cls));
-		LFK_CUDA(c, cudaFuncSetAttribute((k_correct_tiled3<false, false, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cls));
+		LFK_CUDA(c, cudaFuncSetAttribute(k_correct_tile<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+		LFK_CUDA(c, cudaFuncSetAttribute(k_correct_tile<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
 		attr_set[c->device % LFK_MAX_DEVICES] = true;
 	}
-	const bool packed = c->tune.correct == 1; // A/B: packed-fp32 pre-filter (42.6 ms at 256^3; 0 = scalar pre-filter, 30.2 ms)
 	if (!fuse_collide) { LFK_TRY(materialise_old(c)); }
-	if (c->tune.correct == 2) { // production: expanded-form pre-filter with per-row hit masks (27.7 ms at 256^3, r1d sweep)
-		if (fuse_collide) {
-			LFK_LAUNCH(c, (k_correct_tiled3<true, false, false>), grid, CT_THREADS, smem, G, M, c->P, c->Palt.f[PF_PX], c->Palt.f[PF_PY],
-				c->Palt.f[PF_PZ], c->begin, c->typ);
-		} else {
-			LFK_LAUNCH(c, (k_correct_tiled3<false, false, false>), grid, CT_THREADS, smem, G, M, c->P, c->Palt.f[PF_PX], c->Palt.f[PF_PY],
-				c->Palt.f[PF_PZ], c->begin, c->typ);
-		}
-	} else if (c->tune.correct == 5) { // experimental: as 2, 8 candidates per guarded group
-		if (fuse_collide) {
-			LFK_LAUNCH(c, (k_correct_tiled3<true, false, false, 8>), grid, CT_THREADS, smem, G, M, c->P, c->Palt.f[PF_PX],
-				c->Palt.f[PF_PY], c->Palt.f[PF_PZ], c->begin, c->typ);
-		} else {
-			LFK_LAUNCH(c, (k_correct_tiled3<false, false, false, 8>), grid, CT_THREADS, smem, G, M, c->P, c->Palt.f[PF_PX],
-				c->Palt.f[PF_PY], c->Palt.f[PF_PZ], c->begin, c->typ);
-		}
-	} else if (c->tune.correct == 4) { // experimental: as 2, own particles grouped by (y, z) reach class
-		if (fuse_collide) {
-			LFK_LAUNCH(c, (k_correct_tiled3<true, false, true>), grid, CT_THREADS, smem_cls, G, M, c->P, c->Palt.f[PF_PX],
-				c->Palt.f[PF_PY], c->Palt.f[PF_PZ], c->begin, c->typ);
-		} else {
-			LFK_LAUNCH(c, (k_correct_tiled3<false, false, true>), grid, CT_THREADS, smem_cls, G, M, c->P, c->Palt.f[PF_PX],
-				c->Palt.f[PF_PY], c->Palt.f[PF_PZ], c->begin, c->typ);
-		}
-	} else if (c->tune.correct == 3) { // A/B: as 2, records read one refill ahead
-		if (fuse_collide) {
-			LFK_LAUNCH(c, (k_correct_tiled3<true, true, false>), grid, CT_THREADS, smem, G, M, c->P, c->Palt.f[PF_PX], c->Palt.f[PF_PY],
-				c->Palt.f[PF_PZ], c->begin, c->typ);
-		} else {
-			LFK_LAUNCH(c, (k_correct_tiled3<false, true, false>), grid, CT_THREADS, smem, G, M, c->P, c->Palt.f[PF_PX], c->Palt.f[PF_PY],
-				c->Palt.f[PF_PZ], c->begin, c->typ);
-		}
-	} else if (packed) {
-		if (fuse_collide) {
-			LFK_LAUNCH(c, k_correct_tiled2<true>, grid, CT_THREADS, smem, G, M, c->P, c->Palt.f[PF_PX], c->Palt.f[PF_PY],
-				c->Palt.f[PF_PZ], c->begin, c->typ);
-		} else {
-			LFK_LAUNCH(c, k_correct_tiled2<false>, grid, CT_THREADS, smem, G, M, c->P, c->Palt.f[PF_PX], c->Palt.f[PF_PY],
-				c->Palt.f[PF_PZ], c->begin, c->typ);
-		}
-	} else if (fuse_collide) {
-		LFK_LAUNCH(c, k_correct_tiled<true>, grid, CT_THREADS, smem, G, M, c->P, c->Palt.f[PF_PX], c->Palt.f[PF_PY],
+	if (fuse_collide) {
+		LFK_LAUNCH(c, k_correct_tile<true>, grid, CT_THREADS, smem, G, M, c->P, c->Palt.f[PF_PX], c->Palt.f[PF_PY],
 			c->Palt.f[PF_PZ], c->begin, c->typ);
 	} else {
-		LFK_LAUNCH(c, k_correct_tiled<false>, grid, CT_THREADS, smem, G, M, c->P, c->Palt.f[PF_PX], c->Palt.f[PF_PY],
+		LFK_LAUNCH(c, k_correct_tile<false>, grid, CT_THREADS, smem, G, M, c->P, c->Palt.f[PF_PX], c->Palt.f[PF_PY],
 			c->Palt.f[PF_PZ], c->begin, c->typ);
 	}
 	for (int d = 0; d < 3; ++d) {

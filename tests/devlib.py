@@ -31,9 +31,12 @@ def context_for(meta_or_ref, **kw):
 
 
 def canon(parts):
-    """canonical particle order: by cell key, then position bits (the reference's in-cell order is unspecified)"""
-    p = parts["position"]
-    return np.lexsort((p[:, 2], p[:, 1], p[:, 0], parts["raw_cell_index"]))
+    """canonical particle order: by cell key, then position, then velocity and c rows (the reference's in-cell order is
+    unspecified; particles clamped into the same wall corner coincide and differ only in their payload)"""
+    p, v = parts["position"], parts["velocity"]
+    keys = [parts[f][:, k] for f in ("cz", "cy", "cx") for k in (2, 1, 0)]
+    keys += [v[:, 2], v[:, 1], v[:, 0], p[:, 2], p[:, 1], p[:, 0], parts["raw_cell_index"]]
+    return np.lexsort(tuple(keys))
 
 
 def check_device_against_record(ctx, rec, orc, exact=False):

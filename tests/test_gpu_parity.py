@@ -14,11 +14,6 @@ from pinlib import OB, RB
 
 pytestmark = pytest.mark.gpu
 
-# LFK_TEST_EXPERIMENTAL=1 also runs the kernel variants that are written but have never been on a GPU (DESIGN.md
-# section 7): position correction 4 (class-grouped) and 5 (8-wide groups), G2P 2 (interior indexing), multigrid fp16 level-0 storage
-EXPERIMENTAL = os.environ.get("LFK_TEST_EXPERIMENTAL") == "1"
-
-
 def load_golden(scene):
     z = np.load(os.path.join(PL.GOLDEN_DIR, scene + ".npz"))
     rec = {k: z[k] for k in z.files}
@@ -206,30 +201,30 @@ def _device_scene(n=40, method=capi.APIC, **kw):
 
 @pytest.mark.parametrize("method", [capi.APIC, capi.FLIP, capi.PIC])
 def test_p2g_kernel_variants_agree(method):
-    """the z-marching P2G kernel (production) against the brick kernel and the plain gather kernel on the same
-    sorted state, through the staged call (velocity rows in place) and inside the fused step (lean sort: rows read
-    through the permutation); cell types exact, faces to summation-order rounding"""
+    """the z-marching P2G kernel (production) against the plain gather kernel (the reference's per-cell loop) on the
+    same sorted state, through the staged call (velocity rows in place) and inside the fused step (lean sort: rows
+    read through the permutation); cell types exact, faces to summation-order rounding"""
     ctx = _device_scene(method=method, blending_factor=0.95)
     for _ in range(4):
         ctx.time_step()
     ctx.hash()
     outs = {}
-    for name, v in (("march", 0), ("brick", 1), ("gather", 2)):
+    for name, v in (("march", 0), ("gather", 2)):
         ctx.set_tuning("p2g", v)
         ctx.p2g()
         outs[name] = ctx.download_cells().copy()
         if method == capi.FLIP:
             outs[name + "/old"] = ctx.download_old_cells().copy()
-    for other in ("brick", "gather"):
+    for other in ("gather",):
         assert np.array_equal(outs["march"]["type"], outs[other]["type"])
         assert PL.rel_l2(outs["march"]["vel"], outs[other]["vel"]) < 1e-13, other
         if method == capi.FLIP:
             assert PL.rel_l2(outs["march/old"]["vel"], outs[other + "/old"]["vel"]) < 1e-13, other
     assert np.abs(outs["march"]["vel"]).max() > 1.0  # a moving fluid, not an empty comparison
-    # fused steps: march against brick from the same state
+    # fused steps: march against gather from the same state
     parts, cells = ctx.download_particles().copy(), outs["march"]
     res = []
-    for v in (0, 1):
+    for v in (0, 2):
         ctx.set_tuning("p2g", v)
         ctx.set_tuning("warm_start", 0)
         ctx.upload_cells(cells)
@@ -243,88 +238,6 @@ def test_p2g_kernel_variants_agree(method):
     for f in ("position", "velocity", "cx", "cy", "cz"):
         assert PL.rel_l2(pa[f], pb[f]) < 1e-9, f  # two solves in between: agreement to solver tolerance
     ctx.close()
-
-
-def test_position_correction_variants_agree():
-    """scalar fp32 pre-filter (production) against the packed-fp32 and the hit-mask variants: all of them only select
-    candidates for the same fp64 evaluation in the same order, so the corrected positions are bit-identical"""
-    ctx = _device_scene()
-    for _ in range(4):
-        ctx.time_step()
-    ctx.hash()
-    parts = ctx.download_particles().copy()
-    outs = []
-    variants = (0, 1, 2, 3) + ((4, 5) if EXPERIMENTAL else ())
-    for v in variants:
-        ctx.set_tuning("correct", v)
-        ctx.upload_particles(parts)
-        ctx.hash()
-        ctx.correct(0.004)
-        outs.append(ctx.download_particles().copy())
-    for k in range(1, len(variants)):
-        assert np.array_equal(outs[0]["position"].view("u8"), outs[k]["position"].view("u8")), variants[k]
-    moved = np.abs(outs[0]["position"] - parts[np.argsort(parts["raw_cell_index"], kind="stable")]["position"]).max()
-    assert moved > 1e-6
-    # the same inside the fused step (correction + second collision pass in one kernel)
-    res = []
-    fused = (0, 2, 3) + ((4, 5) if EXPERIMENTAL else ())
-    for v in fused:
-        ctx.set_tuning("correct", v)
-        ctx.set_tuning("warm_start", 0)
-        ctx.upload_particles(parts)
-        for _ in range(2):
-            ctx.time_step(0.002)
-        res.append(ctx.download_particles().copy())
-    for k in range(1, len(fused)):
-        for f in ("position", "velocity"):
-            assert np.array_equal(res[0][f].view("u8"), res[k][f].view("u8")), (fused[k], f)
-    ctx.close()
-
-
-@pytest.mark.parametrize("method", [capi.APIC, capi.FLIP, capi.PIC])
-def test_g2p_and_advection_variants_agree(method):
-    """latency-hiding variants (all face samples requested before the first store; two particles per thread in the
-    fused advect + collide kernel) do the same arithmetic per particle: bit-identical particle state after fused
-    steps from the same state, for every transfer method"""
-    ctx = _device_scene(method=method, blending_factor=0.95)
-    for _ in range(3):
-        ctx.time_step()
-    parts, cells = ctx.download_particles().copy(), ctx.download_cells().copy()
-    res = []
-    combos = ((0, 0), (1, 0), (0, 1), (1, 1)) + (((2, 0),) if EXPERIMENTAL else ())
-    for g2p, adv in combos:
-        ctx.set_tuning("g2p", g2p)
-        ctx.set_tuning("advect", adv)
-        ctx.set_tuning("warm_start", 0)
-        ctx.upload_cells(cells)
-        ctx.upload_particles(parts)
-        for _ in range(3):
-            ctx.time_step(0.002)
-        res.append(ctx.download_particles().copy())
-    assert np.abs(res[0]["velocity"]).max() > 1.0
-    for k in range(1, len(combos)):
-        for f in ("position", "velocity", "cx", "cy", "cz"):
-            assert np.array_equal(res[0][f].view("u8"), res[k][f].view("u8")), (combos[k], f)
-    ctx.close()
-
-
-@pytest.mark.skipif(not EXPERIMENTAL, reason="fp16 level-0 multigrid storage has not been on a GPU yet (LFK_TEST_EXPERIMENTAL=1)")
-def test_mg_half_storage_reaches_the_same_tolerance():
-    """fp16 storage of the multigrid level-0 vectors only changes the preconditioner's rounding: same tolerance, about
-    the same iteration count, pressure equal to solver accuracy"""
-    n = 96
-    out = []
-    for half in (0, 1):
-        ctx = capi.Context((n, n, n), cell_size=1.0, max_iterations=2000)
-        ctx.set_tuning("mg_half", half)
-        ctx.synthetic_projection_device(seed=5)
-        res, iters = ctx.pressure_solve(1.0 / 60.0)
-        assert res < 1e-6 and 0 < iters < 100
-        out.append((ctx.download_pressure().copy(), iters))
-        ctx.close()
-    (pa, ia), (pb, ib) = out
-    assert ib <= ia + 3, (ia, ib)
-    assert PL.rel_l2(pa, pb) < 1e-5
 
 
 def test_warm_started_solve_reaches_the_same_tolerance():

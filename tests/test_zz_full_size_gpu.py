@@ -21,7 +21,7 @@ def test_full_size_step_properties_256():
     import bench as B
     n = 256
     ctx = capi.Context((n, n, n), cell_size=1.0, gravity=B.GRAVITY, method=capi.APIC, max_iterations=1000)
-    for k, (start, size) in enumerate(B.scene_boxes(n, n)):
+    for k, (start, size) in enumerate(B.scene_boxes(n, n, n)):
         ctx.seed_box_device(start, size, density=2, seed=20261017, append=k > 0)
     np0 = ctx.num_particles()
     assert np0 > 120_000_000

@@ -16,25 +16,11 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
-NEW = {"p2g": 0, "correct": 2, "g2p": 0, "advect": 0, "mg_half": 0, "mg_tail": 0, "warm_start": 1, "red_blocks": 0}  # the library defaults
-OLD = {"p2g": 1, "correct": 0, "g2p": 0, "advect": 0, "mg_half": 0, "mg_tail": 1, "warm_start": 0, "red_blocks": 16384}  # round r1b
+NEW = {"p2g": 0, "warm_start": 1, "red_blocks": 0}  # the library defaults
 CONFIGS = [
     ("defaults", dict(NEW)),
-    ("defaults+correct_scalar", dict(NEW, correct=0)),
-    ("defaults+correct_prefetch", dict(NEW, correct=3)),
-    ("defaults+mg_half", dict(NEW, mg_half=1)),  # experimental fp16 level-0 multigrid vectors: check residual / iterations
-    ("defaults+correct_classes", dict(NEW, correct=4)),
-    ("defaults+correct_wide", dict(NEW, correct=5)),  # experimental: 8 candidates per guarded group  # experimental: check bit-identity first (tests: add 4 to the variants list)
-    ("defaults+g2p_batch", dict(NEW, g2p=1)),
-    ("defaults+g2p_interior", dict(NEW, g2p=2)),  # experimental: add (2, 0) to test_g2p_and_advection_variants_agree first
-    ("defaults+advect_pair", dict(NEW, advect=1)),
-    ("defaults+all_new", dict(NEW, correct=3, g2p=1, advect=1)),
-    ("defaults+p2g_brick", dict(NEW, p2g=1)),
-    ("defaults+red_blocks_592", dict(NEW, red_blocks=592)),
-    ("defaults+red_blocks_2368", dict(NEW, red_blocks=2368)),
     ("defaults+cold_start", dict(NEW, warm_start=0)),
-    ("defaults+mg_tail_global", dict(NEW, mg_tail=1)),
-    ("r1b", dict(OLD)),
+    ("defaults+p2g_gather", dict(NEW, p2g=2)),
 ]
 
 
@@ -54,7 +40,7 @@ def main():
     n = args.grid
     ctx = capi.Context((n, n, n), device=0, cell_size=1.0, gravity=B.GRAVITY, method=capi.APIC,
                        max_iterations=1000, preconditioner=capi.PRECOND_MULTIGRID)
-    for k, (start, size) in enumerate(B.scene_boxes(n, n)):
+    for k, (start, size) in enumerate(B.scene_boxes(n, n, n)):
         ctx.seed_box_device(start, size, density=2, seed=20261017, append=k > 0)
     npart = ctx.num_particles()
     for key, val in NEW.items():
