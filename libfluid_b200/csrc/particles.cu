@@ -1064,43 +1064,73 @@ int lfkp_cfl(lfk_ctx *c, double *value) {
 // Synthetic seeding (bench scenes): jittered sub-cell sampling like simulation::seed_func
 // (reference include/fluid/simulation.h:80-115), with a counter-based hash RNG instead of pcg32.
 // =========================================================================================================
-__global__ void k_seed_box(GridDesc G, ParticleSoA P, uint32_t *__restrict__ key, int cx0, int cy0, int cz0,
-	int ex, int ey, int ez, double s0, double s1, double s2, double e0, double e1, double e2, double vx, double vy,
-	double vz, uint32_t dens, unsigned long long seed, unsigned long long base, unsigned long long *__restrict__ counter,
-	unsigned long long capacity) {
-	unsigned long long per_cell = (unsigned long long)dens * dens * dens;
-	unsigned long long total = (unsigned long long)ex * ey * ez * per_cell;
-	unsigned long long tid = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
-	if (tid >= total) { return; }
-	unsigned long long sub = tid % per_cell, cell = tid / per_cell;
-	int x = cx0 + (int)(cell % ex), y = cy0 + (int)((cell / ex) % ey), z = cz0 + (int)(cell / ((unsigned long long)ex * ey));
+// candidate `tid` of the seeding lattice: its position, and whether it lies strictly inside the box
+struct SeedBox {
+	int cx0, cy0, cz0, ex, ey, ez;
+	double s0, s1, s2, e0, e1, e2, vx, vy, vz;
+	uint32_t dens;
+	unsigned long long seed;
+};
+__device__ __forceinline__ bool seed_candidate(const GridDesc &G, const SeedBox &B, unsigned long long tid,
+	double *pos, uint32_t *key) {
+	const unsigned long long per_cell = (unsigned long long)B.dens * B.dens * B.dens;
+	const unsigned long long total = (unsigned long long)B.ex * B.ey * B.ez * per_cell;
+	if (tid >= total) { return false; }
+	const unsigned long long sub = tid % per_cell, cell = tid / per_cell;
+	const int x = B.cx0 + (int)(cell % B.ex), y = B.cy0 + (int)((cell / B.ex) % B.ey),
+		z = B.cz0 + (int)(cell / ((unsigned long long)B.ex * B.ey));
 	// reference loop nest: sx outermost, sz innermost
-	int sz_ = (int)(sub % dens), sy_ = (int)((sub / dens) % dens), sx_ = (int)(sub / ((unsigned long long)dens * dens));
-	double small = G.h / (double)dens;
-	unsigned long long gid = ((unsigned long long)(x + (long long)G.nx * (y + (long long)G.ny * z))) * per_cell + sub;
-	unsigned long long r = mix64(seed ^ mix64(gid + 0x9e3779b97f4a7c15ull));
+	const int sz_ = (int)(sub % B.dens), sy_ = (int)((sub / B.dens) % B.dens),
+		sx_ = (int)(sub / ((unsigned long long)B.dens * B.dens));
+	const double small = G.h / (double)B.dens;
+	const unsigned long long gid = ((unsigned long long)(x + (long long)G.nx * (y + (long long)G.ny * z))) * per_cell + sub;
+	unsigned long long r = mix64(B.seed ^ mix64(gid + 0x9e3779b97f4a7c15ull));
 	double j[3];
 #pragma unroll
 	for (int d = 0; d < 3; ++d) {
 		r = mix64(r + 0x9e3779b97f4a7c15ull);
 		j[d] = (double)(r >> 11) * (1.0 / 9007199254740992.0) * small;
 	}
-	double px = G.off[0] + (double)x * G.h + (double)sx_ * small + j[0];
-	double py = G.off[1] + (double)y * G.h + (double)sy_ * small + j[1];
-	double pz = G.off[2] + (double)z * G.h + (double)sz_ * small + j[2];
-	if (!(px > s0 && py > s1 && pz > s2 && px < e0 && py < e1 && pz < e2)) { return; }
-	unsigned long long slot = atomicAdd(counter, 1ull);
-	if (base + slot >= capacity) { return; }
-	unsigned long long i = base + slot;
-	P.f[PF_PX][i] = px;
-	P.f[PF_PY][i] = py;
-	P.f[PF_PZ][i] = pz;
-	P.f[PF_VX][i] = vx;
-	P.f[PF_VY][i] = vy;
-	P.f[PF_VZ][i] = vz;
+	pos[0] = G.off[0] + (double)x * G.h + (double)sx_ * small + j[0];
+	pos[1] = G.off[1] + (double)y * G.h + (double)sy_ * small + j[1];
+	pos[2] = G.off[2] + (double)z * G.h + (double)sz_ * small + j[2];
+	*key = (uint32_t)(x + (long long)G.nx * (y + (long long)G.ny * (z - G.z0 + 1)));
+	return pos[0] > B.s0 && pos[1] > B.s1 && pos[2] > B.s2 && pos[0] < B.e0 && pos[1] < B.e1 && pos[2] < B.e2;
+}
+// Two passes so that the particle ORDER is a pure function of the scene (lattice order), not of the scheduling of an
+// atomic slot counter: run-to-run and rank-to-rank identical arrays.
+#define SEED_THREADS 1024
+__global__ void __launch_bounds__(SEED_THREADS) k_seed_count(GridDesc G, SeedBox B, uint32_t *__restrict__ block_cnt) {
+	const unsigned long long tid = (unsigned long long)blockIdx.x * SEED_THREADS + threadIdx.x;
+	double pos[3];
+	uint32_t key;
+	const int n = __syncthreads_count(seed_candidate(G, B, tid, pos, &key));
+	if (threadIdx.x == 0) { block_cnt[blockIdx.x] = (uint32_t)n; }
+}
+__global__ void __launch_bounds__(SEED_THREADS) k_seed_write(GridDesc G, SeedBox B, ParticleSoA P,
+	uint32_t *__restrict__ keyout, const uint32_t *__restrict__ block_off, unsigned long long base) {
+	__shared__ uint32_t warp_tot[32];
+	const unsigned long long tid = (unsigned long long)blockIdx.x * SEED_THREADS + threadIdx.x;
+	double pos[3];
+	uint32_t key;
+	const bool in = seed_candidate(G, B, tid, pos, &key);
+	const unsigned bal = __ballot_sync(0xffffffffu, in);
+	const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+	if (lane == 0) { warp_tot[w] = (uint32_t)__popc(bal); }
+	__syncthreads();
+	if (!in) { return; }
+	uint32_t before = 0;
+	for (int k = 0; k < w; ++k) { before += warp_tot[k]; }
+	const unsigned long long i = base + block_off[blockIdx.x] + before + (uint32_t)__popc(bal & ((1u << lane) - 1u));
+	P.f[PF_PX][i] = pos[0];
+	P.f[PF_PY][i] = pos[1];
+	P.f[PF_PZ][i] = pos[2];
+	P.f[PF_VX][i] = B.vx;
+	P.f[PF_VY][i] = B.vy;
+	P.f[PF_VZ][i] = B.vz;
 #pragma unroll
 	for (int f = PF_C0; f < PF_C0 + 9; ++f) { P.f[f][i] = 0.0; }
-	key[i] = (uint32_t)(x + (long long)G.nx * (y + (long long)G.ny * (z - G.z0 + 1)));
+	keyout[i] = key;
 }
 
 int lfkp_seed_box(lfk_ctx *c, const double *start, const double *size, const double *vel, uint32_t dens,
@@ -1133,16 +1163,37 @@ int lfkp_seed_box(lfk_ctx *c, const double *start, const double *size, const dou
 	unsigned long long per_cell = (unsigned long long)dens * dens * dens;
 	unsigned long long total = (unsigned long long)ex * ey * ez * per_cell;
 	LFK_TRY(lfkp_reserve_particles(c, c->np + total));
-	unsigned long long *counter = (unsigned long long*)c->d_reduce;
-	LFK_CUDA(c, cudaMemsetAsync(counter, 0, sizeof(unsigned long long), c->stream));
-	LFK_LAUNCH(c, k_seed_box, lfk_blocks((long long)total, 256), 256, 0, G, lfk_own_view(c), c->key + c->first, c0[0], c0[1], c0[2],
-		(int)ex, (int)ey, (int)ez, start[0], start[1], start[2], end[0], end[1], end[2], vel[0], vel[1], vel[2],
-		dens, (unsigned long long)seed, (unsigned long long)c->np, counter, (unsigned long long)(c->cap - c->first));
-	LFK_CUDA(c, cudaMemcpyAsync(c->h_reduce, counter, sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->stream));
-	LFK_CUDA(c, cudaStreamSynchronize(c->stream));
-	unsigned long long added;
-	memcpy(&added, c->h_reduce, sizeof(added));
-	c->np += added;
+	SeedBox B;
+	B.cx0 = c0[0]; B.cy0 = c0[1]; B.cz0 = c0[2];
+	B.ex = (int)ex; B.ey = (int)ey; B.ez = (int)ez;
+	B.s0 = start[0]; B.s1 = start[1]; B.s2 = start[2];
+	B.e0 = end[0]; B.e1 = end[1]; B.e2 = end[2];
+	B.vx = vel[0]; B.vy = vel[1]; B.vz = vel[2];
+	B.dens = dens;
+	B.seed = (unsigned long long)seed;
+	const unsigned nb = lfk_blocks((long long)total, SEED_THREADS);
+	uint32_t *cnt = nullptr; // [nb + 1] counts, [nb + 1] offsets
+	LFK_CUDA(c, cudaMalloc((void**)&cnt, 2 * ((size_t)nb + 1) * sizeof(uint32_t)));
+	uint32_t *off = cnt + nb + 1;
+	int rc = 0;
+	do {
+		k_seed_count<<<nb, SEED_THREADS, 0, c->stream>>>(G, B, cnt);
+		++c->stats.kernel_launches;
+		if ((rc = lfkp_exclusive_scan_u32(c, cnt, off, nb, 0)) != 0) { break; }
+		k_seed_write<<<nb, SEED_THREADS, 0, c->stream>>>(G, B, lfk_own_view(c), c->key + c->first, off,
+			(unsigned long long)c->np);
+		++c->stats.kernel_launches;
+		uint32_t h = 0;
+		cudaError_t e = cudaMemcpyAsync(&h, off + nb, sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream);
+		if (e == cudaSuccess) { e = cudaStreamSynchronize(c->stream); }
+		if (e == cudaSuccess) { e = cudaGetLastError(); }
+		if (e != cudaSuccess) { rc = lfk_fail(c, -(int)e, cudaGetErrorString(e), __FILE__, __LINE__); break; }
+		c->np += h;
+	} while (0);
+	cudaFree(cnt);
+	LFK_TRY(rc);
+	c->ntot = c->np;
+
 	c->old_valid = false;
 	c->table_valid = false;
 	c->keys_valid = false;

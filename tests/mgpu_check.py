@@ -55,6 +55,7 @@ def main():
         if by_id:
             allp = whole.download_particles()
             allp["cx"][:, 0] = np.arange(allp.shape[0], dtype=np.float64)
+            allp["cy"] = allp["position"]  # a second carried tag: where the particle started
             whole.upload_particles(allp)
             zc0 = slabs.z_cell(allp["position"][:, 2], n[2])
             multi.upload_particles(allp[(zc0 >= z0) & (zc0 < z1)])
@@ -85,15 +86,26 @@ def main():
                     continue
                 vmax = max(1.0, np.abs(b["velocity"]).max())
                 if by_id:
+                    for nm, q in (("slab", a), ("whole-scene", b)):  # the payload must have travelled WITH its particle
+                        far = np.abs(q["position"] - q["cy"]).max(axis=1) > 1.5 * (step + 1) + 1.0
+                        if far.any():
+                            failures.append("%s: %s run: %d particles carry another particle's payload" % (tag, nm, int(far.sum())))
                     ids = np.rint(a["cx"][:, 0]).astype(np.int64)
                     order = np.argsort(np.rint(b["cx"][:, 0]).astype(np.int64))
                     if np.unique(ids).size != ids.size or ids.min() < 0 or ids.max() >= b.shape[0]:
                         failures.append("%s: particle ids are not a subset of the whole scene's" % tag)
                         continue
+                    bids = np.rint(b["cx"][:, 0]).astype(np.int64)
+                    if not np.array_equal(bids[order], np.arange(b.shape[0])):
+                        failures.append("%s: the whole-scene run lost its particle ids" % tag)
+                        continue
                     idx = order[ids]
                     d = np.abs(a["position"] - b["position"][idx]).max(axis=1)
                     if d.max() > 1e-6:
-                        failures.append("%s: positions differ by id (max %.3e)" % (tag, d.max()))
+                        w = int(np.argmax(d))
+                        failures.append("%s: positions differ by id (max %.3e; %d of %d particles off; worst id %d at %s vs %s, "
+                                        "z cell %d, slab %d..%d)" % (tag, d.max(), int((d > 1e-6).sum()), d.size, ids[w],
+                                                                     a["position"][w], b["position"][idx[w]], zc[w], z0, z1))
                         continue
                 else:
                     d, idx = cKDTree(b["position"]).query(a["position"])

@@ -262,6 +262,30 @@ def test_warm_started_solve_reaches_the_same_tolerance():
     assert ia <= ib + 6, (ia, ib)
 
 
+@pytest.mark.parametrize("method", [capi.FLIP, capi.PIC])
+def test_untouched_payload_travels_with_its_particle(method):
+    """PIC / FLIP never write the APIC c rows, so they are carried payload: after sorts (lean and full), fused and
+    staged steps every particle must still hold the c rows it was uploaded with (tagged with an id and its start)"""
+    ctx = _device_scene(n=24, method=method, blending_factor=0.95)
+    parts = ctx.download_particles().copy()
+    parts["cx"][:, 0] = np.arange(parts.shape[0])
+    parts["cy"] = parts["position"]
+    ctx.upload_particles(parts)
+    for step in range(4):
+        if step == 2:  # one step through the staged API (full sort)
+            dt = 0.002
+            ctx.advect(dt); ctx.collide(); ctx.hash(); ctx.p2g(); ctx.gravity(dt); ctx.pressure_solve(dt)
+            ctx.apply_pressure(dt); ctx.correct(dt); ctx.collide(); ctx.extrapolate(); ctx.g2p()
+        else:
+            ctx.time_step(0.002)
+        out = ctx.download_particles()
+        ids = np.rint(out["cx"][:, 0]).astype(np.int64)
+        assert np.array_equal(np.sort(ids), np.arange(parts.shape[0])), step
+        assert np.abs(out["position"] - out["cy"]).max() < 1.0, step
+        assert np.array_equal(out["cy"], parts["position"][ids]), step
+    ctx.close()
+
+
 def test_two_gpu_slabs_match_single_gpu():
     """z-slab decomposition with particle migration, ghost copies and NCCL halos against the single-GPU run of the
     same scene (tests/mgpu_check.py under torchrun; needs >= 2 GPUs)."""
