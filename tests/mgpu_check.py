@@ -86,10 +86,11 @@ def main():
                     continue
                 vmax = max(1.0, np.abs(b["velocity"]).max())
                 if by_id:
-                    for nm, q in (("slab", a), ("whole-scene", b)):  # the payload must have travelled WITH its particle
-                        far = np.abs(q["position"] - q["cy"]).max(axis=1) > 1.5 * (step + 1) + 1.0
-                        if far.any():
-                            failures.append("%s: %s run: %d particles carry another particle's payload" % (tag, nm, int(far.sum())))
+                    for nm, q in (("slab", a), ("whole-scene", b)):  # the whole payload must have travelled together
+                        qi = np.clip(np.rint(q["cx"][:, 0]).astype(np.int64), 0, allp.shape[0] - 1)
+                        torn = (q["cy"] != allp["position"][qi]).any(axis=1)
+                        if torn.any():
+                            failures.append("%s: %s run: %d particles carry a torn payload" % (tag, nm, int(torn.sum())))
                     ids = np.rint(a["cx"][:, 0]).astype(np.int64)
                     order = np.argsort(np.rint(b["cx"][:, 0]).astype(np.int64))
                     if np.unique(ids).size != ids.size or ids.min() < 0 or ids.max() >= b.shape[0]:
