@@ -6,6 +6,11 @@
 #include <dlfcn.h>
 #include <nccl.h>
 
+#include <cstddef>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
 namespace {
 struct NcclApi {
 	void *handle = nullptr;
@@ -17,6 +22,7 @@ struct NcclApi {
 	ncclResult_t (*Send)(const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
 	ncclResult_t (*Recv)(void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
 	ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+	ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
 	const char *(*GetErrorString)(ncclResult_t) = nullptr;
 	bool ok = false;
 };
@@ -39,6 +45,7 @@ bool load_nccl() {
 	SYM(Send, "ncclSend");
 	SYM(Recv, "ncclRecv");
 	SYM(AllReduce, "ncclAllReduce");
+	SYM(AllGather, "ncclAllGather");
 	SYM(GetErrorString, "ncclGetErrorString");
 #undef SYM
 	g_nccl.ok = true;
@@ -60,6 +67,154 @@ extern "C" int lfk_nccl_unique_id(void *out128) {
 	return 0;
 }
 
+// =========================================================================================================
+// Halos through peer memory.
+//
+// A halo exchange between z neighbours moves one cell layer (at most nx * ny doubles) each way.  As an NCCL send / recv
+// group it costs ~13 us of launch and handshake for a few microseconds of NVLink traffic, and one PCG iteration needs
+// ~75 of them (every multigrid half-sweep on every level): 2.06 ms per iteration on two GPUs against 1.03 ms on one
+// (profiles/r2a_bench_2gpu.json).  Here every rank owns an ARENA in its own HBM that its two neighbours map with CUDA IPC;
+// one kernel per exchange
+//   1. stores the rank's top / bottom owned layer straight into the upper / lower neighbour's arena (NVLink stores),
+//   2. publishes them: system-scope fence, then -- by the last block to finish -- a release store of the exchange's
+//      epoch number into the neighbour's flag word,
+//   3. waits until its own two flag words have reached the epoch (acquire loads of local memory),
+//   4. copies what the neighbours stored from the arena into the ghost layers.
+// Slots alternate with the parity of the epoch.  That is enough to rule out overwriting a slot that is still being
+// read: a neighbour can start exchange e + 1 only after finishing its own exchange e, which waited for this rank's
+// flag of exchange e, which this rank raised only after finishing exchange e - 1 -- the last reader of the slot that
+// e + 1 writes.  Every rank issues the same sequence of exchanges (as for NCCL), so the epochs agree by construction.
+// A spin that lasts longer than ~4 s raises an error flag instead of hanging the device.
+// =========================================================================================================
+#define ARENA_HEADER 256 // bytes: flag words + block counter + error word
+struct ArenaHeader {
+	unsigned long long sig[2]; // [0] raised by the lower neighbour, [1] by the upper one
+	unsigned long long epoch;  // exchanges completed by this rank (device resident, so that the kernel's arguments never
+	                           // change and a captured CUDA graph of a PCG iteration can be replayed)
+	unsigned counter;          // blocks of the running exchange kernel that have published their stores
+	unsigned error;            // != 0: a wait timed out
+};
+
+__device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned long long v) {
+	asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long *p) {
+	unsigned long long v;
+	asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+	return v;
+}
+// grid-strided copy of `bytes` (a multiple of 4; 16-byte vectors when everything is aligned); SRC_ARENA: the source
+// was written by another GPU -- bypass L1
+template <bool SRC_ARENA> __device__ __forceinline__ void halo_copy(char *dst, const char *src, size_t bytes) {
+	const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x, nth = (size_t)gridDim.x * blockDim.x;
+	if (((((size_t)dst) | ((size_t)src) | bytes) & 15u) == 0) {
+		const uint4 *s4 = reinterpret_cast<const uint4 *>(src);
+		uint4 *d4 = reinterpret_cast<uint4 *>(dst);
+		for (size_t i = tid; i < bytes / 16; i += nth) { d4[i] = SRC_ARENA ? __ldcg(s4 + i) : s4[i]; }
+	} else if (((((size_t)dst) | ((size_t)src) | bytes) & 3u) == 0) {
+		const unsigned *s1 = reinterpret_cast<const unsigned *>(src);
+		unsigned *d1 = reinterpret_cast<unsigned *>(dst);
+		for (size_t i = tid; i < bytes / 4; i += nth) { d1[i] = SRC_ARENA ? __ldcg(s1 + i) : s1[i]; }
+	} else {
+		for (size_t i = tid; i < bytes; i += nth) { dst[i] = SRC_ARENA ? __ldcg(src + i) : src[i]; }
+	}
+}
+
+// up / dn: the neighbours' arenas (NULL at the ends of the rank chain); top / bottom: this rank's boundary layers;
+// ghost_top / ghost_bottom: where the neighbours' layers go
+__global__ void __launch_bounds__(256) k_halo_p2p(char *mine, char *up, char *dn, const char *top, const char *bottom,
+	char *ghost_top, char *ghost_bottom, size_t bytes, size_t slot) {
+	ArenaHeader *H = reinterpret_cast<ArenaHeader *>(mine);
+	// every block reads the epoch before it arrives at the counter below, and the last block to arrive is the one that
+	// advances it: all blocks of a launch see the same number
+	const unsigned long long epoch = *reinterpret_cast<volatile unsigned long long *>(&H->epoch) + 1ull;
+	const size_t par = (size_t)(epoch & 1ull);
+	// receive slots of an arena: [from lower][parity], [from upper][parity]
+	if (up) { halo_copy<false>(up + ARENA_HEADER + (0 * 2 + par) * slot, top, bytes); }       // I am the upper rank's LOWER neighbour
+	if (dn) { halo_copy<false>(dn + ARENA_HEADER + (1 * 2 + par) * slot, bottom, bytes); }    // ... the lower rank's UPPER neighbour
+	__threadfence_system();
+	__syncthreads();
+	__shared__ bool last;
+	if (threadIdx.x == 0) {
+		const unsigned t = atomicAdd(&H->counter, 1u);
+		last = t == gridDim.x - 1;
+		if (last) {
+			H->counter = 0; // every block has arrived; the next exchange is a later launch on the same stream
+			*reinterpret_cast<volatile unsigned long long *>(&H->epoch) = epoch;
+			__threadfence_system();
+			if (up) { st_release_sys(&reinterpret_cast<ArenaHeader *>(up)->sig[0], epoch); }
+			if (dn) { st_release_sys(&reinterpret_cast<ArenaHeader *>(dn)->sig[1], epoch); }
+		}
+		const long long t0 = clock64();
+		bool ok = true;
+		while ((dn && ld_acquire_sys(&H->sig[0]) < epoch) || (up && ld_acquire_sys(&H->sig[1]) < epoch)) {
+			if (clock64() - t0 > 8000000000ll) { // ~4 s at 1.97 GHz: a neighbour is gone
+				H->error = 1u;
+				ok = false;
+				break;
+			}
+		}
+		(void)ok;
+	}
+	__syncthreads();
+	if (dn) { halo_copy<true>(ghost_bottom, mine + ARENA_HEADER + (0 * 2 + par) * slot, bytes); }
+	if (up) { halo_copy<true>(ghost_top, mine + ARENA_HEADER + (1 * 2 + par) * slot, bytes); }
+}
+
+static int arena_setup(lfk_ctx *c) {
+	c->p2p = false;
+	if (c->nranks == 1) { return 0; }
+	if (const char *env = getenv("LFK_P2P")) {
+		if (atoi(env) == 0) { return 0; }
+	}
+	ncclComm_t comm = (ncclComm_t)c->comm;
+	c->arena_slot = (((size_t)c->g.sxy * sizeof(double)) + 255) / 256 * 256;
+	const size_t bytes = ARENA_HEADER + 4 * c->arena_slot;
+	LFK_CUDA(c, cudaMalloc((void**)&c->arena, bytes));
+	LFK_CUDA(c, cudaMemsetAsync(c->arena, 0, bytes, c->stream));
+	// exchange the IPC handles of all arenas (64 bytes each) with an NCCL all-gather; `ok` words tell every rank whether
+	// EVERY rank could map its neighbours, so that all of them take the same path
+	cudaIpcMemHandle_t mine;
+	bool have = cudaIpcGetMemHandle(&mine, c->arena) == cudaSuccess;
+	if (!have) { cudaGetLastError(); memset(&mine, 0, sizeof(mine)); }
+	static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+	char *d_all = nullptr;
+	LFK_CUDA(c, cudaMalloc((void**)&d_all, (size_t)c->nranks * 64 + 64));
+	LFK_CUDA(c, cudaMemcpyAsync(d_all + (size_t)c->nranks * 64, &mine, 64, cudaMemcpyHostToDevice, c->stream));
+	LFK_NCCL(c, g_nccl.AllGather(d_all + (size_t)c->nranks * 64, d_all, 64, ncclChar, comm, c->stream));
+	std::vector<cudaIpcMemHandle_t> all((size_t)c->nranks);
+	LFK_CUDA(c, cudaMemcpyAsync(all.data(), d_all, (size_t)c->nranks * 64, cudaMemcpyDeviceToHost, c->stream));
+	LFK_CUDA(c, cudaStreamSynchronize(c->stream));
+	bool ok = have;
+	const int nb[2] = { c->rank + 1, c->rank - 1 };
+	for (int k = 0; k < 2 && ok; ++k) {
+		if (nb[k] < 0 || nb[k] >= c->nranks) { continue; }
+		void *ptr = nullptr;
+		if (cudaIpcOpenMemHandle(&ptr, all[(size_t)nb[k]], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+			cudaGetLastError();
+			ok = false;
+			break;
+		}
+		c->arena_peer[k] = (char*)ptr;
+	}
+	// agree: sum of (ok ? 0 : 1) over the ranks must be 0
+	double flag = ok ? 0.0 : 1.0;
+	double *d_flag = (double*)d_all; // reuse
+	LFK_CUDA(c, cudaMemcpyAsync(d_flag, &flag, sizeof(double), cudaMemcpyHostToDevice, c->stream));
+	LFK_NCCL(c, g_nccl.AllReduce(d_flag, d_flag, 1, ncclDouble, ncclSum, comm, c->stream));
+	LFK_CUDA(c, cudaMemcpyAsync(&flag, d_flag, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+	LFK_CUDA(c, cudaStreamSynchronize(c->stream)); // (also: every arena is zeroed before anybody can write into it)
+	cudaFree(d_all);
+	c->p2p = flag == 0.0;
+	if (!c->p2p) {
+		for (int k = 0; k < 2; ++k) {
+			if (c->arena_peer[k]) { cudaIpcCloseMemHandle(c->arena_peer[k]); c->arena_peer[k] = nullptr; }
+		}
+	}
+	c->halo_epoch = 0;
+	return 0;
+}
+
 int lfkx_init(lfk_ctx *c, const void *nccl_id128) {
 	if (c->nranks == 1) { return 0; }
 	LFK_REQUIRE(c, nccl_id128 != nullptr, LFK_E_INVALID, "nranks > 1 needs an NCCL unique id");
@@ -69,14 +224,32 @@ int lfkx_init(lfk_ctx *c, const void *nccl_id128) {
 	ncclComm_t comm;
 	LFK_NCCL(c, g_nccl.CommInitRank(&comm, c->nranks, id, c->rank));
 	c->comm = comm;
-	return 0;
+	return arena_setup(c);
 }
 
 int lfkx_destroy(lfk_ctx *c) {
+	for (int k = 0; k < 2; ++k) {
+		if (c->arena_peer[k]) { cudaIpcCloseMemHandle(c->arena_peer[k]); c->arena_peer[k] = nullptr; }
+	}
 	if (c->comm) {
+		// (the neighbours may still be reading this rank's arena in their last exchange: the communicator's destruction
+		// is collective, so it doubles as the barrier before the arena is freed)
 		g_nccl.CommDestroy((ncclComm_t)c->comm);
 		c->comm = nullptr;
 	}
+	if (c->arena) { cudaFree(c->arena); c->arena = nullptr; }
+	c->p2p = false;
+	return 0;
+}
+
+// != 0 once an exchange timed out waiting for a neighbour
+int lfkx_check(lfk_ctx *c) {
+	if (!c->p2p) { return 0; }
+	unsigned err = 0;
+	LFK_CUDA(c, cudaMemcpyAsync(&err, c->arena + offsetof(ArenaHeader, error), sizeof(unsigned), cudaMemcpyDeviceToHost,
+		c->stream));
+	LFK_CUDA(c, cudaStreamSynchronize(c->stream));
+	LFK_REQUIRE(c, err == 0, LFK_E_NCCL, "a peer-memory halo exchange timed out waiting for a neighbour rank");
 	return 0;
 }
 
@@ -88,6 +261,14 @@ static int halo_bytes(lfk_ctx *c, void *field, size_t layer_elems, int nzl, nccl
 	ncclComm_t comm = (ncclComm_t)c->comm;
 	char *f = (char*)field;
 	size_t L = layer_elems * esz;
+	if (c->p2p && c->tune.p2p && L <= c->arena_slot) {
+		++c->halo_epoch;
+		unsigned nb = (unsigned)((L / 16 + 255) / 256);
+		nb = nb < 1 ? 1 : (nb > 64 ? 64 : nb);
+		LFK_LAUNCH(c, k_halo_p2p, nb, 256, 0, c->arena, c->arena_peer[0], c->arena_peer[1], f + (size_t)nzl * L, f + L,
+			f + (size_t)(nzl + 1) * L, f, L, c->arena_slot);
+		return 0;
+	}
 	LFK_NCCL(c, g_nccl.GroupStart());
 	if (c->rank + 1 < c->nranks) {
 		LFK_NCCL(c, g_nccl.Send(f + (size_t)nzl * L, layer_elems, dt, c->rank + 1, comm, c->stream));

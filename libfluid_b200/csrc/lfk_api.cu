@@ -192,6 +192,7 @@ static int free_all(lfk_ctx *c) {
 }
 
 int lfkm_free(lfk_ctx *c); // mg.cu
+int lfks_free_graph(lfk_ctx *c); // pressure.cu
 
 extern "C" int lfk_set_tuning(lfk_ctx *c, const char *key, int value);
 
@@ -323,6 +324,7 @@ extern "C" int lfk_destroy(lfk_ctx *c) {
 	if (!c) { return 0; }
 	cudaSetDevice(c->device);
 	cudaStreamSynchronize(c->stream);
+	lfks_free_graph(c);
 	lfkx_destroy(c);
 	lfkm_free(c);
 	free_all(c);
@@ -788,6 +790,10 @@ extern "C" int lfk_set_tuning(lfk_ctx *c, const char *key, int value) {
 	const std::string k(key);
 	if (k == "p2g") { c->tune.p2g = value; }
 	else if (k == "mg_agg") { c->tune.mg_agg = value; }
+	else if (k == "p2g_warps") { c->tune.p2g_warps = value; }
+	else if (k == "p2p") { c->tune.p2p = value; }
+	else if (k == "graph") { c->tune.graph = value; c->pcg_graph_key = 0; }
+	else if (k == "mg_coarse") { c->tune.mg_coarse = value; c->pcg_graph_key = 0; }
 	else if (k == "warm_start") { c->tune.warm_start = value; }
 	else if (k == "red_blocks") { c->tune.red_blocks = value; }
 	else { return lfk_fail(c, LFK_E_INVALID, "lfk_set_tuning: unknown key", __FILE__, __LINE__); }

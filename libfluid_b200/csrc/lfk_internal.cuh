@@ -47,6 +47,8 @@ struct PcgScalars {
 	double resmax;     // max |r|
 	double bb;         // sum b^2
 	double alpha, beta;
+	double a_scale, inv_a_scale, tolerance; // of the running solve (device resident: the iteration's kernels take no
+	                                        // per-solve arguments, so its captured CUDA graph is reused from step to step)
 	unsigned long long iters;
 	int done;          // 1 once converged / early-out
 	int pad;
@@ -66,7 +68,11 @@ struct MgLevel {
 enum { LFK_TUNE_P2G_MARCH = 0, LFK_TUNE_P2G_GATHER = 2 };
 struct lfk_tuning {
 	int p2g = LFK_TUNE_P2G_MARCH; // 2: the plain per-cell gather (the reference's loop literally; also taken for APIC with h < 1)
+	int p2g_warps = 8; // rows (warps) per block of the marching P2G kernel: 8 at 200 registers, 10 at 168
 	int mg_agg = 0;   // 1: multi-GPU coarse levels agglomerated onto every rank
+	int mg_coarse = 0; // > 0: symmetric sweeps on the coarsest multigrid level of the single-block tail (default 8)
+	int graph = 1;    // 1: the PCG iteration is replayed from a captured CUDA graph (~40 launches), 0: launched one by one
+	int p2p = 1;      // multi-GPU: 1 halos through peer memory (CUDA IPC arenas over NVLink), 0 NCCL send / recv
 	int warm_start = 1; // fused step: start PCG from the previous step's pressure (0: from p = 0 like the reference)
 	int red_blocks = 0; // > 0: cap on the grid of the PCG reduction kernels (default 8 x SM count)
 };
@@ -122,7 +128,17 @@ struct lfk_ctx {
 	int mg_agg_level = -1;         // distributed level they replace; -1 undecided, -2 none
 	std::vector<int> mg_z0;        // global z of the first owned layer, per level (red-black parity)
 	bool mg_valid = false;
+	// one PCG iteration as a CUDA graph (pressure.cu)
+	void *pcg_graph = nullptr;          // cudaGraphExec_t
+	unsigned pcg_graph_launches = 0;    // kernels in it
+	int pcg_graph_key = 0;              // configuration it was captured for
 
+	// multi-GPU halos through peer memory (exchange.cu): one arena per rank, mapped by its z neighbours with CUDA IPC
+	char *arena = nullptr;            // this rank's arena: header (flags, counters) + 2 x 2 receive slots
+	char *arena_peer[2] = { nullptr, nullptr }; // [0] the upper neighbour's arena, [1] the lower one's (mapped)
+	size_t arena_slot = 0;            // bytes per receive slot
+	unsigned long long halo_epoch = 0; // exchanges issued so far (identical on every rank)
+	bool p2p = false;                 // arena mapped on both sides: halos bypass NCCL
 	// multi-GPU particle exchange (exchange.cu)
 	double *xsend[2] = { nullptr, nullptr }, *xrecv = nullptr; // [0] to / from the upper neighbour, [1] the lower one
 	size_t xsend_cap[2] = { 0, 0 }, xrecv_cap = 0;             // in particles (15 doubles each)
@@ -228,6 +244,7 @@ int lfks_export_flags(lfk_ctx *c, uint8_t *d_out_compact);
 // ---- implemented in exchange.cu (multi-GPU; no-ops when nranks == 1) ----
 int lfkx_init(lfk_ctx *c, const void *nccl_id128);
 int lfkx_destroy(lfk_ctx *c);
+int lfkx_check(lfk_ctx *c); // error if a peer-memory exchange timed out
 int lfkx_halo_f64(lfk_ctx *c, double *field);          // fill both z ghost layers of a cell array from the neighbours
 int lfkx_halo_f32(lfk_ctx *c, float *field, int nx, int ny, int nzl);
 int lfkx_halo_u8(lfk_ctx *c, uint8_t *field);
@@ -407,7 +424,8 @@ __device__ __forceinline__ double finish_partials(const double *partials, unsign
 // finalisers of the PCG scalars: run by the last block of the producing kernel on one GPU, or by k_finalize after
 // the NCCL all-reduce of the local partial results on several GPUs
 enum { FIN_BB = 0, FIN_ALPHA = 1, FIN_RESID = 2, FIN_BETA_FIRST = 3, FIN_BETA = 4 };
-__device__ __forceinline__ void pcg_finalize(PcgScalars *scal, int which, double tolerance) {
+__device__ __forceinline__ void pcg_finalize(PcgScalars *scal, int which) {
+	const double tolerance = scal->tolerance;
 	switch (which) {
 	case FIN_BB: // early-out of the reference (src/pressure_solver.cpp:29-35)
 		scal->iters = 0;

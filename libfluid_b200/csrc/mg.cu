@@ -190,9 +190,10 @@ template <bool PROLONG, typename T> __global__ void __launch_bounds__(256) k_mg_
 // last half-sweep of the cycle (colour `colour`) fused with z = x0 / a_scale (fp64), sigma_new = z.r and its finaliser
 template <typename T> __global__ void __launch_bounds__(RED_THREADS) k_mg_final_l0(GridDesc G,
 	const uint16_t *__restrict__ mask, const T *__restrict__ b, const T *__restrict__ X, int colour,
-	const double *__restrict__ r, double *__restrict__ z, double inv_a_scale, PcgScalars *scal, double *partials,
-	unsigned *ticket, int finalize, int first, const float *__restrict__ rescale) {
+	const double *__restrict__ r, double *__restrict__ z, PcgScalars *scal, double *partials,
+	unsigned *ticket, int finalize, int first) {
 	if (scal->done) { return; }
+	const double inv_a_scale = scal->inv_a_scale;
 	double acc = 0.0;
 	struct FinRaw { L0Raw l; double r; };
 	LevelDev none{};
@@ -217,7 +218,7 @@ template <typename T> __global__ void __launch_bounds__(RED_THREADS) k_mg_final_
 		double tot = finish_partials(partials, gridDim.x, 0);
 		if (threadIdx.x == 0) {
 			scal->sigma_new = tot;
-			if (finalize) { pcg_finalize(scal, first ? FIN_BETA_FIRST : FIN_BETA, 0.0); }
+			if (finalize) { pcg_finalize(scal, first ? FIN_BETA_FIRST : FIN_BETA); }
 		}
 	}
 }
@@ -333,6 +334,7 @@ __global__ void __launch_bounds__(128) k_mg_restrict(LevelDev F, LevelDev C, con
 struct TailLevels {
 	LevelDev L[MG_TAIL_MAX_LEVELS];
 	int n;
+	int coarse_sweeps; // symmetric sweeps on the coarsest level
 };
 
 // block-wide loop over the owned cells of a small level (int arithmetic only)
@@ -423,7 +425,7 @@ __device__ __forceinline__ void tail_cycle(const TailLevels &T) {
 		}
 		tail_restrict(T.L[l], T.L[l + 1]);
 	}
-	for (int s = 0; s < MG_COARSE_SWEEPS; ++s) { // coarsest: red, black, black, red
+	for (int s = 0; s < T.coarse_sweeps; ++s) { // coarsest: red, black, black, red
 		tail_half_sweep(T.L[last], 0);
 		tail_half_sweep(T.L[last], 1);
 		tail_half_sweep(T.L[last], 1);
@@ -639,6 +641,7 @@ static int mg_agg_cycle(lfk_ctx *c) {
 	LFK_CUDA(c, cudaMemsetAsync(Gl.x, 0, ((size_t)Gl.ncl + 2) * sizeof(float), c->stream));
 	TailLevels T;
 	T.n = 0;
+	T.coarse_sweeps = c->tune.mg_coarse > 0 ? c->tune.mg_coarse : MG_COARSE_SWEEPS;
 	for (const MgLevel &L : c->mg_agg) { T.L[T.n++] = level_dev(L, 0); }
 	LFK_TRY(launch_tail(c, T));
 	// my layers and the ghost layer either side: global layer index of local layer 0 is z0 - 1 + 1 = z0
@@ -732,6 +735,7 @@ static int vcycle(lfk_ctx *c, size_t l) {
 	if (c->nranks == 1 && l > 0 && Ld.nown <= MG_COARSE_MAX_CELLS && last - l < MG_TAIL_MAX_LEVELS) {
 		TailLevels T; // this level and everything below it: one block, one launch
 		T.n = 0;
+		T.coarse_sweeps = c->tune.mg_coarse > 0 ? c->tune.mg_coarse : MG_COARSE_SWEEPS;
 		for (size_t k = l; k <= last; ++k) {
 			T.L[T.n++] = level_dev(c->mg[k], c->mg_z0[k]);
 		}
@@ -793,14 +797,14 @@ int lfkm_level0(lfk_ctx *c, float **b0, float **x0) {
 }
 
 // z = M^-1 r, sigma_new = z.r.  b0 and the red half of x0 were written by k_pcg_init / k_update_pr.
-int lfkm_apply_preloaded(lfk_ctx *c, double a_scale, unsigned nb, int fin, int first) {
+int lfkm_apply_preloaded(lfk_ctx *c, unsigned nb, int fin, int first) {
 	const GridDesc &G = c->g;
 	MgLevel &L0 = c->mg[0];
 	LFK_TRY(vcycle(c, 0));
 	if (c->nranks > 1) { LFK_TRY(lfkx_halo_f32(c, L0.x, L0.nx, L0.ny, L0.nzl)); }
 	{
-		LFK_LAUNCH(c, k_mg_final_l0<float>, nb, RED_THREADS, 0, G, c->mg_mask, L0.b, L0.x, 0, c->r, c->z, 1.0 / a_scale,
-			c->d_scal, c->partials, c->ticket, fin, first, (const float*)nullptr);
+		LFK_LAUNCH(c, k_mg_final_l0<float>, nb, RED_THREADS, 0, G, c->mg_mask, L0.b, L0.x, 0, c->r, c->z,
+			c->d_scal, c->partials, c->ticket, fin, first);
 	}
 	return 0;
 }

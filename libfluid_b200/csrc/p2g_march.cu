@@ -29,9 +29,9 @@
 #include "p2g_accum.cuh"
 
 #define PM_BX 30
-#define PM_WARPS 8 // warps are placed on the 4 SM sub-partitions (16 K registers each): ceil(warps / 4) * 32 * 200 regs must fit
-#define PM_BY (PM_WARPS - 2)
-#define PM_THREADS (PM_WARPS * 32)
+// WARPS (template parameter): warps per block = rows per block (two of them halo rows).  Warps are placed on the 4 SM
+// sub-partitions (16 K registers each), so ceil(WARPS / 4) * 32 * registers must fit: 8 warps at 200 registers, or 10 at 168.
+#define PM_REGS(WARPS) ((WARPS) <= 8 ? 200 : 168)
 #define PM_STAGE (PB_FIELDS * PB_FSTRIDE)       // doubles per staging buffer
 #define PM_SLOT (3 * 2 * 32)                    // doubles per warp slot: [b][w | wv][lane]
 #define PM_MAX_CHUNK 128                        // z planes per block at most (size of the z-coordinate table)
@@ -136,14 +136,14 @@ struct PMOut { // where one component goes
 
 // Layer L of the march is complete: face plane L - 1 has everything this column contributes.  Combine along x
 // (shuffles) and y (slots), write the plane, rotate the accumulators.
-template <int COMP, int METHOD> __device__ __forceinline__ void pm_finish_layer(const GridDesc &G, const PBParams &Q,
+template <int COMP, int METHOD, int WARPS> __device__ __forceinline__ void pm_finish_layer(const GridDesc &G, const PBParams &Q,
 	int L, int P0, int P1, double *__restrict__ slots, int &par, int warp, int lane, int x, int y, int nfx,
 	const uint32_t *__restrict__ begin, const PMOut &O, double *accw, double *accv) {
 	constexpr int NA = COMP == 0 ? 2 : 3, NB = COMP == 1 ? 2 : 3, NC = COMP == 2 ? 2 : 3;
 	constexpr bool APIC = METHOD == LFK_METHOD_APIC;
 	const int op = L - 1; // local layer index of the finished face plane
 	if (op >= P0 && op < P1) { // block-uniform
-		double *mine = slots + (par * PM_WARPS + warp) * PM_SLOT;
+		double *mine = slots + (par * WARPS + warp) * PM_SLOT;
 #pragma unroll
 		for (int b = 0; b < NB; ++b) {
 			double rw, rv;
@@ -165,9 +165,9 @@ template <int COMP, int METHOD> __device__ __forceinline__ void pm_finish_layer(
 		}
 		__syncthreads();
 		const int fx = lane - 1; // owned face columns: lanes 1 .. 30
-		if (warp >= 1 && warp <= PM_WARPS - 2 && y < G.ny && fx >= 0 && fx < nfx) {
-			const double *below = slots + (par * PM_WARPS + warp - 1) * PM_SLOT;
-			const double *above = slots + (par * PM_WARPS + warp + 1) * PM_SLOT;
+		if (warp >= 1 && warp <= WARPS - 2 && y < G.ny && fx >= 0 && fx < nfx) {
+			const double *below = slots + (par * WARPS + warp - 1) * PM_SLOT;
+			const double *above = slots + (par * WARPS + warp + 1) * PM_SLOT;
 			double sw, sv;
 			if (NB == 3) { // row y-1 (b = 2), row y (b = 1), row y+1 (b = 0)
 				sw = below[(2 * 2 + 0) * 32 + lane];
@@ -212,7 +212,7 @@ template <int COMP, int METHOD> __device__ __forceinline__ void pm_finish_layer(
 	}
 }
 
-template <int COMP, int METHOD> __device__ __forceinline__ void pm_march(const GridDesc &G, const PBParams &Q,
+template <int COMP, int METHOD, int WARPS> __device__ __forceinline__ void pm_march(const GridDesc &G, const PBParams &Q,
 	double *__restrict__ st, double *__restrict__ slots, const double *__restrict__ ztab, int &par,
 	const double *const *fields, const uint32_t *__restrict__ perm, const uint32_t *__restrict__ begin,
 	const double *__restrict__ cxs, const double *__restrict__ cys, int warp, int lane, int x0, int y0, int P0, int P1,
@@ -276,7 +276,7 @@ template <int COMP, int METHOD> __device__ __forceinline__ void pm_march(const G
 		__syncwarp();
 		if (D0.win == 0) { // first window of a layer
 			if (D0.lz > lzA) {
-				pm_finish_layer<COMP, METHOD>(G, Q, D0.lz - 1, P0, P1, slots, par, warp, lane, x, y, nfx, begin, O, accw, accv);
+				pm_finish_layer<COMP, METHOD, WARPS>(G, Q, D0.lz - 1, P0, P1, slots, par, warp, lane, x, y, nfx, begin, O, accw, accv);
 			}
 			const int zi = D0.lz - lzA; // ztab[i]: centre of the layer (lzA - 1 + i)
 			cc[6] = ztab[zi];
@@ -294,26 +294,26 @@ template <int COMP, int METHOD> __device__ __forceinline__ void pm_march(const G
 		R.advance(D2);
 		cur ^= 1;
 	}
-	pm_finish_layer<COMP, METHOD>(G, Q, lzB, P0, P1, slots, par, warp, lane, x, y, nfx, begin, O, accw, accv);
+	pm_finish_layer<COMP, METHOD, WARPS>(G, Q, lzB, P0, P1, slots, par, warp, lane, x, y, nfx, begin, O, accw, accv);
 	cp_async_wait_all();
 }
 
-template <int METHOD> __global__ void __maxnreg__(200) k_p2g_march(GridDesc G, PBParams Q,
+template <int METHOD, int WARPS> __global__ void __maxnreg__(PM_REGS(WARPS)) k_p2g_march(GridDesc G, PBParams Q,
 	ParticleSoA P, const uint32_t *__restrict__ perm, const uint32_t *__restrict__ begin,
 	const double *__restrict__ cxs, const double *__restrict__ cys, const double *__restrict__ czs,
 	double *__restrict__ u, double *__restrict__ v, double *__restrict__ w, double *__restrict__ uo,
 	double *__restrict__ vo, double *__restrict__ wo, uint8_t *__restrict__ typ, int chunk) {
 	extern __shared__ double smem[];
 	double *stage_all = smem;                                   // [WARPS][2][PM_STAGE]
-	double *slots = smem + PM_WARPS * 2 * PM_STAGE;             // [2][WARPS][PM_SLOT]
-	double *ztab = slots + 2 * PM_WARPS * PM_SLOT;              // [PM_MAX_CHUNK + 4]
+	double *slots = smem + WARPS * 2 * PM_STAGE;                // [2][WARPS][PM_SLOT]
+	double *ztab = slots + 2 * WARPS * PM_SLOT;                 // [PM_MAX_CHUNK + 4]
 	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 	double *st = stage_all + warp * (2 * PM_STAGE);
-	const int x0 = blockIdx.x * PM_BX, y0 = blockIdx.y * PM_BY;
+	const int x0 = blockIdx.x * PM_BX, y0 = blockIdx.y * (WARPS - 2);
 	const int P0 = 1 + blockIdx.z * chunk, P1 = min(P0 + chunk, G.nzl + 1);
 	const int nfx = min(PM_BX, G.nx - x0);
 	// z centres of the layers lzA - 1 .. lzB + 1 (global z = local layer - 1 + z0), extrapolated outside the grid
-	for (int i = threadIdx.x; i < P1 - P0 + 4; i += PM_THREADS) {
+	for (int i = threadIdx.x; i < P1 - P0 + 4; i += WARPS * 32) {
 		const int z = (P0 - 2 + i) - 1 + G.z0;
 		ztab[i] = z < 0 ? czs[0] + (double)z * G.h : (z >= G.nz ? czs[G.nz - 1] + (double)(z - G.nz + 1) * G.h : czs[z]);
 	}
@@ -323,12 +323,50 @@ template <int METHOD> __global__ void __maxnreg__(200) k_p2g_march(GridDesc G, P
 	for (int f = 0; f < 15; ++f) { fields[f] = P.f[f]; }
 	int par = 0;
 	const PMOut O0{ u, uo, typ }, O1{ v, vo, typ }, O2{ w, wo, typ };
-	pm_march<0, METHOD>(G, Q, st, slots, ztab, par, fields, perm, begin, cxs, cys, warp, lane, x0, y0, P0, P1, nfx, O0);
-	pm_march<1, METHOD>(G, Q, st, slots, ztab, par, fields, perm, begin, cxs, cys, warp, lane, x0, y0, P0, P1, nfx, O1);
-	pm_march<2, METHOD>(G, Q, st, slots, ztab, par, fields, perm, begin, cxs, cys, warp, lane, x0, y0, P0, P1, nfx, O2);
+	pm_march<0, METHOD, WARPS>(G, Q, st, slots, ztab, par, fields, perm, begin, cxs, cys, warp, lane, x0, y0, P0, P1, nfx, O0);
+	pm_march<1, METHOD, WARPS>(G, Q, st, slots, ztab, par, fields, perm, begin, cxs, cys, warp, lane, x0, y0, P0, P1, nfx, O1);
+	pm_march<2, METHOD, WARPS>(G, Q, st, slots, ztab, par, fields, perm, begin, cxs, cys, warp, lane, x0, y0, P0, P1, nfx, O2);
 }
 
 int lfkp_materialise_vc(lfk_ctx *c);
+
+template <int WARPS> static int p2g_march_launch(lfk_ctx *c, const PBParams &Q, const uint32_t *perm) {
+	const GridDesc &G = c->g;
+	const unsigned nbx = (unsigned)((G.nx + PM_BX - 1) / PM_BX), nby = (unsigned)((G.ny + (WARPS - 2) - 1) / (WARPS - 2));
+	// z chunks: enough blocks for ~6 waves of one block per SM, chunks of 8 .. PM_MAX_CHUNK planes
+	int sms = 148;
+	cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device);
+	int nzc = (int)((6u * (unsigned)sms + nbx * nby - 1) / (nbx * nby));
+	int chunk = (G.nzl + nzc - 1) / nzc;
+	chunk = chunk < 8 ? 8 : chunk;
+	chunk = chunk > PM_MAX_CHUNK ? PM_MAX_CHUNK : chunk;
+	chunk = chunk > G.nzl ? G.nzl : chunk;
+	nzc = (G.nzl + chunk - 1) / chunk;
+	dim3 grid(nbx, nby, (unsigned)nzc);
+	const size_t smem = (size_t)(WARPS * 2 * PM_STAGE + 2 * WARPS * PM_SLOT + PM_MAX_CHUNK + 4) * sizeof(double);
+	static bool attr_set[LFK_MAX_DEVICES] = {}; // function attributes are per device
+	if (!attr_set[c->device % LFK_MAX_DEVICES]) {
+		LFK_CUDA(c, cudaFuncSetAttribute((k_p2g_march<LFK_METHOD_PIC, WARPS>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+		LFK_CUDA(c, cudaFuncSetAttribute((k_p2g_march<LFK_METHOD_FLIP, WARPS>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+		LFK_CUDA(c, cudaFuncSetAttribute((k_p2g_march<LFK_METHOD_APIC, WARPS>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+		attr_set[c->device % LFK_MAX_DEVICES] = true;
+	}
+	switch (c->prm.method) {
+	case LFK_METHOD_PIC:
+		LFK_LAUNCH(c, (k_p2g_march<LFK_METHOD_PIC, WARPS>), grid, WARPS * 32, smem, G, Q, c->P, perm, c->begin, c->ctr[0], c->ctr[1],
+			c->ctr[2], c->vel[0], c->vel[1], c->vel[2], c->vel_old[0], c->vel_old[1], c->vel_old[2], c->typ, chunk);
+		break;
+	case LFK_METHOD_FLIP:
+		LFK_LAUNCH(c, (k_p2g_march<LFK_METHOD_FLIP, WARPS>), grid, WARPS * 32, smem, G, Q, c->P, perm, c->begin, c->ctr[0], c->ctr[1],
+			c->ctr[2], c->vel[0], c->vel[1], c->vel[2], c->vel_old[0], c->vel_old[1], c->vel_old[2], c->typ, chunk);
+		break;
+	default:
+		LFK_LAUNCH(c, (k_p2g_march<LFK_METHOD_APIC, WARPS>), grid, WARPS * 32, smem, G, Q, c->P, perm, c->begin, c->ctr[0], c->ctr[1],
+			c->ctr[2], c->vel[0], c->vel[1], c->vel[2], c->vel_old[0], c->vel_old[1], c->vel_old[2], c->typ, chunk);
+		break;
+	}
+	return 0;
+}
 
 int lfkg_p2g_march(lfk_ctx *c, double gravity_dt, bool add_gravity) {
 	const GridDesc &G = c->g;
@@ -342,38 +380,6 @@ int lfkg_p2g_march(lfk_ctx *c, double gravity_dt, bool add_gravity) {
 	// one permutation serves the velocity and the c rows: make them agree (they differ only after lfkp_permute_c)
 	if (c->prm.method == LFK_METHOD_APIC && c->v_deferred != c->c_deferred) { LFK_TRY(lfkp_materialise_vc(c)); }
 	const uint32_t *perm = c->v_deferred ? c->perm : nullptr;
-	const unsigned nbx = (unsigned)((G.nx + PM_BX - 1) / PM_BX), nby = (unsigned)((G.ny + PM_BY - 1) / PM_BY);
-	// z chunks: enough blocks for ~6 waves of one block per SM, chunks of 8 .. PM_MAX_CHUNK planes
-	int sms = 148;
-	cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device);
-	int nzc = (int)((6u * (unsigned)sms + nbx * nby - 1) / (nbx * nby));
-	int chunk = (G.nzl + nzc - 1) / nzc;
-	chunk = chunk < 8 ? 8 : chunk;
-	chunk = chunk > PM_MAX_CHUNK ? PM_MAX_CHUNK : chunk;
-	chunk = chunk > G.nzl ? G.nzl : chunk;
-	nzc = (G.nzl + chunk - 1) / chunk;
-	dim3 grid(nbx, nby, (unsigned)nzc);
-	const size_t smem = (size_t)(PM_WARPS * 2 * PM_STAGE + 2 * PM_WARPS * PM_SLOT + PM_MAX_CHUNK + 4) * sizeof(double);
-	static bool attr_set[LFK_MAX_DEVICES] = {}; // function attributes are per device
-	if (!attr_set[c->device % LFK_MAX_DEVICES]) {
-		LFK_CUDA(c, cudaFuncSetAttribute(k_p2g_march<LFK_METHOD_PIC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-		LFK_CUDA(c, cudaFuncSetAttribute(k_p2g_march<LFK_METHOD_FLIP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-		LFK_CUDA(c, cudaFuncSetAttribute(k_p2g_march<LFK_METHOD_APIC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-		attr_set[c->device % LFK_MAX_DEVICES] = true;
-	}
-	switch (c->prm.method) {
-	case LFK_METHOD_PIC:
-		LFK_LAUNCH(c, k_p2g_march<LFK_METHOD_PIC>, grid, PM_THREADS, smem, G, Q, c->P, perm, c->begin, c->ctr[0], c->ctr[1],
-			c->ctr[2], c->vel[0], c->vel[1], c->vel[2], c->vel_old[0], c->vel_old[1], c->vel_old[2], c->typ, chunk);
-		break;
-	case LFK_METHOD_FLIP:
-		LFK_LAUNCH(c, k_p2g_march<LFK_METHOD_FLIP>, grid, PM_THREADS, smem, G, Q, c->P, perm, c->begin, c->ctr[0], c->ctr[1],
-			c->ctr[2], c->vel[0], c->vel[1], c->vel[2], c->vel_old[0], c->vel_old[1], c->vel_old[2], c->typ, chunk);
-		break;
-	default:
-		LFK_LAUNCH(c, k_p2g_march<LFK_METHOD_APIC>, grid, PM_THREADS, smem, G, Q, c->P, perm, c->begin, c->ctr[0], c->ctr[1],
-			c->ctr[2], c->vel[0], c->vel[1], c->vel[2], c->vel_old[0], c->vel_old[1], c->vel_old[2], c->typ, chunk);
-		break;
-	}
-	return 0;
+	if (c->tune.p2g_warps == 10) { return p2g_march_launch<10>(c, Q, perm); }
+	return p2g_march_launch<8>(c, Q, perm);
 }

@@ -112,15 +112,16 @@ __device__ __forceinline__ double stencil_apply(const Stencil7 &v, int x, int y,
 	return a_scale * value;
 }
 
-__global__ void k_finalize(PcgScalars *scal, int which, double tolerance) {
+__global__ void k_finalize(PcgScalars *scal, int which) {
 	if (which != FIN_BB && scal->done) { return; }
-	pcg_finalize(scal, which, tolerance);
+	pcg_finalize(scal, which);
 }
 
 __global__ void __launch_bounds__(RED_THREADS) k_spmv_dot(GridDesc G, const uint8_t *__restrict__ flags,
-	const double *__restrict__ s, double *__restrict__ z, double a_scale, PcgScalars *scal,
+	const double *__restrict__ s, double *__restrict__ z, PcgScalars *scal,
 	double *partials, unsigned *ticket, int finalize) {
 	if (scal->done) { return; }
+	const double a_scale = scal->a_scale;
 	double acc = 0.0;
 	rows_pipelined<4, Stencil7>(G.nx, G.ny, G.nzl, 0, -1,
 		[&](int, int, int, long long c) { return stencil_load(G, flags, s, c); },
@@ -135,7 +136,7 @@ __global__ void __launch_bounds__(RED_THREADS) k_spmv_dot(GridDesc G, const uint
 		double tot = finish_partials(partials, gridDim.x, 0);
 		if (threadIdx.x == 0) {
 			scal->zs = tot;
-			if (finalize) { pcg_finalize(scal, FIN_ALPHA, 0.0); }
+			if (finalize) { pcg_finalize(scal, FIN_ALPHA); }
 		}
 	}
 }
@@ -154,12 +155,11 @@ __global__ void __launch_bounds__(256) k_spmv_plain(GridDesc G, const uint8_t *_
 struct MgPreload {
 	float *b0, *x0; // level-0 rhs / solution, or NULL when the preconditioner is not multigrid
 	const uint8_t *flags;
-	double inv_a_scale;
 };
 __device__ __forceinline__ void mg_preload(const GridDesc &G, const MgPreload &M, int x, int y, int lz, long long c,
-	double rv, unsigned f) {
+	double rv, unsigned f, double inv_a_scale) {
 	if (M.b0 == nullptr) { return; }
-	float bv = (float)(rv * M.inv_a_scale);
+	float bv = (float)(rv * inv_a_scale);
 	M.b0[c] = bv;
 	bool red = ((x + y + (lz - 1 + G.z0)) & 1) == 0;
 	M.x0[c] = (red && (f & FL_L) && FL_N(f) > 0) ? bv / (float)FL_N(f) : 0.f;
@@ -167,13 +167,15 @@ __device__ __forceinline__ void mg_preload(const GridDesc &G, const MgPreload &M
 
 // r = b, sum b^2
 __global__ void __launch_bounds__(RED_THREADS) k_pcg_init(GridDesc G, const double *__restrict__ b,
-	double *__restrict__ r, PcgScalars *scal, double *partials, unsigned *ticket, int finalize, MgPreload M) {
+	double *__restrict__ r, PcgScalars *scal, double *partials, unsigned *ticket, int finalize, MgPreload M,
+	double a_scale, double tolerance) {
 	double acc = 0.0;
+	const double inv_a_scale = 1.0 / a_scale;
 	for_own_cells(G, [&](int x, int y, int lz, long long c) {
 		double v = b[c];
 		r[c] = v;
 		acc += v * v;
-		mg_preload(G, M, x, y, lz, c, v, M.flags[c]);
+		mg_preload(G, M, x, y, lz, c, v, M.flags[c], inv_a_scale);
 	});
 	acc = block_sum(acc);
 	if (threadIdx.x == 0) { partials[blockIdx.x] = acc; }
@@ -182,7 +184,10 @@ __global__ void __launch_bounds__(RED_THREADS) k_pcg_init(GridDesc G, const doub
 		if (threadIdx.x == 0) {
 			scal->bb = tot;
 			scal->sigma = 0.0;
-			if (finalize) { pcg_finalize(scal, FIN_BB, 0.0); }
+			scal->a_scale = a_scale; // the iteration's kernels read these from here
+			scal->inv_a_scale = 1.0 / a_scale;
+			scal->tolerance = tolerance;
+			if (finalize) { pcg_finalize(scal, FIN_BB); }
 		}
 	}
 }
@@ -190,15 +195,16 @@ __global__ void __launch_bounds__(RED_THREADS) k_pcg_init(GridDesc G, const doub
 // warm start: r = b - A p, sum b^2 (the early-out of the reference is decided on b, as there)
 __global__ void __launch_bounds__(RED_THREADS) k_pcg_init_warm(GridDesc G, const uint8_t *__restrict__ flags,
 	const double *__restrict__ b, const double *__restrict__ p, double *__restrict__ r, double a_scale,
-	PcgScalars *scal, double *partials, unsigned *ticket, int finalize, MgPreload M) {
+	PcgScalars *scal, double *partials, unsigned *ticket, int finalize, MgPreload M, double tolerance) {
 	double acc = 0.0;
+	const double inv_a_scale = 1.0 / a_scale;
 	for_own_cells(G, [&](int x, int y, int lz, long long c) {
 		const Stencil7 v = stencil_load(G, flags, p, c);
 		const double bv = b[c];
 		const double rv = (v.f & FL_L) ? bv - stencil_apply(v, x, y, a_scale) : bv; // b == 0 off the unknowns
 		r[c] = rv;
 		acc += bv * bv;
-		mg_preload(G, M, x, y, lz, c, rv, v.f);
+		mg_preload(G, M, x, y, lz, c, rv, v.f, inv_a_scale);
 	});
 	acc = block_sum(acc);
 	if (threadIdx.x == 0) { partials[blockIdx.x] = acc; }
@@ -207,14 +213,17 @@ __global__ void __launch_bounds__(RED_THREADS) k_pcg_init_warm(GridDesc G, const
 		if (threadIdx.x == 0) {
 			scal->bb = tot;
 			scal->sigma = 0.0;
-			if (finalize) { pcg_finalize(scal, FIN_BB, 0.0); }
+			scal->a_scale = a_scale; // the iteration's kernels read these from here
+			scal->inv_a_scale = 1.0 / a_scale;
+			scal->tolerance = tolerance;
+			if (finalize) { pcg_finalize(scal, FIN_BB); }
 		}
 	}
 }
 
 // Jacobi: z = r / (a_scale * n)
 __global__ void k_precond_jacobi(GridDesc G, const uint8_t *__restrict__ flags, const double *__restrict__ r,
-	double *__restrict__ z, double a_scale, const PcgScalars *scal) {
+	double *__restrict__ z, const PcgScalars *scal) {
 	if (scal->done) { return; }
 	long long own = (long long)blockIdx.x * blockDim.x + threadIdx.x;
 	if (own >= G.nown) { return; }
@@ -222,7 +231,7 @@ __global__ void k_precond_jacobi(GridDesc G, const uint8_t *__restrict__ flags, 
 	unsigned f = flags[c];
 	double out = 0.0;
 	if ((f & FL_L) && FL_N(f) > 0) {
-		out = r[c] / (a_scale * (double)FL_N(f));
+		out = r[c] / (scal->a_scale * (double)FL_N(f));
 	}
 	z[c] = out;
 }
@@ -239,7 +248,7 @@ __global__ void __launch_bounds__(RED_THREADS) k_dot_zr(GridDesc G, const double
 		double tot = finish_partials(partials, gridDim.x, 0);
 		if (threadIdx.x == 0) {
 			scal->sigma_new = tot;
-			if (finalize) { pcg_finalize(scal, first ? FIN_BETA_FIRST : FIN_BETA, 0.0); }
+			if (finalize) { pcg_finalize(scal, first ? FIN_BETA_FIRST : FIN_BETA); }
 		}
 	}
 }
@@ -247,9 +256,9 @@ __global__ void __launch_bounds__(RED_THREADS) k_dot_zr(GridDesc G, const double
 // p += alpha s ; r -= alpha z ; residual = max |r|
 __global__ void __launch_bounds__(RED_THREADS) k_update_pr(GridDesc G, double *__restrict__ p,
 	double *__restrict__ r, const double *__restrict__ s, const double *__restrict__ z, PcgScalars *scal,
-	double *partials, unsigned *ticket, double tolerance, int finalize, MgPreload M) {
+	double *partials, unsigned *ticket, int finalize, MgPreload M) {
 	if (scal->done) { return; }
-	const double alpha = scal->alpha;
+	const double alpha = scal->alpha, inv_a_scale = scal->inv_a_scale;
 	double m = 0.0;
 	struct PR { double p, s, r, z; unsigned f; };
 	rows_pipelined<4, PR>(G.nx, G.ny, G.nzl, 0, -1,
@@ -267,7 +276,7 @@ __global__ void __launch_bounds__(RED_THREADS) k_update_pr(GridDesc G, double *_
 			p[c] = v.p + alpha * v.s;
 			r[c] = rv;
 			m = fmax(m, fabs(rv));
-			mg_preload(G, M, x, y, lz, c, rv, v.f);
+			mg_preload(G, M, x, y, lz, c, rv, v.f, inv_a_scale);
 		});
 	m = block_max(m);
 	if (threadIdx.x == 0) { partials[blockIdx.x] = m; }
@@ -275,7 +284,7 @@ __global__ void __launch_bounds__(RED_THREADS) k_update_pr(GridDesc G, double *_
 		double tot = finish_partials(partials, gridDim.x, 1);
 		if (threadIdx.x == 0) {
 			scal->resmax = tot;
-			if (finalize) { pcg_finalize(scal, FIN_RESID, tolerance); }
+			if (finalize) { pcg_finalize(scal, FIN_RESID); }
 		}
 	}
 }
@@ -322,25 +331,26 @@ static inline unsigned red_blocks(const lfk_ctx *c) {
 	return lfk_row_blocks(c->g, RED_THREADS, cap < RED_BLOCKS ? cap : RED_BLOCKS);
 }
 
-static int allreduce_scalar(lfk_ctx *c, double *field, bool is_max, int which, double tol) {
+static int allreduce_scalar(lfk_ctx *c, double *field, bool is_max, int which) {
 	if (c->nranks > 1) {
 		LFK_TRY(is_max ? lfkx_allreduce_max(c, field, 1) : lfkx_allreduce_sum(c, field, 1));
-		LFK_LAUNCH(c, k_finalize, 1, 1, 0, c->d_scal, which, tol);
+		LFK_LAUNCH(c, k_finalize, 1, 1, 0, c->d_scal, which);
 	}
 	return 0;
 }
 
+int lfks_free_graph(lfk_ctx *c);
 int lfkm_setup(lfk_ctx *c, double a_scale);                                    // mg.cu
 int lfkm_level0(lfk_ctx *c, float **b0, float **x0);                           // mg.cu
-int lfkm_apply_preloaded(lfk_ctx *c, double a_scale, unsigned nb, int fin, int first); // mg.cu: V-cycle + (z, z.r)
+int lfkm_apply_preloaded(lfk_ctx *c, unsigned nb, int fin, int first); // mg.cu: V-cycle + (z, z.r)
 
 // z = M^-1 r and sigma_new = z.r (+ its finaliser on one GPU)
-static int precondition_and_dot(lfk_ctx *c, double a_scale, unsigned nb, int fin, int first) {
+static int precondition_and_dot(lfk_ctx *c, unsigned nb, int fin, int first) {
 	const GridDesc &G = c->g;
 	if (c->prm.preconditioner == LFK_PRECOND_MULTIGRID) {
-		return lfkm_apply_preloaded(c, a_scale, nb, fin, first);
+		return lfkm_apply_preloaded(c, nb, fin, first);
 	}
-	LFK_LAUNCH(c, k_precond_jacobi, lfk_blocks(G.nown, 256), 256, 0, G, c->flags, c->r, c->z, a_scale, c->d_scal);
+	LFK_LAUNCH(c, k_precond_jacobi, lfk_blocks(G.nown, 256), 256, 0, G, c->flags, c->r, c->z, c->d_scal);
 	LFK_LAUNCH(c, k_dot_zr, nb, RED_THREADS, 0, G, c->z, c->r, c->d_scal, c->partials, c->ticket, fin, first);
 	return 0;
 }
@@ -369,21 +379,62 @@ int lfks_solve(lfk_ctx *c, double dt, double *residual, uint64_t *iters, bool wa
 	if (c->prm.preconditioner == LFK_PRECOND_MULTIGRID && !c->mg_valid) {
 		LFK_TRY(lfkm_setup(c, a_scale));
 	}
-	MgPreload M{ nullptr, nullptr, c->flags, 1.0 / a_scale };
+	MgPreload M{ nullptr, nullptr, c->flags };
 	if (c->prm.preconditioner == LFK_PRECOND_MULTIGRID) {
 		LFK_TRY(lfkm_level0(c, &M.b0, &M.x0));
 	}
 	if (warmed) {
 		if (c->nranks > 1) { LFK_TRY(lfkx_halo_f64(c, c->p)); }
 		LFK_LAUNCH(c, k_pcg_init_warm, nb, RED_THREADS, 0, G, c->flags, c->b, c->p, c->r, a_scale, c->d_scal, c->partials,
-			c->ticket, fin, M);
+			c->ticket, fin, M, tol);
 	} else {
-		LFK_LAUNCH(c, k_pcg_init, nb, RED_THREADS, 0, G, c->b, c->r, c->d_scal, c->partials, c->ticket, fin, M);
+		LFK_LAUNCH(c, k_pcg_init, nb, RED_THREADS, 0, G, c->b, c->r, c->d_scal, c->partials, c->ticket, fin, M, a_scale, tol);
 	}
-	LFK_TRY(allreduce_scalar(c, &c->d_scal->bb, false, FIN_BB, tol));
-	LFK_TRY(precondition_and_dot(c, a_scale, nb, fin, 1));
-	LFK_TRY(allreduce_scalar(c, &c->d_scal->sigma_new, false, FIN_BETA_FIRST, tol));
+	LFK_TRY(allreduce_scalar(c, &c->d_scal->bb, false, FIN_BB));
+	LFK_TRY(precondition_and_dot(c, nb, fin, 1));
+	LFK_TRY(allreduce_scalar(c, &c->d_scal->sigma_new, false, FIN_BETA_FIRST));
 	LFK_LAUNCH(c, k_xpby, eb, 256, 0, G, c->s, c->z, c->d_scal);
+
+	// one iteration (src/pressure_solver.cpp:44-68); with_direction: everything after the residual test
+	auto iteration = [&](bool with_direction) -> int {
+		if (c->nranks > 1) { LFK_TRY(lfkx_halo_f64(c, c->s)); }
+		LFK_LAUNCH(c, k_spmv_dot, nb, RED_THREADS, 0, G, c->flags, c->s, c->z, c->d_scal, c->partials, c->ticket, fin);
+		LFK_TRY(allreduce_scalar(c, &c->d_scal->zs, false, FIN_ALPHA));
+		LFK_LAUNCH(c, k_update_pr, nb, RED_THREADS, 0, G, c->p, c->r, c->s, c->z, c->d_scal, c->partials, c->ticket, fin, M);
+		LFK_TRY(allreduce_scalar(c, &c->d_scal->resmax, true, FIN_RESID));
+		if (with_direction) { // the reference leaves the loop after max_iterations updates of p, r
+			LFK_TRY(precondition_and_dot(c, nb, fin, 0));
+			LFK_TRY(allreduce_scalar(c, &c->d_scal->sigma_new, false, FIN_BETA));
+			LFK_LAUNCH(c, k_xpby, eb, 256, 0, G, c->s, c->z, c->d_scal);
+		}
+		return 0;
+	};
+	// The iteration's kernels take every per-solve quantity from device memory (PcgScalars), so ONE captured CUDA graph
+	// serves every iteration of every solve of this context; it is re-captured only when the launch configuration
+	// changes.  ~40 launches per iteration collapse into one graph launch (launch gaps were ~17 % of the iteration).
+	const bool use_graph = c->tune.graph != 0 && c->nranks == 1;
+	const int graph_key = (int)nb * 4 + c->prm.preconditioner * 2 + 1;
+	if (use_graph && (c->pcg_graph == nullptr || c->pcg_graph_key != graph_key)) {
+		LFK_TRY(lfks_free_graph(c));
+		cudaGraph_t graph = nullptr;
+		const uint64_t before = c->stats.kernel_launches;
+		LFK_CUDA(c, cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
+		const int rc_it = iteration(true);
+		const cudaError_t e_end = cudaStreamEndCapture(c->stream, &graph);
+		if (rc_it != 0 || e_end != cudaSuccess || graph == nullptr) {
+			if (graph) { cudaGraphDestroy(graph); }
+			cudaGetLastError();
+			return lfk_fail(c, rc_it != 0 ? rc_it : -(int)e_end, "capturing the PCG iteration graph failed", __FILE__, __LINE__);
+		}
+		c->pcg_graph_launches = (unsigned)(c->stats.kernel_launches - before);
+		c->stats.kernel_launches = before; // captured, not launched
+		cudaGraphExec_t exec = nullptr;
+		const cudaError_t e_inst = cudaGraphInstantiate(&exec, graph, 0);
+		cudaGraphDestroy(graph);
+		LFK_CUDA(c, e_inst);
+		c->pcg_graph = exec;
+		c->pcg_graph_key = graph_key;
+	}
 
 	// The loop runs entirely from device-resident scalars; the host only polls the `done` flag now and then.
 	// Kernels issued after convergence return immediately, so the iteration count stays exact.
@@ -393,7 +444,7 @@ int lfks_solve(lfk_ctx *c, double dt, double *residual, uint64_t *iters, bool wa
 	const long long per_rank = G.sxy * (long long)G.nz / c->nranks;
 	int poll = per_rank >= (1ll << 22) ? 2 : (per_rank >= (1ll << 18) ? 8 : 16);
 	int issued = 0;
-	bool done = false;
+	bool done = max_it <= 0;
 	// first burst: one short of what the previous solve of this context needed (consecutive steps need about the same
 	// number of iterations), so that at most a couple of no-op iterations are issued past convergence
 	int first_burst = (int)c->last_iters - 1;
@@ -401,17 +452,12 @@ int lfks_solve(lfk_ctx *c, double dt, double *residual, uint64_t *iters, bool wa
 		int want = issued == 0 && first_burst > poll ? first_burst : poll;
 		int burst = max_it - issued < want ? max_it - issued : want;
 		for (int k = 0; k < burst; ++k) {
-			if (c->nranks > 1) { LFK_TRY(lfkx_halo_f64(c, c->s)); }
-			LFK_LAUNCH(c, k_spmv_dot, nb, RED_THREADS, 0, G, c->flags, c->s, c->z, a_scale, c->d_scal, c->partials,
-				c->ticket, fin);
-			LFK_TRY(allreduce_scalar(c, &c->d_scal->zs, false, FIN_ALPHA, tol));
-			LFK_LAUNCH(c, k_update_pr, nb, RED_THREADS, 0, G, c->p, c->r, c->s, c->z, c->d_scal, c->partials,
-				c->ticket, tol, fin, M);
-			LFK_TRY(allreduce_scalar(c, &c->d_scal->resmax, true, FIN_RESID, tol));
-			if (issued + k + 1 < max_it) { // the reference leaves the loop after max_iterations updates of p, r
-				LFK_TRY(precondition_and_dot(c, a_scale, nb, fin, 0));
-				LFK_TRY(allreduce_scalar(c, &c->d_scal->sigma_new, false, FIN_BETA, tol));
-				LFK_LAUNCH(c, k_xpby, eb, 256, 0, G, c->s, c->z, c->d_scal);
+			const bool with_direction = issued + k + 1 < max_it;
+			if (use_graph && with_direction) {
+				LFK_CUDA(c, cudaGraphLaunch((cudaGraphExec_t)c->pcg_graph, c->stream));
+				c->stats.kernel_launches += c->pcg_graph_launches;
+			} else {
+				LFK_TRY(iteration(with_direction));
 			}
 		}
 		issued += burst;
@@ -420,6 +466,7 @@ int lfks_solve(lfk_ctx *c, double dt, double *residual, uint64_t *iters, bool wa
 		done = c->h_scal->done != 0 || issued >= max_it;
 		if (poll < 8 && first_burst <= 2) { poll *= 2; }
 	}
+	if (c->nranks > 1) { LFK_TRY(lfkx_check(c)); }
 	if (warmed && c->h_scal->iters == 0 && c->h_scal->bb < 1e-6) { // early-out of the reference: p = 0 (:29-35)
 		LFK_CUDA(c, cudaMemsetAsync(c->p, 0, (size_t)G.ncl * sizeof(double), c->stream));
 	}
@@ -435,6 +482,14 @@ int lfks_solve(lfk_ctx *c, double dt, double *residual, uint64_t *iters, bool wa
 }
 
 // out = A v on dense vectors (parity hook for _apply_a)
+int lfks_free_graph(lfk_ctx *c) {
+	if (c->pcg_graph) {
+		cudaGraphExecDestroy((cudaGraphExec_t)c->pcg_graph);
+		c->pcg_graph = nullptr;
+	}
+	return 0;
+}
+
 int lfks_apply_a(lfk_ctx *c, double dt, const double *d_v_dense, double *d_out_dense) {
 	const GridDesc &G = c->g;
 	if (!c->system_valid || c->system_dt != dt) {
