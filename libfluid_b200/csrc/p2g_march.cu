@@ -3,8 +3,8 @@
 // issued one window ahead of the arithmetic.
 // Reference: simulation::_transfer_to_grid_{pic,flip,apic}, src/simulation.cpp:293-412, 428-445, 72-78.
 //
-// A block owns the +faces of PM_BX x PM_BY cell columns over a chunk of z planes.  Warp <-> one row y of 32 cells
-// (the PM_BY owned rows plus one halo row either side), lane <-> cell x (30 owned columns plus one halo column either
+// A block owns the +faces of PM_BX x (WARPS - 2) cell columns over a chunk of z planes.  Warp <-> one row y of 32 cells
+// (the WARPS - 2 owned rows plus one halo row either side), lane <-> cell x (30 owned columns plus one halo column either
 // side).  All warps march through the cell layers of the chunk together.  For the layer it is in, a lane runs over
 // the particles of ITS cell and accumulates, in registers, their contributions to the 2 x 3 x 3 faces the cell can
 // reach (per velocity component) -- the per-cell arithmetic of p2g_accum.cuh.  What differs from the brick kernel
@@ -17,7 +17,7 @@
 //     barrier the warp that owns row y adds slot[y-1], slot[y], slot[y+1] in that fixed order, normalises,
 //     classifies, zeroes boundary faces, takes the FLIP snapshot, adds gravity and writes the finished face row.
 // No colouring, no read-modify-write on shared accumulators, one barrier per layer.  Halo recomputation: 32/30 in x,
-// (PM_BY + 2)/PM_BY in y, (chunk + 2)/chunk in z (1.33x .. 1.4x, against 1.65x for the brick).
+// WARPS/(WARPS - 2) in y, (chunk + 2)/chunk in z (1.33x .. 1.4x, against 1.65x for the brick).
 //
 // Staging: per warp two buffers of [field][cell * PB_CSTRIDE + slot]; window n+1 (4 particle slots per cell) is
 // copied with cp.async while window n is being accumulated, and the permutation indices (lean sort: velocity / c
@@ -380,6 +380,6 @@ int lfkg_p2g_march(lfk_ctx *c, double gravity_dt, bool add_gravity) {
 	// one permutation serves the velocity and the c rows: make them agree (they differ only after lfkp_permute_c)
 	if (c->prm.method == LFK_METHOD_APIC && c->v_deferred != c->c_deferred) { LFK_TRY(lfkp_materialise_vc(c)); }
 	const uint32_t *perm = c->v_deferred ? c->perm : nullptr;
-	if (c->tune.p2g_warps == 10) { return p2g_march_launch<10>(c, Q, perm); }
+	// (10 rows per block at 168 registers spill the accumulators: 25.8 ms against 15.2 ms at 256^3, r2c sweep)
 	return p2g_march_launch<8>(c, Q, perm);
 }
