@@ -86,6 +86,7 @@ extern "C" int lfk_nccl_unique_id(void *out128) {
 // e + 1 writes.  Every rank issues the same sequence of exchanges (as for NCCL), so the epochs agree by construction.
 // A spin that lasts longer than ~4 s raises an error flag instead of hanging the device.
 // =========================================================================================================
+#define LL_MAX_BYTES (256u * 1024u) // larger layers take the fence-and-flag protocol
 #define ARENA_HEADER 256 // bytes: flag words + block counter + error word
 struct ArenaHeader {
 	unsigned long long sig[2]; // [0] raised by the lower neighbour, [1] by the upper one
@@ -161,6 +162,70 @@ __global__ void __launch_bounds__(256) k_halo_p2p(char *mine, char *up, char *dn
 	if (up) { halo_copy<true>(ghost_top, mine + ARENA_HEADER + (1 * 2 + par) * slot, bytes); }
 }
 
+// Small layers (the coarse multigrid levels: a few KB) are pure latency, so they use a flag-in-data protocol instead:
+// every 4-byte element travels as an 8-byte word {element, epoch}; an aligned 8-byte store arrives whole, so the receiver
+// simply polls each word until its epoch matches -- no fence, no separate flag, one NVLink traversal per exchange.
+__device__ __forceinline__ void st_ll(char *slot, size_t i, unsigned v, unsigned flag) {
+	asm volatile("st.volatile.global.v2.u32 [%0], {%1, %2};" ::"l"(slot + 8 * i), "r"(v), "r"(flag) : "memory");
+}
+__device__ __forceinline__ bool ld_ll(const char *slot, size_t i, unsigned flag, unsigned &v, unsigned *error) {
+	unsigned f;
+	long long t0 = 0;
+	for (unsigned spins = 0;; ++spins) {
+		asm volatile("ld.volatile.global.v2.u32 {%0, %1}, [%2];" : "=r"(v), "=r"(f) : "l"(slot + 8 * i) : "memory");
+		if (f == flag) { return true; }
+		if ((spins & 1023u) == 1023u) {
+			if (t0 == 0) { t0 = clock64(); }
+			else if (clock64() - t0 > 8000000000ll) { *error = 1u; return false; } // ~4 s: a neighbour is gone
+		}
+	}
+}
+__global__ void __launch_bounds__(256) k_halo_ll(char *mine, char *up, char *dn, const unsigned *top,
+	const unsigned *bottom, unsigned *ghost_top, unsigned *ghost_bottom, size_t nwords, size_t ll_base) {
+	ArenaHeader *H = reinterpret_cast<ArenaHeader *>(mine);
+	const unsigned long long epoch = *reinterpret_cast<volatile unsigned long long *>(&H->epoch) + 1ull;
+	const size_t par = (size_t)(epoch & 1ull);
+	const unsigned flag = (unsigned)epoch; // (arena words start at 0 and epochs at 1)
+	const size_t slot = 2 * LL_MAX_BYTES;
+	mine += ll_base;
+	if (up) { up += ll_base; }
+	if (dn) { dn += ll_base; }
+	H = reinterpret_cast<ArenaHeader *>(mine - ll_base);
+	const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x, nth = (size_t)gridDim.x * blockDim.x;
+	if (up) {
+		char *dst = up + ARENA_HEADER + (0 * 2 + par) * slot;
+		for (size_t i = tid; i < nwords; i += nth) { st_ll(dst, i, top[i], flag); }
+	}
+	if (dn) {
+		char *dst = dn + ARENA_HEADER + (1 * 2 + par) * slot;
+		for (size_t i = tid; i < nwords; i += nth) { st_ll(dst, i, bottom[i], flag); }
+	}
+	if (dn) {
+		const char *src = mine + ARENA_HEADER + (0 * 2 + par) * slot;
+		for (size_t i = tid; i < nwords; i += nth) {
+			unsigned v;
+			if (!ld_ll(src, i, flag, v, &H->error)) { break; }
+			ghost_bottom[i] = v;
+		}
+	}
+	if (up) {
+		const char *src = mine + ARENA_HEADER + (1 * 2 + par) * slot;
+		for (size_t i = tid; i < nwords; i += nth) {
+			unsigned v;
+			if (!ld_ll(src, i, flag, v, &H->error)) { break; }
+			ghost_top[i] = v;
+		}
+	}
+	__syncthreads();
+	if (threadIdx.x == 0) { // the last block to finish advances the epoch (see k_halo_p2p)
+		const unsigned t = atomicAdd(&H->counter, 1u);
+		if (t == gridDim.x - 1) {
+			H->counter = 0;
+			*reinterpret_cast<volatile unsigned long long *>(&H->epoch) = epoch;
+		}
+	}
+}
+
 static int arena_setup(lfk_ctx *c) {
 	c->p2p = false;
 	if (c->nranks == 1) { return 0; }
@@ -169,7 +234,9 @@ static int arena_setup(lfk_ctx *c) {
 	}
 	ncclComm_t comm = (ncclComm_t)c->comm;
 	c->arena_slot = (((size_t)c->g.sxy * sizeof(double)) + 255) / 256 * 256;
-	const size_t bytes = ARENA_HEADER + 4 * c->arena_slot;
+	// [header | 2 x 2 fence-protocol slots of one fp64 layer | 2 x 2 flag-in-data slots] -- the two protocols never share
+	// a slot, so a raw data word can never be mistaken for an {element, epoch} word
+	const size_t bytes = ARENA_HEADER + 4 * c->arena_slot + 4 * (size_t)(2 * LL_MAX_BYTES);
 	LFK_CUDA(c, cudaMalloc((void**)&c->arena, bytes));
 	LFK_CUDA(c, cudaMemsetAsync(c->arena, 0, bytes, c->stream));
 	// exchange the IPC handles of all arenas (64 bytes each) with an NCCL all-gather; `ok` words tell every rank whether
@@ -261,6 +328,14 @@ static int halo_bytes(lfk_ctx *c, void *field, size_t layer_elems, int nzl, nccl
 	ncclComm_t comm = (ncclComm_t)c->comm;
 	char *f = (char*)field;
 	size_t L = layer_elems * esz;
+	if (c->p2p && c->tune.p2p && L % 4 == 0 && L <= LL_MAX_BYTES && (((size_t)f | (size_t)(f + L)) & 3u) == 0) {
+		++c->halo_epoch;
+		unsigned nb = (unsigned)((L / 4 + 255) / 256);
+		nb = nb < 1 ? 1 : (nb > 64 ? 64 : nb);
+		LFK_LAUNCH(c, k_halo_ll, nb, 256, 0, c->arena, c->arena_peer[0], c->arena_peer[1], (const unsigned*)(f + (size_t)nzl * L),
+			(const unsigned*)(f + L), (unsigned*)(f + (size_t)(nzl + 1) * L), (unsigned*)f, L / 4, 4 * c->arena_slot);
+		return 0;
+	}
 	if (c->p2p && c->tune.p2p && L <= c->arena_slot) {
 		++c->halo_epoch;
 		unsigned nb = (unsigned)((L / 16 + 255) / 256);

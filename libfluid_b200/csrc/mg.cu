@@ -560,16 +560,23 @@ int lfkm_free(lfk_ctx *c) {
 	return 0;
 }
 
-// ---- multi-GPU: agglomerated coarse levels (experimental, lfk_set_tuning("mg_agg", 1); never run on a GPU yet) ---
-// Below a few thousand cells in the WHOLE grid a distributed level is pure latency: every half-sweep is an NCCL
-// exchange (~13 us) for microseconds of arithmetic, and the hierarchy has to stop where the slabs stop being aligned
-// to the 2x2x2 aggregates.  With the switch on, the first level whose global size fits the single-block tail kernel
-// is assembled on EVERY rank (operators once per solve, right-hand side once per cycle: each rank writes its own
-// layers into a zeroed global array and one all-reduce adds them up -- exact, every element has one non-zero
-// contributor), the hierarchy continues below it on the global grid down to a handful of cells, the whole tail runs
-// redundantly on every rank in one launch (k_mg_tail*), and the rank copies its own layers plus the two ghost layers
-// of the result back.  Per cycle: one all-reduce instead of ~8 exchanges per distributed level below that point and
-// 16 on the coarsest one.
+// ---- multi-GPU: agglomerated coarse levels (lfk_set_tuning("mg_agg", 0) keeps every level distributed) ------------
+// A small distributed level is pure latency: every half-sweep is a halo exchange (~10 us) for microseconds of arithmetic,
+// and the hierarchy has to stop where the slabs stop being aligned to the 2x2x2 aggregates.  Instead, the first level
+// whose WHOLE-GRID size is at most agg_max_cells() is assembled on EVERY rank (operators once per solve, right-hand side
+// once per cycle: each rank writes its own layers into a zeroed global array and one all-reduce adds them up -- exact,
+// every element has one non-zero contributor), the hierarchy continues below it on the global grid down to a handful
+// of cells, every rank runs that part of the cycle redundantly (vcycle_agg: the generic level kernels, then the
+// single-block tail), and copies its own layers plus the two ghost layers of the result back.  Per cycle: one
+// all-reduce instead of ~8 exchanges per distributed level below that point and 16 on the coarsest one.
+// Largest global level that is agglomerated: every distributed level costs ~8 halo exchanges of ~10 us per cycle however
+// small it is, while a level of a few hundred thousand cells costs ~9 launches of ~5 us when every rank sweeps all of
+// it -- so levels up to this size are cheaper replicated than distributed (2 GPUs, 512 x 256 x 256: 1.68 ms per PCG
+// iteration with the threshold at the single-block tail size of 4096 cells against 2.06 ms fully distributed, r2d).
+static long long agg_max_cells(const lfk_ctx *c) {
+	return c->tune.mg_agg_cells > 0 ? (long long)c->tune.mg_agg_cells : 600000ll;
+}
+
 static int mg_agg_alloc(lfk_ctx *c) {
 	if (!c->mg_agg.empty() || c->mg_agg_level == -2) { return 0; }
 	c->mg_agg_level = -2; // decided: none (unless found below)
@@ -577,11 +584,11 @@ static int mg_agg_alloc(lfk_ctx *c) {
 	int la = -1;
 	for (size_t l = 1; l < c->mg.size(); ++l) { // aligned coarsening: the global depth of level l is nz >> l
 		const long long gnz = G.nz >> l;
-		if ((long long)c->mg[l].nx * c->mg[l].ny * gnz <= MG_COARSE_MAX_CELLS) { la = (int)l; break; }
+		if ((long long)c->mg[l].nx * c->mg[l].ny * gnz <= agg_max_cells(c)) { la = (int)l; break; }
 	}
 	if (la < 0) { return 0; }
 	int nx = c->mg[la].nx, ny = c->mg[la].ny, nz = G.nz >> la;
-	for (int k = 0; k < MG_TAIL_MAX_LEVELS; ++k) {
+	for (int k = 0; k < 16; ++k) {
 		MgLevel L{};
 		L.nx = nx; L.ny = ny; L.nzl = nz; L.nlz = nz + 2;
 		L.sxy = (long long)nx * ny;
@@ -631,6 +638,38 @@ static int mg_agg_setup(lfk_ctx *c) { // after the distributed operators of this
 
 static int launch_tail(lfk_ctx *c, const TailLevels &T);
 
+// V-cycle on the agglomerated (replicated, whole-grid) levels >= k: the generic level kernels without any exchange;
+// levels that fit the single-block tail are finished by it in one launch.  x of level k is zero on entry.
+static int vcycle_agg(lfk_ctx *c, size_t k) {
+	std::vector<MgLevel> &Ls = c->mg_agg;
+	const size_t last = Ls.size() - 1;
+	const LevelDev Ld = level_dev(Ls[k], 0);
+	if (k == last || (Ld.nown <= MG_COARSE_MAX_CELLS && last - k < MG_TAIL_MAX_LEVELS)) {
+		TailLevels T;
+		T.n = 0;
+		T.coarse_sweeps = c->tune.mg_coarse > 0 ? c->tune.mg_coarse : MG_COARSE_SWEEPS;
+		for (size_t j = k; j <= last && T.n < MG_TAIL_MAX_LEVELS; ++j) { T.L[T.n++] = level_dev(Ls[j], 0); }
+		return launch_tail(c, T);
+	}
+	const LevelDev Cd = level_dev(Ls[k + 1], 0);
+	const unsigned nb = row_blocks(Ld.ny, Ld.nzl, 256, 1u << 20);
+	for (int s = 0; s < MG_PRE; ++s) { // red, black
+		LFK_LAUNCH(c, k_mg_rbgs<false>, nb, 256, 0, Ld, 0, Ld, c->d_scal);
+		LFK_LAUNCH(c, k_mg_rbgs<false>, nb, 256, 0, Ld, 1, Ld, c->d_scal);
+	}
+	LFK_LAUNCH(c, k_mg_restrict, row_blocks(Cd.ny, Cd.nzl, 128, 1u << 20), 128, 0, Ld, Cd, c->d_scal);
+	LFK_TRY(vcycle_agg(c, k + 1));
+	for (int s = 0; s < MG_POST; ++s) { // black (the first one applies the prolongation on the fly), red
+		if (s == 0) {
+			LFK_LAUNCH(c, k_mg_rbgs<true>, nb, 256, 0, Ld, 1, Cd, c->d_scal);
+		} else {
+			LFK_LAUNCH(c, k_mg_rbgs<false>, nb, 256, 0, Ld, 1, Ld, c->d_scal);
+		}
+		LFK_LAUNCH(c, k_mg_rbgs<false>, nb, 256, 0, Ld, 0, Ld, c->d_scal);
+	}
+	return 0;
+}
+
 // the cycle of distributed level `la` and everything below it, on the agglomerated grid
 static int mg_agg_cycle(lfk_ctx *c) {
 	const int la = c->mg_agg_level;
@@ -639,11 +678,7 @@ static int mg_agg_cycle(lfk_ctx *c) {
 	const int z0 = c->mg_z0[la];
 	LFK_TRY(mg_agg_gather(c, D, z0, D.b, Gl, Gl.b));
 	LFK_CUDA(c, cudaMemsetAsync(Gl.x, 0, ((size_t)Gl.ncl + 2) * sizeof(float), c->stream));
-	TailLevels T;
-	T.n = 0;
-	T.coarse_sweeps = c->tune.mg_coarse > 0 ? c->tune.mg_coarse : MG_COARSE_SWEEPS;
-	for (const MgLevel &L : c->mg_agg) { T.L[T.n++] = level_dev(L, 0); }
-	LFK_TRY(launch_tail(c, T));
+	LFK_TRY(vcycle_agg(c, 0));
 	// my layers and the ghost layer either side: global layer index of local layer 0 is z0 - 1 + 1 = z0
 	LFK_CUDA(c, cudaMemcpyAsync(D.x, Gl.x + (size_t)Gl.sxy * z0, (size_t)D.sxy * (D.nzl + 2) * sizeof(float),
 		cudaMemcpyDeviceToDevice, c->stream));

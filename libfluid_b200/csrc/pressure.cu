@@ -412,8 +412,9 @@ int lfks_solve(lfk_ctx *c, double dt, double *residual, uint64_t *iters, bool wa
 	// The iteration's kernels take every per-solve quantity from device memory (PcgScalars), so ONE captured CUDA graph
 	// serves every iteration of every solve of this context; it is re-captured only when the launch configuration
 	// changes.  ~40 launches per iteration collapse into one graph launch (launch gaps were ~17 % of the iteration).
-	const bool use_graph = c->tune.graph != 0 && c->nranks == 1;
-	const int graph_key = (int)nb * 4 + c->prm.preconditioner * 2 + 1;
+	// (multi-GPU: the halo kernels and NCCL all-reduces are captured like any other node; lfk_set_tuning("graph", 2))
+	const bool use_graph = c->nranks == 1 ? c->tune.graph != 0 : c->tune.graph == 2;
+	const int graph_key = (((int)nb * 2 + c->prm.preconditioner) * 2 + (c->tune.p2p ? 1 : 0)) * 4 + (c->tune.mg_agg ? 2 : 0) + 1;
 	if (use_graph && (c->pcg_graph == nullptr || c->pcg_graph_key != graph_key)) {
 		LFK_TRY(lfks_free_graph(c));
 		cudaGraph_t graph = nullptr;
