@@ -88,8 +88,10 @@ extern "C" int lfk_nccl_unique_id(void *out128) {
 // =========================================================================================================
 #define LL_MAX_BYTES (256u * 1024u) // larger layers take the fence-and-flag protocol
 #define ARENA_HEADER 256 // bytes: flag words + block counter + error word
+#define ARENA_MAX_RANKS 64
 struct ArenaHeader {
 	unsigned long long sig[2]; // [0] raised by the lower neighbour, [1] by the upper one
+	unsigned long long sepoch; // scalar all-reduces completed by this rank
 	unsigned long long epoch;  // exchanges completed by this rank (device resident, so that the kernel's arguments never
 	                           // change and a captured CUDA graph of a PCG iteration can be replayed)
 	unsigned counter;          // blocks of the running exchange kernel that have published their stores
@@ -226,6 +228,57 @@ __global__ void __launch_bounds__(256) k_halo_ll(char *mine, char *up, char *dn,
 	}
 }
 
+static void arena_unmap(lfk_ctx *c) {
+	for (size_t r = 0; r < c->arena_all.size(); ++r) {
+		if ((int)r != c->rank && c->arena_all[r]) { cudaIpcCloseMemHandle(c->arena_all[r]); }
+	}
+	c->arena_all.clear();
+	c->arena_peer[0] = c->arena_peer[1] = nullptr;
+	if (c->arena_all_d) { cudaFree(c->arena_all_d); c->arena_all_d = nullptr; }
+}
+
+// ---- scalar all-reduce over peer memory, fused with the PCG finaliser ----------------------------------------------
+// Every rank stores its partial value (as two {half, epoch} words) into EVERY rank's arena, then folds the nranks
+// values it received in rank order -- every rank computes the same sum bit for bit -- and runs the finaliser that the
+// single-GPU kernels run in their last block.  One launch of one warp-sized block instead of ncclAllReduce + k_finalize.
+__global__ void __launch_bounds__(ARENA_MAX_RANKS) k_allreduce_ll(char *mine, char *const *all, int nranks, int rank,
+	size_t base, double *field, int is_max, PcgScalars *scal, int which) {
+	ArenaHeader *H = reinterpret_cast<ArenaHeader *>(mine);
+	__shared__ double vals[ARENA_MAX_RANKS];
+	const unsigned long long epoch = *reinterpret_cast<volatile unsigned long long *>(&H->sepoch) + 1ull;
+	const size_t par = (size_t)(epoch & 1ull);
+	const unsigned flag = (unsigned)epoch;
+	const int t = (int)threadIdx.x;
+	if (t < nranks) {
+		const unsigned long long bits = (unsigned long long)__double_as_longlong(*field);
+		char *dst = all[t] + base + (par * ARENA_MAX_RANKS + (size_t)rank) * 16;
+		st_ll(dst, 0, (unsigned)bits, flag);
+		st_ll(dst, 1, (unsigned)(bits >> 32), flag);
+		const char *src = mine + base + (par * ARENA_MAX_RANKS + (size_t)t) * 16;
+		unsigned lo = 0, hi = 0;
+		const bool ok = ld_ll(src, 0, flag, lo, &H->error) && ld_ll(src, 1, flag, hi, &H->error);
+		vals[t] = ok ? __longlong_as_double((long long)(((unsigned long long)hi << 32) | lo)) : 0.0;
+	}
+	__syncthreads();
+	if (t == 0) {
+		double acc = vals[0];
+		for (int r = 1; r < nranks; ++r) { acc = is_max ? fmax(acc, vals[r]) : acc + vals[r]; }
+		*field = acc;
+		*reinterpret_cast<volatile unsigned long long *>(&H->sepoch) = epoch;
+		if (which == FIN_BB || !scal->done) { pcg_finalize(scal, which); }
+	}
+}
+
+int lfkx_allreduce_finalize(lfk_ctx *c, double *field, bool is_max, int which) {
+	if (!(c->p2p && c->tune.p2p && c->arena_all_d)) { return 0; }
+	const size_t base = ARENA_HEADER + 4 * c->arena_slot + 4 * (size_t)(2 * LL_MAX_BYTES);
+	k_allreduce_ll<<<1, ARENA_MAX_RANKS, 0, c->stream>>>(c->arena, c->arena_all_d, c->nranks, c->rank, base, field,
+		is_max ? 1 : 0, c->d_scal, which);
+	++c->stats.kernel_launches;
+	if (cudaGetLastError() != cudaSuccess) { return 0; }
+	return 1;
+}
+
 static int arena_setup(lfk_ctx *c) {
 	c->p2p = false;
 	if (c->nranks == 1) { return 0; }
@@ -236,7 +289,8 @@ static int arena_setup(lfk_ctx *c) {
 	c->arena_slot = (((size_t)c->g.sxy * sizeof(double)) + 255) / 256 * 256;
 	// [header | 2 x 2 fence-protocol slots of one fp64 layer | 2 x 2 flag-in-data slots] -- the two protocols never share
 	// a slot, so a raw data word can never be mistaken for an {element, epoch} word
-	const size_t bytes = ARENA_HEADER + 4 * c->arena_slot + 4 * (size_t)(2 * LL_MAX_BYTES);
+	// ... | scalar all-reduce words [parity][rank][2]]
+	const size_t bytes = ARENA_HEADER + 4 * c->arena_slot + 4 * (size_t)(2 * LL_MAX_BYTES) + 2 * ARENA_MAX_RANKS * 16;
 	LFK_CUDA(c, cudaMalloc((void**)&c->arena, bytes));
 	LFK_CUDA(c, cudaMemsetAsync(c->arena, 0, bytes, c->stream));
 	// exchange the IPC handles of all arenas (64 bytes each) with an NCCL all-gather; `ok` words tell every rank whether
@@ -252,17 +306,25 @@ static int arena_setup(lfk_ctx *c) {
 	std::vector<cudaIpcMemHandle_t> all((size_t)c->nranks);
 	LFK_CUDA(c, cudaMemcpyAsync(all.data(), d_all, (size_t)c->nranks * 64, cudaMemcpyDeviceToHost, c->stream));
 	LFK_CUDA(c, cudaStreamSynchronize(c->stream));
-	bool ok = have;
-	const int nb[2] = { c->rank + 1, c->rank - 1 };
-	for (int k = 0; k < 2 && ok; ++k) {
-		if (nb[k] < 0 || nb[k] >= c->nranks) { continue; }
+	bool ok = have && c->nranks <= ARENA_MAX_RANKS;
+	c->arena_all.assign((size_t)c->nranks, nullptr);
+	c->arena_all[(size_t)c->rank] = c->arena;
+	for (int r = 0; r < c->nranks && ok; ++r) { // every rank maps every arena (the scalar all-reduce writes to all of them)
+		if (r == c->rank) { continue; }
 		void *ptr = nullptr;
-		if (cudaIpcOpenMemHandle(&ptr, all[(size_t)nb[k]], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+		if (cudaIpcOpenMemHandle(&ptr, all[(size_t)r], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
 			cudaGetLastError();
 			ok = false;
 			break;
 		}
-		c->arena_peer[k] = (char*)ptr;
+		c->arena_all[(size_t)r] = (char*)ptr;
+	}
+	if (ok) {
+		if (c->rank + 1 < c->nranks) { c->arena_peer[0] = c->arena_all[(size_t)c->rank + 1]; }
+		if (c->rank > 0) { c->arena_peer[1] = c->arena_all[(size_t)c->rank - 1]; }
+		LFK_CUDA(c, cudaMalloc((void**)&c->arena_all_d, (size_t)c->nranks * sizeof(char*)));
+		LFK_CUDA(c, cudaMemcpyAsync(c->arena_all_d, c->arena_all.data(), (size_t)c->nranks * sizeof(char*),
+			cudaMemcpyHostToDevice, c->stream));
 	}
 	// agree: sum of (ok ? 0 : 1) over the ranks must be 0
 	double flag = ok ? 0.0 : 1.0;
@@ -273,11 +335,7 @@ static int arena_setup(lfk_ctx *c) {
 	LFK_CUDA(c, cudaStreamSynchronize(c->stream)); // (also: every arena is zeroed before anybody can write into it)
 	cudaFree(d_all);
 	c->p2p = flag == 0.0;
-	if (!c->p2p) {
-		for (int k = 0; k < 2; ++k) {
-			if (c->arena_peer[k]) { cudaIpcCloseMemHandle(c->arena_peer[k]); c->arena_peer[k] = nullptr; }
-		}
-	}
+	if (!c->p2p) { arena_unmap(c); }
 	c->halo_epoch = 0;
 	return 0;
 }
@@ -295,9 +353,7 @@ int lfkx_init(lfk_ctx *c, const void *nccl_id128) {
 }
 
 int lfkx_destroy(lfk_ctx *c) {
-	for (int k = 0; k < 2; ++k) {
-		if (c->arena_peer[k]) { cudaIpcCloseMemHandle(c->arena_peer[k]); c->arena_peer[k] = nullptr; }
-	}
+	arena_unmap(c);
 	if (c->comm) {
 		// (the neighbours may still be reading this rank's arena in their last exchange: the communicator's destruction
 		// is collective, so it doubles as the barrier before the arena is freed)

@@ -136,6 +136,8 @@ struct lfk_ctx {
 	// multi-GPU halos through peer memory (exchange.cu): one arena per rank, mapped by its z neighbours with CUDA IPC
 	char *arena = nullptr;            // this rank's arena: header (flags, counters) + 2 x 2 receive slots
 	char *arena_peer[2] = { nullptr, nullptr }; // [0] the upper neighbour's arena, [1] the lower one's (mapped)
+	std::vector<char*> arena_all;     // every rank's arena as mapped here ([rank] = this rank's own)
+	char **arena_all_d = nullptr;     // the same table in device memory
 	size_t arena_slot = 0;            // bytes per receive slot
 	unsigned long long halo_epoch = 0; // exchanges issued so far (identical on every rank)
 	bool p2p = false;                 // arena mapped on both sides: halos bypass NCCL
@@ -255,6 +257,9 @@ int lfkx_exchange_particles(lfk_ctx *c, uint64_t *n_in);
 int lfkx_allreduce_sum(lfk_ctx *c, double *d_vals, int n);
 int lfkx_allreduce_max(lfk_ctx *c, double *d_vals, int n);
 int lfkx_allreduce_sum_f32(lfk_ctx *c, float *d_vals, int n);
+// all-reduce of ONE PCG scalar (a field of *scal) over the ranks + its finaliser (FIN_*), in one kernel over peer memory
+// when the arenas are mapped; returns 1 if it did, 0 if the caller has to use NCCL + k_finalize
+int lfkx_allreduce_finalize(lfk_ctx *c, double *field, bool is_max, int which);
 
 // device helpers ------------------------------------------------------------------------------------------
 #ifdef __CUDACC__

@@ -333,6 +333,7 @@ static inline unsigned red_blocks(const lfk_ctx *c) {
 
 static int allreduce_scalar(lfk_ctx *c, double *field, bool is_max, int which) {
 	if (c->nranks > 1) {
+		if (lfkx_allreduce_finalize(c, field, is_max, which)) { return 0; } // one kernel over peer memory
 		LFK_TRY(is_max ? lfkx_allreduce_max(c, field, 1) : lfkx_allreduce_sum(c, field, 1));
 		LFK_LAUNCH(c, k_finalize, 1, 1, 0, c->d_scal, which);
 	}
@@ -412,8 +413,8 @@ int lfks_solve(lfk_ctx *c, double dt, double *residual, uint64_t *iters, bool wa
 	// The iteration's kernels take every per-solve quantity from device memory (PcgScalars), so ONE captured CUDA graph
 	// serves every iteration of every solve of this context; it is re-captured only when the launch configuration
 	// changes.  ~40 launches per iteration collapse into one graph launch (launch gaps were ~17 % of the iteration).
-	// (multi-GPU: the halo kernels and NCCL all-reduces are captured like any other node; lfk_set_tuning("graph", 2))
-	const bool use_graph = c->nranks == 1 ? c->tune.graph != 0 : c->tune.graph == 2;
+	// (multi-GPU: the peer-memory halo / all-reduce kernels and the NCCL calls are captured like any other node)
+	const bool use_graph = c->tune.graph != 0;
 	const int graph_key = (((int)nb * 2 + c->prm.preconditioner) * 2 + (c->tune.p2p ? 1 : 0)) * 4 + (c->tune.mg_agg ? 2 : 0) + 1;
 	if (use_graph && (c->pcg_graph == nullptr || c->pcg_graph_key != graph_key)) {
 		LFK_TRY(lfks_free_graph(c));
