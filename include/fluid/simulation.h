@@ -149,6 +149,10 @@ namespace fluid {
 		std::size_t pressure_max_iterations = 200; ///< pressure_solver::max_iterations used inside time_step
 		preconditioner pressure_preconditioner = preconditioner::multigrid;
 		int device = 0;                            ///< CUDA ordinal, read when the device context is created
+		/// Sources (seed_cell, velocity coercion) run on the device inside the fused step.  Counts, cells and velocities
+		/// of the spawned particles are the reference's; their positions come from a counter-based generator instead of
+		/// \ref random.  Set to \p false to spawn on the host from \ref random exactly like the reference (staged step).
+		bool device_sources = true;
 		/// Residual / iteration count of the last pressure solve (what post_pressure_solve_callback receives).
 		double last_residual = 0.0;
 		std::size_t last_iterations = 0;
@@ -169,6 +173,7 @@ namespace fluid {
 		// coherence: which side holds the current particles / cells
 		mutable bool _p_host = true, _p_dev = false, _g_host = true, _g_dev = false;
 		mutable bool _hash_host = false, _hash_dev = false;
+		bool _sources_dev = false; // the device holds a non-empty source list
 		vec3s _size;
 
 		void _ensure_ctx() const;
@@ -182,6 +187,7 @@ namespace fluid {
 		bool _needs_staged_step() const;
 		void _staged_time_step(double dt);
 		void _update_sources();
+		void _push_sources();
 		void _coerce_source_velocities();
 	};
 }

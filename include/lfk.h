@@ -157,6 +157,30 @@ int lfk_g2p(lfk_ctx *ctx);
 /* simulation::cfl (src/simulation.cpp:199-205) */
 int lfk_cfl(lfk_ctx *ctx, double *value);
 
+/* ---- fluid sources (simulation::sources, include/fluid/data_structures/source.h:12-22) on the device --------- */
+typedef struct lfk_source {
+	const uint64_t *cells;      /* source::cells as x, y, z triples (whole-grid cell indices) */
+	uint64_t num_cells;
+	double velocity[3];         /* source::velocity */
+	uint32_t target_density_cubic_root; /* source::target_density_cubic_root */
+	int32_t active;             /* source::active */
+	int32_t coerce_velocity;    /* source::coerce_velocity */
+} lfk_source;
+/* Replaces the context's source list (n = 0 clears it).  While at least one source is active, lfk_time_step runs the
+ * reference's source handling on the device: velocity coercion before advection, seed_cell after the first sort of the
+ * step, and a second sort when particles were added (src/simulation.cpp:49-64). */
+int lfk_set_sources(lfk_ctx *ctx, const lfk_source *sources, uint64_t n);
+/* Seed of the counter-based generator that places source particles.  The reference draws from the simulation's pcg32
+ * (simulation.h:176); the device draws uniform positions in the cell from a hash of (seed, step, cell, slot): same
+ * distribution, same counts and velocities, different positions. */
+int lfk_set_rng_seed(lfk_ctx *ctx, uint64_t seed);
+/* the coercion half of _advect_particles (src/simulation.cpp:227-238): particles whose cell belongs to an active
+ * source with coerce_velocity get the source's velocity and zero APIC rows */
+int lfk_coerce_sources(lfk_ctx *ctx);
+/* _update_sources + seed_cell (src/simulation.cpp:756-765, 136-151): every cell of every active source is filled up
+ * to target_density_cubic_root^3 particles; needs the table of the last lfk_hash, invalidates it when *added > 0 */
+int lfk_update_sources(lfk_ctx *ctx, uint64_t *added);
+
 /* ---- fused entry points (what the shim calls when no mid-step callback is installed) --------------------- */
 /* simulation::time_step(dt) without sources (src/simulation.cpp:43-125), entirely on the device */
 int lfk_time_step(lfk_ctx *ctx, double dt);

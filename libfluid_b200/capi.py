@@ -34,6 +34,11 @@ class Params(C.Structure):
                 ("max_iterations", C.c_int32), ("preconditioner", C.c_int32)]
 
 
+class Source(C.Structure):
+    _fields_ = [("cells", C.c_void_p), ("num_cells", C.c_uint64), ("velocity", C.c_double * 3),
+                ("target_density_cubic_root", C.c_uint32), ("active", C.c_int32), ("coerce_velocity", C.c_int32)]
+
+
 class Stats(C.Structure):
     _fields_ = [("kernel_launches", C.c_uint64), ("pcg_iterations", C.c_uint64), ("pcg_residual", C.c_double),
                 ("phase_ms", C.c_double * 16), ("num_particles", C.c_uint64), ("num_fluid_cells", C.c_uint64),
@@ -54,7 +59,8 @@ SYMBOLS = (
     "lfk_upload_cells_slab", "lfk_download_cells_slab", "lfk_upload_old_cells", "lfk_download_old_cells", "lfk_download_table", "lfk_num_fluid_cells",
     "lfk_download_fluid_cells", "lfk_hash", "lfk_advect", "lfk_collide", "lfk_p2g", "lfk_gravity",
     "lfk_pressure_solve", "lfk_download_rhs", "lfk_download_pressure", "lfk_upload_pressure", "lfk_apply_a",
-    "lfk_apply_pressure", "lfk_correct", "lfk_extrapolate", "lfk_g2p", "lfk_cfl", "lfk_time_step",
+    "lfk_apply_pressure", "lfk_correct", "lfk_extrapolate", "lfk_g2p", "lfk_cfl", "lfk_set_sources", "lfk_set_rng_seed",
+    "lfk_coerce_sources", "lfk_update_sources", "lfk_time_step",
     "lfk_time_step_cfl", "lfk_update", "lfk_seed_box_device", "lfk_synthetic_projection_device", "lfk_set_timing",
     "lfk_set_tuning", "lfk_get_stats", "lfk_reset_stats",
 )
@@ -102,6 +108,10 @@ def load_library():
     L.lfk_cfl.argtypes = [vp, C.POINTER(db)]
     L.lfk_time_step_cfl.argtypes = [vp, C.POINTER(db)]
     L.lfk_update.argtypes = [vp, db, C.POINTER(u64)]
+    L.lfk_set_sources.argtypes = [vp, vp, u64]
+    L.lfk_set_rng_seed.argtypes = [vp, u64]
+    L.lfk_coerce_sources.argtypes = [vp]
+    L.lfk_update_sources.argtypes = [vp, C.POINTER(u64)]
     L.lfk_seed_box_device.argtypes = [vp, vp, vp, vp, C.c_uint32, u64, ci]
     L.lfk_synthetic_projection_device.argtypes = [vp, u64]
     L.lfk_set_timing.argtypes = [vp, ci]
@@ -342,6 +352,31 @@ class Context:
     def update(self, dt):
         n = C.c_uint64()
         self._ck(self.L.lfk_update(self.ptr, dt, C.byref(n)))
+        return n.value
+
+    def set_sources(self, sources, seed=None):
+        """sources: list of dicts {cells: (n, 3) integer array of x, y, z, velocity, density (cubic root), active, coerce}"""
+        arr = (Source * max(len(sources), 1))()
+        keep = []
+        for k, s in enumerate(sources):
+            cells = np.ascontiguousarray(np.asarray(s["cells"], dtype=np.uint64).reshape(-1, 3))
+            keep.append(cells)
+            arr[k].cells = cells.ctypes.data
+            arr[k].num_cells = cells.shape[0]
+            arr[k].velocity[:] = [float(v) for v in s.get("velocity", (0, 0, 0))]
+            arr[k].target_density_cubic_root = int(s.get("density", 2))
+            arr[k].active = int(bool(s.get("active", True)))
+            arr[k].coerce_velocity = int(bool(s.get("coerce", False)))
+        self._ck(self.L.lfk_set_sources(self.ptr, C.byref(arr), len(sources)))
+        if seed is not None:
+            self._ck(self.L.lfk_set_rng_seed(self.ptr, int(seed)))
+
+    def coerce_sources(self):
+        self._ck(self.L.lfk_coerce_sources(self.ptr))
+
+    def update_sources(self):
+        n = C.c_uint64()
+        self._ck(self.L.lfk_update_sources(self.ptr, C.byref(n)))
         return n.value
 
     def seed_box_device(self, start, size, velocity=(0, 0, 0), density=2, seed=1, append=False):

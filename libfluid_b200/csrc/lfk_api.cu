@@ -183,6 +183,13 @@ static int free_all(lfk_ctx *c) {
 	dev_free(c->xsend[1]);
 	dev_free(c->xrecv);
 	dev_free(c->xcnt);
+	dev_free(c->src_cell);
+	dev_free(c->src_gcell);
+	dev_free(c->src_of);
+	dev_free(c->src_need);
+	dev_free(c->src_vel);
+	dev_free(c->src_target);
+	dev_free(c->src_map);
 	dev_free(c->xcounts);
 	if (c->h_xcounts) { cudaFreeHost(c->h_xcounts); c->h_xcounts = nullptr; }
 	if (c->staging) { cudaFree(c->staging); c->staging = nullptr; }
@@ -720,14 +727,122 @@ extern "C" int lfk_cfl(lfk_ctx *c, double *value) {
 	return lfkp_cfl(c, value);
 }
 
-// ---- fused step: simulation::time_step(dt) without sources (src/simulation.cpp:43-125) -----------------------
+// ---- fluid sources ------------------------------------------------------------------------------------------
+static void free_sources(lfk_ctx *c) {
+	dev_free(c->src_cell);
+	dev_free(c->src_gcell);
+	dev_free(c->src_of);
+	dev_free(c->src_need);
+	dev_free(c->src_vel);
+	dev_free(c->src_target);
+	c->src_entries = c->src_count = 0;
+	c->src_active = c->src_coerce = false;
+}
+
+extern "C" int lfk_set_sources(lfk_ctx *c, const lfk_source *sources, uint64_t n) {
+	if (!c || (!sources && n)) { return LFK_E_INVALID; }
+	LFK_REQUIRE(c, n < 65535, LFK_E_INVALID, "too many sources");
+	const GridDesc &G = c->g;
+	free_sources(c);
+	struct Entry { uint32_t cell, gcell, src; };
+	std::vector<Entry> ent;
+	std::vector<double> vel(3 * (size_t)n);
+	std::vector<uint32_t> target((size_t)n);
+	std::vector<uint16_t> map;
+	bool any = false, coerce = false;
+	for (uint64_t k = 0; k < n; ++k) {
+		const lfk_source &S = sources[k];
+		LFK_REQUIRE(c, S.cells != nullptr || S.num_cells == 0, LFK_E_INVALID, "source without cells");
+		for (int d = 0; d < 3; ++d) { vel[3 * k + d] = S.velocity[d]; }
+		const uint64_t t = (uint64_t)S.target_density_cubic_root;
+		target[k] = (uint32_t)(t * t * t);
+		if (!S.active) { continue; }
+		any = true;
+		for (uint64_t j = 0; j < S.num_cells; ++j) {
+			const uint64_t x = S.cells[3 * j], y = S.cells[3 * j + 1], z = S.cells[3 * j + 2];
+			LFK_REQUIRE(c, x < (uint64_t)G.nx && y < (uint64_t)G.ny && z < (uint64_t)G.nz, LFK_E_INVALID,
+				"source cell outside the grid");
+			if ((long long)z < G.z0 || (long long)z >= G.z0 + G.nzl) { continue; } // another rank's slab
+			const uint32_t local = (uint32_t)(x + (uint64_t)G.nx * (y + (uint64_t)G.ny * (z - (uint64_t)G.z0 + 1)));
+			ent.push_back({ local, (uint32_t)(x + (uint64_t)G.nx * (y + (uint64_t)G.ny * z)), (uint32_t)k });
+			if (S.coerce_velocity) {
+				coerce = true;
+				if (map.empty()) { map.assign((size_t)G.ncl, 0); }
+				map[local] = (uint16_t)(k + 1); // the reference applies the sources in order: the last one wins
+			}
+		}
+	}
+	c->src_count = (uint32_t)n;
+	c->src_active = any;
+	// every rank must take the same branch in lfk_time_step, whether or not its own slab holds source cells
+	for (uint64_t k = 0; k < n; ++k) { coerce |= sources[k].active && sources[k].coerce_velocity; }
+	c->src_coerce = coerce;
+	if (!any) { return 0; }
+	std::stable_sort(ent.begin(), ent.end(), [](const Entry &a, const Entry &b) { return a.cell < b.cell; });
+	const size_t ne = ent.size();
+	c->src_entries = (uint32_t)ne;
+	std::vector<uint32_t> cell(ne), gcell(ne), of(ne);
+	for (size_t e = 0; e < ne; ++e) { cell[e] = ent[e].cell; gcell[e] = ent[e].gcell; of[e] = ent[e].src; }
+	LFK_TRY(dev_alloc(c, &c->src_cell, ne));
+	LFK_TRY(dev_alloc(c, &c->src_gcell, ne));
+	LFK_TRY(dev_alloc(c, &c->src_of, ne));
+	LFK_TRY(dev_alloc(c, &c->src_need, 2 * (ne + 1)));
+	LFK_TRY(dev_alloc(c, &c->src_vel, 3 * (size_t)n));
+	LFK_TRY(dev_alloc(c, &c->src_target, (size_t)n));
+	if (ne) {
+		LFK_CUDA(c, cudaMemcpyAsync(c->src_cell, cell.data(), ne * 4, cudaMemcpyHostToDevice, c->stream));
+		LFK_CUDA(c, cudaMemcpyAsync(c->src_gcell, gcell.data(), ne * 4, cudaMemcpyHostToDevice, c->stream));
+		LFK_CUDA(c, cudaMemcpyAsync(c->src_of, of.data(), ne * 4, cudaMemcpyHostToDevice, c->stream));
+	}
+	LFK_CUDA(c, cudaMemcpyAsync(c->src_vel, vel.data(), vel.size() * 8, cudaMemcpyHostToDevice, c->stream));
+	LFK_CUDA(c, cudaMemcpyAsync(c->src_target, target.data(), target.size() * 4, cudaMemcpyHostToDevice, c->stream));
+	if (coerce) {
+		if (!c->src_map) { LFK_TRY(dev_alloc(c, &c->src_map, (size_t)G.ncl)); }
+		if (map.empty()) { map.assign((size_t)G.ncl, 0); }
+		LFK_CUDA(c, cudaMemcpyAsync(c->src_map, map.data(), map.size() * 2, cudaMemcpyHostToDevice, c->stream));
+	}
+	LFK_CUDA(c, cudaStreamSynchronize(c->stream)); // the host vectors go out of scope
+	return 0;
+}
+extern "C" int lfk_set_rng_seed(lfk_ctx *c, uint64_t seed) {
+	if (!c) { return LFK_E_INVALID; }
+	c->rng_seed = seed;
+	c->rng_step = 0;
+	return 0;
+}
+extern "C" int lfk_coerce_sources(lfk_ctx *c) {
+	if (!c) { return LFK_E_INVALID; }
+	NEED_PARAMS(c);
+	return lfkp_coerce_sources(c);
+}
+extern "C" int lfk_update_sources(lfk_ctx *c, uint64_t *added) {
+	if (!c) { return LFK_E_INVALID; }
+	NEED_PARAMS(c);
+	return lfkp_update_sources(c, added);
+}
+
+// ---- fused step: simulation::time_step(dt) (src/simulation.cpp:43-125) ---------------------------------------
 // The reference sorts three times per step (:49, :62, :64); only the last sort feeds anything when there are no
 // sources, so one sort after advection + collision is equivalent.  old_position never leaves registers.
 extern "C" int lfk_time_step(lfk_ctx *c, double dt) {
 	if (!c) { return LFK_E_INVALID; }
 	NEED_PARAMS(c);
+	if (c->src_active && c->src_coerce) { LFK_TRY(lfkp_coerce_sources(c)); } // :49 + :227-238
 	LFK_TRY(lfkp_advect_collide(c, dt));            // :50-60
 	LFK_TRY(lfkp_hash(c, true));                    // :62-64 (lean: v / c are read through the permutation)
+	if (c->src_active) {                            // :63-64: seed the source cells, sort again if anything was added
+		uint64_t added = 0;
+		LFK_TRY(lfkp_update_sources(c, &added));
+		if (c->nranks > 1) { // every rank sorts again if ANY rank seeded (the sort's exchange is collective)
+			double flag = added ? 1.0 : 0.0;
+			LFK_CUDA(c, cudaMemcpyAsync(c->d_reduce, &flag, sizeof(double), cudaMemcpyHostToDevice, c->stream));
+			LFK_TRY(lfkx_allreduce_max(c, c->d_reduce, 1));
+			LFK_CUDA(c, cudaMemcpyAsync(&flag, c->d_reduce, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+			LFK_CUDA(c, cudaStreamSynchronize(c->stream));
+			added = flag != 0.0 ? 1 : 0;
+		}
+		if (added) { LFK_TRY(lfkp_hash(c, true)); }
+	}
 	LFK_TRY(lfkg_p2g(c, dt, true));                 // :66-78 (gravity fused)
 	LFK_TRY(lfks_solve(c, dt, nullptr, nullptr, true)); // :83-99 (initial guess: the previous step's pressure)
 	LFK_TRY(lfks_apply_pressure(c, dt));            // :104

@@ -147,6 +147,18 @@ struct lfk_ctx {
 	uint32_t *xcnt = nullptr; size_t xcnt_n = 0;               // per-block emigrant counts + their scans
 	uint32_t *xcounts = nullptr, *h_xcounts = nullptr;         // the 4 message sizes (device / pinned host)
 
+	// fluid sources (lfk_set_sources): entries = (cell, source) pairs sorted by cell, then by source order
+	uint32_t src_entries = 0, src_count = 0; // entries in this rank's slab / sources
+	bool src_active = false, src_coerce = false;
+	uint32_t *src_cell = nullptr;    // [entries] local raw cell index
+	uint32_t *src_gcell = nullptr;   // [entries] whole-grid raw cell index is src_gcell (RNG key) -- low 32 bits
+	uint32_t *src_of = nullptr;      // [entries] source index
+	uint32_t *src_need = nullptr;    // [entries + 1] particles to add per entry / their exclusive scan
+	double *src_vel = nullptr;       // [sources][3]
+	uint32_t *src_target = nullptr;  // [sources] target count (density cubed)
+	uint16_t *src_map = nullptr;     // [ncl] 0, or 1 + index of the LAST coercing source that lists the cell
+	uint64_t rng_seed = 0x5eed5eedull, rng_step = 0;
+
 	// scratch
 	void *staging = nullptr; size_t staging_bytes = 0;
 	uint32_t *scan_tmp = nullptr; size_t scan_tmp_n = 0;
@@ -219,6 +231,8 @@ int lfkp_cfl(lfk_ctx *c, double *value);
 int lfkp_seed_box(lfk_ctx *c, const double *start, const double *size, const double *vel, uint32_t dens,
 	uint64_t seed, int append);
 int lfkp_exclusive_scan_u32(lfk_ctx *c, const uint32_t *in, uint32_t *out, long long n, int from_flags);
+int lfkp_coerce_sources(lfk_ctx *c);
+int lfkp_update_sources(lfk_ctx *c, uint64_t *added);
 int lfkp_reserve_particles(lfk_ctx *c, uint64_t n); // room for n entries behind `first` (may compact to first = 0)
 static inline ParticleSoA lfk_own_view(const lfk_ctx *c) { // the own particles as arrays indexed from 0
 	ParticleSoA v = c->P;

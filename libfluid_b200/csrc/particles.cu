@@ -1061,6 +1061,126 @@ int lfkp_cfl(lfk_ctx *c, double *value) {
 }
 
 // =========================================================================================================
+// N1: fluid sources on the device (reference src/simulation.cpp:136-151, 227-238, 756-765)
+// =========================================================================================================
+// velocity coercion: the reference walks the table of the step's first sort over the source cells; a particle's cell in
+// that table is the key of its current position, so the same particles are found by keying every particle
+__global__ void k_coerce_sources(GridDesc G, ParticleSoA P, unsigned long long n, const uint16_t *__restrict__ src_map,
+	const double *__restrict__ src_vel) {
+	const unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n) { return; }
+	const int x = cell_coord_clamped(P.f[PF_PX][i], G.off[0], G, G.nx);
+	const int y = cell_coord_clamped(P.f[PF_PY][i], G.off[1], G, G.ny);
+	const int z = cell_coord_clamped(P.f[PF_PZ][i], G.off[2], G, G.nz);
+	const int lz = z - G.z0 + 1;
+	if (lz < 1 || lz > G.nzl) { return; }
+	const unsigned k = src_map[x + (long long)G.nx * (y + (long long)G.ny * lz)];
+	if (k == 0) { return; }
+	P.f[PF_VX][i] = src_vel[3 * (k - 1)];
+	P.f[PF_VY][i] = src_vel[3 * (k - 1) + 1];
+	P.f[PF_VZ][i] = src_vel[3 * (k - 1) + 2];
+#pragma unroll
+	for (int f = PF_C0; f < PF_C0 + 9; ++f) { P.f[f][i] = 0.0; }
+}
+
+// seed_cell's bookkeeping: an entry (cell, source) adds max(0, target - num) particles, where num is the cell's count
+// after the earlier entries of the same cell (the reference sets _space_hash(cell).count = target after seeding)
+__global__ void k_source_need(const uint32_t *__restrict__ src_cell, const uint32_t *__restrict__ src_of,
+	const uint32_t *__restrict__ src_target, const uint32_t *__restrict__ cnt, uint32_t *__restrict__ need, uint32_t entries) {
+	const uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
+	if (e >= entries) { return; }
+	const uint32_t cell = src_cell[e];
+	uint32_t e0 = e;
+	while (e0 > 0 && src_cell[e0 - 1] == cell) { --e0; }
+	uint32_t num = cnt[cell], add = 0;
+	for (uint32_t k = e0; k <= e; ++k) {
+		const uint32_t target = src_target[src_of[k]];
+		add = target > num ? target - num : 0u;
+		// (the reference assigns count = target even when the cell held more: later entries then see `target`)
+		num = target;
+	}
+	need[e] = add;
+}
+
+__global__ void k_source_seed(GridDesc G, ParticleSoA P, uint32_t *__restrict__ key, unsigned long long base,
+	const uint32_t *__restrict__ src_cell, const uint32_t *__restrict__ src_gcell, const uint32_t *__restrict__ src_of,
+	const double *__restrict__ src_vel, const uint32_t *__restrict__ off, uint32_t entries, unsigned long long seed,
+	unsigned long long step, int with_old) {
+	const uint32_t e = blockIdx.x;
+	if (e >= entries) { return; }
+	const uint32_t b = off[e], n = off[e + 1] - b;
+	const uint32_t cell = src_cell[e], gcell = src_gcell[e], sidx = src_of[e];
+	const int x = (int)(cell % (uint32_t)G.nx), y = (int)((cell / (uint32_t)G.nx) % (uint32_t)G.ny);
+	const int z = (int)(cell / (uint32_t)(G.nx * G.ny)) - 1 + G.z0;
+	// seed_cell: offset = grid_offset + cell * cell_size, position = offset + U(0, cell_size)^3 (:143-147)
+	const double o0 = G.off[0] + (double)x * G.h, o1 = G.off[1] + (double)y * G.h, o2 = G.off[2] + (double)z * G.h;
+	for (uint32_t k = threadIdx.x; k < n; k += blockDim.x) {
+		unsigned long long r = mix64(seed ^ mix64(step * 0x9e3779b97f4a7c15ull + gcell) ^ mix64(((unsigned long long)e << 32) | k));
+		double j[3];
+#pragma unroll
+		for (int d = 0; d < 3; ++d) {
+			r = mix64(r + 0x9e3779b97f4a7c15ull);
+			j[d] = (double)(r >> 11) * (1.0 / 9007199254740992.0) * G.h;
+		}
+		const unsigned long long i = base + b + k;
+		P.f[PF_PX][i] = o0 + j[0];
+		P.f[PF_PY][i] = o1 + j[1];
+		P.f[PF_PZ][i] = o2 + j[2];
+		P.f[PF_VX][i] = src_vel[3 * sidx];
+		P.f[PF_VY][i] = src_vel[3 * sidx + 1];
+		P.f[PF_VZ][i] = src_vel[3 * sidx + 2];
+#pragma unroll
+		for (int f = PF_C0; f < PF_C0 + 9; ++f) { P.f[f][i] = 0.0; }
+		if (with_old) {
+			P.f[PF_OX][i] = o0 + j[0];
+			P.f[PF_OY][i] = o1 + j[1];
+			P.f[PF_OZ][i] = o2 + j[2];
+		}
+		key[i] = cell;
+	}
+}
+
+int lfkp_coerce_sources(lfk_ctx *c) {
+	if (!c->src_active || !c->src_coerce || c->np == 0) { return 0; }
+	PhaseTimer T(c, LFK_PHASE_ADVECT_COLLIDE);
+	LFK_TRY(lfkp_materialise_vc(c)); // the velocity / c rows are written in particle order
+	LFK_LAUNCH(c, k_coerce_sources, lfk_blocks((long long)c->np, 256), 256, 0, c->g, lfk_own_view(c),
+		(unsigned long long)c->np, c->src_map, c->src_vel);
+	return 0;
+}
+
+int lfkp_update_sources(lfk_ctx *c, uint64_t *added) {
+	if (added) { *added = 0; }
+	if (!c->src_active || c->src_entries == 0) { ++c->rng_step; return 0; }
+	PhaseTimer T(c, LFK_PHASE_SORT);
+	LFK_REQUIRE(c, c->table_valid, LFK_E_STATE, "lfk_update_sources needs the cell table of lfk_hash");
+	const uint32_t ne = c->src_entries;
+	LFK_LAUNCH(c, k_source_need, lfk_blocks(ne, 128), 128, 0, c->src_cell, c->src_of, c->src_target, c->cnt, c->src_need, ne);
+	uint32_t *off = c->src_need + (ne + 1);
+	LFK_TRY(lfkp_exclusive_scan_u32(c, c->src_need, off, ne, 0));
+	uint32_t total = 0;
+	LFK_CUDA(c, cudaMemcpyAsync(&total, off + ne, sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+	LFK_CUDA(c, cudaStreamSynchronize(c->stream));
+	const uint64_t step = c->rng_step++;
+	if (total == 0) { return 0; }
+	LFK_TRY(lfkp_materialise_vc(c)); // appended particles carry their velocity in particle order
+	// multi-GPU: the entries behind the own particles are ghost copies of the upper neighbour's boundary layer; the
+	// next sort brings fresh ones, so they may be overwritten
+	const uint64_t first = c->first, np = c->np;
+	LFK_TRY(lfkp_reserve_particles(c, np + total)); // may move the own particles to the front
+	LFK_LAUNCH(c, k_source_seed, ne, 64, 0, c->g, c->P, c->key, (unsigned long long)(c->first + np), c->src_cell, c->src_gcell,
+		c->src_of, c->src_vel, off, ne, (unsigned long long)c->rng_seed, (unsigned long long)step, c->old_valid ? 1 : 0);
+	(void)first;
+	c->np = np + total;
+	c->ntot = c->first + c->np;
+	c->table_valid = false;
+	c->ordinal_valid = false;
+	c->system_valid = false;
+	if (added) { *added = total; }
+	return 0;
+}
+
+// =========================================================================================================
 // Synthetic seeding (bench scenes): jittered sub-cell sampling like simulation::seed_func
 // (reference include/fluid/simulation.h:80-115), with a counter-based hash RNG instead of pcg32.
 // =========================================================================================================

@@ -218,12 +218,48 @@ namespace fluid {
 			post_correction_callback) {
 			return true; // post_grid_to_particle_transfer_callback fires after the step: the fused path can serve it
 		}
-		for (const auto &s : sources) {
-			if (s && s->active) {
-				return true;
+		if (!device_sources) {
+			for (const auto &s : sources) {
+				if (s && s->active) {
+					return true;
+				}
 			}
 		}
 		return false;
+	}
+
+	// simulation::sources -> lfk_set_sources (the list is small; it is pushed before every fused step because callers
+	// edit `sources`, `active` and `velocity` freely between steps, testbed/main.cpp:156-165)
+	void simulation::_push_sources() {
+		std::vector<lfk_source> list;
+		std::vector<std::vector<std::uint64_t>> cells;
+		bool any = false;
+		for (const auto &s : sources) {
+			lfk_source d{};
+			if (s) {
+				cells.emplace_back();
+				for (vec3s c : s->cells) {
+					cells.back().push_back(c.x);
+					cells.back().push_back(c.y);
+					cells.back().push_back(c.z);
+				}
+				d.cells = cells.back().data();
+				d.num_cells = s->cells.size();
+				for (int k = 0; k < 3; ++k) {
+					d.velocity[k] = s->velocity[k];
+				}
+				d.target_density_cubic_root = static_cast<std::uint32_t>(s->target_density_cubic_root);
+				d.active = s->active ? 1 : 0;
+				d.coerce_velocity = s->coerce_velocity ? 1 : 0;
+				any |= s->active;
+			}
+			list.push_back(d);
+		}
+		if (!any && !_sources_dev) {
+			return;
+		}
+		_check(lfk_set_sources(_ctx, list.data(), any ? list.size() : 0));
+		_sources_dev = any;
 	}
 
 	void simulation::time_step(double dt) {
@@ -232,6 +268,7 @@ namespace fluid {
 		} else {
 			_particles_to_device();
 			_grid_to_device();
+			_push_sources();
 			_check(lfk_time_step(_ctx, dt));
 			_p_host = _g_host = false;
 			_hash_host = false;
