@@ -330,6 +330,26 @@ def _run_ours(args):
                        " + lfk_download_particles + lfk_download_cells_slab, per step, wall clock, max over ranks",
                "pcie_floor_s_per_step": (up_bytes + down_bytes) / args.e2e_steps / 55e9}
         del host_p, host_c
+        # what a per-frame consumer (renderer, mesher, the Maya node's particle cache) costs: the state stays resident
+        # and only the positions stream out, asynchronously on the transfer stream, overlapped with the next step
+        try:
+            pin = capi.PinnedBuffer(cap * 24)
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(args.e2e_steps + 2):
+                ctx.time_step()
+                ctx.wait_transfers()
+                ctx.download_positions_async(pin.ptr.value, cap)
+            ctx.wait_transfers()
+            barrier()
+            dt_s = allmax(time.perf_counter() - t0)
+            e2e["positions_streaming"] = {"value": np_total * (args.e2e_steps + 2) / dt_s, "unit": UNIT,
+                                          "d2h_bytes_per_step": int(ctx.num_particles() * 24), "h2d_bytes_per_step": 0,
+                                          "what": "lfk_time_step_cfl + lfk_download_positions_async (pinned, 24 B per "
+                                                  "particle) per step, the copy overlapped with the next step"}
+            pin.close()
+        except capi.LfkError as ex:
+            e2e["positions_streaming"] = {"unavailable": str(ex)}
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",

@@ -106,6 +106,20 @@ int lfk_num_particles(lfk_ctx *ctx, uint64_t *n);
 int lfk_download_particles(lfk_ctx *ctx, void *aos152, uint64_t capacity, uint64_t *n);
 /* positions only, 24 B per particle (what the mesher / renderer / Maya node consume every frame) */
 int lfk_download_positions(lfk_ctx *ctx, double *xyz, uint64_t capacity, uint64_t *n);
+/* The same, asynchronously: returns as soon as the copy is queued on the context's transfer stream; the next stage
+ * calls may be issued at once and overlap the copy.  xyz must stay valid -- and should be pinned (lfk_host_alloc) -- until
+ * lfk_wait_transfers returns.  This is the per-frame read of testbed/main.cpp:52 and grid_node.cpp:358-366. */
+int lfk_download_positions_async(lfk_ctx *ctx, double *xyz, uint64_t capacity, uint64_t *n);
+int lfk_wait_transfers(lfk_ctx *ctx);
+/* page-locked host memory for hosts that do not link the CUDA runtime themselves */
+int lfk_host_alloc(void **out, uint64_t bytes);
+int lfk_host_free(void *p);
+/* Binary checkpoint of the rank's state (particles as SoA fields, the slab's cells, the solver's warm-start state);
+ * multi-GPU: one file per rank, `path` + ".rank<r>".  Loading it into a context of the same grid and rank layout
+ * continues the run bit for bit.  Replaces the text point cloud of include/fluid/data_structures/point_cloud.h:14-37
+ * for restarts (the host mirror still offers save_to_naive / load_from_naive for interchange). */
+int lfk_checkpoint_save(lfk_ctx *ctx, const char *path);
+int lfk_checkpoint_load(lfk_ctx *ctx, const char *path);
 /* simulation::grid().grid() (mac_grid.h:62-69): the whole nx*ny*nz grid; each rank keeps its slab. */
 int lfk_upload_cells(lfk_ctx *ctx, const void *aos32);
 /* writes the cells this rank owns into the whole-grid array (other entries untouched) */

@@ -55,7 +55,8 @@ class LfkError(RuntimeError):
 SYMBOLS = (
     "lfk_abi_version", "lfk_nccl_unique_id", "lfk_create", "lfk_destroy", "lfk_last_error", "lfk_set_params",
     "lfk_get_params", "lfk_sync", "lfk_slab", "lfk_upload_particles", "lfk_num_particles",
-    "lfk_download_particles", "lfk_download_positions", "lfk_upload_cells", "lfk_download_cells",
+    "lfk_download_particles", "lfk_download_positions", "lfk_download_positions_async", "lfk_wait_transfers",
+    "lfk_host_alloc", "lfk_host_free", "lfk_checkpoint_save", "lfk_checkpoint_load", "lfk_upload_cells", "lfk_download_cells",
     "lfk_upload_cells_slab", "lfk_download_cells_slab", "lfk_upload_old_cells", "lfk_download_old_cells", "lfk_download_table", "lfk_num_fluid_cells",
     "lfk_download_fluid_cells", "lfk_hash", "lfk_advect", "lfk_collide", "lfk_p2g", "lfk_gravity",
     "lfk_pressure_solve", "lfk_download_rhs", "lfk_download_pressure", "lfk_upload_pressure", "lfk_apply_a",
@@ -90,6 +91,12 @@ def load_library():
     L.lfk_num_particles.argtypes = [vp, C.POINTER(u64)]
     L.lfk_download_particles.argtypes = [vp, vp, u64, C.POINTER(u64)]
     L.lfk_download_positions.argtypes = [vp, vp, u64, C.POINTER(u64)]
+    L.lfk_download_positions_async.argtypes = [vp, vp, u64, C.POINTER(u64)]
+    L.lfk_wait_transfers.argtypes = [vp]
+    L.lfk_host_alloc.argtypes = [C.POINTER(vp), u64]
+    L.lfk_host_free.argtypes = [vp]
+    L.lfk_checkpoint_save.argtypes = [vp, C.c_char_p]
+    L.lfk_checkpoint_load.argtypes = [vp, C.c_char_p]
     for n in ("lfk_upload_cells", "lfk_download_cells", "lfk_upload_old_cells", "lfk_download_old_cells",
               "lfk_upload_cells_slab", "lfk_download_cells_slab"):
         getattr(L, n).argtypes = [vp, vp]
@@ -127,6 +134,30 @@ def _ptr(a):
 
 def _v3(v):
     return np.ascontiguousarray(np.asarray(v, dtype=np.float64).reshape(3))
+
+
+class PinnedBuffer:
+    """page-locked host memory from lfk_host_alloc (numpy view in .array)"""
+
+    def __init__(self, nbytes):
+        L = load_library()
+        self.L, self.ptr, self.nbytes = L, C.c_void_p(), int(nbytes)
+        rc = L.lfk_host_alloc(C.byref(self.ptr), self.nbytes)
+        if rc != 0:
+            raise LfkError(rc, (L.lfk_last_error(None) or b"").decode())
+        self.array = np.ctypeslib.as_array(C.cast(self.ptr, C.POINTER(C.c_uint8)), shape=(max(self.nbytes, 1),))
+
+    def close(self):
+        if self.ptr:
+            self.array = None
+            self.L.lfk_host_free(self.ptr)
+            self.ptr = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 def nccl_unique_id():
@@ -233,6 +264,22 @@ class Context:
         got = C.c_uint64()
         self._ck(self.L.lfk_download_positions(self.ptr, _ptr(out), n, C.byref(got)))
         return out
+
+    def download_positions_async(self, ptr, capacity):
+        """queues the positions download into pinned memory at `ptr` (capacity in particles); returns the count"""
+        got = C.c_uint64()
+        self._ck(self.L.lfk_download_positions_async(self.ptr, C.c_void_p(int(ptr)), int(capacity), C.byref(got)))
+        return got.value
+
+    def wait_transfers(self):
+        self._ck(self.L.lfk_wait_transfers(self.ptr))
+
+    def checkpoint_save(self, path):
+        self._ck(self.L.lfk_checkpoint_save(self.ptr, str(path).encode()))
+
+    def checkpoint_load(self, path):
+        self._ck(self.L.lfk_checkpoint_load(self.ptr, str(path).encode()))
+        self.L.lfk_get_params(self.ptr, C.byref(self.params))
 
     def upload_cells(self, arr):
         arr = np.ascontiguousarray(arr, dtype=CELL_DTYPE)

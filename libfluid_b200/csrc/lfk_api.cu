@@ -91,7 +91,7 @@ int lfkp_reserve_particles(lfk_ctx *c, uint64_t n) {
 	return 0;
 }
 
-static int reserve_staging(lfk_ctx *c, size_t bytes) {
+int lfk_reserve_staging(lfk_ctx *c, size_t bytes) {
 	if (bytes <= c->staging_bytes) { return 0; }
 	if (c->staging) {
 		cudaFree(c->staging);
@@ -332,6 +332,7 @@ extern "C" int lfk_destroy(lfk_ctx *c) {
 	cudaSetDevice(c->device);
 	cudaStreamSynchronize(c->stream);
 	lfks_free_graph(c);
+	lfkt_destroy(c);
 	lfkx_destroy(c);
 	lfkm_free(c);
 	free_all(c);
@@ -408,10 +409,8 @@ extern "C" int lfk_upload_particles(lfk_ctx *c, const void *aos152, uint64_t n) 
 	c->c_deferred = false;
 	LFK_TRY(lfkp_reserve_particles(c, n));
 	if (n > 0) {
-		LFK_TRY(reserve_staging(c, (size_t)n * 152));
-		LFK_CUDA(c, cudaMemcpyAsync(c->staging, aos152, (size_t)n * 152, cudaMemcpyHostToDevice, c->stream));
 		c->np = n;
-		LFK_TRY(lfkp_aos_to_soa(c, c->staging, n));
+		LFK_TRY(lfkt_upload_particles_pipelined(c, aos152, n));
 	}
 	c->np = n;
 	c->ntot = n;
@@ -437,11 +436,7 @@ extern "C" int lfk_download_particles(lfk_ctx *c, void *aos152, uint64_t capacit
 	if (c->np == 0) { return 0; }
 	LFK_REQUIRE(c, aos152 != nullptr, LFK_E_INVALID, "NULL particle buffer");
 	LFK_TRY(lfkp_materialise_vc(c));
-	LFK_TRY(reserve_staging(c, (size_t)c->np * 152));
-	LFK_TRY(lfkp_soa_to_aos(c, c->staging, c->np));
-	LFK_CUDA(c, cudaMemcpyAsync(aos152, c->staging, (size_t)c->np * 152, cudaMemcpyDeviceToHost, c->stream));
-	LFK_CUDA(c, cudaStreamSynchronize(c->stream));
-	return 0;
+	return lfkt_download_particles_pipelined(c, aos152, c->np);
 }
 
 extern "C" int lfk_download_positions(lfk_ctx *c, double *xyz, uint64_t capacity, uint64_t *n) {
@@ -451,7 +446,7 @@ extern "C" int lfk_download_positions(lfk_ctx *c, double *xyz, uint64_t capacity
 	LFK_REQUIRE(c, capacity >= c->np, LFK_E_CAPACITY, "position buffer too small");
 	if (c->np == 0) { return 0; }
 	LFK_REQUIRE(c, xyz != nullptr, LFK_E_INVALID, "NULL position buffer");
-	LFK_TRY(reserve_staging(c, (size_t)c->np * 24));
+	LFK_TRY(lfk_reserve_staging(c, (size_t)c->np * 24));
 	LFK_TRY(lfkp_positions_to_aos(c, (double*)c->staging, c->np));
 	LFK_CUDA(c, cudaMemcpyAsync(xyz, c->staging, (size_t)c->np * 24, cudaMemcpyDeviceToHost, c->stream));
 	LFK_CUDA(c, cudaStreamSynchronize(c->stream));
@@ -493,7 +488,7 @@ static int upload_cells_impl(lfk_ctx *c, const void *aos32, double **vel, uint8_
 	PhaseTimer T(c, LFK_PHASE_TRANSFER);
 	int zfirst = std::max(G.z0 - 1, 0), zlast = std::min(G.z0 + G.nzl + 1, G.nz);
 	size_t ncopy = (size_t)(zlast - zfirst) * (size_t)G.sxy;
-	LFK_TRY(reserve_staging(c, ncopy * 32));
+	LFK_TRY(lfk_reserve_staging(c, ncopy * 32));
 	LFK_CUDA(c, cudaMemcpyAsync(c->staging, (const char*)aos32 + (whole_grid ? (size_t)zfirst * G.sxy * 32 : 0), ncopy * 32,
 		cudaMemcpyHostToDevice, c->stream));
 	LFK_LAUNCH(c, k_cells_from_aos, lfk_blocks(G.ncl, 256), 256, 0, G, (const unsigned long long*)c->staging,
@@ -504,7 +499,7 @@ static int download_cells_impl(lfk_ctx *c, void *aos32, double **vel, bool whole
 	const GridDesc &G = c->g;
 	PhaseTimer T(c, LFK_PHASE_TRANSFER);
 	size_t nown = (size_t)G.nown;
-	LFK_TRY(reserve_staging(c, nown * 32));
+	LFK_TRY(lfk_reserve_staging(c, nown * 32));
 	LFK_LAUNCH(c, k_cells_to_aos, lfk_blocks(G.nown, 256), 256, 0, G, (unsigned long long*)c->staging, vel[0],
 		vel[1], vel[2], c->typ);
 	LFK_CUDA(c, cudaMemcpyAsync((char*)aos32 + (whole_grid ? (size_t)G.z0 * G.sxy * 32 : 0), c->staging, nown * 32,
@@ -561,7 +556,7 @@ extern "C" int lfk_download_table(lfk_ctx *c, uint64_t *begin, uint64_t *count) 
 	LFK_REQUIRE(c, c->table_valid, LFK_E_STATE, "no valid cell table (call lfk_hash)");
 	const GridDesc &G = c->g;
 	size_t nown = (size_t)G.nown;
-	LFK_TRY(reserve_staging(c, nown * 16));
+	LFK_TRY(lfk_reserve_staging(c, nown * 16));
 	unsigned long long *db = (unsigned long long*)c->staging, *dc = db + nown;
 	LFK_LAUNCH(c, k_table_to_u64, lfk_blocks(G.nown, 256), 256, 0, G, c->begin, db, dc, (uint32_t)c->first);
 	size_t off = (size_t)G.z0 * G.sxy;
@@ -593,7 +588,7 @@ extern "C" int lfk_download_fluid_cells(lfk_ctx *c, uint64_t *raw, uint64_t capa
 	LFK_REQUIRE(c, capacity >= nf, LFK_E_CAPACITY, "fluid-cell buffer too small");
 	if (nf == 0) { return 0; } // an empty list may come with a NULL buffer (std::vector::data())
 	LFK_REQUIRE(c, raw != nullptr, LFK_E_INVALID, "NULL fluid-cell buffer");
-	LFK_TRY(reserve_staging(c, (size_t)nf * 8));
+	LFK_TRY(lfk_reserve_staging(c, (size_t)nf * 8));
 	LFK_TRY(lfks_fluid_cells(c, (uint64_t*)c->staging));
 	LFK_CUDA(c, cudaMemcpyAsync(raw, c->staging, (size_t)nf * 8, cudaMemcpyDeviceToHost, c->stream));
 	LFK_CUDA(c, cudaStreamSynchronize(c->stream));
@@ -642,7 +637,7 @@ extern "C" int lfk_download_rhs(lfk_ctx *c, double dt, double *b, uint8_t *flags
 	LFK_TRY(fetch_num_fluid(c, &nf));
 	LFK_REQUIRE(c, capacity >= nf, LFK_E_CAPACITY, "rhs buffer too small");
 	if (nf == 0) { return 0; }
-	LFK_TRY(reserve_staging(c, (size_t)nf * 9));
+	LFK_TRY(lfk_reserve_staging(c, (size_t)nf * 9));
 	double *db = (double*)c->staging;
 	uint8_t *df = (uint8_t*)(db + nf);
 	LFK_TRY(lfks_compact(c, c->b, db, c->flags, df));
@@ -660,7 +655,7 @@ extern "C" int lfk_download_pressure(lfk_ctx *c, double *p, uint64_t capacity) {
 	LFK_REQUIRE(c, capacity >= nf, LFK_E_CAPACITY, "pressure buffer too small");
 	if (nf == 0) { return 0; }
 	LFK_REQUIRE(c, p != nullptr, LFK_E_INVALID, "NULL pressure buffer");
-	LFK_TRY(reserve_staging(c, (size_t)nf * 8));
+	LFK_TRY(lfk_reserve_staging(c, (size_t)nf * 8));
 	LFK_TRY(lfks_compact(c, c->p, (double*)c->staging, nullptr, nullptr));
 	LFK_CUDA(c, cudaMemcpyAsync(p, c->staging, (size_t)nf * 8, cudaMemcpyDeviceToHost, c->stream));
 	LFK_CUDA(c, cudaStreamSynchronize(c->stream));
@@ -673,7 +668,7 @@ extern "C" int lfk_upload_pressure(lfk_ctx *c, const double *p, uint64_t n) {
 	uint64_t nf = 0;
 	LFK_TRY(fetch_num_fluid(c, &nf));
 	LFK_REQUIRE(c, n == nf, LFK_E_INVALID, "pressure vector length != number of fluid cells");
-	LFK_TRY(reserve_staging(c, (size_t)(nf ? nf : 1) * 8));
+	LFK_TRY(lfk_reserve_staging(c, (size_t)(nf ? nf : 1) * 8));
 	if (nf) { LFK_CUDA(c, cudaMemcpyAsync(c->staging, p, (size_t)nf * 8, cudaMemcpyHostToDevice, c->stream)); }
 	LFK_TRY(lfks_expand(c, (const double*)c->staging, c->p));
 	c->pressure_valid = true;
@@ -690,7 +685,7 @@ extern "C" int lfk_apply_a(lfk_ctx *c, double dt, const double *v, double *out, 
 	LFK_TRY(fetch_num_fluid(c, &nf));
 	LFK_REQUIRE(c, n == nf, LFK_E_INVALID, "vector length != number of fluid cells");
 	if (nf == 0) { return 0; }
-	LFK_TRY(reserve_staging(c, (size_t)nf * 8));
+	LFK_TRY(lfk_reserve_staging(c, (size_t)nf * 8));
 	LFK_CUDA(c, cudaMemcpyAsync(c->staging, v, (size_t)nf * 8, cudaMemcpyHostToDevice, c->stream));
 	LFK_TRY(lfks_expand(c, (const double*)c->staging, c->s));
 	if (c->nranks > 1) { LFK_TRY(lfkx_halo_f64(c, c->s)); }

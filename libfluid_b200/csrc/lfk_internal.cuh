@@ -159,6 +159,12 @@ struct lfk_ctx {
 	uint16_t *src_map = nullptr;     // [ncl] 0, or 1 + index of the LAST coercing source that lists the cell
 	uint64_t rng_seed = 0x5eed5eedull, rng_step = 0;
 
+	// host transfers (transfer.cu)
+	cudaStream_t copy_stream = nullptr;
+	cudaEvent_t xfer_ev[6] = { nullptr, nullptr, nullptr, nullptr, nullptr, nullptr }; // slot filled / slot free x 2, positions ready / copied
+	void *pos_stage = nullptr; size_t pos_stage_bytes = 0; // device buffer of the asynchronous positions download
+	bool pos_pending = false;
+
 	// scratch
 	void *staging = nullptr; size_t staging_bytes = 0;
 	uint32_t *scan_tmp = nullptr; size_t scan_tmp_n = 0;
@@ -215,8 +221,8 @@ struct PhaseTimer { // accumulates device time of a phase into stats.phase_ms wh
 };
 
 // ---- implemented in particles.cu ----
-int lfkp_aos_to_soa(lfk_ctx *c, const void *d_aos, uint64_t n);
-int lfkp_soa_to_aos(lfk_ctx *c, void *d_aos, uint64_t n);
+int lfkp_aos_to_soa(lfk_ctx *c, const void *d_aos, uint64_t n, uint64_t at = 0);   // particles [at, at + n) of the own view
+int lfkp_soa_to_aos(lfk_ctx *c, void *d_aos, uint64_t n, uint64_t at = 0);
 int lfkp_positions_to_aos(lfk_ctx *c, double *d_xyz, uint64_t n);
 int lfkp_hash(lfk_ctx *c, bool lean);
 int lfkp_materialise_vc(lfk_ctx *c);
@@ -239,6 +245,12 @@ static inline ParticleSoA lfk_own_view(const lfk_ctx *c) { // the own particles 
 	for (int f = 0; f < PF_COUNT; ++f) { v.f[f] += c->first; }
 	return v;
 }
+
+// ---- implemented in transfer.cu: chunked, double-buffered host transfers on a second stream; checkpoints ----
+int lfk_reserve_staging(lfk_ctx *c, size_t bytes); // (lfk_api.cu)
+int lfkt_upload_particles_pipelined(lfk_ctx *c, const void *aos152, uint64_t n);
+int lfkt_download_particles_pipelined(lfk_ctx *c, void *aos152, uint64_t n);
+int lfkt_destroy(lfk_ctx *c);
 
 // ---- implemented in p2g.cu ----
 int lfkg_p2g(lfk_ctx *c, double gravity_dt, bool add_gravity);

@@ -68,19 +68,24 @@ __global__ void k_positions_interleave(double *__restrict__ xyz, const double *_
 	}
 }
 
-int lfkp_aos_to_soa(lfk_ctx *c, const void *d_aos, uint64_t n) {
+static ParticleSoA view_at(const lfk_ctx *c, uint64_t at) {
+	ParticleSoA v = c->P;
+	for (int f = 0; f < PF_COUNT; ++f) { v.f[f] += c->first + at; }
+	return v;
+}
+int lfkp_aos_to_soa(lfk_ctx *c, const void *d_aos, uint64_t n, uint64_t at) {
 	if (n == 0) { return 0; }
 	// raw_cell_index is a whole-grid raw index; device keys are local (one ghost layer below the slab)
 	long long shift = ((long long)1 - c->g.z0) * c->g.sxy;
 	LFK_LAUNCH(c, k_aos_to_soa, lfk_blocks((long long)n, AOS_TILE), AOS_TILE, 0,
-		(const unsigned long long*)d_aos, lfk_own_view(c), c->key + c->first, (unsigned long long)n, shift);
+		(const unsigned long long*)d_aos, view_at(c, at), c->key + c->first + at, (unsigned long long)n, shift);
 	return 0;
 }
-int lfkp_soa_to_aos(lfk_ctx *c, void *d_aos, uint64_t n) {
+int lfkp_soa_to_aos(lfk_ctx *c, void *d_aos, uint64_t n, uint64_t at) {
 	if (n == 0) { return 0; }
 	long long shift = ((long long)1 - c->g.z0) * c->g.sxy;
 	LFK_LAUNCH(c, k_soa_to_aos, lfk_blocks((long long)n, AOS_TILE), AOS_TILE, 0,
-		(unsigned long long*)d_aos, lfk_own_view(c), c->key + c->first, (unsigned long long)n, c->old_valid ? 1 : 0, shift);
+		(unsigned long long*)d_aos, view_at(c, at), c->key + c->first + at, (unsigned long long)n, c->old_valid ? 1 : 0, shift);
 	return 0;
 }
 int lfkp_positions_to_aos(lfk_ctx *c, double *d_xyz, uint64_t n) {

@@ -286,6 +286,47 @@ def test_untouched_payload_travels_with_its_particle(method):
     ctx.close()
 
 
+def test_chunked_transfers_async_positions_and_checkpoint(tmp_path, monkeypatch):
+    """N3: the chunked, double-buffered AoS transfers (forced to many chunks) round-trip bit for bit; the asynchronous
+    positions download returns the positions of the moment it was queued even though the next step is issued before
+    it is waited for; a checkpoint restored into a fresh context continues the run bit for bit (APIC and FLIP)."""
+    monkeypatch.setenv("LFK_XFER_CHUNK", "777")
+    for method in (capi.APIC, capi.FLIP):
+        ctx = _device_scene(n=24, method=method, blending_factor=0.95)
+        for _ in range(2):
+            ctx.time_step()
+        parts = ctx.download_particles().copy()
+        assert parts.shape[0] > 10 * 777
+        ctx.upload_particles(parts)
+        back = ctx.download_particles()
+        assert np.array_equal(back.view("u1"), parts.view("u1"))
+        # asynchronous positions: queue, step, then wait
+        n = ctx.num_particles()
+        pin = capi.PinnedBuffer(n * 24)
+        got = ctx.download_positions_async(pin.ptr.value, n)
+        ctx.time_step(0.002)
+        ctx.wait_transfers()
+        xyz = pin.array[:n * 24].view(np.float64).reshape(n, 3)
+        assert got == n and np.array_equal(xyz, parts["position"])
+        pin.close()
+        # checkpoint -> fresh context -> same continuation
+        path = str(tmp_path / ("ckpt_%d.bin" % method))
+        ctx.checkpoint_save(path)
+        for _ in range(2):
+            ctx.time_step(0.002)
+        a, ca = ctx.download_particles().copy(), ctx.download_cells().copy()
+        fresh = capi.Context((24, 24, 24), cell_size=1.0)
+        fresh.checkpoint_load(path)
+        assert int(fresh.params.method) == method and fresh.num_particles() == n
+        for _ in range(2):
+            fresh.time_step(0.002)
+        b, cb = fresh.download_particles(), fresh.download_cells()
+        assert np.array_equal(a.view("u1"), b.view("u1"))
+        assert np.array_equal(ca["vel"], cb["vel"]) and np.array_equal(ca["type"], cb["type"])
+        fresh.close()
+        ctx.close()
+
+
 @pytest.mark.skipif(not RB.available(), reason="oracle/_ref did not travel to this box")
 def test_sources_on_device_match_reference():
     """N1: velocity coercion and seed_cell on the device against the reference's _advect_particles / _update_sources
