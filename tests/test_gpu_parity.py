@@ -360,14 +360,14 @@ def test_sources_on_device_match_reference():
     assert (b["velocity"][:, 0] == 150.0).sum() > 50  # the scene does exercise coercion
     # ---- seed_cell ----
     ref.collide()
-    ref.hash()
+    ref.update_and_hash()  # (time_step re-keys the particles here, src/simulation.cpp:62; hash() alone would not)
     before = ref.particles()
     _, cnt_before = ref.space_hash()
     ctx.upload_particles(before)
     ctx.hash()
     added = ctx.update_sources()
     ref.update_sources()
-    ref.hash()
+    ref.update_and_hash()
     after_ref = ref.particles()
     assert added == after_ref.shape[0] - before.shape[0] and added > 0
     ctx.hash()
