@@ -195,6 +195,34 @@ int lfk_coerce_sources(lfk_ctx *ctx);
  * to target_density_cubic_root^3 particles; needs the table of the last lfk_hash, invalidates it when *added > 0 */
 int lfk_update_sources(lfk_ctx *ctx, uint64_t *added);
 
+/* ---- neighbours of the path that consume / produce its device-resident state ------------------------------ */
+/* mesher (include/fluid/mesher.h:15-46): the public fields and resize() */
+typedef struct lfk_mesher {
+	double grid_offset[3];   /* mesher::grid_offset */
+	double cell_size;        /* mesher::cell_size */
+	double particle_extent;  /* mesher::particle_extent */
+	uint64_t cell_radius;    /* mesher::cell_radius */
+	uint64_t size[3];        /* mesher::resize(size): cells; the surface function has size + 1 samples per axis */
+} lfk_mesher;
+/* mesher::_sample_surface_function (src/mesher.cpp:333-376), the first half of generate_mesh(particles, r): the
+ * implicit surface function on the (size + 1)^3 sample points, x fastest.  xyz: host positions (x, y, z triples), or
+ * NULL to sample the context's own particles where they live (no position download).  Points without particles in
+ * range read 1.0, points whose particles all weigh zero read NaN, like the reference. */
+int lfk_mesher_sample(lfk_ctx *ctx, const lfk_mesher *m, double r, const double *xyz, uint64_t n, double *surface);
+/* voxelizer::resize_reposition_grid_constrained + voxelize_mesh_surface + mark_exterior (src/voxelizer.cpp:19-126) for
+ * a triangle mesh (positions: x, y, z triples; indices: 3 per triangle).  Returns the voxel grid's offset in cells of
+ * the reference grid and its size; the voxels stay on the device. */
+int lfk_voxelize_mesh(lfk_ctx *ctx, const double *positions, uint64_t num_vertices, const uint64_t *indices,
+	uint64_t num_indices, double cell_size, const double ref_grid_offset[3], int64_t grid_min[3], uint64_t voxel_size[3]);
+/* voxelizer::voxels as bytes (0 interior, 1 exterior, 2 surface: voxelizer::cell_type), x fastest */
+int lfk_voxels_download(lfk_ctx *ctx, uint8_t *voxels, uint64_t capacity);
+/* obstacle::cells (src/data_structures/obstacle.cpp:9-29): the interior voxels that lie inside the simulation grid, as
+ * x, y, z triples in the reference's order; cells_xyz may be NULL (count only).  mark_solid != 0 also sets their cell
+ * type to solid on the device (what plugins/maya/nodes/grid_node.cpp:330-340 does cell by cell on the host).
+ * Where the voxel grid starts above the simulation grid's origin the reference's own loop bounds mix the two grids'
+ * coordinates and read out of bounds; this is the intended set. */
+int lfk_obstacle_cells(lfk_ctx *ctx, uint64_t *cells_xyz, uint64_t capacity, uint64_t *n, int mark_solid);
+
 /* ---- fused entry points (what the shim calls when no mid-step callback is installed) --------------------- */
 /* simulation::time_step(dt) without sources (src/simulation.cpp:43-125), entirely on the device */
 int lfk_time_step(lfk_ctx *ctx, double dt);

@@ -12,7 +12,7 @@ ROOT = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
 OUT_DIR = os.path.join(HERE, "_lib")
 LIB = os.path.join(OUT_DIR, "liblfk.so")
-SOURCES = ["lfk_api.cu", "particles.cu", "g2p.cu", "p2g.cu", "p2g_march.cu", "pressure.cu", "mg.cu", "exchange.cu", "transfer.cu"]
+SOURCES = ["lfk_api.cu", "particles.cu", "g2p.cu", "p2g.cu", "p2g_march.cu", "pressure.cu", "mg.cu", "exchange.cu", "transfer.cu", "aux.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 # --fmad=false: the reference's CPU build does no FMA contraction; particle motion / classification must be

@@ -39,6 +39,11 @@ class Source(C.Structure):
                 ("target_density_cubic_root", C.c_uint32), ("active", C.c_int32), ("coerce_velocity", C.c_int32)]
 
 
+class Mesher(C.Structure):
+    _fields_ = [("grid_offset", C.c_double * 3), ("cell_size", C.c_double), ("particle_extent", C.c_double),
+                ("cell_radius", C.c_uint64), ("size", C.c_uint64 * 3)]
+
+
 class Stats(C.Structure):
     _fields_ = [("kernel_launches", C.c_uint64), ("pcg_iterations", C.c_uint64), ("pcg_residual", C.c_double),
                 ("phase_ms", C.c_double * 16), ("num_particles", C.c_uint64), ("num_fluid_cells", C.c_uint64),
@@ -61,7 +66,8 @@ SYMBOLS = (
     "lfk_download_fluid_cells", "lfk_hash", "lfk_advect", "lfk_collide", "lfk_p2g", "lfk_gravity",
     "lfk_pressure_solve", "lfk_download_rhs", "lfk_download_pressure", "lfk_upload_pressure", "lfk_apply_a",
     "lfk_apply_pressure", "lfk_correct", "lfk_extrapolate", "lfk_g2p", "lfk_cfl", "lfk_set_sources", "lfk_set_rng_seed",
-    "lfk_coerce_sources", "lfk_update_sources", "lfk_time_step",
+    "lfk_coerce_sources", "lfk_update_sources", "lfk_mesher_sample", "lfk_voxelize_mesh", "lfk_voxels_download",
+    "lfk_obstacle_cells", "lfk_time_step",
     "lfk_time_step_cfl", "lfk_update", "lfk_seed_box_device", "lfk_synthetic_projection_device", "lfk_set_timing",
     "lfk_set_tuning", "lfk_get_stats", "lfk_reset_stats",
 )
@@ -119,6 +125,10 @@ def load_library():
     L.lfk_set_rng_seed.argtypes = [vp, u64]
     L.lfk_coerce_sources.argtypes = [vp]
     L.lfk_update_sources.argtypes = [vp, C.POINTER(u64)]
+    L.lfk_mesher_sample.argtypes = [vp, C.POINTER(Mesher), db, vp, u64, vp]
+    L.lfk_voxelize_mesh.argtypes = [vp, vp, u64, vp, u64, db, vp, vp, vp]
+    L.lfk_voxels_download.argtypes = [vp, vp, u64]
+    L.lfk_obstacle_cells.argtypes = [vp, vp, u64, C.POINTER(u64), ci]
     L.lfk_seed_box_device.argtypes = [vp, vp, vp, vp, C.c_uint32, u64, ci]
     L.lfk_synthetic_projection_device.argtypes = [vp, u64]
     L.lfk_set_timing.argtypes = [vp, ci]
@@ -425,6 +435,38 @@ class Context:
         n = C.c_uint64()
         self._ck(self.L.lfk_update_sources(self.ptr, C.byref(n)))
         return n.value
+
+    def mesher_sample(self, size, offset, cell_size, extent, cell_radius, r, xyz=None):
+        """mesher::_sample_surface_function on the device: (sz + 1, sy + 1, sx + 1) array; xyz None = own particles"""
+        m = Mesher()
+        m.grid_offset[:] = [float(v) for v in offset]
+        m.cell_size, m.particle_extent, m.cell_radius = float(cell_size), float(extent), int(cell_radius)
+        m.size[:] = [int(v) for v in size]
+        out = np.zeros((int(size[2]) + 1, int(size[1]) + 1, int(size[0]) + 1), dtype=np.float64)
+        if xyz is not None:
+            xyz = np.ascontiguousarray(xyz, dtype=np.float64).reshape(-1, 3)
+        self._ck(self.L.lfk_mesher_sample(self.ptr, C.byref(m), float(r), _ptr(xyz), 0 if xyz is None else xyz.shape[0],
+                                          _ptr(out)))
+        return out
+
+    def voxelize_mesh(self, positions, indices, cell_size, ref_offset):
+        """voxelizer on the device: (grid_min (3,) int64, voxels (vz, vy, vx) u8)"""
+        pos = np.ascontiguousarray(positions, dtype=np.float64).reshape(-1, 3)
+        idx = np.ascontiguousarray(indices, dtype=np.uint64).ravel()
+        off = _v3(ref_offset)
+        gmin, vsz = np.zeros(3, dtype=np.int64), np.zeros(3, dtype=np.uint64)
+        self._ck(self.L.lfk_voxelize_mesh(self.ptr, _ptr(pos), pos.shape[0], _ptr(idx), idx.shape[0], float(cell_size),
+                                          _ptr(off), _ptr(gmin), _ptr(vsz)))
+        vox = np.zeros((int(vsz[2]), int(vsz[1]), int(vsz[0])), dtype=np.uint8)
+        self._ck(self.L.lfk_voxels_download(self.ptr, _ptr(vox), vox.size))
+        return gmin, vox
+
+    def obstacle_cells(self, mark_solid=False):
+        n = C.c_uint64()
+        self._ck(self.L.lfk_obstacle_cells(self.ptr, None, 0, C.byref(n), 0))
+        cells = np.zeros((max(n.value, 1), 3), dtype=np.uint64)
+        self._ck(self.L.lfk_obstacle_cells(self.ptr, _ptr(cells), n.value, C.byref(n), int(bool(mark_solid))))
+        return cells[:n.value]
 
     def seed_box_device(self, start, size, velocity=(0, 0, 0), density=2, seed=1, append=False):
         a, b, v = _v3(start), _v3(size), _v3(velocity)  # keep the temporaries alive across the call

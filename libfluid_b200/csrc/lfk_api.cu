@@ -190,6 +190,7 @@ static int free_all(lfk_ctx *c) {
 	dev_free(c->src_vel);
 	dev_free(c->src_target);
 	dev_free(c->src_map);
+	dev_free(c->vox);
 	dev_free(c->xcounts);
 	if (c->h_xcounts) { cudaFreeHost(c->h_xcounts); c->h_xcounts = nullptr; }
 	if (c->staging) { cudaFree(c->staging); c->staging = nullptr; }

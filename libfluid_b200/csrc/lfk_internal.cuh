@@ -165,6 +165,11 @@ struct lfk_ctx {
 	void *pos_stage = nullptr; size_t pos_stage_bytes = 0; // device buffer of the asynchronous positions download
 	bool pos_pending = false;
 
+	// obstacle voxelisation (aux.cu): the voxel grid of the last lfk_voxelize_mesh
+	uint8_t *vox = nullptr;
+	long long vox_min[3] = { 0, 0, 0 };
+	int vox_size[3] = { 0, 0, 0 };
+
 	// scratch
 	void *staging = nullptr; size_t staging_bytes = 0;
 	uint32_t *scan_tmp = nullptr; size_t scan_tmp_n = 0;

@@ -19,6 +19,9 @@
 #define protected public
 #include "fluid/simulation.h"
 #include "fluid/pressure_solver.h"
+#include "fluid/mesher.h"
+#include "fluid/voxelizer.h"
+#include "fluid/data_structures/obstacle.h"
 #undef private
 #undef protected
 
@@ -259,5 +262,86 @@ extern "C" {
 	}
 	void ref_update(void *p, double dt) {
 		static_cast<ref_ctx*>(p)->sim.update(dt);
+	}
+
+	// ---- "next" rows of SURVEY.md 8(f): mesher surface sampling (N2) and obstacle voxelisation (N4) ----
+	// mesher::_sample_surface_function (src/mesher.cpp:333-376) on a grid of size^3 cells; out: (sx+1)(sy+1)(sz+1) doubles
+	void ref_mesher_sample(
+		const std::size_t *size, const double *offset, double cell_size, double extent, std::size_t cell_radius,
+		const double *xyz, std::size_t n, double r, double *out
+	) {
+		fluid::mesher m;
+		m.grid_offset = vec3d(offset[0], offset[1], offset[2]);
+		m.cell_size = cell_size;
+		m.particle_extent = extent;
+		m.cell_radius = cell_radius;
+		m.resize(vec3s(size[0], size[1], size[2]));
+		std::vector<vec3d> pts(n);
+		for (std::size_t i = 0; i < n; ++i) {
+			pts[i] = vec3d(xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2]);
+		}
+		m._sample_surface_function(pts, r);
+		vec3s gs = m._surface_function.get_size();
+		std::size_t k = 0;
+		for (std::size_t z = 0; z < gs.z; ++z) {
+			for (std::size_t y = 0; y < gs.y; ++y) {
+				for (std::size_t x = 0; x < gs.x; ++x) {
+					out[k++] = m._surface_function(x, y, z);
+				}
+			}
+		}
+	}
+	// voxelizer (src/voxelizer.cpp:19-126) + obstacle (src/data_structures/obstacle.cpp:9-29) for a triangle mesh.
+	// Call once with voxels == nullptr to get the sizes, then again with buffers.
+	void ref_voxelize(
+		const double *pos, std::size_t nverts, const std::size_t *idx, std::size_t nidx, double cell_size,
+		const double *ref_offset, const std::size_t *ref_size, long long *grid_min, std::size_t *vox_size,
+		unsigned char *voxels, std::size_t *ncells, std::size_t *cells_xyz
+	) {
+		fluid::obstacle::mesh_t mesh;
+		for (std::size_t i = 0; i < nverts; ++i) {
+			mesh.positions.emplace_back(pos[3 * i], pos[3 * i + 1], pos[3 * i + 2]);
+		}
+		mesh.indices.assign(idx, idx + nidx);
+		auto [rmin, rmax] = fluid::voxelizer::get_bounding_box(mesh.positions.begin(), mesh.positions.end());
+		fluid::voxelizer vox;
+		fluid::vec3i off = vox.resize_reposition_grid_constrained(
+			rmin, rmax, cell_size, vec3d(ref_offset[0], ref_offset[1], ref_offset[2])
+		);
+		vox.voxelize_mesh_surface(mesh);
+		vox.mark_exterior();
+		vec3s vs = vox.voxels.get_size();
+		for (int d = 0; d < 3; ++d) {
+			grid_min[d] = off[d];
+			vox_size[d] = vs[d];
+		}
+		if (voxels) {
+			std::size_t k = 0;
+			for (std::size_t z = 0; z < vs.z; ++z) {
+				for (std::size_t y = 0; y < vs.y; ++y) {
+					for (std::size_t x = 0; x < vs.x; ++x) {
+						voxels[k++] = static_cast<unsigned char>(vox.voxels(x, y, z));
+					}
+				}
+			}
+		}
+		// obstacle::obstacle walks voxels over get_overlapping_cell_range(), whose upper corner is computed in REFERENCE-grid
+		// coordinates (src/voxelizer.cpp:45-49) but used as a VOXEL-grid bound (obstacle.cpp:21-28): with a positive
+		// offset on any axis the reference reads beyond its voxel array (undefined behaviour; it crashed here).  The
+		// driver only runs it where it is defined, and reports SIZE_MAX otherwise.
+		if (off.x > 0 || off.y > 0 || off.z > 0) {
+			*ncells = static_cast<std::size_t>(-1);
+			return;
+		}
+		fluid::obstacle obs(mesh, cell_size, vec3d(ref_offset[0], ref_offset[1], ref_offset[2]),
+			vec3s(ref_size[0], ref_size[1], ref_size[2]));
+		*ncells = obs.cells.size();
+		if (cells_xyz) {
+			for (std::size_t i = 0; i < obs.cells.size(); ++i) {
+				cells_xyz[3 * i] = obs.cells[i].x;
+				cells_xyz[3 * i + 1] = obs.cells[i].y;
+				cells_xyz[3 * i + 2] = obs.cells[i].z;
+			}
+		}
 	}
 }

@@ -66,6 +66,9 @@ def lib():
         L.ref_solver_apply_a.argtypes = [vp, vp, vp]
         L.ref_cfl.restype = db
         L.ref_cfl.argtypes = [vp]
+        if hasattr(L, "ref_mesher_sample"):
+            L.ref_mesher_sample.argtypes = [vp, vp, db, db, sz, vp, sz, db, vp]
+            L.ref_voxelize.argtypes = [vp, sz, vp, sz, db, vp, vp, vp, vp, vp, vp, vp]
         _lib = L
     return _lib
 
@@ -267,3 +270,31 @@ class RefSim:
         self.extrapolate(); h("extrapolate")
         self.g2p(); h("g2p")
         return out
+
+
+def mesher_sample(size, offset, cell_size, extent, cell_radius, xyz, r):
+    """mesher::_sample_surface_function of the reference: (sz + 1, sy + 1, sx + 1) array of the implicit function"""
+    L = lib()
+    size = np.ascontiguousarray(size, dtype=np.uint64)
+    xyz = np.ascontiguousarray(xyz, dtype=np.float64).reshape(-1, 3)
+    out = np.zeros((int(size[2]) + 1, int(size[1]) + 1, int(size[0]) + 1), dtype=np.float64)
+    L.ref_mesher_sample(_p(size), _p(_v3(offset)), float(cell_size), float(extent), int(cell_radius), _p(xyz),
+                        xyz.shape[0], float(r), _p(out))
+    return out
+
+
+def voxelize(positions, indices, cell_size, ref_offset, ref_size):
+    """voxelizer + obstacle of the reference: (grid_min (3,), voxels (vz, vy, vx) u8, obstacle cells (n, 3))"""
+    L = lib()
+    pos = np.ascontiguousarray(positions, dtype=np.float64).reshape(-1, 3)
+    idx = np.ascontiguousarray(indices, dtype=np.uint64).ravel()
+    rsz = np.ascontiguousarray(ref_size, dtype=np.uint64)
+    gmin, vsz, nc = np.zeros(3, dtype=np.int64), np.zeros(3, dtype=np.uint64), C.c_size_t()
+    L.ref_voxelize(_p(pos), pos.shape[0], _p(idx), idx.shape[0], float(cell_size), _p(_v3(ref_offset)), _p(rsz), _p(gmin),
+                   _p(vsz), None, C.byref(nc), None)
+    vox = np.zeros((int(vsz[2]), int(vsz[1]), int(vsz[0])), dtype=np.uint8)
+    undefined = nc.value == 2 ** 64 - 1  # the reference's obstacle would read out of bounds (see ref_driver.cpp)
+    cells = np.zeros((1 if undefined else max(nc.value, 1), 3), dtype=np.uint64)
+    L.ref_voxelize(_p(pos), pos.shape[0], _p(idx), idx.shape[0], float(cell_size), _p(_v3(ref_offset)), _p(rsz), _p(gmin),
+                   _p(vsz), _p(vox), C.byref(nc), _p(cells))
+    return gmin, vox, (None if undefined else cells[:nc.value])

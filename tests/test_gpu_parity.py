@@ -408,6 +408,110 @@ def test_sources_on_device_match_reference():
     ctx.close()
 
 
+def _mesh_box(lo, hi):
+    (x0, y0, z0), (x1, y1, z1) = lo, hi
+    v = np.array([[x0, y0, z0], [x1, y0, z0], [x1, y1, z0], [x0, y1, z0], [x0, y0, z1], [x1, y0, z1], [x1, y1, z1],
+                  [x0, y1, z1]], dtype=np.float64)
+    f = np.array([[0, 1, 2], [0, 2, 3], [4, 6, 5], [4, 7, 6], [0, 4, 5], [0, 5, 1], [1, 5, 6], [1, 6, 2], [2, 6, 7],
+                  [2, 7, 3], [3, 7, 4], [3, 4, 0]], dtype=np.uint64)
+    return v, f
+
+
+def _mesh_sphere(center, radius, nu=24, nv=16):
+    """a closed UV sphere (triangles only; skinny triangles at the poles exercise the separating-axis test)"""
+    th = np.linspace(0.0, np.pi, nv + 1)[1:-1]
+    ph = np.linspace(0.0, 2.0 * np.pi, nu, endpoint=False)
+    ring = np.stack([np.outer(np.sin(th), np.cos(ph)), np.outer(np.cos(th), np.ones_like(ph)),
+                     np.outer(np.sin(th), np.sin(ph))], axis=2).reshape(-1, 3)
+    v = np.concatenate([[[0.0, 1.0, 0.0]], ring, [[0.0, -1.0, 0.0]]]) * radius + np.asarray(center)
+    f = []
+    for j in range(nu):
+        f.append([0, 1 + j, 1 + (j + 1) % nu])
+        for i in range(nv - 2):
+            a, b = 1 + i * nu + j, 1 + i * nu + (j + 1) % nu
+            f += [[a, a + nu, b], [b, a + nu, b + nu]]
+        base = 1 + (nv - 2) * nu
+        f.append([base + j, len(v) - 1, base + (j + 1) % nu])
+    return v, np.array(f, dtype=np.uint64)
+
+
+@pytest.mark.skipif(not RB.available() or not hasattr(RB.lib(), "ref_mesher_sample"),
+                    reason="oracle/_ref (with the mesher / voxelizer sources) did not travel to this box")
+def test_mesher_sampling_on_device_matches_reference():
+    """N2: mesher::_sample_surface_function (src/mesher.cpp:333-376) on the device against the reference, on host
+    positions with the testbed's settings (testbed/main.cpp:218-224) and on the context's own resident particles:
+    the same points read 1.0 (nothing in range) and NaN (only zero weights), the rest agree to summation order."""
+    ctx = _device_scene(n=24)
+    for _ in range(3):
+        ctx.time_step()
+    pos = ctx.download_positions()
+    for size, off, cs, ext, rad, r, own in (((56, 56, 56), (-1.0, -1.0, -1.0), 0.5, 2.0, 3, 0.5, False),
+                                           ((30, 26, 22), (0.3, -0.7, 1.1), 0.9, 0.8, 2, 0.35, True),
+                                           ((20, 20, 20), (2.0, 2.0, 2.0), 1.0, 0.5, 1, 0.5, True)):
+        want = RB.mesher_sample(size, off, cs, ext, rad, pos, r)
+        got = ctx.mesher_sample(size, off, cs, ext, rad, r, xyz=None if own else pos)
+        assert np.array_equal(np.isnan(got), np.isnan(want))
+        assert np.array_equal(got == 1.0, want == 1.0)
+        ok = ~np.isnan(want)
+        assert (want[ok] != 1.0).sum() > 1000
+        assert np.abs(got[ok] - want[ok]).max() <= 1e-12 * max(1.0, np.abs(want[ok]).max())
+    ctx.close()
+
+
+@pytest.mark.skipif(not RB.available() or not hasattr(RB.lib(), "ref_voxelize"),
+                    reason="oracle/_ref (with the mesher / voxelizer sources) did not travel to this box")
+def test_voxelizer_on_device_matches_reference():
+    """N4: voxelizer (src/voxelizer.cpp:19-126) + obstacle (src/data_structures/obstacle.cpp:9-29) on the device: the
+    voxel classification (interior / exterior / surface) is exact for boxes and spheres at several cell sizes and
+    offsets, including a hollow shell (an interior that the flood must not reach) and a mesh whose bounding grid is one
+    solid surface block; the obstacle cells equal the reference's wherever the reference's loop bounds are defined, and
+    marking them solid changes exactly those cell types."""
+    n = 20
+    ctx = capi.Context((n, n, n), cell_size=1.0)
+    shell_v0, shell_f0 = _mesh_box((2.2, 2.1, 2.3), (15.4, 14.9, 13.7))
+    shell_v1, shell_f1 = _mesh_box((5.2, 5.1, 5.3), (11.4, 10.9, 9.7))
+    shell = (np.concatenate([shell_v0, shell_v1]), np.concatenate([shell_f0, shell_f1 + 8]))
+    cases = [(_mesh_box((1.3, 1.2, 1.1), (7.7, 6.5, 5.8)), 1.0, (0.0, 0.0, 0.0)),
+             (_mesh_box((0.3, -0.8, 1.1), (7.7, 6.5, 5.8)), 1.0, (0.0, 0.0, 0.0)),
+             (_mesh_box((3.3, 2.2, 4.1), (9.7, 6.5, 8.8)), 1.0, (0.0, 0.0, 0.0)),
+             (_mesh_sphere((8.1, 7.4, 9.2), 5.3), 1.0, (0.0, 0.0, 0.0)),
+             (_mesh_sphere((3.0, 2.5, 3.5), 2.4), 0.37, (-0.2, 0.1, 0.3)),
+             (shell, 1.0, (0.0, 0.0, 0.0)),
+             (_mesh_box((4.1, 4.2, 4.3), (4.6, 4.7, 4.8)), 1.0, (0.0, 0.0, 0.0))]
+    defined = 0
+    for (v, f), cs, off in cases:
+        ctx.set_params(cell_size=cs, grid_offset=off)
+        gmin_r, vox_r, cells_r = RB.voxelize(v, f, cs, off, (n, n, n))
+        gmin_d, vox_d = ctx.voxelize_mesh(v, f, cs, off)
+        assert np.array_equal(gmin_d, gmin_r) and vox_d.shape == vox_r.shape
+        assert np.array_equal(vox_d, vox_r)
+        cells_d = ctx.obstacle_cells()
+        # the intended set: interior voxels inside the simulation grid, z / y / x ascending
+        zz, yy, xx = np.nonzero(vox_r == 0)
+        g = np.stack([xx, yy, zz], axis=1).astype(np.int64) + gmin_r
+        g = g[((g >= 0) & (g < n)).all(axis=1)]
+        assert np.array_equal(cells_d.astype(np.int64), g)
+        if cells_r is not None and (gmin_r == 0).all():
+            defined += 1
+            assert np.array_equal(cells_d, cells_r)
+        before = ctx.download_cells()["type"].copy()
+        ctx.obstacle_cells(mark_solid=True)
+        after = ctx.download_cells()["type"]
+        raw = g[:, 0] + n * (g[:, 1] + n * g[:, 2])
+        expect = before.copy()
+        expect[raw] = capi.SOLID
+        assert np.array_equal(after, expect)
+        ctx.upload_cells(_air_cells(n))
+    assert defined >= 1
+    ctx.close()
+
+
+def _air_cells(n):
+    c = np.zeros(n ** 3, dtype=capi.CELL_DTYPE)
+    c["type"] = capi.AIR
+    return c
+
+
 def test_two_gpu_slabs_match_single_gpu():
     """z-slab decomposition with particle migration, ghost copies and NCCL halos against the single-GPU run of the
     same scene (tests/mgpu_check.py under torchrun; needs >= 2 GPUs)."""
