@@ -133,7 +133,15 @@ extern "C" int lfk_download_positions_async(lfk_ctx *c, double *xyz, uint64_t ca
 	LFK_TRY(lfkp_positions_to_aos(c, (double*)c->pos_stage, c->np));
 	LFK_CUDA(c, cudaEventRecord(ready, c->stream));
 	LFK_CUDA(c, cudaStreamWaitEvent(c->copy_stream, ready, 0));
-	LFK_CUDA(c, cudaMemcpyAsync(xyz, c->pos_stage, bytes, cudaMemcpyDeviceToHost, c->copy_stream));
+	// In pieces: the step that runs meanwhile reads a handful of scalars back per solve (convergence flag, CFL maximum),
+	// and a device-to-host engine serves its queue in order -- behind one 3 GB copy those reads stall the whole step for
+	// the duration of the copy (measured: 127 ms per step instead of 65, tools/stream_probe.py); behind a 4 MB piece
+	// they wait 80 us.
+	const size_t piece = 4u << 20;
+	for (size_t at = 0; at < bytes; at += piece) {
+		const size_t m = bytes - at < piece ? bytes - at : piece;
+		LFK_CUDA(c, cudaMemcpyAsync((char*)xyz + at, (const char*)c->pos_stage + at, m, cudaMemcpyDeviceToHost, c->copy_stream));
+	}
 	LFK_CUDA(c, cudaEventRecord(copied, c->copy_stream));
 	c->pos_pending = true;
 	return 0;
