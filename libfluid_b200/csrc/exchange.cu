@@ -570,8 +570,8 @@ int lfkx_exchange_particles(lfk_ctx *c, uint64_t *n_in) {
 		LFK_LAUNCH(c, k_xch_count, nb, XCH_THREADS, 0, G, V.f[PF_PZ], (unsigned long long)n, has_up, has_dn, cnt_up, cnt_dn);
 		LFK_TRY(lfkp_exclusive_scan_u32(c, cnt_up, off_up, nb, 0));
 		LFK_TRY(lfkp_exclusive_scan_u32(c, cnt_dn, off_dn, nb, 0));
-		LFK_CUDA(c, cudaMemcpyAsync(hc + 0, off_up + nb, sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
-		LFK_CUDA(c, cudaMemcpyAsync(hc + 1, off_dn + nb, sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+		LFK_TRY(lfk_readback(c, hc + 0, off_up + nb, sizeof(uint32_t)));
+		LFK_TRY(lfk_readback(c, hc + 1, off_dn + nb, sizeof(uint32_t)));
 		LFK_CUDA(c, cudaStreamSynchronize(c->stream));
 	}
 	const uint32_t send_up = hc[0], send_dn = hc[1];
@@ -594,7 +594,7 @@ int lfkx_exchange_particles(lfk_ctx *c, uint64_t *n_in) {
 		LFK_NCCL(c, g_nccl.Recv(c->xcounts + 3, 1, ncclUint32, c->rank - 1, comm, c->stream));
 	}
 	LFK_NCCL(c, g_nccl.GroupEnd());
-	LFK_CUDA(c, cudaMemcpyAsync(hc + 2, c->xcounts + 2, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+	LFK_TRY(lfk_readback(c, hc + 2, c->xcounts + 2, 2 * sizeof(uint32_t)));
 	LFK_CUDA(c, cudaStreamSynchronize(c->stream));
 	const uint32_t recv_up = hc[2], recv_dn = hc[3];
 	// payload: what the lower neighbour sent goes first (deterministic append order)

@@ -22,6 +22,16 @@ int lfk_fail(lfk_ctx *ctx, int code, const char *what, const char *file, int lin
 	return code;
 }
 
+__global__ void k_readback(unsigned *__restrict__ dst, const unsigned *__restrict__ src, unsigned nwords) {
+	for (unsigned i = threadIdx.x; i < nwords; i += blockDim.x) { dst[i] = src[i]; }
+	__threadfence_system();
+}
+int lfk_readback(lfk_ctx *c, void *pinned_host, const void *dev, size_t bytes) {
+	LFK_REQUIRE(c, bytes % 4 == 0 && bytes <= 4096, LFK_E_INVALID, "lfk_readback: small word-sized blocks only");
+	LFK_LAUNCH(c, k_readback, 1, 64, 0, (unsigned*)pinned_host, (const unsigned*)dev, (unsigned)(bytes / 4));
+	return 0;
+}
+
 extern "C" int lfk_abi_version(void) {
 	return LFK_ABI_VERSION;
 }

@@ -187,6 +187,11 @@ struct lfk_ctx {
 #define LFK_MAX_PARTIAL_BLOCKS 16384
 
 int lfk_fail(lfk_ctx *ctx, int code, const char *what, const char *file, int line);
+// Small device -> pinned-host read-back issued by a KERNEL (the pinned buffer is device-accessible under unified
+// addressing) instead of the device-to-host copy engine, whose queue is FIFO: behind an asynchronous positions download
+// (transfer.cu) every cudaMemcpyAsync read-back of the step would wait for the whole 3 GB copy (measured: the step took
+// 127 ms instead of 65).  Stream-ordered like the copy it replaces; the caller synchronises the stream as before.
+int lfk_readback(lfk_ctx *c, void *pinned_host, const void *dev, size_t bytes);
 const char *lfk_cuda_err_name(cudaError_t e);
 
 #define LFK_CUDA(ctx, expr) do { cudaError_t e__ = (expr); if (e__ != cudaSuccess) { \

@@ -402,7 +402,7 @@ int lfkp_hash(lfk_ctx *c, bool lean) {
 	if (multi) { // own range of the sorted array = the owned layers; ghosts sit before / behind it, the dead at the end
 		const uint32_t *src[3] = { c->begin + G.sxy, c->begin + G.sxy * (G.nzl + 1), c->begin + G.ncl };
 		for (int k = 0; k < 3; ++k) {
-			LFK_CUDA(c, cudaMemcpyAsync(c->h_xcounts + 4 + k, src[k], sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+			LFK_TRY(lfk_readback(c, c->h_xcounts + 4 + k, src[k], sizeof(uint32_t)));
 		}
 		LFK_CUDA(c, cudaStreamSynchronize(c->stream));
 		c->first = c->h_xcounts[4];
@@ -1059,7 +1059,7 @@ int lfkp_cfl(lfk_ctx *c, double *value) {
 	if (c->nranks > 1) {
 		LFK_TRY(lfkx_allreduce_max(c, c->d_reduce, 1));
 	}
-	LFK_CUDA(c, cudaMemcpyAsync(c->h_reduce, c->d_reduce, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+	LFK_TRY(lfk_readback(c, c->h_reduce, c->d_reduce, sizeof(double)));
 	LFK_CUDA(c, cudaStreamSynchronize(c->stream));
 	*value = c->g.h / sqrt(c->h_reduce[0]);
 	return 0;

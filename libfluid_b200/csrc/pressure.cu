@@ -463,7 +463,7 @@ int lfks_solve(lfk_ctx *c, double dt, double *residual, uint64_t *iters, bool wa
 			}
 		}
 		issued += burst;
-		LFK_CUDA(c, cudaMemcpyAsync(c->h_scal, c->d_scal, sizeof(PcgScalars), cudaMemcpyDeviceToHost, c->stream));
+		LFK_TRY(lfk_readback(c, c->h_scal, c->d_scal, sizeof(PcgScalars)));
 		LFK_CUDA(c, cudaStreamSynchronize(c->stream));
 		done = c->h_scal->done != 0 || issued >= max_it;
 		if (poll < 8 && first_burst <= 2) { poll *= 2; }
