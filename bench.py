@@ -83,8 +83,8 @@ def measured_peak():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-TRAFFIC_KERNEL = {"p2g": "k_p2g_march<2>", "g2p": "k_g2p<2>", "correct_collide": "k_correct_tiled3<1>",
-                  "advect_collide": "k_advect_collide"}
+TRAFFIC_KERNEL = {"p2g": ("k_p2g_march<2, 8>", "k_p2g_march<2>"), "g2p": ("k_g2p<2>",),
+                  "correct_collide": ("k_correct_tile<1>", "k_correct_tiled3<1>"), "advect_collide": ("k_advect_collide",)}
 
 
 def captured_traffic(grid):
@@ -96,7 +96,12 @@ def captured_traffic(grid):
     if not files:
         return {}, None
     tab = json.load(open(files[-1]))["kernels"]
-    out = {ph: tab[k]["dram_bytes_per_launch"] for ph, k in TRAFFIC_KERNEL.items() if k in tab}
+    out = {}
+    for ph, names in TRAFFIC_KERNEL.items():
+        for k in names:
+            if k in tab:
+                out[ph] = tab[k]["dram_bytes_per_launch"]
+                break
     return out, os.path.relpath(files[-1], ROOT)
 
 
