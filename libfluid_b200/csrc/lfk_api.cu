@@ -911,7 +911,6 @@ extern "C" int lfk_set_tuning(lfk_ctx *c, const char *key, int value) {
 	const std::string k(key);
 	if (k == "p2g") { c->tune.p2g = value; }
 	else if (k == "mg_agg") { c->tune.mg_agg = value; }
-	else if (k == "correct") { c->tune.correct = value; }
 	else if (k == "mg_agg_cells") { c->tune.mg_agg_cells = value; }
 	else if (k == "p2p") { c->tune.p2p = value; }
 	else if (k == "graph") { c->tune.graph = value; c->pcg_graph_key = 0; }

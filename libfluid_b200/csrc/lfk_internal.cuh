@@ -68,7 +68,6 @@ struct MgLevel {
 enum { LFK_TUNE_P2G_MARCH = 0, LFK_TUNE_P2G_GATHER = 2 };
 struct lfk_tuning {
 	int p2g = LFK_TUNE_P2G_MARCH; // 2: the plain per-cell gather (the reference's loop literally; also taken for APIC with h < 1)
-	int correct = 0;  // position correction: 0 thread-per-particle scan (k_correct_tile), 1 warp-cooperative (k_correct_coop)
 	int mg_agg = 1;   // multi-GPU: 1 coarse levels agglomerated onto every rank (r2d: 1.68 against 2.06 ms per iteration on 2 GPUs), 0 distributed
 	int mg_agg_cells = 0; // > 0: largest whole-grid level (cells) that is agglomerated (default 600000)
 	int mg_coarse = 0; // > 0: symmetric sweeps on the coarsest multigrid level of the single-block tail (default 8)

@@ -698,7 +698,11 @@ __device__ __forceinline__ void degenerate_kick(const double *p, const double *o
 // Measured alternatives (256^3, 27.6 ms for this kernel): own particles grouped by (y, z) reach class 38.5 ms, 8-wide
 // guarded groups 28.3 ms, packed f32x2 tests 42.6 ms, scalar d^2 test 30.3 ms (r2a sweep); fp64 positions staged in
 // shared memory as well, one 1024-thread block per SM: 35.2 ms (r2b) -- two resident blocks per SM that overlap each
-// other's staging and tails are worth more than the L1 / L2 latency of phase 2.
+// other's staging and tails are worth more than the L1 / L2 latency of phase 2; a warp-cooperative re-mapping (fp64-only
+// staging, a warp scans one own cell's 27-cell neighbourhood with lane <-> candidate and ballots, then lane <-> own
+// particle evaluates from shared memory): bit-identical but 66.3 ms -- 277 warp instructions per particle against 147
+// here (per-slot guards, ballot bookkeeping and the candidate-index searches cost more than the divergence they remove;
+// profiles/r2l_coop_ncu_summary.txt, git history of r2 holds the kernel).
 #define CT_LX 32
 #define CT_TY 2
 #define CT_TZ 2
@@ -985,260 +989,6 @@ template <bool COLLIDE> __global__ void __launch_bounds__(CT_THREADS, 2) k_corre
 	}
 }
 
-// ---- cooperative variant (lfk_set_tuning("correct", 1)) ------------------------------------------------------------
-// Same tiling idea and the same fp64 evaluation in the same order (=> bit-identical output), but the two phases are
-// re-mapped so that neither executes the union of 32 different particles' work:
-//   * the tile is CC_TY rows x 1 layer x CC_LX cells (staged rows: 4 x 3), and ONLY the fp64 positions are staged
-//     (24 B per particle), so both phases run from shared memory and two blocks still fit an SM;
-//   * phase 1 is done by a whole WARP for one own CELL at a time: the <= 288 candidates of the cell's 27-cell
-//     neighbourhood are converted once to fp32 {x, y, z, |q|^2} about the cell centre and held in registers, lane <->
-//     candidate; then, for every own particle of the cell in turn (its constants broadcast by shuffle), each lane tests
-//     ITS candidates (3 FFMA + compare per test) and a ballot turns the 32 results into one hit word.  No divergence
-//     (the own particle is warp-uniform), no shared-memory traffic in the loop, and a cell's candidates are converted
-//     once for its ~8 own particles instead of being re-read by each of them;
-//   * the hit words go to a per-warp scratch; after a group of 4 own cells (~32 own particles) phase 2 runs with lane <->
-//     own particle, reading candidate positions from the staged fp64 arrays (no global-memory latency).
-#define CC_LX 32
-#define CC_TY 2
-#define CC_SY (CC_TY + 2)
-#define CC_SZ 3
-#define CC_ROWS (CC_SY * CC_SZ)
-#define CC_CAP 3712      // staged particles per tile (3 x 8 B each: 87 KB); denser tiles take the global-memory path
-#define CC_WARPS 8
-#define CC_THREADS (CC_WARPS * 32)
-#define CC_NS 9          // 32-candidate slots per own cell; a neighbourhood with more candidates takes the global path
-#define CC_GCELLS 4      // own cells per group
-#define CC_GOWN 64       // own particles of a group that go through the scratch (any beyond: global path)
-
-template <bool COLLIDE> __global__ void __launch_bounds__(CC_THREADS, 2) k_correct_coop(GridDesc G, MotionParams M,
-	ParticleSoA P, double *__restrict__ nx_, double *__restrict__ ny_, double *__restrict__ nz_,
-	const uint32_t *__restrict__ begin, const uint8_t *__restrict__ typ) {
-	extern __shared__ double cc_smem[];
-	double *const sx = cc_smem, *const sy = sx + CC_CAP, *const sz = sy + CC_CAP;      // staged fp64 positions
-	uint32_t *const hits_all = reinterpret_cast<uint32_t *>(sz + CC_CAP);                 // [CC_WARPS][CC_GOWN][CC_NS]
-	__shared__ uint32_t rowstart[CC_ROWS], rowoff[CC_ROWS + 5], cellbeg[CC_ROWS][CC_LX + 3];
-	__shared__ uint32_t wP[CC_WARPS][CC_GCELLS][10], wA[CC_WARPS][CC_GCELLS][9], wNS[CC_WARPS][CC_GCELLS];
-	const double *__restrict__ px = P.f[PF_PX], *__restrict__ py = P.f[PF_PY], *__restrict__ pz = P.f[PF_PZ];
-	const int x0 = blockIdx.x * CC_LX, y0 = blockIdx.y * CC_TY, lz0 = blockIdx.z + 1;
-	const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-
-	// ---- table of the staged rows: row r = (lz0 - 1 + r / CC_SY, y0 - 1 + r % CC_SY), cells x0 - 1 .. x0 + CC_LX ----
-	for (int e = tid; e < CC_ROWS * (CC_LX + 3); e += CC_THREADS) {
-		int r = e / (CC_LX + 3), k = e % (CC_LX + 3);
-		int y = y0 - 1 + r % CC_SY, lz = lz0 - 1 + r / CC_SY;
-		uint32_t v = 0;
-		if (y >= 0 && y < G.ny && lz >= 0 && lz < G.nlz) {
-			long long row = (long long)G.nx * (y + (long long)G.ny * lz);
-			int xa = x0 - 1 < 0 ? 0 : x0 - 1;
-			int xk = x0 - 1 + k;
-			xk = xk < 0 ? 0 : (xk > G.nx ? G.nx : xk);
-			uint32_t base = begin[row + xa];
-			v = begin[row + xk] - base;
-			if (k == 0) { rowstart[r] = base; }
-		} else if (k == 0) {
-			rowstart[r] = 0;
-		}
-		cellbeg[r][k] = v;
-	}
-	__syncthreads();
-	if (tid == 0) {
-		uint32_t acc = 0;
-		for (int r = 0; r < CC_ROWS; ++r) {
-			rowoff[r] = acc;
-			acc += cellbeg[r][CC_LX + 2];
-		}
-		for (int r = CC_ROWS; r < CC_ROWS + 5; ++r) { rowoff[r] = acc; } // (padding for the row search below)
-	}
-	__syncthreads();
-	const uint32_t staged = rowoff[CC_ROWS];
-	// own particles: the two centre-layer rows, cells 1 .. CC_LX of the table
-	uint32_t nown_total = 0;
-#pragma unroll
-	for (int o = 0; o < CC_TY; ++o) {
-		const int r = 1 * CC_SY + (o + 1);
-		if (y0 + o < G.ny) { nown_total += cellbeg[r][CC_LX + 1] - cellbeg[r][1]; }
-	}
-	if (nown_total == 0) { return; }
-	const bool use_stage = staged <= CC_CAP;
-
-	// finishes one own particle: position update, clamp, (fused) collision pass, store
-	auto finish = [&](unsigned long long i, double *p, double sx_, double sy_, double sz_) {
-		double np3[3] = { p[0] + sx_ * M.corr_factor, p[1] + sy_ * M.corr_factor, p[2] + sz_ * M.corr_factor };
-#pragma unroll
-		for (int d = 0; d < 3; ++d) { np3[d] = dclamp_std(np3[d], M.gmin[d], M.gmax[d]); }
-		if (COLLIDE) { collide_one(G, M, typ, p, np3); }
-		nx_[i] = np3[0];
-		ny_[i] = np3[1];
-		nz_[i] = np3[2];
-	};
-
-	if (!use_stage) { // over-full tile: every own particle takes the plain fp64 loop
-		for (int o = 0; o < CC_TY; ++o) {
-			if (y0 + o >= G.ny) { continue; }
-			const int r = 1 * CC_SY + (o + 1);
-			const uint32_t b = rowstart[r] + cellbeg[r][1], n = cellbeg[r][CC_LX + 1] - cellbeg[r][1];
-			for (uint32_t t = tid; t < n; t += CC_THREADS) {
-				const unsigned long long i = (unsigned long long)b + t;
-				double p[3] = { px[i], py[i], pz[i] };
-				double s0 = 0.0, s1 = 0.0, s2 = 0.0;
-				spring_global(G, M, px, py, pz, begin, i, p, s0, s1, s2);
-				finish(i, p, s0, s1, s2);
-			}
-		}
-		return;
-	}
-	for (uint32_t e = tid; e < staged; e += CC_THREADS) {
-		int r = 0; // row of staged entry e
-		if (e >= rowoff[8]) { r = 8; }
-		if (e >= rowoff[r + 4]) { r += 4; }
-		if (e >= rowoff[r + 2]) { r += 2; }
-		if (e >= rowoff[r + 1]) { r += 1; }
-		const uint32_t q = rowstart[r] + (e - rowoff[r]);
-		sx[e] = px[q];
-		sy[e] = py[q];
-		sz[e] = pz[q];
-	}
-	__syncthreads();
-
-	uint32_t *const hits = hits_all + (size_t)warp * CC_GOWN * CC_NS;
-	const float T0 = 0.5f + CT_MARGIN;
-	for (int grp = warp; grp < CC_TY * (CC_LX / CC_GCELLS); grp += CC_WARPS) {
-		const int o = grp / (CC_LX / CC_GCELLS), cq = grp % (CC_LX / CC_GCELLS);
-		if (y0 + o >= G.ny) { continue; }
-		const int r_own = 1 * CC_SY + (o + 1);
-		const int k0 = 1 + CC_GCELLS * cq; // table index of the group's first own cell
-		const uint32_t S0 = rowoff[r_own] + cellbeg[r_own][k0];
-		const uint32_t n4 = cellbeg[r_own][k0 + CC_GCELLS] - cellbeg[r_own][k0];
-		if (n4 == 0) { continue; }
-		const unsigned long long gi0 = (unsigned long long)rowstart[r_own] + cellbeg[r_own][k0];
-		unsigned long long glmask = 0ull; // own particles of the group (by scratch slot) that take the global path
-		// ------------------------------------------------ phase 1: cell by cell
-		for (int kc = 0; kc < CC_GCELLS; ++kc) {
-			const int k = k0 + kc;
-			const uint32_t c0 = cellbeg[r_own][k] - cellbeg[r_own][k0], nk = cellbeg[r_own][k + 1] - cellbeg[r_own][k];
-			if (nk == 0) {
-				if (lane == 0) { wNS[warp][kc] = 0; }
-				continue;
-			}
-			// the nine row windows (cells k - 1 .. k + 1) flattened into one candidate list
-			uint32_t len = 0, start = 0;
-			if (lane < 9) {
-				const int r = (lane / 3) * CC_SY + (o + lane % 3); // (dz + 1) * CC_SY + (o + 1 + dy)
-				start = rowoff[r] + cellbeg[r][k - 1];
-				len = cellbeg[r][k + 2] - cellbeg[r][k - 1];
-			}
-			uint32_t incl = len;
-#pragma unroll
-			for (int d = 1; d < 16; d <<= 1) {
-				const uint32_t t = __shfl_up_sync(0xffffffffu, incl, d);
-				if (lane >= d) { incl += t; }
-			}
-			const uint32_t total = __shfl_sync(0xffffffffu, incl, 8);
-			if (lane < 9) {
-				wP[warp][kc][lane] = incl - len;
-				wA[warp][kc][lane] = start - (incl - len);
-			}
-			if (lane == 9) { wP[warp][kc][9] = total; }
-			const int nslots = (int)((total + 31u) >> 5);
-			const bool overflow = nslots > CC_NS || nk > 32u;
-			if (lane == 0) { wNS[warp][kc] = overflow ? 0u : (uint32_t)nslots; }
-			__syncwarp();
-			if (overflow) { // a clump: the plain fp64 loop for this cell's particles
-				for (uint32_t j = 0; j < nk && c0 + j < CC_GOWN; ++j) { glmask |= 1ull << (c0 + j); }
-				continue;
-			}
-			// candidates of this lane, fp32 about the cell centre, in cell units
-			const double cx = G.off[0] + ((double)(x0 + k - 1) + 0.5) * G.h, cy = G.off[1] + ((double)(y0 + o) + 0.5) * G.h,
-				cz = G.off[2] + ((double)(lz0 - 1 + G.z0) + 0.5) * G.h;
-			float qx[CC_NS], qy[CC_NS], qz[CC_NS], qw[CC_NS];
-			int rr = 0;
-#pragma unroll
-			for (int s = 0; s < CC_NS; ++s) {
-				qx[s] = 0.f; qy[s] = 0.f; qz[s] = 0.f; qw[s] = 1e30f; // never within reach
-				if (s < nslots) {
-					const uint32_t g = 32u * s + lane;
-					if (g < total) {
-						while (g >= wP[warp][kc][rr + 1]) { ++rr; }
-						const uint32_t idx = wA[warp][kc][rr] + g;
-						qx[s] = (float)((sx[idx] - cx) * G.inv_h);
-						qy[s] = (float)((sy[idx] - cy) * G.inv_h);
-						qz[s] = (float)((sz[idx] - cz) * G.inv_h);
-						qw[s] = __fmaf_rn(qz[s], qz[s], __fmaf_rn(qy[s], qy[s], qx[s] * qx[s]));
-					}
-				}
-			}
-			// constants of the cell's own particles, one per lane: n = -2 r, T = 1/2 + margin - |r|^2
-			float onx = 0.f, ony = 0.f, onz = 0.f, oT = -1e30f;
-			if ((uint32_t)lane < nk) {
-				const uint32_t so = S0 + c0 + lane;
-				const float rx = (float)((sx[so] - cx) * G.inv_h), ry = (float)((sy[so] - cy) * G.inv_h),
-					rz = (float)((sz[so] - cz) * G.inv_h);
-				onx = -2.f * rx; ony = -2.f * ry; onz = -2.f * rz;
-				oT = T0 - __fmaf_rn(rz, rz, __fmaf_rn(ry, ry, rx * rx));
-			}
-			for (uint32_t j = 0; j < nk; ++j) {
-				const float ax = __shfl_sync(0xffffffffu, onx, (int)j), ay = __shfl_sync(0xffffffffu, ony, (int)j),
-					az = __shfl_sync(0xffffffffu, onz, (int)j), aT = __shfl_sync(0xffffffffu, oT, (int)j);
-				const uint32_t pl = c0 + j;
-				if (pl >= CC_GOWN) { break; } // (handled by the global path below)
-#pragma unroll
-				for (int s = 0; s < CC_NS; ++s) {
-					if (s < nslots) {
-						const float t = __fmaf_rn(az, qz[s], __fmaf_rn(ay, qy[s], __fmaf_rn(ax, qx[s], qw[s])));
-						const unsigned b = __ballot_sync(0xffffffffu, t < aT);
-						if (lane == 0) { hits[pl * CC_NS + s] = b; }
-					}
-				}
-			}
-		}
-		__syncwarp();
-		// ------------------------------------------------ phase 2: lane <-> own particle of the group
-		for (uint32_t pl = lane; pl < n4; pl += 32) {
-			const uint32_t so = S0 + pl;
-			const unsigned long long i = gi0 + pl;
-			double p[3] = { sx[so], sy[so], sz[so] };
-			double s0 = 0.0, s1 = 0.0, s2 = 0.0;
-			int kc = 0; // own cell of this particle within the group
-#pragma unroll
-			for (int t = 1; t < CC_GCELLS; ++t) {
-				if (pl >= cellbeg[r_own][k0 + t] - cellbeg[r_own][k0]) { kc = t; }
-			}
-			// the particle must sit in the cell it was sorted into (compute_cell_index, unclamped)
-			bool in_cell = true;
-			{
-				const int want[3] = { x0 + k0 + kc - 1, y0 + o, lz0 - 1 + G.z0 };
-#pragma unroll
-				for (int d = 0; d < 3; ++d) {
-					const double f = div_h(p[d] - G.off[d], G);
-					const unsigned long long u = (unsigned long long)f;
-					in_cell = in_cell && u == (unsigned long long)want[d];
-				}
-			}
-			const uint32_t ns = wNS[warp][kc];
-			if (!in_cell || ns == 0 || pl >= CC_GOWN || ((glmask >> (pl < 64 ? pl : 63)) & 1ull)) {
-				spring_global(G, M, px, py, pz, begin, i, p, s0, s1, s2);
-			} else {
-				int rr = 0;
-				for (uint32_t s = 0; s < ns; ++s) {
-					uint32_t m = hits[pl * CC_NS + s];
-					while (m) {
-						const uint32_t g = 32u * s + (uint32_t)(__ffs((int)m) - 1);
-						m &= m - 1u;
-						while (g >= wP[warp][kc][rr + 1]) { ++rr; }
-						const uint32_t idx = wA[warp][kc][rr] + g;
-						if (idx != so) {
-							const double ov[3] = { sx[idx], sy[idx], sz[idx] };
-							pair_exact(M, p, ov, s0, s1, s2);
-						}
-					}
-				}
-			}
-			finish(i, p, s0, s1, s2);
-		}
-		__syncwarp(); // the scratch and the per-cell tables are reused by the next group
-	}
-}
-
 static int correct_impl(lfk_ctx *c, double dt, bool fuse_collide) {
 	PhaseTimer T(c, LFK_PHASE_CORRECT_COLLIDE);
 	LFK_REQUIRE(c, c->table_valid, LFK_E_STATE, "lfk_correct needs the cell table of lfk_hash");
@@ -1255,23 +1005,7 @@ static int correct_impl(lfk_ctx *c, double dt, bool fuse_collide) {
 		attr_set[c->device % LFK_MAX_DEVICES] = true;
 	}
 	if (!fuse_collide) { LFK_TRY(materialise_old(c)); }
-	if (c->tune.correct == 1) { // cooperative variant
-		dim3 cgrid((unsigned)((G.nx + CC_LX - 1) / CC_LX), (unsigned)((G.ny + CC_TY - 1) / CC_TY), (unsigned)G.nzl);
-		const size_t csmem = (size_t)CC_CAP * 3 * sizeof(double) + (size_t)CC_WARPS * CC_GOWN * CC_NS * sizeof(uint32_t);
-		static bool cattr[LFK_MAX_DEVICES] = {};
-		if (!cattr[c->device % LFK_MAX_DEVICES]) {
-			LFK_CUDA(c, cudaFuncSetAttribute(k_correct_coop<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)csmem));
-			LFK_CUDA(c, cudaFuncSetAttribute(k_correct_coop<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)csmem));
-			cattr[c->device % LFK_MAX_DEVICES] = true;
-		}
-		if (fuse_collide) {
-			LFK_LAUNCH(c, k_correct_coop<true>, cgrid, CC_THREADS, csmem, G, M, c->P, c->Palt.f[PF_PX], c->Palt.f[PF_PY],
-				c->Palt.f[PF_PZ], c->begin, c->typ);
-		} else {
-			LFK_LAUNCH(c, k_correct_coop<false>, cgrid, CC_THREADS, csmem, G, M, c->P, c->Palt.f[PF_PX], c->Palt.f[PF_PY],
-				c->Palt.f[PF_PZ], c->begin, c->typ);
-		}
-	} else if (fuse_collide) {
+	if (fuse_collide) {
 		LFK_LAUNCH(c, k_correct_tile<true>, grid, CT_THREADS, smem, G, M, c->P, c->Palt.f[PF_PX], c->Palt.f[PF_PY],
 			c->Palt.f[PF_PZ], c->begin, c->typ);
 	} else {

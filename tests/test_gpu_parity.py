@@ -240,37 +240,6 @@ def test_p2g_kernel_variants_agree(method):
     ctx.close()
 
 
-def test_position_correction_variants_agree():
-    """the thread-per-particle scan and the warp-cooperative kernel only select candidates for the same fp64 evaluation
-    in the same order: bit-identical corrected positions, staged and inside the fused step (with the collision pass)"""
-    ctx = _device_scene()
-    for _ in range(4):
-        ctx.time_step()
-    ctx.hash()
-    parts = ctx.download_particles().copy()
-    outs = []
-    for v in (0, 1):
-        ctx.set_tuning("correct", v)
-        ctx.upload_particles(parts)
-        ctx.hash()
-        ctx.correct(0.004)
-        outs.append(ctx.download_particles().copy())
-    assert np.array_equal(outs[0]["position"].view("u8"), outs[1]["position"].view("u8"))
-    moved = np.abs(outs[0]["position"] - parts[np.argsort(parts["raw_cell_index"], kind="stable")]["position"]).max()
-    assert moved > 1e-6
-    res = []
-    for v in (0, 1):
-        ctx.set_tuning("correct", v)
-        ctx.set_tuning("warm_start", 0)
-        ctx.upload_particles(parts)
-        for _ in range(2):
-            ctx.time_step(0.002)
-        res.append(ctx.download_particles().copy())
-    for f in ("position", "velocity"):
-        assert np.array_equal(res[0][f].view("u8"), res[1][f].view("u8")), f
-    ctx.close()
-
-
 def test_warm_started_solve_reaches_the_same_tolerance():
     """fused step with the previous pressure as initial guess against the reference's p = 0 start: same residual
     tolerance, states agree to solver accuracy, and the warm start does not cost iterations"""

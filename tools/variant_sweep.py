@@ -16,10 +16,9 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
-NEW = {"p2g": 0, "warm_start": 1, "red_blocks": 0, "graph": 1, "mg_coarse": 0, "correct": 0}  # the library defaults
+NEW = {"p2g": 0, "warm_start": 1, "red_blocks": 0, "graph": 1, "mg_coarse": 0}  # the library defaults
 CONFIGS = [
     ("defaults", dict(NEW)),
-    ("defaults+correct_coop", dict(NEW, correct=1)),
     ("defaults+no_graph", dict(NEW, graph=0)),
     ("defaults+cold_start", dict(NEW, warm_start=0)),
 ]
