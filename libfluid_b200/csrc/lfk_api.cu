@@ -835,7 +835,7 @@ extern "C" int lfk_time_step(lfk_ctx *c, double dt) {
 	NEED_PARAMS(c);
 	if (c->src_active && c->src_coerce) { LFK_TRY(lfkp_coerce_sources(c)); } // :49 + :227-238
 	LFK_TRY(lfkp_advect_collide(c, dt));            // :50-60
-	LFK_TRY(lfkp_hash(c, true));                    // :62-64 (lean: v / c are read through the permutation)
+	LFK_TRY(lfkp_hash(c, c->tune.lean_sort != 0));  // :62-64 (lean: v / c are read through the permutation)
 	if (c->src_active) {                            // :63-64: seed the source cells, sort again if anything was added
 		uint64_t added = 0;
 		LFK_TRY(lfkp_update_sources(c, &added));
@@ -847,7 +847,7 @@ extern "C" int lfk_time_step(lfk_ctx *c, double dt) {
 			LFK_CUDA(c, cudaStreamSynchronize(c->stream));
 			added = flag != 0.0 ? 1 : 0;
 		}
-		if (added) { LFK_TRY(lfkp_hash(c, true)); }
+		if (added) { LFK_TRY(lfkp_hash(c, c->tune.lean_sort != 0)); }
 	}
 	LFK_TRY(lfkg_p2g(c, dt, true));                 // :66-78 (gravity fused)
 	LFK_TRY(lfks_solve(c, dt, nullptr, nullptr, true)); // :83-99 (initial guess: the previous step's pressure)
@@ -911,6 +911,7 @@ extern "C" int lfk_set_tuning(lfk_ctx *c, const char *key, int value) {
 	const std::string k(key);
 	if (k == "p2g") { c->tune.p2g = value; }
 	else if (k == "mg_agg") { c->tune.mg_agg = value; }
+	else if (k == "lean_sort") { c->tune.lean_sort = value; }
 	else if (k == "mg_agg_cells") { c->tune.mg_agg_cells = value; }
 	else if (k == "p2p") { c->tune.p2p = value; }
 	else if (k == "graph") { c->tune.graph = value; c->pcg_graph_key = 0; }
