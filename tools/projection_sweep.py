@@ -40,14 +40,15 @@ def main():
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-        box = [capi.nccl_unique_id() if rank == 0 else None]
-        dist.broadcast_object_list(box, src=0)
-        nccl_id = box[0]
     peak, peak_src = B.measured_peak()
     dt = 1.0 / 60.0
     rows = []
     for n in [int(g) for g in args.grids.split(",") if g]:
         row = {"grid": n, "n_gpus": world}
+        if dist is not None:  # one NCCL id per communicator (a unique id cannot be reused after its communicator is gone)
+            box = [capi.nccl_unique_id() if rank == 0 else None]
+            dist.broadcast_object_list(box, src=0)
+            nccl_id = box[0]
         try:
             ctx = capi.Context((n, n, n), device=local_rank, nranks=world, rank=rank, nccl_id=nccl_id, cell_size=1.0,
                                max_iterations=5000, preconditioner=capi.PRECOND_MULTIGRID)
