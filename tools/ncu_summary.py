@@ -43,10 +43,19 @@ def main():
             print("%-30s %-16s %s" % (label, U[i], "  ".join("%14.6g" % float(r[i].replace(",", "")) for r in raw[2:])))
     rows = list(csv.reader(open(base + "_source.csv")))
     heads = [i for i, r in enumerate(rows) if r and r[0] == "Address"]
+    import re
+    seen = set()
     for k, h0 in enumerate(heads):
         hi = heads[k + 1] - 1 if k + 1 < len(heads) else len(rows)
         Hs = rows[h0]
         body = [r for r in rows[h0 + 1:hi] if len(r) > 5]
+        # newer ncu exports name every section (and may repeat a kernel: one section per captured launch)
+        label = None
+        if h0 > 0 and rows[h0 - 1] and rows[h0 - 1][0] == "Kernel Name":
+            label = re.sub(r"\(int\)|\(bool\)", "", re.sub(r"\(GridDesc.*|\(LevelDev.*|\(TailLevels.*", "", rows[h0 - 1][1])).replace("void ", "")
+            if (label, len(body)) in seen:
+                continue
+            seen.add((label, len(body)))
         si, ii, src = Hs.index("# Samples"), Hs.index("Instructions Executed"), Hs.index("Source")
         tot = sum(num(r[si]) for r in body) or 1
         toti = sum(num(r[ii]) for r in body) or 1
@@ -56,7 +65,7 @@ def main():
                 stall[h] = sum(num(r[i]) for r in body if len(r) > i)
         ssum = sum(stall.values()) or 1
         print("\n== %s: %d SASS lines, %d stall samples, %.1f M warp instructions" %
-              (names[k] if k < len(names) else k, len(body), tot, toti / 1e6))
+              (label or (names[k] if k < len(names) else k), len(body), tot, toti / 1e6))
         print("stall reasons (%% of samples): " + ", ".join("%s %.1f" % (h[6:], 100.0 * v / ssum) for h, v in
               sorted(stall.items(), key=lambda kv: -kv[1])[:8]))
         for n, r in sorted(enumerate(body), key=lambda nr: -num(nr[1][si]))[:top]:
