@@ -702,7 +702,8 @@ __device__ __forceinline__ void degenerate_kick(const double *p, const double *o
 // staging, a warp scans one own cell's 27-cell neighbourhood with lane <-> candidate and ballots, then lane <-> own
 // particle evaluates from shared memory): bit-identical but 66.3 ms -- 277 warp instructions per particle against 147
 // here (per-slot guards, ballot bookkeeping and the candidate-index searches cost more than the divergence they remove;
-// profiles/r2l_coop_ncu_summary.txt, git history of r2 holds the kernel).
+// profiles/r2l_coop_ncu_summary.txt, git history of r2 holds the kernel); two or three neighbour positions in flight in
+// phase 2 instead of one: 27.7 / 28.2 ms against 27.3 (r2q sweep).
 #define CT_LX 32
 #define CT_TY 2
 #define CT_TZ 2
