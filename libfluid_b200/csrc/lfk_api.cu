@@ -912,7 +912,6 @@ extern "C" int lfk_set_tuning(lfk_ctx *c, const char *key, int value) {
 	if (k == "p2g") { c->tune.p2g = value; }
 	else if (k == "mg_agg") { c->tune.mg_agg = value; }
 	else if (k == "lean_sort") { c->tune.lean_sort = value; }
-	else if (k == "correct_pf") { c->tune.correct_pf = value; }
 	else if (k == "mg_agg_cells") { c->tune.mg_agg_cells = value; }
 	else if (k == "p2p") { c->tune.p2p = value; }
 	else if (k == "graph") { c->tune.graph = value; c->pcg_graph_key = 0; }

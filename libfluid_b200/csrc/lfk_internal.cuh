@@ -68,7 +68,6 @@ struct MgLevel {
 enum { LFK_TUNE_P2G_MARCH = 0, LFK_TUNE_P2G_GATHER = 2 };
 struct lfk_tuning {
 	int p2g = LFK_TUNE_P2G_MARCH; // 2: the plain per-cell gather (the reference's loop literally; also taken for APIC with h < 1)
-	int correct_pf = 2; // position correction: neighbour positions in flight while one is evaluated (1, 2 or 3)
 	int lean_sort = 1; // fused step: 1 the sort permutes positions only and P2G reads velocity / c rows through the
 	                   // permutation, 0 the sort permutes the whole payload
 	int mg_agg = 1;   // multi-GPU: 1 coarse levels agglomerated onto every rank (r2d: 1.68 against 2.06 ms per iteration on 2 GPUs), 0 distributed

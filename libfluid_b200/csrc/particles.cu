@@ -784,7 +784,7 @@ __device__ void spring_global(const GridDesc &G, const MotionParams &M, const do
 	}
 }
 
-template <bool COLLIDE, int PF> __global__ void __launch_bounds__(CT_THREADS, 2) k_correct_tile(GridDesc G, MotionParams M,
+template <bool COLLIDE> __global__ void __launch_bounds__(CT_THREADS, 2) k_correct_tile(GridDesc G, MotionParams M,
 	ParticleSoA P, double *__restrict__ nx_, double *__restrict__ ny_, double *__restrict__ nz_,
 	const uint32_t *__restrict__ begin, const uint8_t *__restrict__ typ) {
 	extern __shared__ float4 stage[];                            // [CT_CAP] fp32 scan entries
@@ -944,9 +944,8 @@ template <bool COLLIDE, int PF> __global__ void __launch_bounds__(CT_THREADS, 2)
 			if (nr > CT_LIST) { // more records than the list holds (very crowded rows): plain fp64 loop instead
 				spring_global(G, M, px, py, pz, begin, i, p, sx, sy, sz);
 			} else {
-				// Phase 2: the recorded candidates in staging order, fp64, from the original positions; the positions of
-				// the next PF candidates are in flight while one is evaluated (PF = 1: r1 kernel; the loads go to L1 / L2,
-				// 19 % of the kernel's stall samples were long-scoreboard waits on them)
+				// Phase 2: the recorded candidates in staging order, fp64, from the original positions; the next
+				// candidate's position is fetched one iteration ahead of its use
 				int k = 0;
 				uint32_t m = 0, jb = 0;
 				auto next_hit = [&](uint32_t &j) -> bool { // advances to the next recorded candidate
@@ -960,34 +959,20 @@ template <bool COLLIDE, int PF> __global__ void __launch_bounds__(CT_THREADS, 2)
 					m &= m - 1u;
 					return true;
 				};
-				uint32_t jq[PF];
-				double oq[PF][3];
-				int have = 0; // candidates fetched and not yet evaluated (a FIFO in registers: slot 0 is the oldest)
-#pragma unroll
-				for (int q = 0; q < PF; ++q) {
-					jq[q] = (uint32_t)i;
-					if (have == q && next_hit(jq[q])) { ++have; }
-					oq[q][0] = px[jq[q]];
-					oq[q][1] = py[jq[q]];
-					oq[q][2] = pz[jq[q]];
-				}
-				while (have > 0) {
+				uint32_t j = 0;
+				bool have = next_hit(j);
+				double ov[3] = { 0.0, 0.0, 0.0 };
+				if (have) { ov[0] = px[j]; ov[1] = py[j]; ov[2] = pz[j]; }
+				while (have) {
 					uint32_t jn = (uint32_t)i;
-					const bool more = have == PF && next_hit(jn);
+					const bool more = next_hit(jn);
 					const double on[3] = { px[jn], py[jn], pz[jn] };
-					if (jq[0] != (uint32_t)i) { pair_exact(M, p, oq[0], sx, sy, sz); }
-#pragma unroll
-					for (int q = 0; q + 1 < PF; ++q) {
-						jq[q] = jq[q + 1];
-						oq[q][0] = oq[q + 1][0];
-						oq[q][1] = oq[q + 1][1];
-						oq[q][2] = oq[q + 1][2];
-					}
-					jq[PF - 1] = jn;
-					oq[PF - 1][0] = on[0];
-					oq[PF - 1][1] = on[1];
-					oq[PF - 1][2] = on[2];
-					if (!more) { --have; }
+					if (j != (uint32_t)i) { pair_exact(M, p, ov, sx, sy, sz); }
+					have = more;
+					j = jn;
+					ov[0] = on[0];
+					ov[1] = on[1];
+					ov[2] = on[2];
 				}
 			}
 		}
@@ -1005,32 +990,28 @@ template <bool COLLIDE, int PF> __global__ void __launch_bounds__(CT_THREADS, 2)
 	}
 }
 
-template <bool COLLIDE, int PF> static int correct_launch(lfk_ctx *c, const MotionParams &M) {
-	const GridDesc &G = c->g;
-	dim3 grid((unsigned)((G.nx + CT_LX - 1) / CT_LX), (unsigned)((G.ny + CT_TY - 1) / CT_TY),
-		(unsigned)((G.nzl + CT_TZ - 1) / CT_TZ));
-	const size_t smem = (size_t)CT_CAP * sizeof(float4);
-	static bool attr_set[LFK_MAX_DEVICES] = {}; // function attributes are per device (and per instantiation)
-	if (!attr_set[c->device % LFK_MAX_DEVICES]) {
-		LFK_CUDA(c, cudaFuncSetAttribute((k_correct_tile<COLLIDE, PF>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-		attr_set[c->device % LFK_MAX_DEVICES] = true;
-	}
-	LFK_LAUNCH(c, (k_correct_tile<COLLIDE, PF>), grid, CT_THREADS, smem, G, M, c->P, c->Palt.f[PF_PX], c->Palt.f[PF_PY],
-		c->Palt.f[PF_PZ], c->begin, c->typ);
-	return 0;
-}
-
 static int correct_impl(lfk_ctx *c, double dt, bool fuse_collide) {
 	PhaseTimer T(c, LFK_PHASE_CORRECT_COLLIDE);
 	LFK_REQUIRE(c, c->table_valid, LFK_E_STATE, "lfk_correct needs the cell table of lfk_hash");
 	if (c->np == 0) { return 0; }
 	MotionParams M = motion_params(c, dt);
+	const GridDesc &G = c->g;
+	dim3 grid((unsigned)((G.nx + CT_LX - 1) / CT_LX), (unsigned)((G.ny + CT_TY - 1) / CT_TY),
+		(unsigned)((G.nzl + CT_TZ - 1) / CT_TZ));
+	const size_t smem = (size_t)CT_CAP * sizeof(float4);
+	static bool attr_set[LFK_MAX_DEVICES] = {}; // function attributes are per device
+	if (!attr_set[c->device % LFK_MAX_DEVICES]) {
+		LFK_CUDA(c, cudaFuncSetAttribute(k_correct_tile<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+		LFK_CUDA(c, cudaFuncSetAttribute(k_correct_tile<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+		attr_set[c->device % LFK_MAX_DEVICES] = true;
+	}
 	if (!fuse_collide) { LFK_TRY(materialise_old(c)); }
-	const int pf = c->tune.correct_pf;
 	if (fuse_collide) {
-		LFK_TRY(pf == 1 ? (correct_launch<true, 1>(c, M)) : (pf == 3 ? (correct_launch<true, 3>(c, M)) : (correct_launch<true, 2>(c, M))));
+		LFK_LAUNCH(c, k_correct_tile<true>, grid, CT_THREADS, smem, G, M, c->P, c->Palt.f[PF_PX], c->Palt.f[PF_PY],
+			c->Palt.f[PF_PZ], c->begin, c->typ);
 	} else {
-		LFK_TRY(pf == 1 ? (correct_launch<false, 1>(c, M)) : (pf == 3 ? (correct_launch<false, 3>(c, M)) : (correct_launch<false, 2>(c, M))));
+		LFK_LAUNCH(c, k_correct_tile<false>, grid, CT_THREADS, smem, G, M, c->P, c->Palt.f[PF_PX], c->Palt.f[PF_PY],
+			c->Palt.f[PF_PZ], c->begin, c->typ);
 	}
 	for (int d = 0; d < 3; ++d) {
 		double *t = c->P.f[PF_PX + d];

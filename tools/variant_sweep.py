@@ -16,11 +16,9 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
-NEW = {"p2g": 0, "warm_start": 1, "red_blocks": 0, "graph": 1, "mg_coarse": 0, "lean_sort": 1, "correct_pf": 2}  # the library defaults
+NEW = {"p2g": 0, "warm_start": 1, "red_blocks": 0, "graph": 1, "mg_coarse": 0, "lean_sort": 1}  # the library defaults
 CONFIGS = [
     ("defaults", dict(NEW)),
-    ("defaults+correct_pf1", dict(NEW, correct_pf=1)),
-    ("defaults+correct_pf3", dict(NEW, correct_pf=3)),
     ("defaults+full_sort", dict(NEW, lean_sort=0)),
     ("defaults+no_graph", dict(NEW, graph=0)),
     ("defaults+cold_start", dict(NEW, warm_start=0)),
