@@ -227,7 +227,8 @@ def _run_ours(args):
 
     def agree(ok, what):
         """every rank learns whether ANY rank failed a local check before the next collective is entered"""
-        if allmax(0.0 if ok else 1.0) != 0.0:
+        from libfluid_b200 import slabs
+        if not slabs.agree(ok, dist, device="cuda"):
             if not ok:
                 sys.stderr.write("[rank %d] %s\n" % (rank, what))
             raise SystemExit(3)

@@ -48,3 +48,45 @@ def split_after_sort(zc, z0, nzl):
     """What the cell sort makes of the merged set: masks (ghost_low, own, ghost_high)."""
     zc = np.asarray(zc)
     return zc == z0 - 1, (zc >= z0) & (zc < z0 + nzl), zc == z0 + nzl
+
+
+def agree(ok, dist=None, device=None):
+    """True iff EVERY rank passed True.  A rank that fails a local check (buffer too small, allocation failed) must not
+    raise on its own while its peers walk into the step's collectives (the round-1 hang of bench.py --gpus 2): every
+    rank learns the outcome first and all of them leave together."""
+    if dist is None or not dist.is_initialized() or dist.get_world_size() == 1:
+        return bool(ok)
+    import torch
+    t = torch.tensor([0.0 if ok else 1.0], dtype=torch.float64, device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item()) == 0.0
+
+
+def multigrid_layout(nx, ny, nz, nranks, agg_max_cells=600000, tail_cells=4096):
+    """Host mirror of mg_alloc / mg_agg_alloc (libfluid_b200/csrc/mg.cu): the distributed multigrid levels
+    [(nx, ny, nz_global)], and the index of the first level that is agglomerated onto every rank (None: none).  It is a
+    pure function of the whole grid and the rank count -- every rank must build the same hierarchy, or the exchanges
+    inside the V-cycle would not pair up."""
+    layout = [slab_range(nz, nranks, r) for r in range(nranks)]
+    z0 = [a for a, _ in layout]
+    nzl = [b for _, b in layout]
+    levels = []
+    gx, gy, gz = nx, ny, nz
+    for _ in range(16):
+        levels.append((gx, gy, gz))
+        aligned = True
+        if nranks > 1:
+            aligned = gz % 2 == 0 and all(a % 2 == 0 and b % 2 == 0 and b >= 2 for a, b in zip(z0, nzl))
+        lx, ly, lz = (gx, gy, max(nzl)) if nranks > 1 else (gx, gy, gz)
+        if not aligned or (lx <= 2 and ly <= 2 and lz <= 2):
+            break
+        gx, gy, gz = (gx + 1) // 2, (gy + 1) // 2, (gz + 1) // 2
+        z0 = [a // 2 for a in z0]
+        nzl = [(b + 1) // 2 for b in nzl]
+    agg = None
+    if nranks > 1:
+        for l in range(1, len(levels)):
+            if levels[l][0] * levels[l][1] * (nz >> l) <= agg_max_cells:
+                agg = l
+                break
+    return levels, agg

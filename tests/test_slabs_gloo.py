@@ -106,3 +106,65 @@ def test_slab_rules():
     assert list(up) == [False, False, False, False, True, True, True]
     assert list(dn) == [True, True, True, False, False, False, False]
     assert list(dead) == [True, False, False, False, False, False, True]
+
+
+def _agree_worker(rank, world, port, ret):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        out = []
+        # bench.py's end-to-end loop: the particle count of a rank drifts from step to step; the ranks agree on every
+        # local capacity check BEFORE the step's collectives -- one rank overflowing must stop all of them, together
+        cap = 1000
+        count = 990 + 3 * rank
+        for step in range(6):
+            count += 4 * rank  # rank 1 gains particles, rank 0 does not
+            ok = slabs.agree(count <= cap, dist)
+            out.append(ok)
+            if not ok:
+                break
+            t = torch.ones(1)
+            dist.all_reduce(t)  # the "step": a collective every rank must enter
+        ret[rank] = out
+    except BaseException as ex:  # noqa: BLE001
+        ret[rank] = "%s: %s" % (type(ex).__name__, ex)
+    finally:
+        dist.destroy_process_group()
+
+
+def test_ranks_agree_on_local_failures_over_gloo():
+    ctx = mp.get_context("spawn")
+    ret = ctx.Manager().dict()
+    port = _free_port()
+    procs = [ctx.Process(target=_agree_worker, args=(r, 2, port, ret)) for r in range(2)]
+    [p.start() for p in procs]
+    [p.join(120) for p in procs]
+    assert all(not p.is_alive() for p in procs)  # nobody is left waiting in a collective
+    assert ret[0] == ret[1] == [True, False]     # rank 1 overflows at its second step; rank 0 stops with it
+
+
+def test_multigrid_layout_is_rank_independent():
+    # the bench grids: 8 slabs of 64 layers coarsen to 1 layer per rank; agglomeration starts at the 64^3 level
+    levels, agg = slabs.multigrid_layout(512, 512, 512, 8)
+    assert levels[0] == (512, 512, 512) and levels[-1] == (8, 8, 8) and len(levels) == 7 and agg == 3
+    levels, agg = slabs.multigrid_layout(512, 256, 256, 2)
+    assert agg == 2 and levels[agg] == (128, 64, 64)
+    # unequal, odd slabs: level 0 is the only distributed level, nothing to agglomerate
+    levels, agg = slabs.multigrid_layout(24, 20, 19, 2)
+    assert levels == [(24, 20, 19)] and agg is None
+    # one GPU: down to 2^3, no agglomeration
+    levels, agg = slabs.multigrid_layout(256, 256, 256, 1)
+    assert levels[-1] == (2, 2, 2) and agg is None
+
+
+def test_bench_workload_shapes():
+    import bench
+    assert bench.workload_dims(256, 1) == (256, 256, 256)
+    assert bench.workload_dims(256, 2) == (512, 256, 256)
+    assert bench.workload_dims(256, 4) == (512, 512, 256)
+    assert bench.workload_dims(256, 8) == (512, 512, 512)       # BASELINE configs[3]
+    for w in (1, 2, 4, 8, 3):
+        nx, ny, nz = bench.workload_dims(256, w)
+        assert nx * ny * nz == w * 256 ** 3                     # weak scaling: 256^3 cells per GPU
+    boxes = bench.scene_boxes(512, 512, 512)
+    assert boxes[0][1][2] == 512.0 and boxes[0][1][1] < 512.0   # the water spans z, leaves air on top
