@@ -476,18 +476,9 @@ __device__ __forceinline__ bool cell_is_free(const GridDesc &G, const uint8_t *_
 	return typ[x + (long long)G.nx * (y + (long long)G.ny * lz)] != LFK_CELL_SOLID;
 }
 
-// true iff the segment from -> to leaves its cell (the march below would take at least one step)
-__device__ __forceinline__ bool collide_crosses(const GridDesc &G, const double *from, const double *to) {
-	bool same = true;
-#pragma unroll
-	for (int d = 0; d < 3; ++d) {
-		same = same && (int)floor(div_h(from[d] - G.off[d], G)) == (int)floor(div_h(to[d] - G.off[d], G));
-	}
-	return !same;
-}
-
-__device__ void collide_march(const GridDesc &G, const MotionParams &M, const uint8_t *__restrict__ typ,
+__device__ void collide_one(const GridDesc &G, const MotionParams &M, const uint8_t *__restrict__ typ,
 	double *from, double *to) {
+	const double h = G.h;
 	for (int j = 0; j < 3; ++j) {
 		bool into_wall = false;
 		double gf[3], gt[3], inv[3], normal[3], t[3];
@@ -558,10 +549,6 @@ __device__ void collide_march(const GridDesc &G, const MotionParams &M, const ui
 			break;
 		}
 	}
-}
-
-__device__ void collide_pushout(const GridDesc &G, const MotionParams &M, const uint8_t *__restrict__ typ, double *to) {
-	const double h = G.h;
 	// skin push-out: cell index and in-cell position are computed once, before the per-axis pushes
 	double cp[3];
 	int ci[3];
@@ -589,12 +576,6 @@ __device__ void collide_pushout(const GridDesc &G, const MotionParams &M, const 
 			}
 		}
 	}
-}
-
-__device__ void collide_one(const GridDesc &G, const MotionParams &M, const uint8_t *__restrict__ typ,
-	double *from, double *to) {
-	collide_march(G, M, typ, from, to);
-	collide_pushout(G, M, typ, to);
 }
 
 __global__ void k_advect(MotionParams M, ParticleSoA P, unsigned long long n) {
@@ -625,50 +606,19 @@ __global__ void k_collide(GridDesc G, MotionParams M, ParticleSoA P, const uint8
 	P.f[PF_PZ][i] = to[2];
 }
 
-// advect + collide in one pass: old_position is the pre-advection position held in registers.
-// Only a minority of the particles leaves its cell in a step, but nearly every warp holds one that does, and then the
-// whole warp steps through the DDA march (458 instructions per particle in r1, 47 % of the copy peak at ideal DRAM
-// traffic).  Here the particles that cross a cell boundary are queued in shared memory and marched by the first threads
-// of the block, densely packed; the others only take the skin push-out.  Per particle the arithmetic is unchanged
-// (bit-identical results); which thread does it is not.
-#define AC_THREADS 128
-__global__ void __launch_bounds__(AC_THREADS) k_advect_collide(GridDesc G, MotionParams M, ParticleSoA P,
-	const uint8_t *__restrict__ typ, unsigned long long n) {
-	__shared__ double qf[3][AC_THREADS], qt[3][AC_THREADS];
-	__shared__ unsigned qi[AC_THREADS], qn;
-	const unsigned long long base = (unsigned long long)blockIdx.x * AC_THREADS, i = base + threadIdx.x;
-	if (threadIdx.x == 0) { qn = 0; }
-	__syncthreads();
-	if (i < n) {
-		double from[3] = { P.f[PF_PX][i], P.f[PF_PY][i], P.f[PF_PZ][i] };
-		const double v[3] = { P.f[PF_VX][i], P.f[PF_VY][i], P.f[PF_VZ][i] };
-		double to[3] = { from[0], from[1], from[2] };
-		advect_one(M, to, v);
-		if (collide_crosses(G, from, to)) {
-			const unsigned k = atomicAdd(&qn, 1u);
-#pragma unroll
-			for (int d = 0; d < 3; ++d) {
-				qf[d][k] = from[d];
-				qt[d][k] = to[d];
-			}
-			qi[k] = threadIdx.x;
-		} else {
-			collide_pushout(G, M, typ, to);
-			P.f[PF_PX][i] = to[0];
-			P.f[PF_PY][i] = to[1];
-			P.f[PF_PZ][i] = to[2];
-		}
-	}
-	__syncthreads();
-	if (threadIdx.x < qn) {
-		double from[3] = { qf[0][threadIdx.x], qf[1][threadIdx.x], qf[2][threadIdx.x] };
-		double to[3] = { qt[0][threadIdx.x], qt[1][threadIdx.x], qt[2][threadIdx.x] };
-		collide_one(G, M, typ, from, to);
-		const unsigned long long j = base + qi[threadIdx.x];
-		P.f[PF_PX][j] = to[0];
-		P.f[PF_PY][j] = to[1];
-		P.f[PF_PZ][j] = to[2];
-	}
+// advect + collide in one pass: old_position is the pre-advection position held in registers
+__global__ void k_advect_collide(GridDesc G, MotionParams M, ParticleSoA P, const uint8_t *__restrict__ typ,
+	unsigned long long n) {
+	unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n) { return; }
+	double from[3] = { P.f[PF_PX][i], P.f[PF_PY][i], P.f[PF_PZ][i] };
+	double v[3] = { P.f[PF_VX][i], P.f[PF_VY][i], P.f[PF_VZ][i] };
+	double to[3] = { from[0], from[1], from[2] };
+	advect_one(M, to, v);
+	collide_one(G, M, typ, from, to);
+	P.f[PF_PX][i] = to[0];
+	P.f[PF_PY][i] = to[1];
+	P.f[PF_PZ][i] = to[2];
 }
 
 static int materialise_old(lfk_ctx *c) {
@@ -711,7 +661,7 @@ int lfkp_advect_collide(lfk_ctx *c, double dt) {
 	}
 	LFK_TRY(lfkp_materialise_vc(c));
 	if (c->np > 0) {
-		LFK_LAUNCH(c, k_advect_collide, lfk_blocks((long long)c->np, AC_THREADS), AC_THREADS, 0, c->g, motion_params(c, dt),
+		LFK_LAUNCH(c, k_advect_collide, lfk_blocks((long long)c->np, 128), 128, 0, c->g, motion_params(c, dt),
 			lfk_own_view(c), c->typ, (unsigned long long)c->np);
 	}
 	c->table_valid = false;
