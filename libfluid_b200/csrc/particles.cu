@@ -606,7 +606,9 @@ __global__ void k_collide(GridDesc G, MotionParams M, ParticleSoA P, const uint8
 	P.f[PF_PZ][i] = to[2];
 }
 
-// advect + collide in one pass: old_position is the pre-advection position held in registers
+// advect + collide in one pass: old_position is the pre-advection position held in registers.  (Queueing the particles
+// that cross a cell boundary in shared memory and marching them densely packed was measured: 3.26 ms against 3.02 ms
+// at 256^3, r2r sweep -- the block barrier and the queue cost more than the divergence of the march.)
 __global__ void k_advect_collide(GridDesc G, MotionParams M, ParticleSoA P, const uint8_t *__restrict__ typ,
 	unsigned long long n) {
 	unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
