@@ -507,33 +507,38 @@ __device__ __forceinline__ uint32_t block_rank(bool flag, uint32_t *warp_tot /* 
 	return before + (uint32_t)__popc(b & ((1u << lane) - 1u));
 }
 
+// messages are field-major ([field][particle]): both the pack stores and the unpack loads are coalesced (the r1 layout,
+// 15 doubles per particle record, wrote and read 8 bytes at a stride of 120)
 __global__ void __launch_bounds__(XCH_THREADS) k_xch_pack(GridDesc G, ParticleSoA P, unsigned long long n, int has_up,
 	int has_dn, const uint32_t *__restrict__ off_up, const uint32_t *__restrict__ off_dn, double *__restrict__ send_up,
-	double *__restrict__ send_dn) {
+	double *__restrict__ send_dn, size_t n_up, size_t n_dn) {
 	__shared__ uint32_t wt[32];
 	unsigned long long i = (unsigned long long)blockIdx.x * XCH_THREADS + threadIdx.x;
 	bool up = false, dn = false, dead = false;
 	if (i < n) { xch_classify(G, P.f[PF_PZ][i], has_up, has_dn, up, dn, dead); }
 	const uint32_t ru = block_rank(up, wt), rd = block_rank(dn, wt);
 	if (up) {
-		double *rec = send_up + (size_t)(off_up[blockIdx.x] + ru) * XCH_FIELDS;
-		for (int f = 0; f < XCH_FIELDS; ++f) { rec[f] = P.f[f][i]; }
+		double *rec = send_up + (size_t)(off_up[blockIdx.x] + ru);
+		for (int f = 0; f < XCH_FIELDS; ++f) { rec[(size_t)f * n_up] = P.f[f][i]; }
 	}
 	if (dn) {
-		double *rec = send_dn + (size_t)(off_dn[blockIdx.x] + rd) * XCH_FIELDS;
-		for (int f = 0; f < XCH_FIELDS; ++f) { rec[f] = P.f[f][i]; }
+		double *rec = send_dn + (size_t)(off_dn[blockIdx.x] + rd);
+		for (int f = 0; f < XCH_FIELDS; ++f) { rec[(size_t)f * n_dn] = P.f[f][i]; }
 	}
 	if (dead) { P.f[PF_PZ][i] = __longlong_as_double(0x7ff8000000000000ll); } // NaN: the sort drops it
 }
 
+// recv: [message of the lower neighbour: XCH_FIELDS x n_dn][message of the upper neighbour: XCH_FIELDS x n_up]
 __global__ void k_xch_unpack(ParticleSoA P, unsigned long long at, const double *__restrict__ recv,
-	unsigned long long n, int with_old) {
+	unsigned long long n_dn, unsigned long long n_up, int with_old) {
 	unsigned long long j = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
-	if (j >= n) { return; }
-	const double *rec = recv + j * XCH_FIELDS;
-	for (int f = 0; f < XCH_FIELDS; ++f) { P.f[f][at + j] = rec[f]; }
+	if (j >= n_dn + n_up) { return; }
+	const bool lower = j < n_dn;
+	const double *msg = lower ? recv : recv + n_dn * XCH_FIELDS;
+	const unsigned long long cnt = lower ? n_dn : n_up, k = lower ? j : j - n_dn;
+	for (int f = 0; f < XCH_FIELDS; ++f) { P.f[f][at + j] = msg[(size_t)f * cnt + k]; }
 	if (with_old) { // old_position == position for a particle in flight between two steps
-		for (int d = 0; d < 3; ++d) { P.f[PF_OX + d][at + j] = rec[d]; }
+		for (int d = 0; d < 3; ++d) { P.f[PF_OX + d][at + j] = msg[(size_t)d * cnt + k]; }
 	}
 }
 
@@ -579,7 +584,7 @@ int lfkx_exchange_particles(lfk_ctx *c, uint64_t *n_in) {
 	LFK_TRY(grow(c, &c->xsend[1], &c->xsend_cap[1], send_dn));
 	if (n > 0) {
 		LFK_LAUNCH(c, k_xch_pack, nb, XCH_THREADS, 0, G, V, (unsigned long long)n, has_up, has_dn, off_up, off_dn,
-			c->xsend[0], c->xsend[1]);
+			c->xsend[0], c->xsend[1], (size_t)send_up, (size_t)send_dn);
 	}
 	// message sizes
 	LFK_CUDA(c, cudaMemcpyAsync(c->xcounts, hc, 2 * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
@@ -616,7 +621,7 @@ int lfkx_exchange_particles(lfk_ctx *c, uint64_t *n_in) {
 	if (nrecv > 0) {
 		LFK_TRY(lfkp_reserve_particles(c, n + nrecv)); // may move the own particles to the front (first = 0)
 		LFK_LAUNCH(c, k_xch_unpack, lfk_blocks((long long)nrecv, 256), 256, 0, c->P, (unsigned long long)(c->first + n),
-			c->xrecv, (unsigned long long)nrecv, c->old_valid ? 1 : 0);
+			c->xrecv, (unsigned long long)recv_dn, (unsigned long long)recv_up, c->old_valid ? 1 : 0);
 	}
 	c->stats.exchanged_particles = (uint64_t)send_up + send_dn;
 	*n_in = n + nrecv;
