@@ -240,15 +240,16 @@ int lfk_synthetic_projection_device(lfk_ctx *ctx, uint64_t seed);
 
 /* ---- instrumentation ------------------------------------------------------------------------------------ */
 int lfk_set_timing(lfk_ctx *ctx, int enabled);
-/* A/B switches between kernel variants that compute the same result (profiling aid; every default is the production
- * path).  Keys: "p2g" 0 z-marching kernel, 1 brick kernel, 2 plain gather; "correct" 2 hit-mask pre-filter (default),
- * 0 scalar pre-filter, 1 packed-fp32 pre-filter, 3 hit-mask with record prefetch, 4 hit-mask with own particles grouped
- * by reach class, 5 hit-mask with 8-wide groups (4, 5: experimental, unmeasured); "g2p" 0 / 1 (all face samples
- * requested before the first store) / 2 (1 + constant-offset indexing for interior particles; experimental, unmeasured); "advect" 0 / 1 (two particles per thread); "mg_half" 0 / 1 (fp16 storage of the multigrid
- * level-0 vectors; experimental, unmeasured); "mg_agg" 0 / 1 (multi-GPU: coarse multigrid levels
- * agglomerated onto every rank; experimental, unmeasured; must be set on every rank alike); "mg_tail" 0 / 1; "spmv" 0 / 1;
- * "warm_start" 1 / 0; "red_blocks" n.  The environment variable LFK_TUNE="key=value,..." applies the same switches
- * to every context of the process.  Unknown key: LFK_E_INVALID. */
+/* A/B switches between code paths that compute the same result (profiling aid; every default is the production
+ * path).  Keys: "p2g" 0 z-marching kernel / 2 plain per-cell gather (the reference's loop literally); "lean_sort" 1 the
+ * fused step permutes positions only and P2G reads velocity / c rows through the permutation / 0 full-payload sort;
+ * "warm_start" 1 the fused step starts PCG from the previous pressure / 0 from p = 0 like the reference; "graph" 1 the
+ * PCG iteration is replayed from a captured CUDA graph / 0 launched kernel by kernel; "red_blocks" n caps the grid of
+ * the PCG reduction kernels; "mg_coarse" n symmetric sweeps on the coarsest multigrid level (default 8).
+ * Multi-GPU (set them on every rank alike): "p2p" 1 halos and PCG scalars through CUDA-IPC peer memory / 0 NCCL;
+ * "mg_agg" 1 coarse multigrid levels agglomerated onto every rank / 0 distributed; "mg_agg_cells" n largest whole-grid
+ * level that is agglomerated (default 600000).  The environment variable LFK_TUNE="key=value,..." applies the same
+ * switches to every context of the process.  Unknown key: LFK_E_INVALID. */
 int lfk_set_tuning(lfk_ctx *ctx, const char *key, int value);
 int lfk_get_stats(lfk_ctx *ctx, lfk_stats *out);
 int lfk_reset_stats(lfk_ctx *ctx);
