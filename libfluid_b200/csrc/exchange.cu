@@ -86,7 +86,7 @@ extern "C" int lfk_nccl_unique_id(void *out128) {
 // e + 1 writes.  Every rank issues the same sequence of exchanges (as for NCCL), so the epochs agree by construction.
 // A spin that lasts longer than ~4 s raises an error flag instead of hanging the device.
 // =========================================================================================================
-#define LL_MAX_BYTES (256u * 1024u) // larger layers take the fence-and-flag protocol
+#define LL_MAX_BYTES (1024u * 1024u) // capacity of a flag-in-data slot; layers above lfk_tuning::ll_kb take the fence-and-flag protocol
 #define ARENA_HEADER 256 // bytes: flag words + block counter + error word
 #define ARENA_MAX_RANKS 64
 struct ArenaHeader {
@@ -384,10 +384,11 @@ static int halo_bytes(lfk_ctx *c, void *field, size_t layer_elems, int nzl, nccl
 	ncclComm_t comm = (ncclComm_t)c->comm;
 	char *f = (char*)field;
 	size_t L = layer_elems * esz;
-	if (c->p2p && c->tune.p2p && L % 4 == 0 && L <= LL_MAX_BYTES && (((size_t)f | (size_t)(f + L)) & 3u) == 0) {
+	if (c->p2p && c->tune.p2p && L % 4 == 0 && L <= LL_MAX_BYTES && L <= (size_t)c->tune.ll_kb * 1024u &&
+		(((size_t)f | (size_t)(f + L)) & 3u) == 0) {
 		++c->halo_epoch;
 		unsigned nb = (unsigned)((L / 4 + 255) / 256);
-		nb = nb < 1 ? 1 : (nb > 64 ? 64 : nb);
+		nb = nb < 1 ? 1 : (nb > 128 ? 128 : nb);
 		LFK_LAUNCH(c, k_halo_ll, nb, 256, 0, c->arena, c->arena_peer[0], c->arena_peer[1], (const unsigned*)(f + (size_t)nzl * L),
 			(const unsigned*)(f + L), (unsigned*)(f + (size_t)(nzl + 1) * L), (unsigned*)f, L / 4, 4 * c->arena_slot);
 		return 0;

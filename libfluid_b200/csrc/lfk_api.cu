@@ -914,6 +914,7 @@ extern "C" int lfk_set_tuning(lfk_ctx *c, const char *key, int value) {
 	else if (k == "lean_sort") { c->tune.lean_sort = value; }
 	else if (k == "mg_agg_cells") { c->tune.mg_agg_cells = value; }
 	else if (k == "p2p") { c->tune.p2p = value; }
+	else if (k == "ll_kb") { c->tune.ll_kb = value; c->pcg_graph_key = 0; }
 	else if (k == "graph") { c->tune.graph = value; c->pcg_graph_key = 0; }
 	else if (k == "mg_coarse") { c->tune.mg_coarse = value; c->pcg_graph_key = 0; }
 	else if (k == "warm_start") { c->tune.warm_start = value; }

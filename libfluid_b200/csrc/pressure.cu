@@ -415,7 +415,7 @@ int lfks_solve(lfk_ctx *c, double dt, double *residual, uint64_t *iters, bool wa
 	// changes.  ~40 launches per iteration collapse into one graph launch (launch gaps were ~17 % of the iteration).
 	// (multi-GPU: the peer-memory halo / all-reduce kernels and the NCCL calls are captured like any other node)
 	const bool use_graph = c->tune.graph != 0;
-	const int graph_key = (((int)nb * 2 + c->prm.preconditioner) * 2 + (c->tune.p2p ? 1 : 0)) * 4 + (c->tune.mg_agg ? 2 : 0) + 1;
+	const int graph_key = (((int)nb * 2 + c->prm.preconditioner) * 2 + (c->tune.p2p ? 1 : 0)) * 4 + (c->tune.mg_agg ? 2 : 0) + 1 + 4099 * c->tune.ll_kb;
 	if (use_graph && (c->pcg_graph == nullptr || c->pcg_graph_key != graph_key)) {
 		LFK_TRY(lfks_free_graph(c));
 		cudaGraph_t graph = nullptr;
