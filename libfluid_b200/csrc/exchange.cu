@@ -86,7 +86,7 @@ extern "C" int lfk_nccl_unique_id(void *out128) {
 // e + 1 writes.  Every rank issues the same sequence of exchanges (as for NCCL), so the epochs agree by construction.
 // A spin that lasts longer than ~4 s raises an error flag instead of hanging the device.
 // =========================================================================================================
-#define LL_MAX_BYTES (1024u * 1024u) // capacity of a flag-in-data slot; layers above lfk_tuning::ll_kb take the fence-and-flag protocol
+#define LL_MAX_BYTES (2048u * 1024u) // capacity of a flag-in-data slot; layers above lfk_tuning::ll_kb take the fence-and-flag protocol
 #define ARENA_HEADER 256 // bytes: flag words + block counter + error word
 #define ARENA_MAX_RANKS 64
 struct ArenaHeader {

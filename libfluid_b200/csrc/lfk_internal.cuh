@@ -74,7 +74,8 @@ struct lfk_tuning {
 	int mg_agg_cells = 0; // > 0: largest whole-grid level (cells) that is agglomerated (default 600000)
 	int mg_coarse = 0; // > 0: symmetric sweeps on the coarsest multigrid level of the single-block tail (default 8)
 	int graph = 1;    // 1: the PCG iteration is replayed from a captured CUDA graph (~40 launches), 0: launched one by one
-	int ll_kb = 256;  // multi-GPU: layers up to this size (KB, <= 1024) use the flag-in-data halo protocol
+	int ll_kb = 1024; // multi-GPU: layers up to this size (KB, <= 2048) use the flag-in-data halo protocol (4 GPUs,
+	                  // 512 x 512 layers: 1.33 ms per PCG iteration at 1024, 1.36 at 256, 1.46 at 64; r2v)
 	int p2p = 1;      // multi-GPU: 1 halos through peer memory (CUDA IPC arenas over NVLink), 0 NCCL send / recv
 	int warm_start = 1; // fused step: start PCG from the previous step's pressure (0: from p = 0 like the reference)
 	int red_blocks = 0; // > 0: cap on the grid of the PCG reduction kernels (default 8 x SM count)
