@@ -352,11 +352,26 @@ int lfkx_init(lfk_ctx *c, const void *nccl_id128) {
 	return arena_setup(c);
 }
 
+// rendezvous of all ranks on the context's stream (a one-element all-reduce + synchronisation)
+static void comm_barrier(lfk_ctx *c) {
+	if (!c->comm || !c->d_reduce) { return; }
+	if (g_nccl.AllReduce(c->d_reduce, c->d_reduce, 1, ncclDouble, ncclSum, (ncclComm_t)c->comm, c->stream) == ncclSuccess) {
+		cudaStreamSynchronize(c->stream);
+	}
+}
+
 int lfkx_destroy(lfk_ctx *c) {
-	arena_unmap(c);
+	if (c->p2p) {
+		// CUDA IPC: an importer must close its mapping before the exporter frees the allocation.  Every rank first
+		// reaches this point (nobody issues another exchange), then unmaps its peers, then -- after a second rendezvous
+		// -- frees its own arena.
+		comm_barrier(c);
+		arena_unmap(c);
+		comm_barrier(c);
+	} else {
+		arena_unmap(c);
+	}
 	if (c->comm) {
-		// (the neighbours may still be reading this rank's arena in their last exchange: the communicator's destruction
-		// is collective, so it doubles as the barrier before the arena is freed)
 		g_nccl.CommDestroy((ncclComm_t)c->comm);
 		c->comm = nullptr;
 	}
