@@ -245,10 +245,12 @@ int lfk_set_timing(lfk_ctx *ctx, int enabled);
  * fused step permutes positions only and P2G reads velocity / c rows through the permutation / 0 full-payload sort;
  * "warm_start" 1 the fused step starts PCG from the previous pressure / 0 from p = 0 like the reference; "graph" 1 the
  * PCG iteration is replayed from a captured CUDA graph / 0 launched kernel by kernel; "red_blocks" n caps the grid of
- * the PCG reduction kernels; "mg_coarse" n symmetric sweeps on the coarsest multigrid level (default 8).
+ * the PCG reduction kernels; "mg_coarse" n symmetric sweeps on the coarsest multigrid level (default 8); "p2g_chunk" n
+ * z planes per block of the marching P2G kernel (8 .. 128, default: about 6 waves of one block per SM).
  * Multi-GPU (set them on every rank alike): "p2p" 1 halos and PCG scalars through CUDA-IPC peer memory / 0 NCCL;
  * "mg_agg" 1 coarse multigrid levels agglomerated onto every rank / 0 distributed; "mg_agg_cells" n largest whole-grid
- * level that is agglomerated (default 600000).  The environment variable LFK_TUNE="key=value,..." applies the same
+ * level that is agglomerated (default 600000); "ll_kb" n halo layers up to n KB (<= 2048, default 1024) travel as
+ * {element, epoch} words (no fence, no flag round trip).  The environment variable LFK_TUNE="key=value,..." applies the same
  * switches to every context of the process.  Unknown key: LFK_E_INVALID. */
 int lfk_set_tuning(lfk_ctx *ctx, const char *key, int value);
 int lfk_get_stats(lfk_ctx *ctx, lfk_stats *out);

@@ -24,6 +24,7 @@ struct G2PArgs {
 	// an own particle of the bottom layer into the ghost layer; its z-faces then reach one layer further down.
 	const double *w_below, *wo_below;
 	double blend;
+	unsigned long long *speed2; // max |v|^2 over the particles of this launch (bits of a non-negative double), for cfl()
 };
 
 struct FaceFetch { // the 3 clamped cell coordinates per axis of get_face_samples, and their "clamped" bits
@@ -127,9 +128,7 @@ template <int K> __device__ __forceinline__ void face_samples_interior(const Gri
 // round trips per particle; the kernel is latency bound), and particles whose 3 x 3 x 3 cell neighbourhood is interior
 // take face_samples_interior (index arithmetic was 37 % of the instructions, ncu r1d).  Measured at 256^3 (r2a sweep):
 // 4.09 ms against 4.59 ms component by component and 4.47 ms batched with clamped indexing.
-template <int METHOD> __global__ void __launch_bounds__(128) k_g2p(GridDesc G, G2PArgs A, unsigned long long n) {
-	unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
-	if (i >= n) { return; }
+template <int METHOD> __device__ __forceinline__ double g2p_one(const GridDesc &G, const G2PArgs &A, unsigned long long i) {
 	constexpr bool APIC = METHOD == LFK_METHOD_APIC;
 	const double p[3] = { A.px[i], A.py[i], A.pz[i] };
 	long long gi[3];
@@ -204,6 +203,30 @@ template <int METHOD> __global__ void __launch_bounds__(128) k_g2p(GridDesc G, G
 		A.vd[1][i] = vn[1];
 		A.vd[2][i] = vn[2];
 	}
+	// squared_length() as the reference's cfl() evaluates it (src/simulation.cpp:199-205): no contraction
+	return __dadd_rn(__dadd_rn(__dmul_rn(vn[0], vn[0]), __dmul_rn(vn[1], vn[1])), __dmul_rn(vn[2], vn[2]));
+}
+
+// The new velocities' largest |v|^2 is folded in here, so that the cfl() of the next step needs no pass of its own over
+// the particles (3.1 GB at 256^3, 0.48 ms).  The maximum does not depend on the order; a NaN speed is skipped like
+// std::max(m, s) skips it.
+template <int METHOD> __global__ void __launch_bounds__(128, METHOD == LFK_METHOD_FLIP ? 1 : 7) k_g2p(GridDesc G, G2PArgs A, unsigned long long n) {
+	const unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+	double s2 = 0.0;
+	if (i < n) {
+		const double s = g2p_one<METHOD>(G, A, i);
+		s2 = 0.0 < s ? s : 0.0;
+	}
+	// non-negative doubles order like their bit patterns: maximum of the high words, then of the low words among the
+	// lanes that hold it
+	const unsigned long long bits = (unsigned long long)__double_as_longlong(s2);
+	const unsigned hi = (unsigned)(bits >> 32), lo = (unsigned)bits;
+	const unsigned mhi = __reduce_max_sync(0xffffffffu, hi);
+	const unsigned mlo = __reduce_max_sync(0xffffffffu, hi == mhi ? lo : 0u);
+	if ((threadIdx.x & 31) == 0) {
+		const unsigned long long m = ((unsigned long long)mhi << 32) | mlo;
+		if (m > *(volatile unsigned long long*)A.speed2) { atomicMax(A.speed2, m); }
+	}
 }
 
 int lfkp_g2p(lfk_ctx *c) {
@@ -218,8 +241,12 @@ int lfkp_g2p(lfk_ctx *c) {
 		for (int d = 0; d < 3; ++d) { LFK_TRY(lfkx_halo_f64(c, c->vel[d])); }
 		LFK_TRY(lfkx_layer_below(c, c->vel[2], c->wlow[0]));
 	}
+	// the launch also leaves max |v|^2 of the own particles in the cfl cache (lfkp_cfl)
+	unsigned long long *speed2 = (unsigned long long*)(c->d_reduce + LFK_REDUCE_SPEED2);
+	LFK_CUDA(c, cudaMemsetAsync(speed2, 0, sizeof(double), c->stream));
 	if (c->np > 0) {
 		G2PArgs A;
+		A.speed2 = speed2;
 		// own particles are entries [first, first + np); the permutation holds absolute source indices
 		const uint64_t o = c->first;
 		A.px = c->P.f[PF_PX] + o;
@@ -257,5 +284,6 @@ int lfkp_g2p(lfk_ctx *c) {
 	}
 	c->v_deferred = false;
 	c->c_deferred = false;
+	c->speed2_valid = true;
 	return 0;
 }

@@ -418,6 +418,7 @@ extern "C" int lfk_upload_particles(lfk_ctx *c, const void *aos152, uint64_t n) 
 	c->ntot = 0;
 	c->v_deferred = false;
 	c->c_deferred = false;
+	c->speed2_valid = false;
 	LFK_TRY(lfkp_reserve_particles(c, n));
 	if (n > 0) {
 		c->np = n;
@@ -910,6 +911,7 @@ extern "C" int lfk_set_tuning(lfk_ctx *c, const char *key, int value) {
 	if (!c || !key) { return LFK_E_INVALID; }
 	const std::string k(key);
 	if (k == "p2g") { c->tune.p2g = value; }
+	else if (k == "p2g_chunk") { c->tune.p2g_chunk = value; }
 	else if (k == "mg_agg") { c->tune.mg_agg = value; }
 	else if (k == "lean_sort") { c->tune.lean_sort = value; }
 	else if (k == "mg_agg_cells") { c->tune.mg_agg_cells = value; }

@@ -66,8 +66,11 @@ struct MgLevel {
 
 // A/B switches and tuning knobs (lfk_set_tuning; the defaults are the production path)
 enum { LFK_TUNE_P2G_MARCH = 0, LFK_TUNE_P2G_GATHER = 2 };
+#define LFK_REDUCE_SPEED2 8
+
 struct lfk_tuning {
 	int p2g = LFK_TUNE_P2G_MARCH; // 2: the plain per-cell gather (the reference's loop literally; also taken for APIC with h < 1)
+	int p2g_chunk = 0; // > 0: z planes per block of the marching P2G kernel (8 .. 128; default: ~6 waves of one block per SM)
 	int lean_sort = 1; // fused step: 1 the sort permutes positions only and P2G reads velocity / c rows through the
 	                   // permutation, 0 the sort permutes the whole payload
 	int mg_agg = 1;   // multi-GPU: 1 coarse levels agglomerated onto every rank (r2d: 1.68 against 2.06 ms per iteration on 2 GPUs), 0 distributed
@@ -178,7 +181,10 @@ struct lfk_ctx {
 	void *staging = nullptr; size_t staging_bytes = 0;
 	uint32_t *scan_tmp = nullptr; size_t scan_tmp_n = 0;
 	uint32_t *bigcells = nullptr; unsigned *bigcount = nullptr; unsigned bigcap = 0;
-	double *d_reduce = nullptr;     // small device scratch for reductions (cfl etc.)
+	double *d_reduce = nullptr;     // small device scratch for reductions (cfl etc.), 16 doubles
+	// d_reduce[LFK_REDUCE_SPEED2]: max |v|^2 of the own particles as the last G2P left it; valid until anything else
+	// writes particle velocities or changes the particle set (uploads, seeding, sources, checkpoint load)
+	bool speed2_valid = false;
 	double *h_reduce = nullptr;     // pinned
 
 	// stats

@@ -337,7 +337,7 @@ template <int WARPS> static int p2g_march_launch(lfk_ctx *c, const PBParams &Q, 
 	int sms = 148;
 	cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->device);
 	int nzc = (int)((6u * (unsigned)sms + nbx * nby - 1) / (nbx * nby));
-	int chunk = (G.nzl + nzc - 1) / nzc;
+	int chunk = c->tune.p2g_chunk > 0 ? c->tune.p2g_chunk : (G.nzl + nzc - 1) / nzc;
 	chunk = chunk < 8 ? 8 : chunk;
 	chunk = chunk > PM_MAX_CHUNK ? PM_MAX_CHUNK : chunk;
 	chunk = chunk > G.nzl ? G.nzl : chunk;

@@ -74,6 +74,7 @@ static ParticleSoA view_at(const lfk_ctx *c, uint64_t at) {
 	return v;
 }
 int lfkp_aos_to_soa(lfk_ctx *c, const void *d_aos, uint64_t n, uint64_t at) {
+	c->speed2_valid = false;
 	if (n == 0) { return 0; }
 	// raw_cell_index is a whole-grid raw index; device keys are local (one ghost layer below the slab)
 	long long shift = ((long long)1 - c->g.z0) * c->g.sxy;
@@ -1053,8 +1054,13 @@ __global__ void k_max_speed2(const double *__restrict__ vx, const double *__rest
 
 int lfkp_cfl(lfk_ctx *c, double *value) {
 	PhaseTimer T(c, LFK_PHASE_CFL);
-	LFK_CUDA(c, cudaMemsetAsync(c->d_reduce, 0, sizeof(double), c->stream));
-	if (c->np > 0) {
+	if (c->speed2_valid) { // the last G2P folded the maximum in (g2p.cu); nothing has touched the velocities since
+		LFK_CUDA(c, cudaMemcpyAsync(c->d_reduce, c->d_reduce + LFK_REDUCE_SPEED2, sizeof(double), cudaMemcpyDeviceToDevice,
+			c->stream));
+	} else {
+		LFK_CUDA(c, cudaMemsetAsync(c->d_reduce, 0, sizeof(double), c->stream));
+	}
+	if (c->np > 0 && !c->speed2_valid) {
 		unsigned nb = lfk_blocks((long long)c->np, 256);
 		if (nb > 148 * 8) { nb = 148 * 8; }
 		// (the maximum does not depend on the order, so a velocity payload still in pre-sort order is fine -- but then it
@@ -1154,6 +1160,7 @@ __global__ void k_source_seed(GridDesc G, ParticleSoA P, uint32_t *__restrict__ 
 
 int lfkp_coerce_sources(lfk_ctx *c) {
 	if (!c->src_active || !c->src_coerce || c->np == 0) { return 0; }
+	c->speed2_valid = false;
 	PhaseTimer T(c, LFK_PHASE_ADVECT_COLLIDE);
 	LFK_TRY(lfkp_materialise_vc(c)); // the velocity / c rows are written in particle order
 	LFK_LAUNCH(c, k_coerce_sources, lfk_blocks((long long)c->np, 256), 256, 0, c->g, lfk_own_view(c),
@@ -1164,6 +1171,7 @@ int lfkp_coerce_sources(lfk_ctx *c) {
 int lfkp_update_sources(lfk_ctx *c, uint64_t *added) {
 	if (added) { *added = 0; }
 	if (!c->src_active || c->src_entries == 0) { ++c->rng_step; return 0; }
+	c->speed2_valid = false;
 	PhaseTimer T(c, LFK_PHASE_SORT);
 	LFK_REQUIRE(c, c->table_valid, LFK_E_STATE, "lfk_update_sources needs the cell table of lfk_hash");
 	const uint32_t ne = c->src_entries;
@@ -1268,6 +1276,7 @@ __global__ void __launch_bounds__(SEED_THREADS) k_seed_write(GridDesc G, SeedBox
 int lfkp_seed_box(lfk_ctx *c, const double *start, const double *size, const double *vel, uint32_t dens,
 	uint64_t seed, int append) {
 	const GridDesc &G = c->g;
+	c->speed2_valid = false;
 	if (!append) {
 		c->np = 0;
 		c->first = 0;

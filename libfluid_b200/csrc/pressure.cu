@@ -715,6 +715,7 @@ int lfks_synthetic_projection(lfk_ctx *c, uint64_t seed) {
 	c->np = 0;
 	c->first = 0;
 	c->ntot = 0;
+	c->speed2_valid = false;
 	c->table_valid = false;
 	c->ordinal_valid = false;
 	c->system_valid = false;

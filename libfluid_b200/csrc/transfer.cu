@@ -244,6 +244,7 @@ extern "C" int lfk_checkpoint_save(lfk_ctx *c, const char *path) {
 
 extern "C" int lfk_checkpoint_load(lfk_ctx *c, const char *path) {
 	if (!c || !path) { return LFK_E_INVALID; }
+	c->speed2_valid = false;
 	FILE *f = fopen(ckpt_path(c, path).c_str(), "rb");
 	LFK_REQUIRE(c, f != nullptr, LFK_E_INVALID, "checkpoint: cannot open the file");
 	Bounce B(c);

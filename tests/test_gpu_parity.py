@@ -192,6 +192,36 @@ def test_fused_step_equals_staged_step_on_device(scene):
     assert PL.rel_l2(ca["vel"], cb["vel"]) < 1e-13
 
 
+@pytest.mark.parametrize("method", [capi.APIC, capi.FLIP, capi.PIC])
+def test_cfl_after_a_step_is_the_exact_maximum_and_tracks_later_edits(method):
+    """cfl() after a fused or staged step comes from the maximum the G2P kernel folded in; it must be the exact
+    h / sqrt(max |v|^2) of the particles as downloaded, and anything that rewrites the particles afterwards (upload,
+    seeding) must be seen by the next cfl()."""
+    def expect(p):
+        v = p["velocity"]
+        s = v[:, 0] * v[:, 0]
+        s = s + v[:, 1] * v[:, 1]
+        s = s + v[:, 2] * v[:, 2]
+        return 1.0 / np.sqrt(s.max())
+
+    ctx = _device_scene(24, method)
+    for step in range(3):
+        ctx.time_step()
+        assert ctx.cfl() == expect(ctx.download_particles())
+    ctx.hash()  # a staged G2P on the sorted state refreshes the cache as well
+    ctx.g2p()
+    assert ctx.cfl() == expect(ctx.download_particles())
+    p = ctx.download_particles().copy()
+    p["velocity"] *= 0.25
+    p["velocity"][7] = (1e4, -2e4, 3e4)
+    ctx.upload_particles(p)
+    assert ctx.cfl() == expect(p)
+    ctx.time_step()
+    ctx.seed_box_device((1.0, 20.0, 1.0), (2.0, 2.0, 2.0), velocity=(5e5, 0.0, 0.0), density=2, seed=5, append=True)
+    assert ctx.cfl() == 1.0 / 5e5
+    ctx.close()
+
+
 def _device_scene(n=40, method=capi.APIC, **kw):
     """a sloshing block that fills ~half of an n^3 box, stepped a few times so that cells hold 0..20 particles"""
     ctx = capi.Context((n, n, n), cell_size=1.0, gravity=(0.0, -981.0, 0.0), method=method, max_iterations=2000, **kw)

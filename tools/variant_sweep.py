@@ -16,12 +16,16 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
-NEW = {"p2g": 0, "warm_start": 1, "red_blocks": 0, "graph": 1, "mg_coarse": 0, "lean_sort": 1}  # the library defaults
+NEW = {"p2g": 0, "warm_start": 1, "red_blocks": 0, "graph": 1, "mg_coarse": 0, "lean_sort": 1, "p2g_chunk": 0}  # the library defaults
 CONFIGS = [
     ("defaults", dict(NEW)),
     ("defaults+full_sort", dict(NEW, lean_sort=0)),
     ("defaults+no_graph", dict(NEW, graph=0)),
     ("defaults+cold_start", dict(NEW, warm_start=0)),
+    ("defaults+p2g_chunk16", dict(NEW, p2g_chunk=16)),
+    ("defaults+p2g_chunk32", dict(NEW, p2g_chunk=32)),
+    ("defaults+p2g_chunk64", dict(NEW, p2g_chunk=64)),
+    ("defaults+p2g_chunk128", dict(NEW, p2g_chunk=128)),
 ]
 
 
