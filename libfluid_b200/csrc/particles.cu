@@ -674,7 +674,10 @@ int lfkp_advect_collide(lfk_ctx *c, double dt) {
 // =========================================================================================================
 // A3: position correction (reference src/simulation.cpp:562-610)
 // =========================================================================================================
-__device__ __forceinline__ void degenerate_kick(const double *p, const double *o, double *out3) {
+#ifndef CT_KICK_INLINE
+#define CT_KICK_INLINE __forceinline__
+#endif
+__device__ CT_KICK_INLINE void degenerate_kick(const double *p, const double *o, double *out3) {
 	unsigned long long s = 0x9e3779b97f4a7c15ull;
 #pragma unroll
 	for (int k = 0; k < 3; ++k) { s = mix64(s ^ (unsigned long long)__double_as_longlong(p[k])); }
@@ -694,7 +697,7 @@ __device__ __forceinline__ void degenerate_kick(const double *p, const double *o
 // |r - q|^2 < 1/2 + margin is  w + n.q < T,  T = 1/2 + margin - |r|^2: three FFMA and a compare; hits are bits of a per-row
 // mask with compile-time positions, one {mask, index of the window's first particle} record per 32 candidates.
 // Every staged row is followed by CT_PAD entries that can never hit, so the 4-wide groups need no tail handling.
-// Rounding: |coordinates| <= 17.1 cells, every intermediate below 620 with an error below 4e-5; the margin of 2e-3 cells^2
+// Rounding: |coordinates| <= 17.1 cells (CT_LX <= 32), every intermediate below 620 with an error below 4e-5; the margin of 2e-3 cells^2
 // covers their sum 10x over, so the filter never drops a true neighbour.
 // Phase 2 (fp64): the recorded candidates in staging order (= the reference's order: rows by z then y, cells by x,
 // particles in sorted order), evaluated from the original positions => the result is the plain fp64 loop's, bit for bit.
@@ -707,15 +710,38 @@ __device__ __forceinline__ void degenerate_kick(const double *p, const double *o
 // here (per-slot guards, ballot bookkeeping and the candidate-index searches cost more than the divergence they remove;
 // profiles/r2l_coop_ncu_summary.txt, git history of r2 holds the kernel); two or three neighbour positions in flight in
 // phase 2 instead of one: 27.7 / 28.2 ms against 27.3 (r2q sweep).
-#define CT_LX 32
+// Tile geometry (r3c-r3f sweeps at 256^3, tools/build_variant.py + tools/gpu_variants.sh; ms for this kernel):
+//   threads x blocks/SM, CT_LX, CT_CAP      L1 left     ms
+//   512 x 2, 32, 5120 (rounds 1-2)           60 KB     26.98
+//   512 x 2, 32, 4960                        92 KB     26.34   (2 x 82 KB of shared memory fit the 164 KB carve-out)
+//   384 x 2, 32, 5120 (68 registers)         60 KB     29.59   (24 warps per SM instead of 32)
+//   256 x 4, 16, 2688                        60 KB     26.27   <- production
+//   256 x 4, 16, 2432                        92 KB     25.96   (3 % headroom over a uniform 8 per cell: too tight)
+//   256 x 4, 16, 3072                        28 KB     27.16
+//   320 x 3, 20, 3200                        92 KB     26.44
+//   256 x 4,  8, 1536                       124 KB     26.97   (x halo 10 / 8)
+//   512 x 2, 16, 2688                       156 KB     28.30   (one pass per thread, coarse blocks)
+//   128 x 8,  8, 1536                        28 KB     29.21
+// i.e. 32 resident warps are needed, smaller blocks overlap each other's staging and tails better, and phase 2's
+// neighbour loads want the L1 that the shared-memory carve-out leaves (about 0.3 ms per 32 KB).
+#ifndef CT_LX
+#define CT_LX 16
+#endif
 #define CT_TY 2
 #define CT_TZ 2
 #define CT_SY (CT_TY + 2)
 #define CT_SZ (CT_TZ + 2)
 #define CT_ROWS (CT_SY * CT_SZ)
 #define CT_OWN (CT_TY * CT_TZ)
-#define CT_CAP 5120           // staged particles per tile (80 KB); denser tiles take the global-memory path
-#define CT_THREADS 512
+#ifndef CT_CAP
+#define CT_CAP 2688           // staged particles per tile (42 KB; a uniform 8 per cell stages 2352); denser tiles take the global-memory path
+#endif
+#ifndef CT_THREADS
+#define CT_THREADS 256
+#endif
+#ifndef CT_BLOCKS
+#define CT_BLOCKS 4 // resident blocks per SM the register budget is set for
+#endif
 #define CT_PAD 3
 #define CT_LIST 16
 #define CT_MARGIN 2e-3f
@@ -787,7 +813,7 @@ __device__ void spring_global(const GridDesc &G, const MotionParams &M, const do
 	}
 }
 
-template <bool COLLIDE> __global__ void __launch_bounds__(CT_THREADS, 2) k_correct_tile(GridDesc G, MotionParams M,
+template <bool COLLIDE> __global__ void __launch_bounds__(CT_THREADS, CT_BLOCKS) k_correct_tile(GridDesc G, MotionParams M,
 	ParticleSoA P, double *__restrict__ nx_, double *__restrict__ ny_, double *__restrict__ nz_,
 	const uint32_t *__restrict__ begin, const uint8_t *__restrict__ typ) {
 	extern __shared__ float4 stage[];                            // [CT_CAP] fp32 scan entries

@@ -5,8 +5,8 @@ the compiled reference driven live (oracle/_ref travels to the GPU box; nothing 
     consecutive recorded steps (all of them with PCG iterations);
   * configs[1]: 128^3 column collapse with the solid box, FLIP 0.95, 1.2e6 particles, one recorded step after two
     plain ones;
-  * a 48 x 20 x 12 scene whose water crosses x = 30 and x = 32 (the P2G block width and the position-correction tile
-    width) with motion along x;
+  * a 48 x 20 x 12 scene whose water crosses x = 16, 30 and 32 (the position-correction tile width is 16, the P2G block
+    width 30) with motion along x;
   * a scene seeded at 27 particles per cell, so that the position correction's staged tile overflows and every
     particle takes its global-memory path.
 Tolerances: those of devlib.check_device_against_record.

@@ -36,9 +36,12 @@ def main():
     ap.add_argument("--warmup", type=int, default=4)
     ap.add_argument("--tag", default="sweep")
     ap.add_argument("--only", default="")
+    ap.add_argument("--lib", default="", help="a variant library built by tools/build_variant.py")
     args = ap.parse_args()
     import torch
     from libfluid_b200 import capi
+    if args.lib:
+        capi.LIB_PATH = os.path.abspath(args.lib)
     import bench as B
 
     torch.cuda.set_device(0)
