@@ -210,7 +210,13 @@ template <int METHOD> __device__ __forceinline__ double g2p_one(const GridDesc &
 // The new velocities' largest |v|^2 is folded in here, so that the cfl() of the next step needs no pass of its own over
 // the particles (3.1 GB at 256^3, 0.48 ms).  The maximum does not depend on the order; a NaN speed is skipped like
 // std::max(m, s) skips it.
-template <int METHOD> __global__ void __launch_bounds__(128, METHOD == LFK_METHOD_FLIP ? 1 : 7) k_g2p(GridDesc G, G2PArgs A, unsigned long long n) {
+#ifndef G2P_THREADS
+#define G2P_THREADS 128
+#endif
+#ifndef G2P_BLOCKS
+#define G2P_BLOCKS 7 // resident blocks per SM the register budget of the PIC / APIC instantiations is set for (72 registers)
+#endif
+template <int METHOD> __global__ void __launch_bounds__(G2P_THREADS, METHOD == LFK_METHOD_FLIP ? 1 : G2P_BLOCKS) k_g2p(GridDesc G, G2PArgs A, unsigned long long n) {
 	const unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
 	double s2 = 0.0;
 	if (i < n) {
@@ -263,17 +269,17 @@ int lfkp_g2p(lfk_ctx *c) {
 		A.w_below = c->rank > 0 ? c->wlow[0] : nullptr;
 		A.wo_below = c->rank > 0 ? c->wlow[1] : nullptr;
 		A.blend = c->prm.blending_factor;
-		unsigned nb = lfk_blocks((long long)c->np, 128);
+		unsigned nb = lfk_blocks((long long)c->np, G2P_THREADS);
 		unsigned long long n = c->np;
 		switch (method) {
 		case LFK_METHOD_PIC:
-			LFK_LAUNCH(c, k_g2p<LFK_METHOD_PIC>, nb, 128, 0, c->g, A, n);
+			LFK_LAUNCH(c, k_g2p<LFK_METHOD_PIC>, nb, G2P_THREADS, 0, c->g, A, n);
 			break;
 		case LFK_METHOD_FLIP:
-			LFK_LAUNCH(c, k_g2p<LFK_METHOD_FLIP>, nb, 128, 0, c->g, A, n);
+			LFK_LAUNCH(c, k_g2p<LFK_METHOD_FLIP>, nb, G2P_THREADS, 0, c->g, A, n);
 			break;
 		default:
-			LFK_LAUNCH(c, k_g2p<LFK_METHOD_APIC>, nb, 128, 0, c->g, A, n);
+			LFK_LAUNCH(c, k_g2p<LFK_METHOD_APIC>, nb, G2P_THREADS, 0, c->g, A, n);
 			break;
 		}
 		if (indirect) {

@@ -34,6 +34,12 @@ __device__ __forceinline__ float l0_ld_b(const float *__restrict__ p, long long 
 __device__ __forceinline__ float l0_ld_x(const float *__restrict__ p, long long i) { return p[i]; }
 __device__ __forceinline__ void l0_st_x(float *__restrict__ p, long long i, float v) { p[i] = v; }
 
+#ifndef L0_U
+#define L0_U 4  // cells in flight per thread in the level-0 half-sweeps (rows_pipelined)
+#endif
+#ifndef FIN_U
+#define FIN_U 4 // ... and in the last half-sweep (fp64 z, z.r)
+#endif
 #define MG_OMEGA 1.8f
 #define MG_PRE 2
 #define MG_POST 2
@@ -178,7 +184,7 @@ template <bool PROLONG, typename T> __global__ void __launch_bounds__(256) k_mg_
 	const uint16_t *__restrict__ mask, const T *__restrict__ b, T *__restrict__ X, int colour, LevelDev C,
 	const PcgScalars *scal) {
 	if (scal->done) { return; }
-	rows_pipelined<4, L0Raw>(G.nx, G.ny, G.nzl, G.z0, colour,
+	rows_pipelined<L0_U, L0Raw>(G.nx, G.ny, G.nzl, G.z0, colour,
 		[&](int x, int y, int lz, long long c) { return l0_load<PROLONG, T>(G, mask, b, X, C, x, y, lz, c); },
 		[&](int x, int y, int lz, long long c, const L0Raw &r) {
 			float s = r.b + l0_offdiag_sum(r);
@@ -197,7 +203,7 @@ template <typename T> __global__ void __launch_bounds__(RED_THREADS) k_mg_final_
 	double acc = 0.0;
 	struct FinRaw { L0Raw l; double r; };
 	LevelDev none{};
-	rows_pipelined<4, FinRaw>(G.nx, G.ny, G.nzl, 0, -1,
+	rows_pipelined<FIN_U, FinRaw>(G.nx, G.ny, G.nzl, 0, -1,
 		[&](int x, int y, int lz, long long c) {
 			FinRaw v;
 			v.l = l0_load<false, T>(G, mask, b, X, none, x, y, lz, c);

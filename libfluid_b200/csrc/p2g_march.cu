@@ -31,7 +31,10 @@
 #define PM_BX 30
 // WARPS (template parameter): warps per block = rows per block (two of them halo rows).  Warps are placed on the 4 SM
 // sub-partitions (16 K registers each), so ceil(WARPS / 4) * 32 * registers must fit: 8 warps at 200 registers, or 10 at 168.
-#define PM_REGS(WARPS) ((WARPS) <= 8 ? 200 : 168)
+#ifndef PM_REGS8
+#define PM_REGS8 224
+#endif
+#define PM_REGS(WARPS) ((WARPS) <= 8 ? PM_REGS8 : 168)
 #define PM_STAGE (PB_FIELDS * PB_FSTRIDE)       // doubles per staging buffer
 #define PM_SLOT (3 * 2 * 32)                    // doubles per warp slot: [b][w | wv][lane]
 #define PM_MAX_CHUNK 128                        // z planes per block at most (size of the z-coordinate table)
@@ -48,6 +51,30 @@ __device__ __forceinline__ void cp_async_commit() {
 __device__ __forceinline__ void cp_async_wait_1() {
 	asm volatile("cp.async.wait_group 1;" ::: "memory");
 }
+// split block barrier (mbarrier): a warp announces that its row partials of a layer are in shared memory and only waits
+// when it needs its neighbours' -- one layer later -- so warps whose rows hold fewer particles run ahead instead of
+// idling at a __syncthreads() per layer
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, unsigned count) {
+	asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(unsigned long long *bar) {
+	asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"((unsigned)__cvta_generic_to_shared(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity) {
+	asm volatile("{\n"
+		".reg .pred p;\n"
+		"LAB_WAIT:\n"
+		"mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+		"@p bra LAB_DONE;\n"
+		"bra LAB_WAIT;\n"
+		"LAB_DONE:\n"
+		"}" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(parity) : "memory");
+}
+struct PMSync { // per-thread view of the block's split barrier
+	unsigned long long *bar;
+	unsigned phase; // parity of the next phase to wait for
+	int pend;       // local layer index of the face plane whose row partials are announced but not yet combined (-1: none)
+};
 __device__ __forceinline__ int warp_max_i(int v) {
 #pragma unroll
 	for (int o = 16; o > 0; o >>= 1) { v = max(v, __shfl_xor_sync(PM_FULL, v, o)); }
@@ -134,15 +161,72 @@ struct PMOut { // where one component goes
 	uint8_t *__restrict__ typ;
 };
 
+// The row partials of face plane `op` are complete in slot set `set` on every warp: the warp that owns row y adds
+// slot[y-1], slot[y], slot[y+1] in that fixed order, normalises, classifies, zeroes boundary faces, takes the FLIP
+// snapshot, adds gravity and writes the finished face row.
+template <int COMP, int METHOD, int WARPS> __device__ __forceinline__ void pm_store_plane(const GridDesc &G, const PBParams &Q,
+	int op, const double *__restrict__ set, int warp, int lane, int x, int y, int nfx,
+	const uint32_t *__restrict__ begin, const PMOut &O) {
+	constexpr int NB = COMP == 1 ? 2 : 3;
+	constexpr bool APIC = METHOD == LFK_METHOD_APIC;
+	const int fx = lane - 1; // owned face columns: lanes 1 .. 30
+	if (warp >= 1 && warp <= WARPS - 2 && y < G.ny && fx >= 0 && fx < nfx) {
+		const double *mine = set + warp * PM_SLOT;
+		const double *below = set + (warp - 1) * PM_SLOT;
+		const double *above = set + (warp + 1) * PM_SLOT;
+		double sw, sv;
+		if (NB == 3) { // row y-1 (b = 2), row y (b = 1), row y+1 (b = 0)
+			sw = below[(2 * 2 + 0) * 32 + lane];
+			sv = below[(2 * 2 + 1) * 32 + lane];
+			sw += mine[(1 * 2 + 0) * 32 + lane];
+			sv += mine[(1 * 2 + 1) * 32 + lane];
+			sw += above[(0 * 2 + 0) * 32 + lane];
+			sv += above[(0 * 2 + 1) * 32 + lane];
+		} else { // staggered in y: row y (b = 1), row y+1 (b = 0)
+			sw = mine[(1 * 2 + 0) * 32 + lane];
+			sv = mine[(1 * 2 + 1) * 32 + lane];
+			sw += above[(0 * 2 + 0) * 32 + lane];
+			sv += above[(0 * 2 + 1) * 32 + lane];
+		}
+		const int z = op - 1 + G.z0;
+		const long long me = x + (long long)G.nx * (y + (long long)G.ny * op);
+		double r = sw > 1e-6 ? sv / sw : 0.0; // src/simulation.cpp:380-386
+		const bool edge = COMP == 0 ? x == G.nx - 1 : (COMP == 1 ? y == G.ny - 1 : z == G.nz - 1);
+		if (METHOD == LFK_METHOD_FLIP) { O.old[me] = edge ? 0.0 : r; } // :340-344
+		if (APIC && edge) { r = 0.0; }                                  // :397
+		if (Q.add_gravity) { r += Q.gdt[COMP]; }                        // :72-78
+		O.out[me] = r;
+		if (COMP == 0) { // classification, once per cell (:388-393)
+			const uint8_t t = O.typ[me];
+			if (t != LFK_CELL_SOLID) {
+				O.typ[me] = (begin[me + 1] - begin[me]) > 0 ? LFK_CELL_FLUID : LFK_CELL_AIR;
+			}
+		}
+	}
+}
+
+// the announced plane, if any: wait until every warp has announced it, then combine and write it
+template <int COMP, int METHOD, int WARPS> __device__ __forceinline__ void pm_complete_pending(const GridDesc &G, const PBParams &Q,
+	const double *__restrict__ slots, int par, PMSync &S, int warp, int lane, int x, int y, int nfx,
+	const uint32_t *__restrict__ begin, const PMOut &O) {
+	if (S.pend < 0) { return; } // block-uniform
+	mbar_wait(S.bar, S.phase);
+	S.phase ^= 1u;
+	pm_store_plane<COMP, METHOD, WARPS>(G, Q, S.pend, slots + (par ^ 1) * WARPS * PM_SLOT, warp, lane, x, y, nfx, begin, O);
+	S.pend = -1;
+}
+
 // Layer L of the march is complete: face plane L - 1 has everything this column contributes.  Combine along x
-// (shuffles) and y (slots), write the plane, rotate the accumulators.
+// (shuffles), announce the row partials (slots; combined along y one layer later), rotate the accumulators.
 template <int COMP, int METHOD, int WARPS> __device__ __forceinline__ void pm_finish_layer(const GridDesc &G, const PBParams &Q,
-	int L, int P0, int P1, double *__restrict__ slots, int &par, int warp, int lane, int x, int y, int nfx,
+	int L, int P0, int P1, double *__restrict__ slots, int &par, PMSync &S, int warp, int lane, int x, int y, int nfx,
 	const uint32_t *__restrict__ begin, const PMOut &O, double *accw, double *accv) {
 	constexpr int NA = COMP == 0 ? 2 : 3, NB = COMP == 1 ? 2 : 3, NC = COMP == 2 ? 2 : 3;
-	constexpr bool APIC = METHOD == LFK_METHOD_APIC;
 	const int op = L - 1; // local layer index of the finished face plane
 	if (op >= P0 && op < P1) { // block-uniform
+		// the plane announced one layer ago used the other slot set; once every warp has announced it, nobody reads
+		// the set written below any more (its last readers combined it before they announced that plane)
+		pm_complete_pending<COMP, METHOD, WARPS>(G, Q, slots, par, S, warp, lane, x, y, nfx, begin, O);
 		double *mine = slots + (par * WARPS + warp) * PM_SLOT;
 #pragma unroll
 		for (int b = 0; b < NB; ++b) {
@@ -163,41 +247,9 @@ template <int COMP, int METHOD, int WARPS> __device__ __forceinline__ void pm_fi
 			mine[(b * 2 + 0) * 32 + lane] = rw;
 			mine[(b * 2 + 1) * 32 + lane] = rv;
 		}
-		__syncthreads();
-		const int fx = lane - 1; // owned face columns: lanes 1 .. 30
-		if (warp >= 1 && warp <= WARPS - 2 && y < G.ny && fx >= 0 && fx < nfx) {
-			const double *below = slots + (par * WARPS + warp - 1) * PM_SLOT;
-			const double *above = slots + (par * WARPS + warp + 1) * PM_SLOT;
-			double sw, sv;
-			if (NB == 3) { // row y-1 (b = 2), row y (b = 1), row y+1 (b = 0)
-				sw = below[(2 * 2 + 0) * 32 + lane];
-				sv = below[(2 * 2 + 1) * 32 + lane];
-				sw += mine[(1 * 2 + 0) * 32 + lane];
-				sv += mine[(1 * 2 + 1) * 32 + lane];
-				sw += above[(0 * 2 + 0) * 32 + lane];
-				sv += above[(0 * 2 + 1) * 32 + lane];
-			} else { // staggered in y: row y (b = 1), row y+1 (b = 0)
-				sw = mine[(1 * 2 + 0) * 32 + lane];
-				sv = mine[(1 * 2 + 1) * 32 + lane];
-				sw += above[(0 * 2 + 0) * 32 + lane];
-				sv += above[(0 * 2 + 1) * 32 + lane];
-			}
-			const int z = op - 1 + G.z0;
-			const long long me = x + (long long)G.nx * (y + (long long)G.ny * op);
-			double r = sw > 1e-6 ? sv / sw : 0.0; // src/simulation.cpp:380-386
-			const bool edge = COMP == 0 ? x == G.nx - 1 : (COMP == 1 ? y == G.ny - 1 : z == G.nz - 1);
-			if (METHOD == LFK_METHOD_FLIP) { O.old[me] = edge ? 0.0 : r; } // :340-344
-			if (APIC && edge) { r = 0.0; }                                  // :397
-			if (Q.add_gravity) { r += Q.gdt[COMP]; }                        // :72-78
-			O.out[me] = r;
-			if (COMP == 0) { // classification, once per cell (:388-393)
-				const uint8_t t = O.typ[me];
-				if (t != LFK_CELL_SOLID) {
-					O.typ[me] = (begin[me + 1] - begin[me]) > 0 ? LFK_CELL_FLUID : LFK_CELL_AIR;
-				}
-			}
-		}
-		par ^= 1; // the next flush writes the other slot set: one barrier per layer is enough
+		mbar_arrive(S.bar); // release: this thread's partials are visible to whoever completes the phase
+		S.pend = op;
+		par ^= 1;
 	}
 	// rotate: plane c+1 of this layer is plane c of the next one
 #pragma unroll
@@ -213,7 +265,7 @@ template <int COMP, int METHOD, int WARPS> __device__ __forceinline__ void pm_fi
 }
 
 template <int COMP, int METHOD, int WARPS> __device__ __forceinline__ void pm_march(const GridDesc &G, const PBParams &Q,
-	double *__restrict__ st, double *__restrict__ slots, const double *__restrict__ ztab, int &par,
+	double *__restrict__ st, double *__restrict__ slots, const double *__restrict__ ztab, int &par, PMSync &S,
 	const double *const *fields, const uint32_t *__restrict__ perm, const uint32_t *__restrict__ begin,
 	const double *__restrict__ cxs, const double *__restrict__ cys, int warp, int lane, int x0, int y0, int P0, int P1,
 	int nfx, const PMOut &O) {
@@ -276,7 +328,7 @@ template <int COMP, int METHOD, int WARPS> __device__ __forceinline__ void pm_ma
 		__syncwarp();
 		if (D0.win == 0) { // first window of a layer
 			if (D0.lz > lzA) {
-				pm_finish_layer<COMP, METHOD, WARPS>(G, Q, D0.lz - 1, P0, P1, slots, par, warp, lane, x, y, nfx, begin, O, accw, accv);
+				pm_finish_layer<COMP, METHOD, WARPS>(G, Q, D0.lz - 1, P0, P1, slots, par, S, warp, lane, x, y, nfx, begin, O, accw, accv);
 			}
 			const int zi = D0.lz - lzA; // ztab[i]: centre of the layer (lzA - 1 + i)
 			cc[6] = ztab[zi];
@@ -294,7 +346,8 @@ template <int COMP, int METHOD, int WARPS> __device__ __forceinline__ void pm_ma
 		R.advance(D2);
 		cur ^= 1;
 	}
-	pm_finish_layer<COMP, METHOD, WARPS>(G, Q, lzB, P0, P1, slots, par, warp, lane, x, y, nfx, begin, O, accw, accv);
+	pm_finish_layer<COMP, METHOD, WARPS>(G, Q, lzB, P0, P1, slots, par, S, warp, lane, x, y, nfx, begin, O, accw, accv);
+	pm_complete_pending<COMP, METHOD, WARPS>(G, Q, slots, par, S, warp, lane, x, y, nfx, begin, O);
 	cp_async_wait_all();
 }
 
@@ -307,6 +360,8 @@ template <int METHOD, int WARPS> __global__ void __maxnreg__(PM_REGS(WARPS)) k_p
 	double *stage_all = smem;                                   // [WARPS][2][PM_STAGE]
 	double *slots = smem + WARPS * 2 * PM_STAGE;                // [2][WARPS][PM_SLOT]
 	double *ztab = slots + 2 * WARPS * PM_SLOT;                 // [PM_MAX_CHUNK + 4]
+	__shared__ unsigned long long layer_bar;
+	if (threadIdx.x == 0) { mbar_init(&layer_bar, WARPS * 32); }
 	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 	double *st = stage_all + warp * (2 * PM_STAGE);
 	const int x0 = blockIdx.x * PM_BX, y0 = blockIdx.y * (WARPS - 2);
@@ -322,10 +377,11 @@ template <int METHOD, int WARPS> __global__ void __maxnreg__(PM_REGS(WARPS)) k_p
 #pragma unroll
 	for (int f = 0; f < 15; ++f) { fields[f] = P.f[f]; }
 	int par = 0;
+	PMSync S{ &layer_bar, 0u, -1 };
 	const PMOut O0{ u, uo, typ }, O1{ v, vo, typ }, O2{ w, wo, typ };
-	pm_march<0, METHOD, WARPS>(G, Q, st, slots, ztab, par, fields, perm, begin, cxs, cys, warp, lane, x0, y0, P0, P1, nfx, O0);
-	pm_march<1, METHOD, WARPS>(G, Q, st, slots, ztab, par, fields, perm, begin, cxs, cys, warp, lane, x0, y0, P0, P1, nfx, O1);
-	pm_march<2, METHOD, WARPS>(G, Q, st, slots, ztab, par, fields, perm, begin, cxs, cys, warp, lane, x0, y0, P0, P1, nfx, O2);
+	pm_march<0, METHOD, WARPS>(G, Q, st, slots, ztab, par, S, fields, perm, begin, cxs, cys, warp, lane, x0, y0, P0, P1, nfx, O0);
+	pm_march<1, METHOD, WARPS>(G, Q, st, slots, ztab, par, S, fields, perm, begin, cxs, cys, warp, lane, x0, y0, P0, P1, nfx, O1);
+	pm_march<2, METHOD, WARPS>(G, Q, st, slots, ztab, par, S, fields, perm, begin, cxs, cys, warp, lane, x0, y0, P0, P1, nfx, O2);
 }
 
 int lfkp_materialise_vc(lfk_ctx *c);
@@ -380,6 +436,7 @@ int lfkg_p2g_march(lfk_ctx *c, double gravity_dt, bool add_gravity) {
 	// one permutation serves the velocity and the c rows: make them agree (they differ only after lfkp_permute_c)
 	if (c->prm.method == LFK_METHOD_APIC && c->v_deferred != c->c_deferred) { LFK_TRY(lfkp_materialise_vc(c)); }
 	const uint32_t *perm = c->v_deferred ? c->perm : nullptr;
-	// (10 rows per block at 168 registers spill the accumulators: 25.8 ms against 15.2 ms at 256^3, r2c sweep)
+	// (10 rows per block at 168 registers spill the accumulators: 25.8 ms against 15.2 ms at 256^3, r2c sweep; 8 rows:
+	// 200 registers 14.75 ms, 224 (no spills) 14.05, 255 14.05, r3k)
 	return p2g_march_launch<8>(c, Q, perm);
 }

@@ -610,6 +610,9 @@ __global__ void k_collide(GridDesc G, MotionParams M, ParticleSoA P, const uint8
 // advect + collide in one pass: old_position is the pre-advection position held in registers.  (Queueing the particles
 // that cross a cell boundary in shared memory and marching them densely packed was measured: 3.26 ms against 3.02 ms
 // at 256^3, r2r sweep -- the block barrier and the queue cost more than the divergence of the march.)
+#ifndef ADV_THREADS
+#define ADV_THREADS 128
+#endif
 __global__ void k_advect_collide(GridDesc G, MotionParams M, ParticleSoA P, const uint8_t *__restrict__ typ,
 	unsigned long long n) {
 	unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -664,7 +667,7 @@ int lfkp_advect_collide(lfk_ctx *c, double dt) {
 	}
 	LFK_TRY(lfkp_materialise_vc(c));
 	if (c->np > 0) {
-		LFK_LAUNCH(c, k_advect_collide, lfk_blocks((long long)c->np, 128), 128, 0, c->g, motion_params(c, dt),
+		LFK_LAUNCH(c, k_advect_collide, lfk_blocks((long long)c->np, ADV_THREADS), ADV_THREADS, 0, c->g, motion_params(c, dt),
 			lfk_own_view(c), c->typ, (unsigned long long)c->np);
 	}
 	c->table_valid = false;

@@ -112,6 +112,14 @@ __device__ __forceinline__ double stencil_apply(const Stencil7 &v, int x, int y,
 	return a_scale * value;
 }
 
+// cells in flight per thread (rows_pipelined) of the two fp64 stencil / update passes
+#ifndef SPMV_U
+#define SPMV_U 4
+#endif
+#ifndef UPD_U
+#define UPD_U 4
+#endif
+
 __global__ void k_finalize(PcgScalars *scal, int which) {
 	if (which != FIN_BB && scal->done) { return; }
 	pcg_finalize(scal, which);
@@ -123,7 +131,7 @@ __global__ void __launch_bounds__(RED_THREADS) k_spmv_dot(GridDesc G, const uint
 	if (scal->done) { return; }
 	const double a_scale = scal->a_scale;
 	double acc = 0.0;
-	rows_pipelined<4, Stencil7>(G.nx, G.ny, G.nzl, 0, -1,
+	rows_pipelined<SPMV_U, Stencil7>(G.nx, G.ny, G.nzl, 0, -1,
 		[&](int, int, int, long long c) { return stencil_load(G, flags, s, c); },
 		[&](int x, int y, int, long long c, const Stencil7 &v) {
 			const double out = (v.f & FL_L) ? stencil_apply(v, x, y, a_scale) : 0.0;
@@ -261,7 +269,7 @@ __global__ void __launch_bounds__(RED_THREADS) k_update_pr(GridDesc G, double *_
 	const double alpha = scal->alpha, inv_a_scale = scal->inv_a_scale;
 	double m = 0.0;
 	struct PR { double p, s, r, z; unsigned f; };
-	rows_pipelined<4, PR>(G.nx, G.ny, G.nzl, 0, -1,
+	rows_pipelined<UPD_U, PR>(G.nx, G.ny, G.nzl, 0, -1,
 		[&](int, int, int, long long c) {
 			PR v;
 			v.p = p[c];

@@ -10,7 +10,7 @@ import json, sys
 for l in open(sys.argv[1]):
     if l.startswith("{"):
         d = json.loads(l)
-        print("   wall %.2f  " % d["ms_per_step_wall"], {k: round(v, 2) for k, v in d["phase_ms"].items() if v > 1.0})
+        print("   wall %.2f  pcg/it %.4f  " % (d["ms_per_step_wall"], d["pcg_ms_per_iter"]), {k: round(v, 2) for k, v in d["phase_ms"].items() if v > 1.0})
 PY
 }
 echo "== production"; timeout -k 5 200 python tools/variant_sweep.py --grid 256 --tag ${tag}_prod --only defaults > gpurun_out/${tag}_prod.log 2>&1; show gpurun_out/${tag}_prod.log
