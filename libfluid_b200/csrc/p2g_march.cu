@@ -88,14 +88,12 @@ struct PMRow {
 	int ok;                  // this lane's cell is inside the grid in x and y
 	int lzB;                 // last layer of the march
 	uint32_t pref_pb, pref_pe;
+	// (no select on the loaded values -- a consumer right behind the load would stall the warp for the whole memory
+	// latency: a lane outside the grid reads the same entry twice and gets an empty range)
 	__device__ __forceinline__ void load(int lz, uint32_t &pb, uint32_t &pe) const {
-		pb = 0;
-		pe = 0;
-		if (ok) {
-			const long long c = row0 + rstride * lz;
-			pb = begin[c];
-			pe = begin[c + 1];
-		}
+		const long long c = ok ? row0 + rstride * lz : 0;
+		pb = begin[c];
+		pe = begin[c + ok];
 	}
 	// next window of the stream; every layer has at least one (possibly empty) window
 	__device__ __forceinline__ void advance(PMWin &D) {
@@ -127,7 +125,11 @@ __device__ __forceinline__ void pm_perm_load(const PMWin &D, const uint32_t *__r
 		const int t = k * 32 + lane, sc = t / PB_WIN, ss = t % PB_WIN;
 		const uint32_t qb = __shfl_sync(PM_FULL, D.pb, sc), qe = __shfl_sync(PM_FULL, D.pe, sc);
 		const uint32_t q = qb + (uint32_t)D.win + (uint32_t)ss;
-		R[k] = (perm != nullptr && D.valid && q < qe) ? perm[q] : q;
+		// slots past the end of their cell read entry 0 (their index is never used): the loaded value goes straight
+		// into R[k], nothing waits for it before the next window's pm_issue (r3l: a select behind the load stalled the
+		// warp for the memory latency once per window, 13 % of the kernel's stall samples)
+		const uint32_t qs = (D.valid && q < qe) ? q : 0u;
+		R[k] = perm != nullptr ? perm[qs] : q;
 	}
 }
 
@@ -165,12 +167,11 @@ struct PMOut { // where one component goes
 // slot[y-1], slot[y], slot[y+1] in that fixed order, normalises, classifies, zeroes boundary faces, takes the FLIP
 // snapshot, adds gravity and writes the finished face row.
 template <int COMP, int METHOD, int WARPS> __device__ __forceinline__ void pm_store_plane(const GridDesc &G, const PBParams &Q,
-	int op, const double *__restrict__ set, int warp, int lane, int x, int y, int nfx,
-	const uint32_t *__restrict__ begin, const PMOut &O) {
+	int op, const double *__restrict__ set, int warp, int lane, int x, int y, bool owner, uint8_t type_now,
+	uint32_t count_now, const PMOut &O) {
 	constexpr int NB = COMP == 1 ? 2 : 3;
 	constexpr bool APIC = METHOD == LFK_METHOD_APIC;
-	const int fx = lane - 1; // owned face columns: lanes 1 .. 30
-	if (warp >= 1 && warp <= WARPS - 2 && y < G.ny && fx >= 0 && fx < nfx) {
+	if (owner) {
 		const double *mine = set + warp * PM_SLOT;
 		const double *below = set + (warp - 1) * PM_SLOT;
 		const double *above = set + (warp + 1) * PM_SLOT;
@@ -197,10 +198,7 @@ template <int COMP, int METHOD, int WARPS> __device__ __forceinline__ void pm_st
 		if (Q.add_gravity) { r += Q.gdt[COMP]; }                        // :72-78
 		O.out[me] = r;
 		if (COMP == 0) { // classification, once per cell (:388-393)
-			const uint8_t t = O.typ[me];
-			if (t != LFK_CELL_SOLID) {
-				O.typ[me] = (begin[me + 1] - begin[me]) > 0 ? LFK_CELL_FLUID : LFK_CELL_AIR;
-			}
+			if (type_now != LFK_CELL_SOLID) { O.typ[me] = count_now > 0 ? LFK_CELL_FLUID : LFK_CELL_AIR; }
 		}
 	}
 }
@@ -210,9 +208,21 @@ template <int COMP, int METHOD, int WARPS> __device__ __forceinline__ void pm_co
 	const double *__restrict__ slots, int par, PMSync &S, int warp, int lane, int x, int y, int nfx,
 	const uint32_t *__restrict__ begin, const PMOut &O) {
 	if (S.pend < 0) { return; } // block-uniform
+	const int fx = lane - 1; // owned face columns: lanes 1 .. 30
+	const bool owner = warp >= 1 && warp <= WARPS - 2 && y < G.ny && fx >= 0 && fx < nfx;
+	// the cell's type and particle count (classification) are requested before the wait, not behind it
+	uint8_t type_now = LFK_CELL_SOLID;
+	uint32_t b0 = 0, b1 = 0;
+	if (COMP == 0 && owner) {
+		const long long me = x + (long long)G.nx * (y + (long long)G.ny * S.pend);
+		type_now = O.typ[me];
+		b0 = begin[me];
+		b1 = begin[me + 1];
+	}
 	mbar_wait(S.bar, S.phase);
 	S.phase ^= 1u;
-	pm_store_plane<COMP, METHOD, WARPS>(G, Q, S.pend, slots + (par ^ 1) * WARPS * PM_SLOT, warp, lane, x, y, nfx, begin, O);
+	pm_store_plane<COMP, METHOD, WARPS>(G, Q, S.pend, slots + (par ^ 1) * WARPS * PM_SLOT, warp, lane, x, y, owner, type_now,
+		b1 - b0, O);
 	S.pend = -1;
 }
 

@@ -1,7 +1,7 @@
 #!/bin/bash
 # Runs ON a 1-GPU box: times the "defaults" configuration of tools/variant_sweep.py for the production library and
 # for every compile-time variant in libfluid_b200/_lib/variants/ (tools/build_variant.py).  Usage: gpu_variants.sh <tag> [names]
-set -u
+set -u; shopt -s nullglob
 tag=$1; names=${2:-}
 mkdir -p gpurun_out
 export PYTHONFAULTHANDLER=1
