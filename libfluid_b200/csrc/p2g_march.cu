@@ -32,7 +32,7 @@
 // WARPS (template parameter): warps per block = rows per block (two of them halo rows).  Warps are placed on the 4 SM
 // sub-partitions (16 K registers each), so ceil(WARPS / 4) * 32 * registers must fit: 8 warps at 200 registers, or 10 at 168.
 #ifndef PM_REGS8
-#define PM_REGS8 224
+#define PM_REGS8 216
 #endif
 #define PM_REGS(WARPS) ((WARPS) <= 8 ? PM_REGS8 : 168)
 #define PM_STAGE (PB_FIELDS * PB_FSTRIDE)       // doubles per staging buffer
@@ -447,6 +447,7 @@ int lfkg_p2g_march(lfk_ctx *c, double gravity_dt, bool add_gravity) {
 	if (c->prm.method == LFK_METHOD_APIC && c->v_deferred != c->c_deferred) { LFK_TRY(lfkp_materialise_vc(c)); }
 	const uint32_t *perm = c->v_deferred ? c->perm : nullptr;
 	// (10 rows per block at 168 registers spill the accumulators: 25.8 ms against 15.2 ms at 256^3, r2c sweep; 8 rows:
-	// 200 registers 14.75 ms, 224 (no spills) 14.05, 255 14.05, r3k)
+	// 200 registers 14.75 ms, 224 (no spills) 14.05, 255 14.05, r3k; after the r3l load fixes 208: 13.55, 216: 12.73,
+	// 224: 13.07, 232: 13.06, 255: 13.10, r3o -- register allocation luck decides at this level)
 	return p2g_march_launch<8>(c, Q, perm);
 }

@@ -980,12 +980,16 @@ template <bool COLLIDE> __global__ void __launch_bounds__(CT_THREADS, CT_BLOCKS)
 				// candidate's position is fetched one iteration ahead of its use
 				int k = 0;
 				uint32_t m = 0, jb = 0;
+				// the record after the current one is fetched while the current one is worked off (the records live in local
+				// memory; r3n: 10.7 % of the kernel's stall samples sat on the compare behind that load; r3p: 26.96 -> 26.44 ms)
+				uint2 rnext = rec[0];
 				auto next_hit = [&](uint32_t &j) -> bool { // advances to the next recorded candidate
 					while (m == 0u) {
 						if (k >= nr) { return false; }
-						m = rec[k].x;
-						jb = rec[k].y;
+						m = rnext.x;
+						jb = rnext.y;
 						++k;
+						rnext = rec[k < CT_LIST ? k : CT_LIST - 1];
 					}
 					j = jb + (uint32_t)(__ffs((int)m) - 1);
 					m &= m - 1u;
