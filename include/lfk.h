@@ -168,7 +168,9 @@ int lfk_correct(lfk_ctx *ctx, double dt);
 int lfk_extrapolate(lfk_ctx *ctx);
 /* _transfer_from_grid (src/simulation.cpp:447-560, src/mac_grid.cpp:40-112) */
 int lfk_g2p(lfk_ctx *ctx);
-/* simulation::cfl (src/simulation.cpp:199-205) */
+/* simulation::cfl (src/simulation.cpp:199-205).  After a G2P (staged or inside lfk_time_step) the maximum |v|^2 comes
+ * from that kernel; anything that rewrites particles afterwards (uploads, seeding, sources, checkpoint load) makes the
+ * next call reduce over the particles again.  The value is the same either way (a maximum has no order). */
 int lfk_cfl(lfk_ctx *ctx, double *value);
 
 /* ---- fluid sources (simulation::sources, include/fluid/data_structures/source.h:12-22) on the device --------- */

@@ -1,4 +1,4 @@
-// Shared by the P2G kernels (p2g_brick.cu, p2g_march.cu): the per-cell register accumulation of one velocity
+// Used by the marching P2G kernel (p2g_march.cu): the per-cell register accumulation of one velocity
 // component from particles staged in shared memory as [field][cell * PB_CSTRIDE + slot].
 // Reference: simulation::_transfer_to_grid_{pic,flip,apic}, src/simulation.cpp:293-412.
 #pragma once

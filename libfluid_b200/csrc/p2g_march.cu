@@ -7,17 +7,19 @@
 // (the WARPS - 2 owned rows plus one halo row either side), lane <-> cell x (30 owned columns plus one halo column either
 // side).  All warps march through the cell layers of the chunk together.  For the layer it is in, a lane runs over
 // the particles of ITS cell and accumulates, in registers, their contributions to the 2 x 3 x 3 faces the cell can
-// reach (per velocity component) -- the per-cell arithmetic of p2g_accum.cuh.  What differs from the brick kernel
-// (p2g_brick.cu, kept as the A/B reference) is where the sums go next:
+// reach (per velocity component) -- the per-cell arithmetic of p2g_accum.cuh.  Where the sums go next:
 //   * along z the accumulators ROTATE: the partial sum a column holds for face plane k collects the contributions
 //     of its cells in layers k-1, k, k+1 without leaving the registers, and is flushed once, when the march has
 //     passed layer k+1 (3x fewer flushed values than one flush per cell);
 //   * along x the three (two) columns that reach a face are combined with warp shuffles;
-//   * along y each warp writes its three (two) row partials into its own shared-memory slot, and after one block
-//     barrier the warp that owns row y adds slot[y-1], slot[y], slot[y+1] in that fixed order, normalises,
-//     classifies, zeroes boundary faces, takes the FLIP snapshot, adds gravity and writes the finished face row.
-// No colouring, no read-modify-write on shared accumulators, one barrier per layer.  Halo recomputation: 32/30 in x,
-// WARPS/(WARPS - 2) in y, (chunk + 2)/chunk in z (1.33x .. 1.4x, against 1.65x for the brick).
+//   * along y each warp writes its three (two) row partials into its own shared-memory slot and ANNOUNCES them on an
+//     mbarrier; one layer later it waits for the announcements of all warps, and the warp that owns row y adds
+//     slot[y-1], slot[y], slot[y+1] in that fixed order, normalises, classifies, zeroes boundary faces, takes the
+//     FLIP snapshot, adds gravity and writes the finished face row.  Two slot sets alternate, so a warp whose rows
+//     hold fewer particles runs up to one layer ahead of the others instead of idling at a block barrier per layer
+//     (the __syncthreads() form: 15.3 ms at 256^3, this form 14.75, r3k).
+// No colouring, no read-modify-write on shared accumulators.  Halo recomputation: 32/30 in x, WARPS/(WARPS - 2) in y,
+// (chunk + 2)/chunk in z (1.33x .. 1.4x).
 //
 // Staging: per warp two buffers of [field][cell * PB_CSTRIDE + slot]; window n+1 (4 particle slots per cell) is
 // copied with cp.async while window n is being accumulated, and the permutation indices (lean sort: velocity / c
