@@ -145,7 +145,7 @@ def pcg(A, b, M, tol_abs, maxit=2000):
     return x, maxit
 
 
-# ---- experiments behind DESIGN.md section 7 (python tools/mg_prototype.py 64 wave,full --experiments) -------------
+# ---- experiments behind DESIGN.md section 3.2 (python tools/mg_prototype.py 64 wave,full --experiments) -------------
 def _quant(dtype):
     return lambda v: v.astype(dtype).astype(np.float64)
 
